@@ -1,0 +1,95 @@
+// api.cu -- context lifetime + error plumbing of libsentio_b200.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void sb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void ce_model_free(CeModel* m);  // cross_encoder.cu
+
+extern "C" {
+
+const char* sb_last_error(void) { return g_err; }
+
+int sb_version(void) { return 1000; }
+
+int sb_create(int device, sb_ctx** out) {
+  SB_REQUIRE(out != nullptr, SB_ERR_ARG, "sb_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    sb_set_error("sb_create: no CUDA device visible (%s); libsentio_b200 has no CPU fallback",
+                 e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return SB_ERR_CUDA;
+  }
+  SB_REQUIRE(device >= 0 && device < ndev, SB_ERR_ARG, "sb_create: device %d out of range [0,%d)", device, ndev);
+  DeviceGuard g(device);
+  cudaDeviceProp prop;
+  SB_CUDA(cudaGetDeviceProperties(&prop, device));
+  SB_REQUIRE(prop.major == 10, SB_ERR_UNSUPPORTED,
+             "sb_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
+             prop.minor);
+  sb_ctx* ctx = new sb_ctx();
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  cudaError_t se = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (se != cudaSuccess) {
+    sb_set_error("sb_create: cudaStreamCreate failed: %s", cudaGetErrorString(se));
+    delete ctx;
+    return SB_ERR_CUDA;
+  }
+  *out = ctx;
+  return SB_OK;
+}
+
+void sb_destroy(sb_ctx* ctx) {
+  if (!ctx) return;
+  DeviceGuard g(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int s = 0; s < SB_MAX_DENSE_SLOTS; ++s) {
+    if (ctx->dense[s].rows) cudaFree(ctx->dense[s].rows);
+    if (ctx->dense[s].inv_norm) cudaFree(ctx->dense[s].inv_norm);
+  }
+  Bm25Index& b = ctx->bm25;
+  if (b.indptr) cudaFree(b.indptr);
+  if (b.post_doc) cudaFree(b.post_doc);
+  if (b.post_ratio) cudaFree(b.post_ratio);
+  if (b.dnorm) cudaFree(b.dnorm);
+  if (b.idf) cudaFree(b.idf);
+  if (ctx->ce) ce_model_free(ctx->ce);
+  ctx->q_dev.release();
+  ctx->cand_dev.release();
+  ctx->out_ids_dev.release();
+  ctx->out_sc_dev.release();
+  ctx->out_cnt_dev.release();
+  ctx->misc_dev.release();
+  ctx->misc2_dev.release();
+  ctx->misc3_dev.release();
+  ctx->acc_dev.release();
+  ctx->pin_in.release();
+  ctx->pin_out.release();
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int sb_num_sms(sb_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
+
+int sb_sync(sb_ctx* ctx) {
+  SB_REQUIRE(ctx != nullptr, SB_ERR_ARG, "sb_sync: ctx is NULL");
+  DeviceGuard g(ctx->device);
+  SB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SB_OK;
+}
+
+void* sb_stream(sb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+}  // extern "C"

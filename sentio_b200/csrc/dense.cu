@@ -1,0 +1,770 @@
+// dense.cu -- K1: brute-force cosine top-k over an HBM-resident fp16 corpus.
+//
+// Replaces the Qdrant `client.search(...)` behind DenseRetriever.retrieve (reference src/core/retrievers/dense.py:41-64).
+//
+// Pipeline per pass of QB (1/2/4) queries:
+//   dense_scan_kernel   persistent, one CTA per SM.  A producer warp streams row tiles HBM -> smem with 1-D bulk
+//                       async copies (cp.async.bulk, the TMA engine; SASS UBLKCP) through an mbarrier ring; 8 consumer
+//                       warps compute fp32 dot products (queries live in registers), apply the stored inverse row norm
+//                       and push candidates that beat the CTA's running K'-th best into a smem candidate buffer that
+//                       is compacted by an in-smem bitonic sort.  Output: one sorted top-K' list per CTA per query
+//                       (K' = k + slack, power of two).
+//   dense_merge_kernel  one CTA per query: truncating bitonic merge tree over the per-CTA lists, exact fp64 re-score
+//                       of the K' survivors against the STORED fp16 rows, final sort by (score desc, id asc), write k.
+//
+// Algorithmic HBM bytes per pass = n_pad * d_pad * 2 (+ n_pad * 4 for the inverse norms); see DESIGN.md.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumerThreads = kConsumerWarps * 32;
+constexpr int kScanThreads = kConsumerThreads + 32;  // + 1 producer warp
+constexpr int kMergeThreads = 1024;
+constexpr int kRowPad = 32;  // n_pad granularity (max tile rows)
+
+// ------------------------------------------------------------------------------------------------ load kernels
+// One warp per row.  f32 input: x16 = fp16(x / ||x||) (division in fp64, single rounding); f16 input: verbatim.
+// inv_norm = 1/||x16|| of the stored values (fp64 accumulate), 0 for all-zero rows.
+template <typename TIn>
+__global__ void dense_store_rows_kernel(const TIn* __restrict__ in, int64_t n_rows, int32_t d, int32_t d_pad,
+                                        __half* __restrict__ rows, float* __restrict__ inv_norm, int64_t row0,
+                                        bool normalise) {
+  int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (r >= n_rows) return;
+  const TIn* src = in + r * (int64_t)d;
+  __half* dst = rows + (row0 + r) * (int64_t)d_pad;
+  double scale = 1.0;
+  if (normalise) {
+    double ss = 0.0;
+    for (int i = lane; i < d; i += 32) {
+      double v = (double)(float)src[i];
+      ss += v * v;
+    }
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    scale = ss > 0.0 ? sqrt(ss) : 1.0;
+  }
+  double ss16 = 0.0;
+  for (int i = lane; i < d_pad; i += 32) {
+    __half h = __float2half(0.f);
+    if (i < d) {
+      double v = (double)(float)src[i];
+      h = normalise ? __double2half(v / scale) : __float2half((float)v);
+    }
+    dst[i] = h;
+    double hv = (double)__half2float(h);
+    ss16 += hv * hv;
+  }
+  for (int o = 16; o; o >>= 1) ss16 += __shfl_xor_sync(0xffffffffu, ss16, o);
+  if (lane == 0) inv_norm[row0 + r] = ss16 > 0.0 ? (float)(1.0 / sqrt(ss16)) : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------ scan kernel
+struct ScanParams {
+  const __half* rows;
+  const float* inv_norm;
+  const float* q;            // [QB][d_pad] fp32 (zero padded) for THIS pass
+  unsigned long long* cand;  // [QB][grid][kprime] composite keys, sorted descending per list
+  int64_t n;                 // valid rows
+  int32_t d_pad;
+  int32_t ch;                // 16-byte chunks per row = d_pad / 8
+  int32_t num_tiles;
+  int32_t kprime;
+  int32_t cap;               // candidate buffer capacity per query (power of two, >= 2*kprime, > kprime + tile rows)
+  int32_t stages;
+  uint32_t tile_bytes;
+};
+
+// Sum V per-lane partials across the warp: afterwards the lanes with (lane % (32/V)) == 0 hold value index lane/(32/V).
+template <int V>
+__device__ __forceinline__ float warp_reduce_multi(float (&v)[V], int lane) {
+  int off = 16;
+#pragma unroll
+  for (int half = V / 2; half >= 1; half >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int t = 0; t < half; ++t) {
+      float send = upper ? v[t] : v[t + half];
+      float keep = upper ? v[t + half] : v[t];
+      v[t] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+    off >>= 1;
+  }
+  float r = v[0];
+  for (; off >= 1; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+  return r;
+}
+
+// Descending bitonic sort of `len` (power of two) 64-bit keys in shared memory by the 256 consumer threads.
+__device__ __forceinline__ void consumer_bitonic_sort_desc(unsigned long long* buf, int len, int t) {
+  for (int k = 2; k <= len; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = t; i < len; i += kConsumerThreads) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          unsigned long long a = buf[i], b = buf[ixj];
+          bool desc = (i & k) == 0;
+          if (desc ? (a < b) : (a > b)) {
+            buf[i] = b;
+            buf[ixj] = a;
+          }
+        }
+      }
+      named_bar_sync(1, kConsumerThreads);
+    }
+  }
+}
+
+template <int NCHUNK, int QB, int RW>
+__global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanParams p) {
+  constexpr int R = kConsumerWarps * RW;  // rows per tile
+  constexpr int V = RW * QB;              // partial sums per lane
+  constexpr int LPV = 32 / V;             // lanes per value after the reduction
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* tiles = smem;
+  unsigned long long* cbuf = reinterpret_cast<unsigned long long*>(smem + (size_t)p.stages * p.tile_bytes);
+  unsigned long long* bars = cbuf + (size_t)QB * p.cap;  // full[stages], empty[stages]
+  volatile int* cnt = reinterpret_cast<volatile int*>(bars + 2 * p.stages);
+  volatile float* thr = reinterpret_cast<volatile float*>(const_cast<int*>(cnt) + QB);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int stages = p.stages;
+  const uint32_t bar_full0 = smem_u32(bars), bar_empty0 = smem_u32(bars + stages);
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(bar_full0 + 8 * s, 1);
+      mbar_init(bar_empty0 + 8 * s, kConsumerWarps);
+    }
+    mbar_fence_init();
+  }
+  if (tid < QB) {
+    cnt[tid] = 0;
+    thr[tid] = -INFINITY;
+  }
+  __syncthreads();
+
+  const int grid = gridDim.x;
+  const int my_tiles = ((int)blockIdx.x < p.num_tiles) ? (p.num_tiles - 1 - (int)blockIdx.x) / grid + 1 : 0;
+  const uint32_t row_bytes = (uint32_t)p.d_pad * 2u;
+
+  if (warp == kConsumerWarps) {
+    // ------------------------------------------------------------ producer warp: one elected lane drives the TMA ring
+    if (lane == 0) {
+      const uint64_t policy = policy_evict_first();
+      const uint32_t tiles_s = smem_u32(tiles);
+      for (int i = 0; i < my_tiles; ++i) {
+        const int s = i % stages;
+        const uint32_t use = (uint32_t)(i / stages);
+        if (i >= stages) mbar_wait(bar_empty0 + 8 * s, (use & 1u) ^ 1u);
+        const int64_t tile = (int64_t)blockIdx.x + (int64_t)i * grid;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.rows) + (size_t)tile * p.tile_bytes;
+        mbar_expect_tx(bar_full0 + 8 * s, p.tile_bytes);
+        bulk_g2s(tiles_s + (uint32_t)s * p.tile_bytes, src, p.tile_bytes, bar_full0 + 8 * s, policy);
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------- consumer warps
+  // query slices in registers: lane owns 16-byte chunk c = lane + 32*j of every row
+  float qr[QB][NCHUNK][8];
+#pragma unroll
+  for (int q = 0; q < QB; ++q) {
+#pragma unroll
+    for (int j = 0; j < NCHUNK; ++j) {
+      const int c = lane + 32 * j;
+      if (c < p.ch) {
+        const float4* src = reinterpret_cast<const float4*>(p.q + (size_t)q * p.d_pad + (size_t)c * 8);
+        float4 a = __ldg(src), b = __ldg(src + 1);
+        qr[q][j][0] = a.x; qr[q][j][1] = a.y; qr[q][j][2] = a.z; qr[q][j][3] = a.w;
+        qr[q][j][4] = b.x; qr[q][j][5] = b.y; qr[q][j][6] = b.z; qr[q][j][7] = b.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) qr[q][j][e] = 0.f;
+      }
+    }
+  }
+
+  const int vi = lane / LPV;          // which (row, query) this lane owns after the reduction
+  const int ri = vi / QB, qi = vi % QB;
+  const bool leader = (lane % LPV) == 0;
+  const int trigger = p.cap - R;
+
+  for (int i = 0; i < my_tiles; ++i) {
+    const int s = i % stages;
+    const uint32_t use = (uint32_t)(i / stages);
+    const int64_t tile = (int64_t)blockIdx.x + (int64_t)i * grid;
+    const int64_t grow = tile * R + warp * RW + ri;
+    float invn = 0.f;
+    if (leader) invn = __ldg(p.inv_norm + grow);  // issued before the wait: latency overlaps the TMA wait
+
+    mbar_wait(bar_full0 + 8 * s, use & 1u);
+
+    float acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = 0.f;
+    const uint8_t* wbase = tiles + (size_t)s * p.tile_bytes + (size_t)(warp * RW) * row_bytes;
+#pragma unroll
+    for (int j = 0; j < NCHUNK; ++j) {
+      const int c = lane + 32 * j;
+      if (c < p.ch) {
+#pragma unroll
+        for (int r = 0; r < RW; ++r) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(wbase + (size_t)r * row_bytes + (size_t)c * 16);
+          const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+          const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+          const float2 x2 = __half22float2(*reinterpret_cast<const __half2*>(&raw.z));
+          const float2 x3 = __half22float2(*reinterpret_cast<const __half2*>(&raw.w));
+#pragma unroll
+          for (int q = 0; q < QB; ++q) {
+            float a = acc[r * QB + q];
+            a = fmaf(x0.x, qr[q][j][0], a);
+            a = fmaf(x0.y, qr[q][j][1], a);
+            a = fmaf(x1.x, qr[q][j][2], a);
+            a = fmaf(x1.y, qr[q][j][3], a);
+            a = fmaf(x2.x, qr[q][j][4], a);
+            a = fmaf(x2.y, qr[q][j][5], a);
+            a = fmaf(x3.x, qr[q][j][6], a);
+            a = fmaf(x3.y, qr[q][j][7], a);
+            acc[r * QB + q] = a;
+          }
+        }
+      }
+    }
+    // all smem reads of this stage are consumed (their values fed the FMAs above) -> release the slot
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty0 + 8 * s);
+
+    const float dot = warp_reduce_multi<V>(acc, lane);
+    if (leader) {
+      const float score = dot * invn;
+      if (grow < p.n && score > thr[qi]) {
+        const int pos = atomicAdd(const_cast<int*>(&cnt[qi]), 1);
+        if (pos < p.cap) cbuf[(size_t)qi * p.cap + pos] = make_key32(score, (uint32_t)grow);
+      }
+    }
+    bool need = false;
+#pragma unroll
+    for (int q = 0; q < QB; ++q) need |= (cnt[q] > trigger);
+    need = named_bar_or(2, kConsumerThreads, need);
+    if (need) {
+      for (int q = 0; q < QB; ++q) {
+        const int c = cnt[q];
+        if (c > trigger) {  // uniform: read after the barrier, nobody appends until the next tile
+          unsigned long long* buf = cbuf + (size_t)q * p.cap;
+          const int nvalid = min(c, p.cap);
+          for (int z = nvalid + tid; z < p.cap; z += kConsumerThreads) buf[z] = 0ull;
+          named_bar_sync(1, kConsumerThreads);
+          consumer_bitonic_sort_desc(buf, p.cap, tid);
+          if (tid == 0) {
+            cnt[q] = min(nvalid, p.kprime);
+            if (nvalid >= p.kprime) thr[q] = key32_score(buf[p.kprime - 1]);
+          }
+        }
+      }
+      named_bar_sync(1, kConsumerThreads);
+    }
+  }
+
+  // -------------------------------------------------------------- final: sort every buffer, emit the top-K' list
+  named_bar_sync(1, kConsumerThreads);
+  for (int q = 0; q < QB; ++q) {
+    unsigned long long* buf = cbuf + (size_t)q * p.cap;
+    const int nvalid = min((int)cnt[q], p.cap);
+    for (int z = nvalid + tid; z < p.cap; z += kConsumerThreads) buf[z] = 0ull;
+    named_bar_sync(1, kConsumerThreads);
+    consumer_bitonic_sort_desc(buf, p.cap, tid);
+    unsigned long long* out = p.cand + ((size_t)q * grid + blockIdx.x) * p.kprime;
+    for (int z = tid; z < p.kprime; z += kConsumerThreads) out[z] = buf[z];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ merge kernel
+struct MergeParams {
+  unsigned long long* cand;  // [QB][G][kprime]
+  int32_t G;
+  int32_t kprime;
+  const __half* rows;
+  const float* q;  // [QB][d_pad]
+  int32_t d_pad;
+  int32_t ch;
+  int64_t id_base;
+  int32_t k;
+  int64_t* out_ids;     // [.][k]  (already offset to this pass' first query)
+  double* out_scores;   // [.][k]
+  int32_t* out_counts;  // [.]
+  int32_t lists_in_smem;
+};
+
+__global__ void __launch_bounds__(kMergeThreads, 1) dense_merge_kernel(const MergeParams p) {
+  extern __shared__ __align__(16) uint8_t msmem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int qi = blockIdx.x;
+  const int G = p.G, K = p.kprime;
+  unsigned long long* ek = reinterpret_cast<unsigned long long*>(msmem);       // [K] exact score keys
+  uint32_t* ei = reinterpret_cast<uint32_t*>(ek + K);                           // [K] row index
+  double* qq_s = reinterpret_cast<double*>(ei + K + (K & 1));                   // [1]
+  unsigned long long* L = p.cand + (size_t)qi * G * K;
+  if (p.lists_in_smem) {
+    unsigned long long* Ls = reinterpret_cast<unsigned long long*>(qq_s + 2);
+    for (int i = tid; i < G * K; i += kMergeThreads) Ls[i] = L[i];
+    L = Ls;
+  }
+  __syncthreads();
+
+  // truncating bitonic merge tree: list a (stride 2^(l+1)) <- top-K of (a U a+2^l)
+  for (int step = 1; step < G; step <<= 1) {
+    const int pairs = (G - step + 2 * step - 1) / (2 * step);  // lists a = 2*step*pi with partner a+step < G
+    // phase 1: C[i] = max(A[i], B[K-1-i])  (bitonic, holds the K largest of the union)
+    for (int t = tid; t < pairs * K; t += kMergeThreads) {
+      const int pi = t / K, i = t - pi * K;
+      const int a = pi * 2 * step, b = a + step;
+      if (b < G) {
+        unsigned long long x = L[(size_t)a * K + i], y = L[(size_t)b * K + (K - 1 - i)];
+        if (y > x) L[(size_t)a * K + i] = y;
+      }
+    }
+    __syncthreads();
+    // phase 2: bitonic merge network -> descending
+    for (int j = K >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < pairs * (K >> 1); t += kMergeThreads) {
+        const int pi = t / (K >> 1), h = t - pi * (K >> 1);
+        const int a = pi * 2 * step;
+        if (a + step < G) {
+          const int i = ((h / j) * 2 * j) + (h % j);
+          unsigned long long* A = L + (size_t)a * K;
+          unsigned long long x = A[i], y = A[i + j];
+          if (x < y) {
+            A[i] = y;
+            A[i + j] = x;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // exact fp64 re-score of the K survivors against the stored fp16 rows
+  const float* q = p.q + (size_t)qi * p.d_pad;
+  if (warp == 0) {
+    double s = 0.0;
+    for (int i = lane; i < p.d_pad; i += 32) {
+      double v = (double)q[i];
+      s += v * v;
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) qq_s[0] = s;
+  }
+  __syncthreads();
+  const double qn = sqrt(qq_s[0]);
+  for (int c = warp; c < K; c += kMergeThreads / 32) {
+    const unsigned long long key = L[c];
+    unsigned long long okey = 0ull;
+    uint32_t idx = 0xffffffffu;
+    if (key != 0ull) {
+      idx = key32_idx(key);
+      const uint4* row = reinterpret_cast<const uint4*>(p.rows + (size_t)idx * p.d_pad);
+      double dot = 0.0, xx = 0.0;
+      for (int ch = lane; ch < p.ch; ch += 32) {
+        const uint4 raw = __ldg(row + ch);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+        const float4 qa = *reinterpret_cast<const float4*>(q + (size_t)ch * 8);
+        const float4 qb = *reinterpret_cast<const float4*>(q + (size_t)ch * 8 + 4);
+        const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 xf = __half22float2(h2[e]);
+          const double x0 = (double)xf.x, x1 = (double)xf.y;
+          dot += x0 * (double)qv[2 * e];
+          dot += x1 * (double)qv[2 * e + 1];
+          xx += x0 * x0;
+          xx += x1 * x1;
+        }
+      }
+      for (int o = 16; o; o >>= 1) {
+        dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        xx += __shfl_xor_sync(0xffffffffu, xx, o);
+      }
+      const double den = qn * sqrt(xx);
+      const double score = den > 0.0 ? dot / den : 0.0;
+      okey = f64_orderable(score);
+      if (okey == 0ull) okey = 1ull;  // keep 0 reserved for "empty"
+    }
+    if (lane == 0) {
+      ek[c] = okey;
+      ei[c] = idx;
+    }
+  }
+  __syncthreads();
+  // final sort by (exact score desc, row index asc)
+  for (int kk = 2; kk <= K; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < K; i += kMergeThreads) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = ek[i], b = ek[ixj];
+          const uint32_t ia = ei[i], ib = ei[ixj];
+          const bool a_before_b = (a > b) || (a == b && ia < ib);
+          const bool desc = (i & kk) == 0;
+          if (desc ? !a_before_b : a_before_b) {
+            if (!(a == b && ia == ib)) {
+              ek[i] = b; ek[ixj] = a;
+              ei[i] = ib; ei[ixj] = ia;
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  int64_t* oid = p.out_ids + (size_t)qi * p.k;
+  double* osc = p.out_scores + (size_t)qi * p.k;
+  for (int i = tid; i < p.k; i += kMergeThreads) {
+    const bool valid = (i < K) && ek[i] != 0ull;
+    oid[i] = valid ? p.id_base + (int64_t)ei[i] : -1;
+    osc[i] = valid ? orderable_f64(ek[i]) : 0.0;
+  }
+  if (tid == 0) {
+    int c = 0;
+    const int lim = min(p.k, K);
+    // valid entries are a prefix (empty keys sort last)
+    int lo = 0, hi = lim;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (ek[mid] != 0ull) lo = mid + 1; else hi = mid;
+    }
+    c = lo;
+    p.out_counts[qi] = c;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+struct ScanPlan {
+  int nchunk, rw, qb_max, kprime, cap, stages, grid, num_tiles;
+  uint32_t tile_bytes;
+  size_t scan_smem, merge_smem;
+  int lists_in_smem;
+};
+
+int supported_nchunk(int ch) {
+  const int need = (ch + 31) / 32;
+  static const int sup[] = {1, 2, 3, 4, 6, 8, 12, 16};
+  for (int s : sup)
+    if (s >= need) return s;
+  return -1;
+}
+
+int make_plan(sb_ctx* ctx, const DenseIndex& ix, int k, ScanPlan* pl) {
+  const int ch = ix.d_pad / 8;
+  pl->nchunk = supported_nchunk(ch);
+  SB_REQUIRE(pl->nchunk > 0, SB_ERR_UNSUPPORTED, "dense: dimension %d too large (max 4096)", ix.d);
+  pl->rw = pl->nchunk <= 4 ? 4 : (pl->nchunk <= 8 ? 2 : 1);
+  pl->qb_max = pl->nchunk <= 4 ? 4 : (pl->nchunk <= 8 ? 2 : 1);
+  const int slack = 28;
+  pl->kprime = next_pow2(k + slack);
+  if (pl->kprime < 32) pl->kprime = 32;
+  SB_REQUIRE(pl->kprime <= 1024, SB_ERR_UNSUPPORTED, "dense: top_k %d too large (max %d)", k, 1024 - slack);
+  const int R = kConsumerWarps * pl->rw;
+  pl->cap = pl->kprime * 4;
+  if (pl->cap < 256) pl->cap = 256;
+  pl->tile_bytes = (uint32_t)R * (uint32_t)ix.d_pad * 2u;
+  pl->num_tiles = (int)(ix.n_pad / R);
+  const size_t budget = ctx->smem_optin;
+  // shrink the candidate buffers / query batch until at least 2 stages fit
+  for (;;) {
+    const size_t fixed = (size_t)pl->qb_max * pl->cap * 8 + 2 * 8 * 8 + 64 + 128;
+    if (fixed + 2 * (size_t)pl->tile_bytes <= budget) break;
+    if (pl->cap > 2 * pl->kprime && pl->cap - R > pl->kprime) { pl->cap >>= 1; continue; }
+    if (pl->qb_max > 1) { pl->qb_max >>= 1; continue; }
+    sb_set_error("dense: configuration does not fit shared memory (d=%d, k=%d)", ix.d, k);
+    return SB_ERR_UNSUPPORTED;
+  }
+  SB_REQUIRE(pl->cap - R >= pl->kprime, SB_ERR_UNSUPPORTED, "dense: internal cap/trigger invariant violated");
+  const size_t fixed = (size_t)pl->qb_max * pl->cap * 8;
+  int stages = (int)((budget - fixed - 512) / pl->tile_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  pl->stages = stages;
+  pl->scan_smem = (size_t)stages * pl->tile_bytes + fixed + 2 * 8 * (size_t)stages + 64;
+  pl->grid = ctx->num_sms < pl->num_tiles ? ctx->num_sms : pl->num_tiles;
+  if (pl->grid < 1) pl->grid = 1;
+  const size_t small = (size_t)pl->kprime * 12 + 64;
+  const size_t lists = (size_t)pl->grid * pl->kprime * 8;
+  pl->lists_in_smem = (small + lists + 64 <= budget) ? 1 : 0;
+  pl->merge_smem = small + (pl->lists_in_smem ? lists : 0) + 64;
+  return SB_OK;
+}
+
+template <int NCHUNK, int QB, int RW>
+int launch_scan(const ScanParams& sp, const ScanPlan& pl, cudaStream_t st) {
+  auto kern = dense_scan_kernel<NCHUNK, QB, RW>;
+  SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.scan_smem));
+  kern<<<pl.grid, kScanThreads, pl.scan_smem, st>>>(sp);
+  SB_CUDA(cudaGetLastError());
+  return SB_OK;
+}
+
+template <int NCHUNK, int RW>
+int dispatch_qb(int qb, const ScanParams& sp, const ScanPlan& pl, cudaStream_t st) {
+  if constexpr (NCHUNK <= 4) {
+    if (qb == 4) return launch_scan<NCHUNK, 4, RW>(sp, pl, st);
+  }
+  if constexpr (NCHUNK <= 8) {
+    if (qb == 2) return launch_scan<NCHUNK, 2, RW>(sp, pl, st);
+  }
+  return launch_scan<NCHUNK, 1, RW>(sp, pl, st);
+}
+
+int dispatch_scan(int qb, const ScanParams& sp, const ScanPlan& pl, cudaStream_t st) {
+  switch (pl.nchunk) {
+    case 1: return dispatch_qb<1, 4>(qb, sp, pl, st);
+    case 2: return dispatch_qb<2, 4>(qb, sp, pl, st);
+    case 3: return dispatch_qb<3, 4>(qb, sp, pl, st);
+    case 4: return dispatch_qb<4, 4>(qb, sp, pl, st);
+    case 6: return dispatch_qb<6, 2>(qb, sp, pl, st);
+    case 8: return dispatch_qb<8, 2>(qb, sp, pl, st);
+    case 12: return dispatch_qb<12, 1>(qb, sp, pl, st);
+    case 16: return dispatch_qb<16, 1>(qb, sp, pl, st);
+  }
+  sb_set_error("dense: unsupported chunk count %d", pl.nchunk);
+  return SB_ERR_UNSUPPORTED;
+}
+
+// q_pad: [B][d_pad] fp32 device, zero padded.  Enqueues all passes on `st`.
+int dense_topk_enqueue(sb_ctx* ctx, const DenseIndex& ix, const float* q_pad, int B, int k, int64_t* out_ids,
+                       double* out_scores, int32_t* out_counts, cudaStream_t st) {
+  ScanPlan pl;
+  int rc = make_plan(ctx, ix, k, &pl);
+  if (rc) return rc;
+  rc = ctx->cand_dev.reserve((size_t)pl.qb_max * pl.grid * pl.kprime * 8);
+  if (rc) return rc;
+  SB_CUDA(cudaFuncSetAttribute(dense_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.merge_smem));
+  int b0 = 0;
+  while (b0 < B) {
+    int qb = pl.qb_max;
+    while (qb > B - b0) qb >>= 1;
+    ScanParams sp;
+    sp.rows = ix.rows;
+    sp.inv_norm = ix.inv_norm;
+    sp.q = q_pad + (size_t)b0 * ix.d_pad;
+    sp.cand = ctx->cand_dev.as<unsigned long long>();
+    sp.n = ix.n;
+    sp.d_pad = ix.d_pad;
+    sp.ch = ix.d_pad / 8;
+    sp.num_tiles = pl.num_tiles;
+    sp.kprime = pl.kprime;
+    sp.cap = pl.cap;
+    sp.stages = pl.stages;
+    sp.tile_bytes = pl.tile_bytes;
+    rc = dispatch_scan(qb, sp, pl, st);
+    if (rc) return rc;
+    MergeParams mp;
+    mp.cand = sp.cand;
+    mp.G = pl.grid;
+    mp.kprime = pl.kprime;
+    mp.rows = ix.rows;
+    mp.q = sp.q;
+    mp.d_pad = ix.d_pad;
+    mp.ch = sp.ch;
+    mp.id_base = ix.id_base;
+    mp.k = k;
+    mp.out_ids = out_ids + (size_t)b0 * k;
+    mp.out_scores = out_scores + (size_t)b0 * k;
+    mp.out_counts = out_counts + b0;
+    mp.lists_in_smem = pl.lists_in_smem;
+    dense_merge_kernel<<<qb, kMergeThreads, pl.merge_smem, st>>>(mp);
+    SB_CUDA(cudaGetLastError());
+    b0 += qb;
+  }
+  return SB_OK;
+}
+
+__global__ void fill_empty_topk_kernel(int64_t* ids, double* sc, int32_t* cnt, int B, int k) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * k) {
+    ids[i] = -1;
+    sc[i] = 0.0;
+  }
+  if (i < B) cnt[i] = 0;
+}
+
+__global__ void dense_fetch_kernel(const __half* rows, int d, int d_pad, int64_t n, int64_t id_base,
+                                   const int64_t* ids, int n_ids, float* out) {
+  int r = blockIdx.x;
+  if (r >= n_ids) return;
+  int64_t idx = ids[r] - id_base;
+  for (int i = threadIdx.x; i < d; i += blockDim.x)
+    out[(size_t)r * d + i] = (idx >= 0 && idx < n) ? __half2float(rows[(size_t)idx * d_pad + i]) : 0.f;
+}
+
+}  // namespace
+
+// Shared with other translation units (hybrid batch path, scorers).
+int sb_dense_pad_queries(sb_ctx* ctx, const DenseIndex& ix, const float* q, int B, bool q_on_device, float** q_pad_out,
+                         cudaStream_t st) {
+  int rc = ctx->q_dev.reserve((size_t)B * ix.d_pad * sizeof(float));
+  if (rc) return rc;
+  float* qp = ctx->q_dev.as<float>();
+  if (ix.d_pad != ix.d) SB_CUDA(cudaMemsetAsync(qp, 0, (size_t)B * ix.d_pad * sizeof(float), st));
+  SB_CUDA(cudaMemcpy2DAsync(qp, (size_t)ix.d_pad * sizeof(float), q, (size_t)ix.d * sizeof(float),
+                            (size_t)ix.d * sizeof(float), (size_t)B,
+                            q_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  *q_pad_out = qp;
+  return SB_OK;
+}
+
+extern "C" {
+
+int sb_dense_load(sb_ctx* ctx, int slot, const void* vecs, int64_t n, int32_t d, int32_t dtype, int64_t id_base) {
+  SB_REQUIRE(ctx != nullptr, SB_ERR_ARG, "sb_dense_load: ctx is NULL");
+  SB_REQUIRE(slot >= 0 && slot < SB_MAX_DENSE_SLOTS, SB_ERR_ARG, "sb_dense_load: bad slot %d", slot);
+  SB_REQUIRE(n >= 0 && d > 0 && d <= 4096, SB_ERR_ARG, "sb_dense_load: bad shape n=%lld d=%d", (long long)n, d);
+  SB_REQUIRE(n < (1ll << 31), SB_ERR_ARG, "sb_dense_load: a shard holds at most 2^31-1 rows");
+  SB_REQUIRE(dtype == SB_F32 || dtype == SB_F16, SB_ERR_ARG, "sb_dense_load: dtype must be SB_F32 or SB_F16");
+  SB_REQUIRE(n == 0 || vecs != nullptr, SB_ERR_ARG, "sb_dense_load: vecs is NULL");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  DenseIndex& ix = ctx->dense[slot];
+  SB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ix.rows) cudaFree(ix.rows);
+  if (ix.inv_norm) cudaFree(ix.inv_norm);
+  ix = DenseIndex();
+  ix.n = n;
+  ix.d = d;
+  ix.d_pad = (d + 7) / 8 * 8;
+  ix.n_pad = (n + kRowPad - 1) / kRowPad * kRowPad;
+  ix.id_base = id_base;
+  if (n == 0) return SB_OK;
+  SB_CUDA(cudaMalloc(&ix.rows, (size_t)ix.n_pad * ix.d_pad * sizeof(__half)));
+  SB_CUDA(cudaMalloc(&ix.inv_norm, (size_t)ix.n_pad * sizeof(float)));
+  SB_CUDA(cudaMemsetAsync(ix.rows, 0, (size_t)ix.n_pad * ix.d_pad * sizeof(__half), ctx->stream));
+  SB_CUDA(cudaMemsetAsync(ix.inv_norm, 0, (size_t)ix.n_pad * sizeof(float), ctx->stream));
+  // staged upload: chunks of rows through a device staging buffer
+  const size_t esz = dtype == SB_F32 ? 4 : 2;
+  const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)((256ull << 20) / ((size_t)d * esz)));
+  int rc = ctx->misc_dev.reserve((size_t)std::min<int64_t>(chunk_rows, n) * d * esz);
+  if (rc) return rc;
+  for (int64_t r0 = 0; r0 < n; r0 += chunk_rows) {
+    const int64_t nr = std::min<int64_t>(chunk_rows, n - r0);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(vecs) + (size_t)r0 * d * esz;
+    SB_CUDA(cudaMemcpyAsync(ctx->misc_dev.p, src, (size_t)nr * d * esz, cudaMemcpyHostToDevice, ctx->stream));
+    const int wpb = 8;
+    const unsigned blocks = (unsigned)((nr + wpb - 1) / wpb);
+    if (dtype == SB_F32)
+      dense_store_rows_kernel<float><<<blocks, wpb * 32, 0, ctx->stream>>>(ctx->misc_dev.as<float>(), nr, d, ix.d_pad,
+                                                                           ix.rows, ix.inv_norm, r0, true);
+    else
+      dense_store_rows_kernel<__half><<<blocks, wpb * 32, 0, ctx->stream>>>(ctx->misc_dev.as<__half>(), nr, d,
+                                                                            ix.d_pad, ix.rows, ix.inv_norm, r0, false);
+    SB_CUDA(cudaGetLastError());
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));  // staging buffer is reused by the next chunk
+  }
+  return SB_OK;
+}
+
+int64_t sb_dense_count(sb_ctx* ctx, int slot) {
+  if (!ctx || slot < 0 || slot >= SB_MAX_DENSE_SLOTS) return -1;
+  return ctx->dense[slot].n;
+}
+
+int32_t sb_dense_dim(sb_ctx* ctx, int slot) {
+  if (!ctx || slot < 0 || slot >= SB_MAX_DENSE_SLOTS) return -1;
+  return ctx->dense[slot].d;
+}
+
+int sb_dense_topk_dev(sb_ctx* ctx, int slot, const float* q_dev, int32_t B, int32_t k, int64_t* out_ids_dev,
+                      double* out_scores_dev, int32_t* out_counts_dev, void* stream) {
+  SB_REQUIRE(ctx != nullptr, SB_ERR_ARG, "sb_dense_topk_dev: ctx is NULL");
+  SB_REQUIRE(slot >= 0 && slot < SB_MAX_DENSE_SLOTS, SB_ERR_ARG, "sb_dense_topk_dev: bad slot %d", slot);
+  SB_REQUIRE(B >= 0 && k > 0, SB_ERR_ARG, "sb_dense_topk_dev: bad B=%d k=%d", B, k);
+  if (B == 0) return SB_OK;
+  SB_REQUIRE(q_dev && out_ids_dev && out_scores_dev && out_counts_dev, SB_ERR_ARG, "sb_dense_topk_dev: NULL buffer");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = pick_stream(ctx, stream);
+  const DenseIndex& ix = ctx->dense[slot];
+  SB_REQUIRE(ix.d > 0, SB_ERR_STATE, "sb_dense_topk: dense slot %d has no index loaded", slot);
+  if (ix.n == 0) {
+    fill_empty_topk_kernel<<<(B * k + 255) / 256, 256, 0, st>>>(out_ids_dev, out_scores_dev, out_counts_dev, B, k);
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+  }
+  float* q_pad = nullptr;
+  int rc = sb_dense_pad_queries(ctx, ix, q_dev, B, true, &q_pad, st);
+  if (rc) return rc;
+  return dense_topk_enqueue(ctx, ix, q_pad, B, k, out_ids_dev, out_scores_dev, out_counts_dev, st);
+}
+
+int sb_dense_topk(sb_ctx* ctx, int slot, const float* q, int32_t B, int32_t k, int64_t* out_ids, double* out_scores,
+                  int32_t* out_counts) {
+  SB_REQUIRE(ctx != nullptr, SB_ERR_ARG, "sb_dense_topk: ctx is NULL");
+  SB_REQUIRE(slot >= 0 && slot < SB_MAX_DENSE_SLOTS, SB_ERR_ARG, "sb_dense_topk: bad slot %d", slot);
+  SB_REQUIRE(B >= 0 && k > 0, SB_ERR_ARG, "sb_dense_topk: bad B=%d k=%d", B, k);
+  if (B == 0) return SB_OK;
+  SB_REQUIRE(q && out_ids && out_scores && out_counts, SB_ERR_ARG, "sb_dense_topk: NULL buffer");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const DenseIndex& ix = ctx->dense[slot];
+  SB_REQUIRE(ix.d > 0, SB_ERR_STATE, "sb_dense_topk: dense slot %d has no index loaded", slot);
+  if (ix.n == 0) {
+    for (int i = 0; i < B * k; ++i) { out_ids[i] = -1; out_scores[i] = 0.0; }
+    for (int i = 0; i < B; ++i) out_counts[i] = 0;
+    return SB_OK;
+  }
+  int rc;
+  const size_t qbytes = (size_t)B * ix.d * sizeof(float);
+  if ((rc = ctx->pin_in.reserve(qbytes))) return rc;
+  memcpy(ctx->pin_in.p, q, qbytes);
+  float* q_pad = nullptr;
+  if ((rc = sb_dense_pad_queries(ctx, ix, ctx->pin_in.as<float>(), B, false, &q_pad, st))) return rc;
+  const size_t nid = (size_t)B * k;
+  if ((rc = ctx->out_ids_dev.reserve(nid * 8))) return rc;
+  if ((rc = ctx->out_sc_dev.reserve(nid * 8))) return rc;
+  if ((rc = ctx->out_cnt_dev.reserve((size_t)B * 4))) return rc;
+  if ((rc = dense_topk_enqueue(ctx, ix, q_pad, B, k, ctx->out_ids_dev.as<int64_t>(), ctx->out_sc_dev.as<double>(),
+                               ctx->out_cnt_dev.as<int32_t>(), st)))
+    return rc;
+  if ((rc = ctx->pin_out.reserve(nid * 16 + (size_t)B * 4))) return rc;
+  uint8_t* po = ctx->pin_out.as<uint8_t>();
+  SB_CUDA(cudaMemcpyAsync(po, ctx->out_ids_dev.p, nid * 8, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(po + nid * 8, ctx->out_sc_dev.p, nid * 8, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(po + nid * 16, ctx->out_cnt_dev.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  memcpy(out_ids, po, nid * 8);
+  memcpy(out_scores, po + nid * 8, nid * 8);
+  memcpy(out_counts, po + nid * 16, (size_t)B * 4);
+  return SB_OK;
+}
+
+int sb_dense_fetch(sb_ctx* ctx, int slot, const int64_t* ids, int32_t n_ids, float* out) {
+  SB_REQUIRE(ctx != nullptr, SB_ERR_ARG, "sb_dense_fetch: ctx is NULL");
+  SB_REQUIRE(slot >= 0 && slot < SB_MAX_DENSE_SLOTS, SB_ERR_ARG, "sb_dense_fetch: bad slot %d", slot);
+  if (n_ids <= 0) return SB_OK;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  const DenseIndex& ix = ctx->dense[slot];
+  SB_REQUIRE(ix.d > 0 && ix.n > 0, SB_ERR_STATE, "sb_dense_fetch: dense slot %d is empty", slot);
+  int rc;
+  if ((rc = ctx->misc2_dev.reserve((size_t)n_ids * 8))) return rc;
+  if ((rc = ctx->misc3_dev.reserve((size_t)n_ids * ix.d * 4))) return rc;
+  SB_CUDA(cudaMemcpyAsync(ctx->misc2_dev.p, ids, (size_t)n_ids * 8, cudaMemcpyHostToDevice, ctx->stream));
+  dense_fetch_kernel<<<n_ids, 128, 0, ctx->stream>>>(ix.rows, ix.d, ix.d_pad, ix.n, ix.id_base,
+                                                     ctx->misc2_dev.as<int64_t>(), n_ids, ctx->misc3_dev.as<float>());
+  SB_CUDA(cudaGetLastError());
+  SB_CUDA(cudaMemcpyAsync(out, ctx->misc3_dev.p, (size_t)n_ids * ix.d * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SB_OK;
+}
+
+}  // extern "C"

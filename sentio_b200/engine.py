@@ -1,0 +1,291 @@
+"""B200Engine -- thin Python owner of one ``sb_ctx`` (one GPU / one corpus shard).
+
+Host-buffer methods take / return NumPy arrays and go through the host entry points of the C ABI (H2D/D2H inside the
+call).  ``*_dev`` methods take / return torch CUDA tensors, enqueue on torch's CURRENT stream and do not synchronise;
+they are what the batched hybrid path, the multi-GPU shard path and bench.py's device-resident leg use.
+torch is plumbing here (device memory, streams, torch.distributed) -- all arithmetic runs in libsentio_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from ._lib import SbCeConfig, SentioB200Error, check, load_library
+from .index import Bm25IndexData
+
+FUSION_METHODS = {"rrf": 0, "weighted_rrf": 1, "comb_sum": 2}
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _tptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class B200Engine:
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        h = C.c_void_p()
+        check(self._lib.sb_create(int(device), C.byref(h)), "sb_create")
+        self._h = h
+        self.device = int(device)
+        self.dense_dim = {}
+        self.dense_count = {}
+        self.bm25: Bm25IndexData | None = None
+        self.bm25_id_base = 0
+        self.ce_config = None
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.sb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def num_sms(self) -> int:
+        return int(self._lib.sb_num_sms(self._h))
+
+    def sync(self) -> None:
+        check(self._lib.sb_sync(self._h), "sb_sync")
+
+    def _stream(self):
+        import torch
+
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ K1 dense
+    def load_dense(self, vecs: np.ndarray, id_base: int = 0, slot: int = 0) -> None:
+        v = np.ascontiguousarray(vecs)
+        if v.ndim != 2:
+            raise ValueError("vecs must be [n, d]")
+        if v.dtype == np.float16:
+            dt = 1
+        else:
+            v = np.ascontiguousarray(v, dtype=np.float32)
+            dt = 0
+        n, d = v.shape
+        check(self._lib.sb_dense_load(self._h, slot, _ptr(v), n, d, dt, int(id_base)), "sb_dense_load")
+        self.dense_dim[slot] = d
+        self.dense_count[slot] = n
+
+    def dense_topk(self, q: np.ndarray, k: int, slot: int = 0):
+        q = np.ascontiguousarray(np.atleast_2d(q), dtype=np.float32)
+        B, d = q.shape
+        if slot not in self.dense_dim:
+            raise SentioB200Error(f"dense slot {slot} has no index loaded")
+        if d != self.dense_dim[slot]:
+            raise ValueError(f"query dimension {d} != index dimension {self.dense_dim[slot]}")
+        ids = np.empty((B, k), dtype=np.int64)
+        sc = np.empty((B, k), dtype=np.float64)
+        cnt = np.empty(B, dtype=np.int32)
+        check(self._lib.sb_dense_topk(self._h, slot, _ptr(q), B, k, _ptr(ids), _ptr(sc), _ptr(cnt)), "sb_dense_topk")
+        return ids, sc, cnt
+
+    def dense_topk_dev(self, q_t, k: int, slot: int = 0, out=None):
+        import torch
+
+        B, d = q_t.shape
+        assert q_t.is_cuda and q_t.dtype == torch.float32 and q_t.is_contiguous()
+        if out is None:
+            dev = q_t.device
+            out = (torch.empty((B, k), dtype=torch.int64, device=dev), torch.empty((B, k), dtype=torch.float64, device=dev),
+                   torch.empty((B,), dtype=torch.int32, device=dev))
+        ids, sc, cnt = out
+        check(self._lib.sb_dense_topk_dev(self._h, slot, _tptr(q_t), B, k, _tptr(ids), _tptr(sc), _tptr(cnt),
+                                          self._stream()), "sb_dense_topk_dev")
+        return ids, sc, cnt
+
+    def dense_fetch(self, ids: Sequence[int], slot: int = 0) -> np.ndarray:
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        out = np.empty((len(ids), self.dense_dim[slot]), dtype=np.float32)
+        check(self._lib.sb_dense_fetch(self._h, slot, _ptr(ids), len(ids), _ptr(out)), "sb_dense_fetch")
+        return out
+
+    # ------------------------------------------------------------------ K2 BM25
+    def load_bm25(self, data: Bm25IndexData, id_base: int = 0) -> None:
+        variant = 1 if data.variant == "plus" else 0
+        indptr = np.ascontiguousarray(data.indptr, dtype=np.int64)
+        post_doc = np.ascontiguousarray(data.post_doc, dtype=np.int32)
+        post_tf = np.ascontiguousarray(data.post_tf, dtype=np.uint16)
+        doc_len = np.ascontiguousarray(data.doc_len, dtype=np.int32)
+        idf = np.ascontiguousarray(data.idf, dtype=np.float64)
+        check(self._lib.sb_bm25_load(self._h, _ptr(indptr), _ptr(post_doc), _ptr(post_tf), len(idf), len(post_doc),
+                                     _ptr(doc_len), len(doc_len), float(data.avgdl), _ptr(idf), variant, float(data.k1),
+                                     float(data.b), float(data.delta), int(id_base)), "sb_bm25_load")
+        self.bm25 = data
+        self.bm25_id_base = int(id_base)
+
+    @staticmethod
+    def pack_queries(term_id_lists: Sequence[Sequence[int]]):
+        off = np.zeros(len(term_id_lists) + 1, dtype=np.int32)
+        for i, t in enumerate(term_id_lists):
+            off[i + 1] = off[i] + len(t)
+        flat = np.zeros(max(int(off[-1]), 1), dtype=np.int32)
+        for i, t in enumerate(term_id_lists):
+            flat[off[i]:off[i + 1]] = np.asarray(t, dtype=np.int32)
+        return flat, off
+
+    def bm25_topk(self, term_id_lists: Sequence[Sequence[int]], k: int):
+        B = len(term_id_lists)
+        flat, off = self.pack_queries(term_id_lists)
+        ids = np.empty((B, k), dtype=np.int64)
+        sc = np.empty((B, k), dtype=np.float64)
+        cnt = np.empty(B, dtype=np.int32)
+        check(self._lib.sb_bm25_topk(self._h, _ptr(flat), _ptr(off), B, k, _ptr(ids), _ptr(sc), _ptr(cnt)),
+              "sb_bm25_topk")
+        return ids, sc, cnt
+
+    def bm25_topk_dev(self, terms_t, off_t, B: int, n_terms: int, max_len: int, k: int, out=None):
+        import torch
+
+        if out is None:
+            dev = off_t.device
+            out = (torch.empty((B, k), dtype=torch.int64, device=dev), torch.empty((B, k), dtype=torch.float64, device=dev),
+                   torch.empty((B,), dtype=torch.int32, device=dev))
+        ids, sc, cnt = out
+        check(self._lib.sb_bm25_topk_dev(self._h, _tptr(terms_t), _tptr(off_t), B, n_terms, max_len, k, _tptr(ids),
+                                         _tptr(sc), _tptr(cnt), self._stream()), "sb_bm25_topk_dev")
+        return ids, sc, cnt
+
+    def bm25_scores(self, term_ids: Sequence[int]) -> np.ndarray:
+        t = np.ascontiguousarray(term_ids, dtype=np.int32)
+        n = int(self._lib.sb_bm25_count(self._h))
+        out = np.zeros(n, dtype=np.float64)
+        check(self._lib.sb_bm25_scores(self._h, _ptr(t), len(t), _ptr(out)), "sb_bm25_scores")
+        return out
+
+    # ------------------------------------------------------------------ K3 fusion
+    def fuse(self, method: str, rrf_k: float, w_dense: float, w_sparse: float, k: int, dense=None, sparse=None,
+             plugin=None, extra: np.ndarray | None = None):
+        """Each list is (ids [B,stride] int64, scores [B,stride] float64, counts [B] int32) or None.
+
+        ``extra``: [B, n_extra, e_stride] float64 or None.  Returns (ids, scores, src, counts)."""
+        if method not in FUSION_METHODS:
+            raise ValueError(f"Unknown fusion_method: {method}")  # same error the reference raises (hybrid.py:238)
+        lists = []
+        B = None
+        for lst in (dense, sparse, plugin):
+            if lst is None:
+                lists.append((None, None, None, 0))
+                continue
+            i = np.ascontiguousarray(np.atleast_2d(lst[0]), dtype=np.int64)
+            s = np.ascontiguousarray(np.atleast_2d(lst[1]), dtype=np.float64)
+            c = np.ascontiguousarray(np.atleast_1d(lst[2]), dtype=np.int32)
+            B = i.shape[0] if B is None else B
+            assert i.shape == s.shape and i.shape[0] == B and c.shape[0] == B
+            lists.append((i, s, c, i.shape[1]))
+        if B is None:
+            raise ValueError("fuse needs at least one list")
+        n_extra = e_stride = 0
+        ex = None
+        if extra is not None and extra.size:
+            ex = np.ascontiguousarray(extra, dtype=np.float64)
+            assert ex.ndim == 3 and ex.shape[0] == B
+            n_extra, e_stride = ex.shape[1], ex.shape[2]
+        ids = np.empty((B, k), dtype=np.int64)
+        sc = np.empty((B, k), dtype=np.float64)
+        src = np.empty((B, k), dtype=np.int32)
+        cnt = np.empty(B, dtype=np.int32)
+        (di, ds, dn, dstr), (si, ss, sn, sstr), (pi, ps, pn, pstr) = lists
+        check(self._lib.sb_fuse(self._h, FUSION_METHODS[method], float(rrf_k), float(w_dense), float(w_sparse), B,
+                                _ptr(di), _ptr(ds), _ptr(dn), dstr, _ptr(si), _ptr(ss), _ptr(sn), sstr,
+                                _ptr(pi), _ptr(ps), _ptr(pn), pstr, _ptr(ex), n_extra, e_stride, k,
+                                _ptr(ids), _ptr(sc), _ptr(src), _ptr(cnt)), "sb_fuse")
+        return ids, sc, src, cnt
+
+    def fuse_dev(self, method: str, rrf_k: float, w_dense: float, w_sparse: float, k: int, dense, sparse, out=None):
+        import torch
+
+        di, ds, dn = dense
+        si, ss, sn = sparse
+        B = di.shape[0]
+        if out is None:
+            dev = di.device
+            out = (torch.empty((B, k), dtype=torch.int64, device=dev), torch.empty((B, k), dtype=torch.float64, device=dev),
+                   torch.empty((B, k), dtype=torch.int32, device=dev), torch.empty((B,), dtype=torch.int32, device=dev))
+        ids, sc, src, cnt = out
+        check(self._lib.sb_fuse_dev(self._h, FUSION_METHODS[method], float(rrf_k), float(w_dense), float(w_sparse), B,
+                                    _tptr(di), _tptr(ds), _tptr(dn), di.shape[1], _tptr(si), _tptr(ss), _tptr(sn),
+                                    si.shape[1], None, None, None, 0, None, 0, 0, k, _tptr(ids), _tptr(sc), _tptr(src),
+                                    _tptr(cnt), self._stream()), "sb_fuse_dev")
+        return ids, sc, src, cnt
+
+    # ------------------------------------------------------------------ K4 scorers
+    def semantic_mmr(self, q: np.ndarray, cand: np.ndarray | None = None, cand_ids=None, w_sem: float = 0.7,
+                     lambda_: float = 0.7, w_mmr: float = 0.5, want_sem: bool = True, want_mmr: bool = True,
+                     slot: int = 0):
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1)
+        d = q.shape[0]
+        if cand is not None:
+            cand = np.ascontiguousarray(cand, dtype=np.float32)
+            n = cand.shape[0]
+            assert cand.ndim == 2 and cand.shape[1] == d
+            ids = None
+        else:
+            ids = np.ascontiguousarray(cand_ids, dtype=np.int64)
+            n = len(ids)
+        sem = np.zeros(n, dtype=np.float64) if want_sem else None
+        mmr = np.zeros(n, dtype=np.float64) if want_mmr else None
+        if n:
+            check(self._lib.sb_semantic_mmr(self._h, slot, _ptr(q), d, _ptr(cand), _ptr(ids), n, float(w_sem),
+                                            float(lambda_), float(w_mmr), _ptr(sem), _ptr(mmr)), "sb_semantic_mmr")
+        return sem, mmr
+
+    # ------------------------------------------------------------------ K5 cross-encoder
+    def ce_load(self, weights: np.ndarray, cfg: dict) -> None:
+        w = np.ascontiguousarray(weights, dtype=np.float32).reshape(-1)
+        c = SbCeConfig(int(cfg["vocab_size"]), int(cfg["hidden"]), int(cfg["layers"]), int(cfg["heads"]),
+                       int(cfg["intermediate"]), int(cfg["max_pos"]), int(cfg.get("type_vocab", 2)),
+                       float(cfg.get("ln_eps", 1e-12)))
+        check(self._lib.sb_ce_load(self._h, _ptr(w), w.size, C.byref(c)), "sb_ce_load")
+        self.ce_config = dict(cfg)
+
+    def ce_score(self, input_ids: np.ndarray, token_type: np.ndarray, lengths: np.ndarray):
+        ids = np.ascontiguousarray(input_ids, dtype=np.int32)
+        tt = np.ascontiguousarray(token_type, dtype=np.int32)
+        ln = np.ascontiguousarray(lengths, dtype=np.int32)
+        P, S = ids.shape
+        logits = np.empty(P, dtype=np.float32)
+        sig = np.empty(P, dtype=np.float32)
+        if P:
+            check(self._lib.sb_ce_score(self._h, _ptr(ids), _ptr(tt), _ptr(ln), P, S, _ptr(logits), _ptr(sig)),
+                  "sb_ce_score")
+        return logits, sig
+
+    def ce_score_dev(self, ids_t, tt_t, len_t, out=None):
+        import torch
+
+        P, S = ids_t.shape
+        if out is None:
+            out = (torch.empty((P,), dtype=torch.float32, device=ids_t.device),
+                   torch.empty((P,), dtype=torch.float32, device=ids_t.device))
+        check(self._lib.sb_ce_score_dev(self._h, _tptr(ids_t), _tptr(tt_t), _tptr(len_t), P, S, _tptr(out[0]),
+                                        _tptr(out[1]), self._stream()), "sb_ce_score_dev")
+        return out
+
+    # ------------------------------------------------------------------ K6 shard merge
+    def merge_shards_dev(self, ids0, scores0, counts0, shard_stride_bytes: int, G: int, out=None):
+        """ids0/scores0/counts0: shard 0's [B,k] / [B,k] / [B] views inside the all-gathered record buffer."""
+        import torch
+
+        B, k = ids0.shape
+        if out is None:
+            dev = ids0.device
+            out = (torch.empty((B, k), dtype=torch.int64, device=dev), torch.empty((B, k), dtype=torch.float64, device=dev),
+                   torch.empty((B,), dtype=torch.int32, device=dev))
+        check(self._lib.sb_merge_shards_dev(self._h, _tptr(ids0), _tptr(scores0), _tptr(counts0),
+                                            int(shard_stride_bytes), int(G), B, k, _tptr(out[0]), _tptr(out[1]),
+                                            _tptr(out[2]), self._stream()), "sb_merge_shards_dev")
+        return out

@@ -1,0 +1,151 @@
+"""HybridPipeline -- batched, optionally sharded, arrays-in / arrays-out form of the hot path.
+
+One process per GPU.  Each rank owns a contiguous doc-id range of the corpus (dense rows + BM25 postings with
+corpus-global idf/avgdl).  A batch of B queries runs:
+
+    local K1 dense top-k  +  local K2 BM25 top-k          (raw scores, shard-local)
+    ONE all-gather of the per-rank record {dense ids/scores/counts, sparse ids/scores/counts}   (world > 1)
+    K6 merge to the GLOBAL top-k per signal  ->  K3 fusion on global ranks  ->  [K5 rerank]
+
+``*_dev`` methods keep everything on the device on torch's current stream (bench.py's resident leg);
+``search_*`` methods take host NumPy inputs and return host NumPy outputs (the e2e leg).
+torch / torch.distributed are plumbing only (device buffers, streams, the NCCL all-gather).
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import numpy as np
+
+from .engine import B200Engine
+from .index import Bm25IndexData
+
+
+class HybridPipeline:
+    def __init__(self, device: int | None = 0, rank: int = 0, world: int = 1, group=None, engine=None):
+        """``engine`` may be injected (the CPU/gloo tests pass an oracle-backed double together with device=None);
+        the product path always builds a real ``B200Engine`` on ``cuda:device``."""
+        import torch
+
+        self.torch = torch
+        self.device = device
+        self.rank, self.world, self.group = rank, world, group
+        if engine is None:
+            if device is None:
+                raise ValueError("HybridPipeline needs a CUDA device (there is no CPU path)")
+            torch.cuda.set_device(device)
+            engine = B200Engine(device)
+        self.engine = engine
+        self._torch_device = "cpu" if device is None else f"cuda:{device}"
+        self.id_base = 0
+        self._bufs = {}
+
+    # ------------------------------------------------------------------ loading
+    def load_dense(self, vecs: np.ndarray, id_base: int = 0) -> None:
+        self.engine.load_dense(vecs, id_base=id_base, slot=0)
+        self.id_base = id_base
+
+    def load_bm25(self, data: Bm25IndexData, id_base: int = 0) -> None:
+        self.engine.load_bm25(data, id_base=id_base)
+
+    # ------------------------------------------------------------------ helpers
+    def _buf(self, name, shape, dtype):
+        t = self._bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = self.torch.empty(shape, dtype=dtype, device=self._torch_device)
+            self._bufs[name] = t
+        return t
+
+    def _to_dev(self, arr: np.ndarray):
+        t = self.torch.from_numpy(arr)
+        if self.device is None:
+            return t
+        return t.pin_memory().to(self._torch_device, non_blocking=True)
+
+    def _record_layout(self, B: int, k: int, signals: int):
+        """Byte layout of one rank's all-gather record: per signal ids[B,k] i64 | scores[B,k] f64 | counts[B] i32."""
+        per = B * k * 8 * 2 + ((B * 4 + 7) // 8) * 8
+        return per, per * signals
+
+    def _views(self, rec, B, k, sig):
+        t = self.torch
+        per, _ = self._record_layout(B, k, 1)
+        base = sig * per
+        ids = rec[base: base + B * k * 8].view(t.int64).view(B, k)
+        sc = rec[base + B * k * 8: base + B * k * 16].view(t.float64).view(B, k)
+        cnt = rec[base + B * k * 16: base + B * k * 16 + B * 4].view(t.int32)
+        return ids, sc, cnt
+
+    def _gather(self, rec):
+        """The single collective of the path: all-gather of the per-rank record over NCCL (NVLink/NVSwitch)."""
+        import torch.distributed as dist
+
+        out = self._buf("gathered", (self.world, rec.numel()), self.torch.uint8)
+        dist.all_gather_into_tensor(out.view(-1), rec, group=self.group)
+        return out
+
+    # ------------------------------------------------------------------ device-resident path
+    def dense_dev(self, q_t, k: int):
+        """q_t [B,d] fp32 cuda -> global (ids, scores, counts) on this rank."""
+        t = self.torch
+        B = q_t.shape[0]
+        if self.world == 1:
+            out = (self._buf("d_ids", (B, k), t.int64), self._buf("d_sc", (B, k), t.float64),
+                   self._buf("d_cnt", (B,), t.int32))
+            return self.engine.dense_topk_dev(q_t, k, out=out)
+        _, nbytes = self._record_layout(B, k, 1)
+        rec = self._buf("rec1", (nbytes,), t.uint8)
+        self.engine.dense_topk_dev(q_t, k, out=self._views(rec, B, k, 0))
+        g = self._gather(rec)
+        ids0, sc0, cnt0 = self._views(g[0], B, k, 0)
+        out = (self._buf("d_ids", (B, k), t.int64), self._buf("d_sc", (B, k), t.float64),
+               self._buf("d_cnt", (B,), t.int32))
+        return self.engine.merge_shards_dev(ids0, sc0, cnt0, nbytes, self.world, out=out)
+
+    def hybrid_dev(self, q_t, terms_t, off_t, n_terms: int, max_len: int, k: int, method: str = "rrf",
+                   rrf_k: float = 60, w_dense: float = 0.5, w_sparse: float = 0.5):
+        """Dense + BM25 + fusion for a batch; returns fused (ids, scores, src, counts) device tensors."""
+        t = self.torch
+        B = q_t.shape[0]
+        per, nbytes = self._record_layout(B, k, 2)
+        rec = self._buf("rec2", (nbytes,), t.uint8)
+        dv = self._views(rec, B, k, 0)
+        sv = self._views(rec, B, k, 1)
+        self.engine.dense_topk_dev(q_t, k, out=dv)
+        self.engine.bm25_topk_dev(terms_t, off_t, B, n_terms, max_len, k, out=sv)
+        if self.world > 1:
+            g = self._gather(rec)
+            d0 = self._views(g[0], B, k, 0)
+            s0 = self._views(g[0], B, k, 1)
+            dv = self.engine.merge_shards_dev(*d0, nbytes, self.world,
+                                              out=(self._buf("gd_ids", (B, k), t.int64),
+                                                   self._buf("gd_sc", (B, k), t.float64),
+                                                   self._buf("gd_cnt", (B,), t.int32)))
+            sv = self.engine.merge_shards_dev(*s0, nbytes, self.world,
+                                              out=(self._buf("gs_ids", (B, k), t.int64),
+                                                   self._buf("gs_sc", (B, k), t.float64),
+                                                   self._buf("gs_cnt", (B,), t.int32)))
+        out = (self._buf("f_ids", (B, k), t.int64), self._buf("f_sc", (B, k), t.float64),
+               self._buf("f_src", (B, k), t.int32), self._buf("f_cnt", (B,), t.int32))
+        return self.engine.fuse_dev(method, rrf_k, w_dense, w_sparse, k, dv, sv, out=out)
+
+    # ------------------------------------------------------------------ host (e2e) path
+    def search_dense(self, q: np.ndarray, k: int):
+        """Host in / host out.  world == 1: straight through the C-ABI host entry point."""
+        if self.world == 1:
+            return self.engine.dense_topk(q, k)
+        t = self.torch
+        q_t = self._to_dev(np.ascontiguousarray(q, dtype=np.float32))
+        ids, sc, cnt = self.dense_dev(q_t, k)
+        return ids.cpu().numpy(), sc.cpu().numpy(), cnt.cpu().numpy()
+
+    def search_hybrid(self, q: np.ndarray, term_lists: Sequence[Sequence[int]], k: int, method: str = "rrf",
+                      rrf_k: float = 60, w_dense: float = 0.5, w_sparse: float = 0.5):
+        flat, off = B200Engine.pack_queries(term_lists)
+        max_len = int(np.diff(off).max()) if len(off) > 1 else 0
+        q_t = self._to_dev(np.ascontiguousarray(q, dtype=np.float32))
+        terms_t = self._to_dev(flat)
+        off_t = self._to_dev(off)
+        ids, sc, src, cnt = self.hybrid_dev(q_t, terms_t, off_t, int(off[-1]), max_len, k, method, rrf_k, w_dense,
+                                            w_sparse)
+        return ids.cpu().numpy(), sc.cpu().numpy(), src.cpu().numpy(), cnt.cpu().numpy()

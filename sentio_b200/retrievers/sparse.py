@@ -1,0 +1,119 @@
+"""BM25Retriever -- BM25 Okapi / Plus over GPU-resident CSR postings (K2).
+
+Same surface as reference src/core/retrievers/sparse.py:33-203: ``BM25Retriever(documents=None, variant="okapi",
+cache_dir=None)``, ``index``, ``save``, ``load``, ``retrieve``; tokeniser ``text.lower().split()``; ``BM25_VARIANT`` /
+``SPARSE_CACHE_DIR`` environment overrides; results are the corpus ``Document`` objects themselves with
+``metadata["bm25_score"]`` written in place; scores <= 0 are dropped; any failure returns ``[]``.
+
+Deviation (documented in DESIGN.md): ties are ordered (score desc, corpus position asc) -- the reference's
+``np.argsort(-scores)`` is an unstable introsort whose tie order is implementation defined.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import pickle
+
+import numpy as np
+
+from ..document import Document
+from ..engine import B200Engine
+from ..index import Bm25IndexData, build_bm25_from_texts
+from .base import BaseRetriever
+
+logger = logging.getLogger(__name__)
+
+
+class BM25Retriever(BaseRetriever):
+    def __init__(self, documents: list[Document] | None = None, variant: str = "okapi", cache_dir: str | None = None,
+                 device: int = 0, k1: float = 1.5, b: float = 0.75, epsilon: float = 0.25, delta: float = 1.0):
+        self.bm25: Bm25IndexData | None = None  # the name the reference uses for its rank_bm25 object
+        self.doc_ids: list[str] = []
+        self.doc_map: dict[str, Document] = {}
+        self.tokenized_corpus: list[list[str]] = []
+        self.variant = os.environ.get("BM25_VARIANT", variant).lower()
+        self.cache_dir = cache_dir or os.environ.get("SPARSE_CACHE_DIR", ".sparse_cache")
+        self._params = dict(k1=k1, b=b, epsilon=epsilon, delta=delta)
+        self._device = device
+        self._engine: B200Engine | None = None
+        if documents:
+            self.index(documents)
+
+    # ------------------------------------------------------------------ build / persist
+    def _upload(self) -> None:
+        if self._engine is None:
+            self._engine = B200Engine(self._device)
+        self._engine.load_bm25(self.bm25, id_base=0)
+
+    def index(self, documents: list[Document]) -> None:
+        if not documents:
+            logger.warning("Empty document list provided for BM25 indexing")
+            return
+        self.doc_ids = [doc.id for doc in documents]
+        self.doc_map = {doc.id: doc for doc in documents}
+        variant = "plus" if self.variant == "plus" else "okapi"
+        self.bm25 = build_bm25_from_texts((doc.text for doc in documents), variant=variant, **self._params)
+        self.tokenized_corpus = []  # not retained: the CSR index replaces it (reconstruct lazily if ever needed)
+        self._upload()
+        logger.info("BM25 (%s) index on GPU: %d docs, %d terms, %d postings", variant, self.bm25.n_docs,
+                    self.bm25.n_terms, len(self.bm25.post_doc))
+
+    def save(self, filepath: str | None = None) -> None:
+        if not self.bm25:
+            logger.warning("Cannot save empty BM25 index")
+            return
+        if not filepath:
+            os.makedirs(self.cache_dir, exist_ok=True)
+            filepath = os.path.join(self.cache_dir, "bm25_index.pkl")
+        try:
+            with open(filepath, "wb") as f:
+                pickle.dump({"format": "sentio_b200.bm25retriever.v1", "bm25": self.bm25, "doc_ids": self.doc_ids,
+                             "doc_map": self.doc_map, "variant": self.variant}, f, protocol=pickle.HIGHEST_PROTOCOL)
+        except Exception as exc:  # same contract as the reference: log, do not raise
+            logger.error("Failed to save BM25 index: %s", exc)
+
+    def load(self, filepath: str | None = None) -> bool:
+        if not filepath:
+            filepath = os.path.join(self.cache_dir, "bm25_index.pkl")
+        try:
+            if not os.path.exists(filepath):
+                logger.warning("BM25 index file not found: %s", filepath)
+                return False
+            with open(filepath, "rb") as f:
+                data = pickle.load(f)
+            self.bm25 = data["bm25"]
+            self.doc_ids = data["doc_ids"]
+            self.doc_map = data.get("doc_map", {})
+            self.variant = data.get("variant", "okapi")
+            self._upload()
+            return True
+        except Exception as exc:
+            logger.error("Failed to load BM25 index: %s", exc)
+            return False
+
+    # ------------------------------------------------------------------ query
+    def retrieve(self, query: str, top_k: int = 10) -> list[Document]:
+        if not self.bm25 or self._engine is None:
+            logger.warning("BM25 index not initialized")
+            return []
+        try:
+            terms = self.bm25.term_ids(query.lower().split())
+            ids, scores, counts = self._engine.bm25_topk([terms], int(top_k))
+            results = []
+            for j in range(int(counts[0])):
+                row = int(ids[0, j])
+                doc_id = self.doc_ids[row]
+                doc = self.doc_map.get(doc_id)
+                if doc is None:
+                    doc = Document(id=doc_id, text="")
+                doc.metadata["bm25_score"] = float(scores[0, j])
+                results.append(doc)
+            return results
+        except Exception as exc:
+            logger.error("BM25 retrieval error: %s", exc)
+            return []
+
+    def retrieve_batch_arrays(self, queries: list[str], top_k: int):
+        """Batched extension: (rows, scores, counts) arrays for many queries in one GPU batch."""
+        terms = [self.bm25.term_ids(q.lower().split()) for q in queries]
+        return self._engine.bm25_topk(terms, int(top_k))

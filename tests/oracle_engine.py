@@ -1,0 +1,109 @@
+"""OracleEngine -- an oracle-backed stand-in for B200Engine used ONLY by the CPU (`not gpu`) tests to exercise the host
+logic (retriever classes, pipeline sharding, gloo all-gather) without a GPU.  It is test infrastructure: it imports
+oracle/ and must never be reachable from the product."""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import dense as dense_oracle
+from oracle import fusion as fusion_oracle
+from oracle import scorers as scorers_oracle
+from oracle.rank_bm25_port import FastBM25
+
+
+class OracleEngine:
+    device = None
+
+    def __init__(self):
+        self.rows = {}
+        self.id_base = {}
+        self.dense_dim = {}
+        self.bm25 = None
+        self.fast = None
+        self.bm25_id_base = 0
+
+    def close(self):
+        pass
+
+    # K1
+    def load_dense(self, vecs, id_base=0, slot=0):
+        self.rows[slot] = dense_oracle.stored_rows(np.asarray(vecs))
+        self.id_base[slot] = id_base
+        self.dense_dim[slot] = self.rows[slot].shape[1]
+
+    def dense_topk(self, q, k, slot=0):
+        q = np.atleast_2d(np.asarray(q, dtype=np.float32))
+        B = q.shape[0]
+        ids = np.full((B, k), -1, np.int64)
+        sc = np.zeros((B, k))
+        cnt = np.zeros(B, np.int32)
+        for b in range(B):
+            i, s = dense_oracle.dense_topk(self.rows[slot], q[b], k)
+            ids[b, :len(i)] = i + self.id_base[slot]
+            sc[b, :len(i)] = s
+            cnt[b] = len(i)
+        return ids, sc, cnt
+
+    def dense_fetch(self, ids, slot=0):
+        return self.rows[slot][np.asarray(ids) - self.id_base[slot]].astype(np.float32)
+
+    # K2
+    def load_bm25(self, data, id_base=0):
+        self.bm25 = data
+        self.bm25_id_base = id_base
+        self.fast = FastBM25(data.indptr, data.post_doc, data.post_tf, data.doc_len, data.idf, data.avgdl,
+                             data.variant, data.k1, data.b, data.delta)
+
+    def bm25_scores(self, term_ids):
+        return self.fast.get_scores(list(term_ids))
+
+    def bm25_topk(self, term_id_lists, k):
+        B = len(term_id_lists)
+        ids = np.full((B, k), -1, np.int64)
+        sc = np.zeros((B, k))
+        cnt = np.zeros(B, np.int32)
+        for b, terms in enumerate(term_id_lists):
+            s = self.fast.get_scores(list(terms))
+            order = np.argsort(-s, kind="stable")[:k]
+            order = [i for i in order if s[i] > 0]
+            ids[b, :len(order)] = np.asarray(order, dtype=np.int64) + self.bm25_id_base
+            sc[b, :len(order)] = s[order]
+            cnt[b] = len(order)
+        return ids, sc, cnt
+
+    # K3
+    def fuse(self, method, rrf_k, w_dense, w_sparse, k, dense=None, sparse=None, plugin=None, extra=None):
+        def rows(lst, b):
+            if lst is None:
+                return []
+            i, s, c = lst
+            return [(int(i[b, j]), float(s[b, j])) for j in range(int(c[b]))]
+
+        B = next(x for x in (dense, sparse, plugin) if x is not None)[0].shape[0]
+        ids = np.full((B, k), -1, np.int64)
+        sc = np.zeros((B, k))
+        src = np.zeros((B, k), np.int32)
+        cnt = np.zeros(B, np.int32)
+        if int(rrf_k) == rrf_k:
+            rrf_k = int(rrf_k)
+        for b in range(B):
+            d, s, p = rows(dense, b), rows(sparse, b), rows(plugin, b)
+            ex = [list(extra[b, e]) for e in range(extra.shape[1])] if extra is not None else None
+            out = fusion_oracle.fuse(method, rrf_k, w_dense, w_sparse, d, s, p, k, ex)
+            d_set, s_set = {i for i, _ in d}, {i for i, _ in s}
+            for j, (doc_id, score, _has) in enumerate(out):
+                ids[b, j], sc[b, j] = doc_id, score
+                src[b, j] = (1 if doc_id in d_set else 0) | (2 if doc_id in s_set else 0)
+            cnt[b] = len(out)
+        return ids, sc, src, cnt
+
+    # K4
+    def semantic_mmr(self, q, cand=None, cand_ids=None, w_sem=0.7, lambda_=0.7, w_mmr=0.5, want_sem=True,
+                     want_mmr=True, slot=0):
+        if cand is None:
+            cand = self.dense_fetch(cand_ids, slot)
+        q64 = np.asarray(q, dtype=np.float32).astype(np.float64)
+        c64 = [np.asarray(c, dtype=np.float32).astype(np.float64) for c in cand]
+        sem = np.asarray(scorers_oracle.semantic(q64, c64, w_sem)) if want_sem else None
+        mmr = np.asarray(scorers_oracle.mmr(q64, c64, lambda_, w_mmr)) if want_mmr else None
+        return sem, mmr
