@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- retrieval queries/sec on BASELINE.json's configurations.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload dense|hybrid] [--batch B] [--n-docs N] [--dim D] [--top-k K]
+
+A "step" = one batch of B synthetic queries through the hot path.  Default workload = BASELINE.json configs[1]:
+1 M docs x 1024-d, dense-only cosine top_k=100 on 1 x B200.  For --gpus N > 1 the SAME corpus is partitioned N ways
+(contiguous doc ranges), every rank scans its shard and ONE NCCL all-gather of the per-shard top-k is followed by the
+merge kernel -> strong scaling (total work fixed).
+
+value   : whole-job queries/sec, inputs already resident in HBM (device entry points, CUDA-event timed, max over ranks)
+e2e     : the same metric through the host-buffer C-ABI entry point (pinned host queries -> H2D -> kernels -> D2H results)
+roofline: dominant kernel (dense_scan_kernel) algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json hbm_gbs
+cpu_baseline / --impl reference: the reference's CPU path (exact cosine in NumPy: fp32 `X @ q` with BLAS on all host
+          cores + full np.argsort, oracle/dense.py:fast_topk_f32; BM25 via the rank_bm25 restatement) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "retrieval queries/sec @1M docs,1024-d,top_k=100"
+UNIT = "queries/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="dense", choices=["dense", "hybrid"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--n-docs", type=int, default=1_000_000)
+    ap.add_argument("--dim", type=int, default=1024)
+    ap.add_argument("--top-k", type=int, default=100)
+    ap.add_argument("--cpu-sample", type=int, default=24, help="queries in the bounded CPU-baseline sample")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.device), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- synthetic workload
+def make_workload(args, need_f32_host=False):
+    from sentio_b200 import synth
+
+    t0 = time.time()
+    x16 = synth.dense_corpus(args.n_docs, args.dim)
+    queries = synth.query_vectors(1024, args.dim)
+    wl = {"x16": x16, "q": queries, "gen_s": None}
+    if args.workload == "hybrid":
+        flat, off = synth.text_corpus_tokens(args.n_docs)
+        wl["flat"], wl["off"] = flat, off
+        wl["q_tokens"] = synth.query_tokens(1024)
+    wl["gen_s"] = round(time.time() - t0, 1)
+    return wl
+
+
+# --------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference(args, wl, n_queries):
+    """Times the reference's CPU path on this box's host cores on a bounded sample of the same workload."""
+    from oracle import dense as dense_oracle
+
+    cores = os.cpu_count() or 1
+    x16 = wl["x16"]
+    x32 = x16.astype(np.float32)
+    x32 /= np.linalg.norm(x32, axis=1, keepdims=True)  # Qdrant normalises at upsert; the scan is then a plain dot
+    q = wl["q"]
+    fast = None
+    if args.workload == "hybrid":
+        from oracle import fusion as fusion_oracle
+        from oracle.rank_bm25_port import FastBM25
+        from sentio_b200.index import build_bm25_from_token_ids
+
+        idx = build_bm25_from_token_ids(wl["flat"], wl["off"])
+        fast = FastBM25(idx.indptr, idx.post_doc, idx.post_tf, idx.doc_len, idx.idf, idx.avgdl)
+        terms = [idx.term_ids(t) for t in wl["q_tokens"]]
+    for i in range(2):  # warm-up
+        dense_oracle.fast_topk_f32(x32, q[i], args.top_k)
+    t0 = time.perf_counter()
+    for i in range(n_queries):
+        di, ds = dense_oracle.fast_topk_f32(x32, q[i % len(q)], args.top_k)
+        if fast is not None:
+            s = fast.get_scores(list(terms[i % len(terms)]))
+            order = np.argsort(-s)[: args.top_k]
+            sp = [(int(j), float(s[j])) for j in order if s[j] > 0]
+            fusion_oracle.fuse("rrf", 60, 0.5, 0.5, [(int(a), float(b)) for a, b in zip(di, ds)], sp, [], args.top_k)
+    dt = time.perf_counter() - t0
+    kind = "port"
+    sample = (f"{n_queries} queries of the same workload; dense = fp32 X@q (NumPy/BLAS, {cores} threads) + np.argsort"
+              + ("; BM25 = CSR restatement of rank_bm25 get_scores + np.argsort; rrf fusion in Python" if fast else ""))
+    return {"value": n_queries / dt, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}, dt / n_queries
+
+
+# --------------------------------------------------------------------------------------------- main
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload_name = (f"{args.n_docs}-doc synthetic, {args.dim}-d, "
+                     + ("dense-only cosine" if args.workload == "dense" else "hybrid dense+BM25 rrf")
+                     + f" top_k={args.top_k}")
+    config = {"workload": workload_name, "batch_queries_per_step": args.batch, "store_dtype": "fp16",
+              "shards": max(world, 1), "l2_policy": "corpus (2.05 GB) is larger than L2 (126 MB); no flush needed",
+              "query_set": "1024 seeded unit vectors, cycled"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        wl = make_workload(args)
+        per_step = max(1, min(args.batch, 4))
+        total = per_step * (args.steps + args.warmup)
+        base, per_q = cpu_reference(args, wl, total)
+        line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_q * per_step * 1e3,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {**config, "batch_queries_per_step": per_step},
+                "cpu_baseline": {**base, "sample": f"{per_step} queries per step; " + base["sample"]},
+                "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    from sentio_b200.pipeline import HybridPipeline
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    wl = make_workload(args)
+    n = args.n_docs
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    pipe = HybridPipeline(local_rank, rank=rank, world=world)
+    pipe.load_dense(wl["x16"][lo:hi], id_base=lo)
+    idx = None
+    if args.workload == "hybrid":
+        from sentio_b200.index import build_bm25_from_token_ids
+
+        idx = build_bm25_from_token_ids(wl["flat"], wl["off"])
+        pipe.load_bm25(idx.shard(lo, hi) if world > 1 else idx, id_base=lo)
+    eng = pipe.engine
+    B, k = args.batch, args.top_k
+    dev = f"cuda:{local_rank}"
+    q_all = torch.from_numpy(wl["q"]).to(dev)
+    n_q = q_all.shape[0]
+    terms_dev = None
+    if idx is not None:
+        term_lists = [idx.term_ids(t) for t in wl["q_tokens"]]
+
+    def batch_slice(step):
+        s = (step * B) % n_q
+        idxs = [(s + i) % n_q for i in range(B)]
+        return idxs
+
+    def dev_inputs(step):
+        ids = batch_slice(step)
+        qt = q_all[ids].contiguous()
+        if idx is None:
+            return (qt,)
+        flat, off = eng.pack_queries([term_lists[i] for i in ids])
+        return (qt, torch.from_numpy(flat).to(dev), torch.from_numpy(off).to(dev), int(off[-1]),
+                int(np.diff(off).max()))
+
+    def run_dev(inp):
+        if idx is None:
+            return pipe.dense_dev(inp[0], k)
+        return pipe.hybrid_dev(inp[0], inp[1], inp[2], inp[3], inp[4], k, "rrf", 60, 0.5, 0.5)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- resident leg: inputs already in HBM, device entry points, CUDA events on torch's current stream
+    inputs = [dev_inputs(s) for s in range(args.warmup + args.steps)]
+    for s in range(args.warmup):
+        run_dev(inputs[s])
+    barrier()
+    eng.profile(True)
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for s in range(args.steps):
+        run_dev(inputs[args.warmup + s])
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.launch_count() - launches0
+    n_scan, scan_ms = eng.profile_read("dense_scan")
+    eng.profile(False)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = B * args.steps / (ms_total / 1e3)
+
+    # ---------------- e2e leg: host (pinned by the library) buffers in, host results out, every step
+    host_batches = [wl["q"][batch_slice(s)] for s in range(args.warmup + args.steps)]
+    host_terms = None
+    if idx is not None:
+        host_terms = [[term_lists[i] for i in batch_slice(s)] for s in range(args.warmup + args.steps)]
+
+    def run_host(s):
+        if idx is None:
+            return pipe.search_dense(host_batches[s], k)
+        return pipe.search_hybrid(host_batches[s], host_terms[s], k, "rrf", 60, 0.5, 0.5)
+
+    for s in range(args.warmup):
+        run_host(s)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        out = run_host(args.warmup + s)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    h2d = B * args.dim * 4 + (0 if idx is None else sum(len(x) for x in host_terms[0]) * 4 + (B + 1) * 4)
+    d2h = B * k * 16 + B * 4 + (B * k * 4 if idx is not None else 0)
+    e2e = {"value": B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "timer": "host wall clock around the public host-buffer call (includes H2D, kernels, D2H, sync)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------- roofline of the dominant kernel (dense_scan_kernel), this rank's shard
+    peak, peak_src = peaks()
+    rows = hi - lo
+    n_pad = (rows + 31) // 32 * 32
+    d_pad = (args.dim + 7) // 8 * 8
+    alg_bytes = n_pad * d_pad * 2 + n_pad * 4
+    avg_ms = scan_ms / max(n_scan, 1)
+    achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if n_scan else 0.0
+    roofline = {"bound": "hbm", "kernel": "dense_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms, "launches_timed": n_scan,
+                "queries_per_launch": 4, "share_of_step": scan_ms / ms_total}
+    prof = os.path.join(ROOT, "profiles", "r01_dense_scan_ncu.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---------------- bounded CPU baseline on this box's host cores (rank 0, N=1 only)
+    cpu = None
+    if world == 1:
+        cpu, _ = cpu_reference(args, wl, args.cpu_sample)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f16 store / f32 scan / f64 exact re-score",
+            "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "corpus_gen_s": wl["gen_s"]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

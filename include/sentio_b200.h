@@ -60,6 +60,16 @@ int sb_num_sms(sb_ctx* ctx);
 int sb_sync(sb_ctx* ctx);
 /* the context's cudaStream_t (as void*), so torch can order its own work against it */
 void* sb_stream(sb_ctx* ctx);
+/* number of kernels this library has launched on behalf of the context (bench.py's gpu_launches) */
+int64_t sb_launch_count(sb_ctx* ctx);
+/*
+ * Optional per-kernel timing for the roofline leg of bench.py: when enabled every launch of the kernels below is
+ * bracketed by a CUDA event pair on the launching stream; sb_profile_read drains the finished pairs of one kernel id
+ * (0 dense_scan, 1 dense_merge, 2 bm25_score, 3 bm25_select+final, 4 fuse, 5 cross-encoder forward) and returns the
+ * launch count and the summed device time in milliseconds.
+ */
+int sb_profile(sb_ctx* ctx, int enable);
+int sb_profile_read(sb_ctx* ctx, int kernel_id, int64_t* n_out, double* ms_out);
 
 /* ---------------------------------------------------------------- K1: dense cosine top-k -------------------- */
 /*

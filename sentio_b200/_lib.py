@@ -33,6 +33,9 @@ SIGNATURES = {
     "sb_num_sms": (C.c_int, [C.c_void_p]),
     "sb_sync": (C.c_int, [C.c_void_p]),
     "sb_stream": (C.c_void_p, [C.c_void_p]),
+    "sb_launch_count": (C.c_int64, [C.c_void_p]),
+    "sb_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "sb_profile_read": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "sb_dense_load": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64]),
     "sb_dense_count": (C.c_int64, [C.c_void_p, C.c_int]),
     "sb_dense_dim": (C.c_int32, [C.c_void_p, C.c_int]),

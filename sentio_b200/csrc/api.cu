@@ -77,6 +77,8 @@ void sb_destroy(sb_ctx* ctx) {
   ctx->acc_dev.release();
   ctx->pin_in.release();
   ctx->pin_out.release();
+  for (auto& r : ctx->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : ctx->prof_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -91,5 +93,41 @@ int sb_sync(sb_ctx* ctx) {
 }
 
 void* sb_stream(sb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int64_t sb_launch_count(sb_ctx* ctx) { return ctx ? (int64_t)ctx->launches : -1; }
+
+int sb_profile(sb_ctx* ctx, int enable) {
+  SB_REQUIRE(ctx != nullptr, SB_ERR_ARG, "sb_profile: ctx is NULL");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->prof_on = enable != 0;
+  return SB_OK;
+}
+
+int sb_profile_read(sb_ctx* ctx, int kernel_id, int64_t* n_out, double* ms_out) {
+  SB_REQUIRE(ctx != nullptr && n_out && ms_out, SB_ERR_ARG, "sb_profile_read: NULL argument");
+  SB_REQUIRE(kernel_id >= 0 && kernel_id < SB_PROF_COUNT, SB_ERR_ARG, "sb_profile_read: bad kernel id %d", kernel_id);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  int64_t n = 0;
+  double ms = 0.0;
+  std::vector<sb_ctx::ProfRec> keep;
+  for (auto& r : ctx->prof_recs) {
+    if (r.id != kernel_id) {
+      keep.push_back(r);
+      continue;
+    }
+    SB_CUDA(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    SB_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms += t;
+    ++n;
+    ctx->prof_pool.push_back(r.a);
+    ctx->prof_pool.push_back(r.b);
+  }
+  ctx->prof_recs.swap(keep);
+  *n_out = n;
+  *ms_out = ms;
+  return SB_OK;
+}
 
 }  // extern "C"

@@ -292,6 +292,7 @@ int bm25_score_subbatch(sb_ctx* ctx, const int32_t* q_terms_dev, const int32_t* 
   int rc = ctx->misc_dev.reserve((size_t)max_len * (nq + 1) * sizeof(int32_t));
   if (rc) return rc;
   int32_t* chunk_prefix = ctx->misc_dev.as<int32_t>();
+  ctx->launches += 1;
   bm25_plan_kernel<<<max_len, 32, 0, st>>>(q_terms_dev, q_off_dev, nq, max_len, ix.indptr, ix.idf, ix.n_terms,
                                            chunk_prefix);
   SB_CUDA(cudaGetLastError());
@@ -308,6 +309,7 @@ int bm25_score_subbatch(sb_ctx* ctx, const int32_t* q_terms_dev, const int32_t* 
     sp.ratio = ix.post_ratio;
     sp.idf = ix.idf;
     sp.n_docs = ix.n_docs;
+    ProfScope ps(ctx, SB_PROF_BM25_SCORE, st, ix.variant == SB_BM25_PLUS ? 2 : 1);
     if (ix.variant == SB_BM25_PLUS) {
       sp.acc = scratch;
       bm25_score_kernel<true><<<grid, kScoreThreads, 0, st>>>(sp);
@@ -372,6 +374,7 @@ int bm25_topk_enqueue(sb_ctx* ctx, const int32_t* q_terms_dev, const int32_t* q_
     sp.cap = cap;
     sp.list_key = ctx->misc2_dev.as<unsigned long long>();
     sp.list_idx = ctx->misc3_dev.as<uint32_t>();
+    ProfScope ps(ctx, SB_PROF_BM25_SELECT, st, 2);
     bm25_select_kernel<<<dim3(cq, nq), kSelThreads, sel_smem, st>>>(sp);
     SB_CUDA(cudaGetLastError());
     bm25_final_kernel<<<nq, kSelThreads, fin_smem, st>>>(sp.list_key, sp.list_idx, cq, kprime, len_pow2, k,

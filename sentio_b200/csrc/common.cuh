@@ -119,6 +119,12 @@ struct sb_ctx {
   DenseIndex dense[SB_MAX_DENSE_SLOTS];
   Bm25Index bm25;
   CeModel* ce = nullptr;
+  // bookkeeping: kernels launched by this library, optional per-kernel CUDA-event timing (bench.py roofline leg)
+  uint64_t launches = 0;
+  bool prof_on = false;
+  struct ProfRec { int id; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
   // scratch
   DevBuf q_dev, cand_dev, out_ids_dev, out_sc_dev, out_cnt_dev, misc_dev, misc2_dev, misc3_dev, acc_dev;
   PinBuf pin_in, pin_out;
@@ -134,6 +140,39 @@ struct DeviceGuard {
     int cur = -1;
     cudaGetDevice(&cur);
     if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+// kernel ids for sb_profile_read
+enum { SB_PROF_DENSE_SCAN = 0, SB_PROF_DENSE_MERGE = 1, SB_PROF_BM25_SCORE = 2, SB_PROF_BM25_SELECT = 3,
+       SB_PROF_FUSE = 4, SB_PROF_CE = 5, SB_PROF_COUNT = 6 };
+
+static inline cudaEvent_t prof_event(sb_ctx* ctx) {
+  if (!ctx->prof_pool.empty()) {
+    cudaEvent_t e = ctx->prof_pool.back();
+    ctx->prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+// bracket `n_kernels` launches of kernel `id` on stream st with an event pair when profiling is enabled
+struct ProfScope {
+  sb_ctx* ctx;
+  cudaStream_t st;
+  cudaEvent_t b = nullptr;
+  ProfScope(sb_ctx* c, int id, cudaStream_t s, int n_kernels = 1) : ctx(c), st(s) {
+    ctx->launches += (uint64_t)n_kernels;
+    if (ctx->prof_on) {
+      cudaEvent_t a = prof_event(ctx);
+      b = prof_event(ctx);
+      cudaEventRecord(a, st);
+      ctx->prof_recs.push_back({id, a, b});
+    }
+  }
+  ~ProfScope() {
+    if (b) cudaEventRecord(b, st);
   }
 };
 

@@ -14,6 +14,8 @@
 //
 // Algorithmic HBM bytes per pass = n_pad * d_pad * 2 (+ n_pad * 4 for the inverse norms); see DESIGN.md.
 #include <math.h>
+#include <string.h>
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -566,7 +568,10 @@ int dense_topk_enqueue(sb_ctx* ctx, const DenseIndex& ix, const float* q_pad, in
     sp.cap = pl.cap;
     sp.stages = pl.stages;
     sp.tile_bytes = pl.tile_bytes;
-    rc = dispatch_scan(qb, sp, pl, st);
+    {
+      ProfScope ps(ctx, SB_PROF_DENSE_SCAN, st);
+      rc = dispatch_scan(qb, sp, pl, st);
+    }
     if (rc) return rc;
     MergeParams mp;
     mp.cand = sp.cand;
@@ -582,7 +587,10 @@ int dense_topk_enqueue(sb_ctx* ctx, const DenseIndex& ix, const float* q_pad, in
     mp.out_scores = out_scores + (size_t)b0 * k;
     mp.out_counts = out_counts + b0;
     mp.lists_in_smem = pl.lists_in_smem;
-    dense_merge_kernel<<<qb, kMergeThreads, pl.merge_smem, st>>>(mp);
+    {
+      ProfScope ps(ctx, SB_PROF_DENSE_MERGE, st);
+      dense_merge_kernel<<<qb, kMergeThreads, pl.merge_smem, st>>>(mp);
+    }
     SB_CUDA(cudaGetLastError());
     b0 += qb;
   }

@@ -312,7 +312,10 @@ int sb_fuse_enqueue(sb_ctx* ctx, int32_t method, double rrf_k, double w_dense, d
   fp.out_counts = out_counts;
   const size_t smem = (size_t)fp.m_max * (8 + 8 + 8 + 4 + 4) + 16;
   SB_CUDA(cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fuse_kernel<<<B, kFuseThreads, smem, st>>>(fp);
+  {
+    ProfScope ps(ctx, SB_PROF_FUSE, st);
+    fuse_kernel<<<B, kFuseThreads, smem, st>>>(fp);
+  }
   SB_CUDA(cudaGetLastError());
   return SB_OK;
 }
@@ -420,6 +423,7 @@ int sb_merge_shards_dev(sb_ctx* ctx, const int64_t* in_ids, const double* in_sco
   DeviceGuard g(ctx->device);
   cudaStream_t st = pick_stream(ctx, stream);
   SB_CUDA(cudaFuncSetAttribute(merge_shards_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, len * 16));
+  ctx->launches += 1;
   merge_shards_kernel<<<B, 256, (size_t)len * 16, st>>>(in_ids, in_scores, in_counts, shard_stride_bytes, G, B, k, len,
                                                         out_ids, out_scores, out_counts);
   SB_CUDA(cudaGetLastError());

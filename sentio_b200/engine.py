@@ -60,6 +60,19 @@ class B200Engine:
     def sync(self) -> None:
         check(self._lib.sb_sync(self._h), "sb_sync")
 
+    def launch_count(self) -> int:
+        return int(self._lib.sb_launch_count(self._h))
+
+    PROF_IDS = {"dense_scan": 0, "dense_merge": 1, "bm25_score": 2, "bm25_select": 3, "fuse": 4, "ce": 5}
+
+    def profile(self, enable: bool) -> None:
+        check(self._lib.sb_profile(self._h, 1 if enable else 0), "sb_profile")
+
+    def profile_read(self, kernel: str):
+        n, ms = C.c_int64(0), C.c_double(0.0)
+        check(self._lib.sb_profile_read(self._h, self.PROF_IDS[kernel], C.byref(n), C.byref(ms)), "sb_profile_read")
+        return int(n.value), float(ms.value)
+
     def _stream(self):
         import torch
 

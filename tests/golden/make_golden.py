@@ -193,8 +193,27 @@ def scorer_cases(ns):
                                                        "Deep learning uses neural networks"], expected=kw))
 
 
+class _StableArgsortNumpy:
+    """numpy proxy whose argsort defaults to kind="stable".
+
+    Documented deviation (SURVEY.md section 7 "tie semantics"): the reference's `np.argsort(-scores)`
+    (sparse.py:180) is an unstable introsort, so its order among EXACT BM25 score ties is implementation defined; the
+    fixtures (and the product) resolve such ties by ascending corpus position."""
+
+    def __getattr__(self, name):
+        return getattr(np, name)
+
+    @staticmethod
+    def argsort(a, *args, **kw):
+        kw.setdefault("kind", "stable")
+        return np.argsort(a, *args, **kw)
+
+
 def hybrid_e2e_cases(ns):
     """Full reference stack: DenseRetriever over an exact-cosine Qdrant stand-in + BM25Retriever + HybridRetriever."""
+    import src.core.retrievers.sparse as ref_sparse
+
+    ref_sparse.np = _StableArgsortNumpy()
     rng = np.random.default_rng(21)
     dim = 64
     emb = HashEmbedder(dim)

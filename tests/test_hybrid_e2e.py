@@ -1,0 +1,115 @@
+"""Whole-stack parity against the reference's own classes (golden hybrid_e2e.json = reference DenseRetriever +
+BM25Retriever + HybridRetriever + scorer plugins executed in the build container).
+
+* CPU (`not gpu`): our retriever classes driven by the oracle-backed engine double -> pins the HOST logic.
+* GPU: the same classes on the real engine / C ABI -> the parity test proper.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from helpers import HashEmbedder
+from sentio_b200.document import Document
+from sentio_b200.retrievers.dense import DenseRetriever
+from sentio_b200.retrievers.hybrid import HybridRetriever
+from sentio_b200.retrievers.scorers import KeywordMatchScorer, MMRScorer, SemanticSimilarityScorer
+
+
+def _run(gold, make_store, make_sparse, fusion_engine, scorer_engine):
+    emb = HashEmbedder(gold["dim"])
+    vecs = np.asarray([emb.embed_sync(t) for t in gold["texts"]], dtype=np.float32)
+    payloads = [{"content": t, "metadata": {"source": f"s{i % 7}"}} for i, t in enumerate(gold["texts"])]
+    store = make_store(vecs, gold["ids"], payloads)
+    for run in gold["runs"]:
+        corpus = [Document(id=i, text=t, metadata={"source": "corpus"}) for i, t in zip(gold["ids"], gold["texts"])]
+        dense = DenseRetriever(client=store, embedder=emb, collection_name="Sentio_docs")
+        sparse = make_sparse(corpus)
+        plugins = None
+        if run["plugins"]:
+            plugins = [SemanticSimilarityScorer(embedder=emb, weight=0.8, engine=scorer_engine),
+                       KeywordMatchScorer(weight=0.2),
+                       MMRScorer(embedder=emb, lambda_=0.5, weight=0.5, engine=scorer_engine)]
+        hr = HybridRetriever(dense_retriever=dense, sparse_retriever=sparse, rrf_k=60, scorer_plugins=plugins,
+                             fusion_method=run["method"], dense_weight=0.6, sparse_weight=0.4, engine=fusion_engine)
+        for q, want in zip(gold["queries"], run["results"]):
+            got = hr.retrieve(q, top_k=15)
+            assert [d.id for d in got] == [w[0] for w in want], (run["method"], run["plugins"], q)
+            gs = np.asarray([d.metadata["score"] for d in got])
+            ws = np.asarray([w[1] for w in want])
+            if run["plugins"]:
+                assert np.allclose(gs, ws, rtol=1e-9, atol=1e-12)
+            else:
+                assert np.array_equal(gs, ws), (run["method"], q)  # rrf / comb_sum arithmetic is bit-exact
+            assert all(d.metadata["hybrid_score"] == d.metadata["score"] for d in got)
+
+
+class _OracleStore:
+    """QdrantClient-shaped store on the oracle engine double (CPU host-logic test only)."""
+
+    def __init__(self, vecs, ids, payloads):
+        from oracle_engine import OracleEngine
+        from sentio_b200.vector_store import ScoredPoint
+
+        self.eng = OracleEngine()
+        self.eng.load_dense(vecs)
+        self.ids, self.payloads, self.SP = ids, payloads, ScoredPoint
+
+    def collection_exists(self, collection_name):
+        return collection_name == "Sentio_docs"
+
+    def search(self, collection_name, query_vector, limit=10, with_payload=True, with_vectors=False):
+        i, s, c = self.eng.dense_topk(np.asarray(query_vector, np.float32)[None], limit)
+        return [self.SP(id=self.ids[int(i[0, j])], score=float(s[0, j]), payload=self.payloads[int(i[0, j])])
+                for j in range(int(c[0]))]
+
+
+def test_host_logic_with_oracle_engine(monkeypatch):
+    from oracle_engine import OracleEngine
+    from sentio_b200.retrievers import sparse as sparse_mod
+
+    monkeypatch.delenv("BM25_VARIANT", raising=False)
+    monkeypatch.setenv("CACHE_COLLECTION_NAME", "web_cache")
+    monkeypatch.setattr(sparse_mod, "B200Engine", lambda device=0: OracleEngine())
+    eng = OracleEngine()
+    _run(load_golden("hybrid_e2e"), _OracleStore, lambda corpus: sparse_mod.BM25Retriever(documents=corpus), eng, eng)
+
+
+@pytest.mark.gpu
+def test_gpu_stack_matches_reference(engine, monkeypatch):
+    from sentio_b200.retrievers.sparse import BM25Retriever
+    from sentio_b200.vector_store import B200VectorStore
+
+    monkeypatch.delenv("BM25_VARIANT", raising=False)
+
+    def make_store(vecs, ids, payloads):
+        st = B200VectorStore(0)
+        st.create_collection("Sentio_docs", vecs, ids=ids, payloads=payloads)
+        return st
+
+    _run(load_golden("hybrid_e2e"), make_store, lambda corpus: BM25Retriever(documents=corpus), engine, engine)
+
+
+@pytest.mark.gpu
+def test_pipeline_batch_equals_per_query_classes(engine):
+    """HybridPipeline (device-resident batch path) == dense_topk + bm25_topk + fuse composed per query."""
+    from sentio_b200 import synth
+    from sentio_b200.index import build_bm25_from_token_ids
+    from sentio_b200.pipeline import HybridPipeline
+
+    n, d, k, B = 30000, 256, 100, 19
+    x = synth.dense_corpus(n, d)
+    flat, off = synth.text_corpus_tokens(n, vocab=4000)
+    idx = build_bm25_from_token_ids(flat, off)
+    pipe = HybridPipeline(0)
+    pipe.load_dense(x)
+    pipe.load_bm25(idx)
+    q = synth.query_vectors(B, d)
+    terms = [idx.term_ids(t) for t in synth.query_tokens(B, vocab=4000)]
+    for method in ("rrf", "comb_sum"):
+        ids, sc, src, cnt = pipe.search_hybrid(q, terms, k, method=method, rrf_k=60, w_dense=0.6, w_sparse=0.4)
+        engine.load_dense(x)
+        engine.load_bm25(idx)
+        dl = engine.dense_topk(q, k)
+        sl = engine.bm25_topk(terms, k)
+        f = engine.fuse(method, 60, 0.6, 0.4, k, dense=dl, sparse=sl)
+        assert np.array_equal(ids, f[0]) and np.array_equal(sc, f[1]) and np.array_equal(cnt, f[3])
