@@ -1,0 +1,290 @@
+// ce_gemm.cu -- tcgen05 / TMEM / TMA GEMM for the cross-encoder (K5):  D[M,N] = A[M,K] * W[N,K]^T  (+ epilogue)
+//
+// A (activations) and W (nn.Linear weights) are both K-major fp16, accumulation is fp32 in tensor memory.
+// One 128 x 128 output tile per CTA, K consumed in 64-element (128-byte, SWIZZLE_128B) chunks through a 3-stage
+// TMA -> mbarrier -> tcgen05.mma ring; warp roles: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
+// MMA issuer (one elected lane), warps 2..5 = epilogue (tcgen05.ld 32x32b, one accumulator row per thread).
+// Two CTAs are resident per SM (96 KB smem, 128 TMEM columns each) so one tile's epilogue overlaps another's mainloop.
+//
+// Epilogues:  BIAS_F16        out16 = acc + bias                      (QKV projection)
+//             BIAS_GELU_F16   out16 = gelu_erf(acc + bias)            (FFN up-projection)
+//             BIAS_RES_F32    out32 = acc + bias + residual32         (attention output / FFN down-projection, pre-LN)
+//
+// Bound: tensor pipe (2*M*N*K flops); see DESIGN.md for the per-pair flop count.
+#include <cuda.h>
+
+#include "ce_gemm.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int kStages = 3;
+constexpr int kGemmThreads = 192;
+constexpr uint32_t kTileABytes = BM * BK * 2, kTileBBytes = BN * BK * 2;
+constexpr uint32_t kStageBytes = kTileABytes + kTileBBytes;
+constexpr uint32_t kTmemCols = 128;
+constexpr size_t kGemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cf. cute::UMMA::SmemDescriptor): start address >> 4,
+// LBO = 1 (unused for swizzled K-major), SBO = 1024 B (8 rows x 128 B swizzle atom) >> 4, version = 1, layout = 2.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29).
+__device__ __forceinline__ uint32_t make_idesc() {
+  uint32_t d = 0;
+  d |= 1u << 4;                     // c_format = F32
+  d |= 0u << 7;                     // a_format = F16
+  d |= 0u << 10;                    // b_format = F16
+  d |= (uint32_t)(BN >> 3) << 17;   // n_dim
+  d |= (uint32_t)(BM >> 4) << 24;   // m_dim
+  return d;
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 2)
+ce_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N, int K,
+               const float* __restrict__ bias, const float* __restrict__ residual, __half* __restrict__ out16,
+               float* __restrict__ out32) {
+  extern __shared__ uint8_t gsm_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t raw = smem_u32(gsm_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gsm = gsm_raw + (base - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gsm + kStages * kStageBytes);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kStages), bar_acc = smem_u32(bars + 2 * kStages);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int num_k = K / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_acc, 1);
+    mbar_fence_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_k; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t use = (uint32_t)(kb / kStages);
+        if (kb >= kStages) mbar_wait(bar_empty + 8 * s, (use & 1u) ^ 1u);
+        const uint32_t sa = base + (uint32_t)s * kStageBytes, sb = sa + kTileABytes;
+        mbar_expect_tx(bar_full + 8 * s, kStageBytes);
+        tma_load_2d(sa, &map_a, kb * BK, m0, bar_full + 8 * s);
+        tma_load_2d(sb, &map_w, kb * BK, n0, bar_full + 8 * s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc();
+      for (int kb = 0; kb < num_k; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t use = (uint32_t)(kb / kStages);
+        mbar_wait(bar_full + 8 * s, use & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = base + (uint32_t)s * kStageBytes, sb = sa + kTileABytes;
+        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+          umma_f16(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+        }
+        umma_commit(bar_empty + 8 * s);  // frees this smem stage once the MMAs above have read it
+      }
+      umma_commit(bar_acc);  // accumulator complete
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue warps 2..5
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    mbar_wait(bar_acc, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = m0 + quad * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < M) {
+        const int col = n0 + c0;
+        if (EPI == CE_EPI_BIAS_RES_F32) {
+          float* o = out32 + (size_t)row * N + col;
+          const float* r = residual + (size_t)row * N + col;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 rb = *reinterpret_cast<const float4*>(r + j);
+            const float4 bb = *reinterpret_cast<const float4*>(bias + col + j);
+            float4 w;
+            w.x = __uint_as_float(v[j + 0]) + bb.x + rb.x;
+            w.y = __uint_as_float(v[j + 1]) + bb.y + rb.y;
+            w.z = __uint_as_float(v[j + 2]) + bb.z + rb.z;
+            w.w = __uint_as_float(v[j + 3]) + bb.w + rb.w;
+            *reinterpret_cast<float4*>(o + j) = w;
+          }
+        } else {
+          __half* o = out16 + (size_t)row * N + col;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float x = __uint_as_float(v[j + e]) + __ldg(bias + col + j + e);
+              f[e] = (EPI == CE_EPI_BIAS_GELU_F16) ? gelu_erf(x) : x;
+            }
+            uint4 pk;
+            __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
+            __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&h0);
+            pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2);
+            pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(o + j) = pk;
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(kTmemCols) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace
+
+// rows x cols fp16 row-major (cols contiguous) -> 2-D tensor map with a 64 x 128 box and 128-byte swizzle
+int ce_make_tensor_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols) {
+  EncodeTiledFn enc = get_encode();
+  SB_REQUIRE(enc != nullptr, SB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  SB_REQUIRE(cols % BK == 0, SB_ERR_ARG, "ce_gemm: K=%lld must be a multiple of %d", (long long)cols, BK);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SB_REQUIRE(r == CUDA_SUCCESS, SB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return SB_OK;
+}
+
+int ce_gemm_launch(int epi, const CUtensorMap& map_a, const CUtensorMap& map_w, int M, int N, int K, const float* bias,
+                   const float* residual, __half* out16, float* out32, cudaStream_t st) {
+  SB_REQUIRE(N % BN == 0 && K % BK == 0, SB_ERR_ARG, "ce_gemm: N=%d / K=%d must be multiples of %d / %d", N, K, BN, BK);
+  dim3 grid(N / BN, (M + BM - 1) / BM);
+  switch (epi) {
+    case CE_EPI_BIAS_F16: {
+      static bool once = false;
+      if (!once) {
+        SB_CUDA(cudaFuncSetAttribute(ce_gemm_kernel<CE_EPI_BIAS_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)kGemmSmem));
+        once = true;
+      }
+      ce_gemm_kernel<CE_EPI_BIAS_F16><<<grid, kGemmThreads, kGemmSmem, st>>>(map_a, map_w, M, N, K, bias, residual,
+                                                                             out16, out32);
+      break;
+    }
+    case CE_EPI_BIAS_GELU_F16: {
+      static bool once = false;
+      if (!once) {
+        SB_CUDA(cudaFuncSetAttribute(ce_gemm_kernel<CE_EPI_BIAS_GELU_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)kGemmSmem));
+        once = true;
+      }
+      ce_gemm_kernel<CE_EPI_BIAS_GELU_F16><<<grid, kGemmThreads, kGemmSmem, st>>>(map_a, map_w, M, N, K, bias,
+                                                                                  residual, out16, out32);
+      break;
+    }
+    case CE_EPI_BIAS_RES_F32: {
+      static bool once = false;
+      if (!once) {
+        SB_CUDA(cudaFuncSetAttribute(ce_gemm_kernel<CE_EPI_BIAS_RES_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)kGemmSmem));
+        once = true;
+      }
+      ce_gemm_kernel<CE_EPI_BIAS_RES_F32><<<grid, kGemmThreads, kGemmSmem, st>>>(map_a, map_w, M, N, K, bias, residual,
+                                                                                 out16, out32);
+      break;
+    }
+    default:
+      sb_set_error("ce_gemm: unknown epilogue %d", epi);
+      return SB_ERR_ARG;
+  }
+  SB_CUDA(cudaGetLastError());
+  return SB_OK;
+}

@@ -24,7 +24,7 @@ namespace {
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kScanThreads = kConsumerThreads + 32;  // + 1 producer warp
-constexpr int kMergeThreads = 1024;
+constexpr int kMergeThreads = 512;
 constexpr int kRowPad = 32;  // n_pad granularity (max tile rows)
 
 // ------------------------------------------------------------------------------------------------ load kernels
@@ -120,7 +120,22 @@ __device__ __forceinline__ void consumer_bitonic_sort_desc(unsigned long long* b
   }
 }
 
-template <int NCHUNK, int QB, int RW>
+// two fp32 FMAs per instruction (SASS FFMA2): the 3-register FFMA issues at half rate on sm_100, FFMA2 restores
+// the full 128 FMA/clk/SM; operands are (lo, hi) float pairs packed in 64-bit registers.
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long pack_f2(float lo, float hi) {
+  return ((unsigned long long)__float_as_uint(hi) << 32) | (unsigned long long)__float_as_uint(lo);
+}
+__device__ __forceinline__ unsigned long long h2_to_f2(uint32_t h2) {
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h2));
+  return pack_f2(f.x, f.y);
+}
+
+template <int NCHUNK, int QB, int RW, bool EXACT>
 __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanParams p) {
   constexpr int R = kConsumerWarps * RW;  // rows per tile
   constexpr int V = RW * QB;              // partial sums per lane
@@ -172,21 +187,23 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
   }
 
   // -------------------------------------------------------------- consumer warps
-  // query slices in registers: lane owns 16-byte chunk c = lane + 32*j of every row
-  float qr[QB][NCHUNK][8];
+  // query slices in registers as (even, odd) fp32 pairs: lane owns 16-byte chunk c = lane + 32*j of every row
+  unsigned long long qr[QB][NCHUNK][4];
 #pragma unroll
   for (int q = 0; q < QB; ++q) {
 #pragma unroll
     for (int j = 0; j < NCHUNK; ++j) {
       const int c = lane + 32 * j;
-      if (c < p.ch) {
+      if (EXACT || c < p.ch) {
         const float4* src = reinterpret_cast<const float4*>(p.q + (size_t)q * p.d_pad + (size_t)c * 8);
-        float4 a = __ldg(src), b = __ldg(src + 1);
-        qr[q][j][0] = a.x; qr[q][j][1] = a.y; qr[q][j][2] = a.z; qr[q][j][3] = a.w;
-        qr[q][j][4] = b.x; qr[q][j][5] = b.y; qr[q][j][6] = b.z; qr[q][j][7] = b.w;
+        const float4 a = __ldg(src), b = __ldg(src + 1);
+        qr[q][j][0] = pack_f2(a.x, a.y);
+        qr[q][j][1] = pack_f2(a.z, a.w);
+        qr[q][j][2] = pack_f2(b.x, b.y);
+        qr[q][j][3] = pack_f2(b.z, b.w);
       } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) qr[q][j][e] = 0.f;
+        for (int e = 0; e < 4; ++e) qr[q][j][e] = 0ull;
       }
     }
   }
@@ -206,42 +223,55 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
 
     mbar_wait(bar_full0 + 8 * s, use & 1u);
 
-    float acc[V];
+    unsigned long long acc[V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = 0.f;
-    const uint8_t* wbase = tiles + (size_t)s * p.tile_bytes + (size_t)(warp * RW) * row_bytes;
+    for (int v = 0; v < V; ++v) acc[v] = 0ull;
+    const uint8_t* wbase = tiles + (size_t)s * p.tile_bytes + (size_t)(warp * RW) * row_bytes + (size_t)lane * 16;
+    // software pipeline: the 16-byte chunks of step j+1 are in flight while step j is multiplied
+    uint4 cur[RW], nxt[RW];
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+      cur[r] = make_uint4(0u, 0u, 0u, 0u);
+      if (EXACT || lane < p.ch) cur[r] = *reinterpret_cast<const uint4*>(wbase + (size_t)r * row_bytes);
+    }
 #pragma unroll
     for (int j = 0; j < NCHUNK; ++j) {
-      const int c = lane + 32 * j;
-      if (c < p.ch) {
+      if (j + 1 < NCHUNK) {
 #pragma unroll
         for (int r = 0; r < RW; ++r) {
-          const uint4 raw = *reinterpret_cast<const uint4*>(wbase + (size_t)r * row_bytes + (size_t)c * 16);
-          const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-          const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-          const float2 x2 = __half22float2(*reinterpret_cast<const __half2*>(&raw.z));
-          const float2 x3 = __half22float2(*reinterpret_cast<const __half2*>(&raw.w));
-#pragma unroll
-          for (int q = 0; q < QB; ++q) {
-            float a = acc[r * QB + q];
-            a = fmaf(x0.x, qr[q][j][0], a);
-            a = fmaf(x0.y, qr[q][j][1], a);
-            a = fmaf(x1.x, qr[q][j][2], a);
-            a = fmaf(x1.y, qr[q][j][3], a);
-            a = fmaf(x2.x, qr[q][j][4], a);
-            a = fmaf(x2.y, qr[q][j][5], a);
-            a = fmaf(x3.x, qr[q][j][6], a);
-            a = fmaf(x3.y, qr[q][j][7], a);
-            acc[r * QB + q] = a;
-          }
+          nxt[r] = make_uint4(0u, 0u, 0u, 0u);
+          if (EXACT || lane + 32 * (j + 1) < p.ch)
+            nxt[r] = *reinterpret_cast<const uint4*>(wbase + (size_t)r * row_bytes + (size_t)(j + 1) * 512);
         }
+      }
+#pragma unroll
+      for (int r = 0; r < RW; ++r) {
+        const unsigned long long x0 = h2_to_f2(cur[r].x), x1 = h2_to_f2(cur[r].y);
+        const unsigned long long x2 = h2_to_f2(cur[r].z), x3 = h2_to_f2(cur[r].w);
+#pragma unroll
+        for (int q = 0; q < QB; ++q) {
+          unsigned long long a = acc[r * QB + q];
+          a = ffma2(x0, qr[q][j][0], a);
+          a = ffma2(x1, qr[q][j][1], a);
+          a = ffma2(x2, qr[q][j][2], a);
+          a = ffma2(x3, qr[q][j][3], a);
+          acc[r * QB + q] = a;
+        }
+      }
+      if (j + 1 < NCHUNK) {
+#pragma unroll
+        for (int r = 0; r < RW; ++r) cur[r] = nxt[r];
       }
     }
     // all smem reads of this stage are consumed (their values fed the FMAs above) -> release the slot
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_empty0 + 8 * s);
 
-    const float dot = warp_reduce_multi<V>(acc, lane);
+    float part[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+      part[v] = __uint_as_float((uint32_t)(acc[v] & 0xffffffffull)) + __uint_as_float((uint32_t)(acc[v] >> 32));
+    const float dot = warp_reduce_multi<V>(part, lane);
     if (leader) {
       const float score = dot * invn;
       if (grow < p.n && score > thr[qi]) {
@@ -286,60 +316,65 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
 }
 
 // ------------------------------------------------------------------------------------------------ merge kernel
+constexpr int kSelCap = 2048;  // shared-memory capacity of the threshold-selected candidate set
+
 struct MergeParams {
-  unsigned long long* cand;  // [QB][G][kprime]
+  unsigned long long* cand;  // [nq][G][kprime] sorted descending lists (clobbered only on the slow path)
   int32_t G;
   int32_t kprime;
+  int32_t heads_per_list;    // R = ceil(kprime / G)
+  int32_t heads_pow2;        // power of two >= G * R  (<= kSelCap)
   const __half* rows;
-  const float* q;  // [QB][d_pad]
+  const float* q;            // [nq][d_pad]
   int32_t d_pad;
   int32_t ch;
   int64_t id_base;
   int32_t k;
-  int64_t* out_ids;     // [.][k]  (already offset to this pass' first query)
-  double* out_scores;   // [.][k]
-  int32_t* out_counts;  // [.]
-  int32_t lists_in_smem;
+  int64_t* out_ids;          // [nq][k]
+  double* out_scores;        // [nq][k]
+  int32_t* out_counts;       // [nq]
 };
 
-__global__ void __launch_bounds__(kMergeThreads, 1) dense_merge_kernel(const MergeParams p) {
-  extern __shared__ __align__(16) uint8_t msmem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int qi = blockIdx.x;
-  const int G = p.G, K = p.kprime;
-  unsigned long long* ek = reinterpret_cast<unsigned long long*>(msmem);       // [K] exact score keys
-  uint32_t* ei = reinterpret_cast<uint32_t*>(ek + K);                           // [K] row index
-  double* qq_s = reinterpret_cast<double*>(ei + K + (K & 1));                   // [1]
-  unsigned long long* L = p.cand + (size_t)qi * G * K;
-  if (p.lists_in_smem) {
-    unsigned long long* Ls = reinterpret_cast<unsigned long long*>(qq_s + 2);
-    for (int i = tid; i < G * K; i += kMergeThreads) Ls[i] = L[i];
-    L = Ls;
+__device__ __forceinline__ void block_sort_desc_u64(unsigned long long* a, int len, int tid, int nt) {
+  for (int k = 2; k <= len; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < len; i += nt) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long x = a[i], y = a[ixj];
+          const bool desc = (i & k) == 0;
+          if (desc ? (x < y) : (x > y)) {
+            a[i] = y;
+            a[ixj] = x;
+          }
+        }
+      }
+      __syncthreads();
+    }
   }
-  __syncthreads();
+}
 
-  // truncating bitonic merge tree: list a (stride 2^(l+1)) <- top-K of (a U a+2^l)
+// Slow path (adversarial score distributions only): truncating bitonic merge tree over the G lists, in place.
+__device__ void merge_tree_inplace(unsigned long long* L, int G, int K, int tid, int nt) {
   for (int step = 1; step < G; step <<= 1) {
-    const int pairs = (G - step + 2 * step - 1) / (2 * step);  // lists a = 2*step*pi with partner a+step < G
-    // phase 1: C[i] = max(A[i], B[K-1-i])  (bitonic, holds the K largest of the union)
-    for (int t = tid; t < pairs * K; t += kMergeThreads) {
+    const int pairs = (G - step + 2 * step - 1) / (2 * step);
+    for (int t = tid; t < pairs * K; t += nt) {
       const int pi = t / K, i = t - pi * K;
       const int a = pi * 2 * step, b = a + step;
       if (b < G) {
-        unsigned long long x = L[(size_t)a * K + i], y = L[(size_t)b * K + (K - 1 - i)];
+        const unsigned long long x = L[(size_t)a * K + i], y = L[(size_t)b * K + (K - 1 - i)];
         if (y > x) L[(size_t)a * K + i] = y;
       }
     }
     __syncthreads();
-    // phase 2: bitonic merge network -> descending
     for (int j = K >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < pairs * (K >> 1); t += kMergeThreads) {
+      for (int t = tid; t < pairs * (K >> 1); t += nt) {
         const int pi = t / (K >> 1), h = t - pi * (K >> 1);
         const int a = pi * 2 * step;
         if (a + step < G) {
           const int i = ((h / j) * 2 * j) + (h % j);
           unsigned long long* A = L + (size_t)a * K;
-          unsigned long long x = A[i], y = A[i + j];
+          const unsigned long long x = A[i], y = A[i + j];
           if (x < y) {
             A[i] = y;
             A[i + j] = x;
@@ -349,22 +384,82 @@ __global__ void __launch_bounds__(kMergeThreads, 1) dense_merge_kernel(const Mer
       __syncthreads();
     }
   }
+}
 
-  // exact fp64 re-score of the K survivors against the stored fp16 rows
+// One CTA per query.  (1) a lower bound of the global K'-th best key = the K'-th largest among the first
+// R = ceil(K'/G) entries of every list; (2) every list contributes its (short) prefix >= bound to a shared-memory set;
+// (3) that set is sorted -> global top-K'; (4) exact fp64 re-score against the stored fp16 rows; (5) final order.
+__global__ void __launch_bounds__(kMergeThreads, 1) dense_merge_kernel(const MergeParams p) {
+  extern __shared__ __align__(16) uint8_t msmem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
+  const int qi = blockIdx.x;
+  const int G = p.G, K = p.kprime;
+  unsigned long long* sel = reinterpret_cast<unsigned long long*>(msmem);   // [kSelCap]
+  unsigned long long* ek = sel + kSelCap;                                   // [K] exact score keys
+  uint32_t* ei = reinterpret_cast<uint32_t*>(ek + K);                       // [K] row index
+  __shared__ double qq_s;
+  __shared__ int s_nsel;
+  __shared__ unsigned long long s_bound;
+  unsigned long long* L = p.cand + (size_t)qi * G * K;
+
+  // (1) bound from the list heads
+  const int R = p.heads_per_list, nh = G * R, HP = p.heads_pow2;
+  for (int t = tid; t < HP; t += nt) sel[t] = t < nh ? L[(size_t)(t / R) * K + (t % R)] : 0ull;
+  if (tid == 0) s_nsel = 0;
+  __syncthreads();
+  block_sort_desc_u64(sel, HP, tid, nt);
+  if (tid == 0) s_bound = nh >= K ? sel[K - 1] : 0ull;
+  __syncthreads();
+  const unsigned long long bound = s_bound;
+  __syncthreads();  // sel is reused below
+
+  // (2) gather every list's prefix >= bound (lists are sorted descending; empty slots are key 0)
+  for (int g = warp; g < G; g += nw) {
+    const unsigned long long* lst = L + (size_t)g * K;
+    for (int base = 0; base < K; base += 32) {
+      const unsigned long long key = lst[base + lane];
+      const bool pass = key >= bound && key != 0ull;
+      const unsigned m = __ballot_sync(0xffffffffu, pass);
+      if (m == 0u) break;
+      int pos = 0;
+      if (lane == 0) pos = atomicAdd(&s_nsel, __popc(m));
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+      if (pass) {
+        const int at = pos + __popc(m & ((1u << lane) - 1u));
+        if (at < kSelCap) sel[at] = key;
+      }
+      if (m != 0xffffffffu) break;
+    }
+  }
+  __syncthreads();
+  const int nsel = s_nsel;
+  if (nsel <= kSelCap) {
+    int P = 32;
+    while (P < nsel || P < K) P <<= 1;
+    for (int t = nsel + tid; t < P; t += nt) sel[t] = 0ull;
+    __syncthreads();
+    block_sort_desc_u64(sel, P, tid, nt);
+  } else {
+    merge_tree_inplace(L, G, K, tid, nt);
+    for (int t = tid; t < K; t += nt) sel[t] = L[t];
+    __syncthreads();
+  }
+
+  // (4) exact fp64 re-score of the K survivors against the stored fp16 rows
   const float* q = p.q + (size_t)qi * p.d_pad;
   if (warp == 0) {
     double s = 0.0;
     for (int i = lane; i < p.d_pad; i += 32) {
-      double v = (double)q[i];
+      const double v = (double)q[i];
       s += v * v;
     }
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) qq_s[0] = s;
+    if (lane == 0) qq_s = s;
   }
   __syncthreads();
-  const double qn = sqrt(qq_s[0]);
-  for (int c = warp; c < K; c += kMergeThreads / 32) {
-    const unsigned long long key = L[c];
+  const double qn = sqrt(qq_s);
+  for (int c = warp; c < K; c += nw) {
+    const unsigned long long key = sel[c];
     unsigned long long okey = 0ull;
     uint32_t idx = 0xffffffffu;
     if (key != 0ull) {
@@ -402,21 +497,19 @@ __global__ void __launch_bounds__(kMergeThreads, 1) dense_merge_kernel(const Mer
     }
   }
   __syncthreads();
-  // final sort by (exact score desc, row index asc)
+  // (5) final sort by (exact score desc, row index asc)
   for (int kk = 2; kk <= K; kk <<= 1) {
     for (int j = kk >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < K; i += kMergeThreads) {
+      for (int i = tid; i < K; i += nt) {
         const int ixj = i ^ j;
         if (ixj > i) {
           const unsigned long long a = ek[i], b = ek[ixj];
           const uint32_t ia = ei[i], ib = ei[ixj];
           const bool a_before_b = (a > b) || (a == b && ia < ib);
           const bool desc = (i & kk) == 0;
-          if (desc ? !a_before_b : a_before_b) {
-            if (!(a == b && ia == ib)) {
-              ek[i] = b; ek[ixj] = a;
-              ei[i] = ib; ei[ixj] = ia;
-            }
+          if ((desc ? !a_before_b : a_before_b) && !(a == b && ia == ib)) {
+            ek[i] = b; ek[ixj] = a;
+            ei[i] = ib; ei[ixj] = ia;
           }
         }
       }
@@ -425,22 +518,18 @@ __global__ void __launch_bounds__(kMergeThreads, 1) dense_merge_kernel(const Mer
   }
   int64_t* oid = p.out_ids + (size_t)qi * p.k;
   double* osc = p.out_scores + (size_t)qi * p.k;
-  for (int i = tid; i < p.k; i += kMergeThreads) {
+  for (int i = tid; i < p.k; i += nt) {
     const bool valid = (i < K) && ek[i] != 0ull;
     oid[i] = valid ? p.id_base + (int64_t)ei[i] : -1;
     osc[i] = valid ? orderable_f64(ek[i]) : 0.0;
   }
   if (tid == 0) {
-    int c = 0;
-    const int lim = min(p.k, K);
-    // valid entries are a prefix (empty keys sort last)
-    int lo = 0, hi = lim;
+    int lo = 0, hi = min(p.k, K);  // valid entries are a prefix (empty keys sort last)
     while (lo < hi) {
-      int mid = (lo + hi) >> 1;
+      const int mid = (lo + hi) >> 1;
       if (ek[mid] != 0ull) lo = mid + 1; else hi = mid;
     }
-    c = lo;
-    p.out_counts[qi] = c;
+    p.out_counts[qi] = lo;
   }
 }
 
@@ -455,7 +544,7 @@ struct ScanPlan {
   int nchunk, rw, qb_max, kprime, cap, stages, grid, num_tiles;
   uint32_t tile_bytes;
   size_t scan_smem, merge_smem;
-  int lists_in_smem;
+  int heads_per_list, heads_pow2;
 };
 
 int supported_nchunk(int ch) {
@@ -500,18 +589,24 @@ int make_plan(sb_ctx* ctx, const DenseIndex& ix, int k, ScanPlan* pl) {
   pl->scan_smem = (size_t)stages * pl->tile_bytes + fixed + 2 * 8 * (size_t)stages + 64;
   pl->grid = ctx->num_sms < pl->num_tiles ? ctx->num_sms : pl->num_tiles;
   if (pl->grid < 1) pl->grid = 1;
-  const size_t small = (size_t)pl->kprime * 12 + 64;
-  const size_t lists = (size_t)pl->grid * pl->kprime * 8;
-  pl->lists_in_smem = (small + lists + 64 <= budget) ? 1 : 0;
-  pl->merge_smem = small + (pl->lists_in_smem ? lists : 0) + 64;
+  pl->heads_per_list = (pl->kprime + pl->grid - 1) / pl->grid;
+  pl->heads_pow2 = next_pow2(pl->grid * pl->heads_per_list);
+  SB_REQUIRE(pl->heads_pow2 <= kSelCap, SB_ERR_UNSUPPORTED, "dense: internal merge capacity exceeded");
+  pl->merge_smem = (size_t)kSelCap * 8 + (size_t)pl->kprime * 12 + 64;
   return SB_OK;
 }
 
 template <int NCHUNK, int QB, int RW>
 int launch_scan(const ScanParams& sp, const ScanPlan& pl, cudaStream_t st) {
-  auto kern = dense_scan_kernel<NCHUNK, QB, RW>;
-  SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.scan_smem));
-  kern<<<pl.grid, kScanThreads, pl.scan_smem, st>>>(sp);
+  if (sp.ch == NCHUNK * 32) {
+    auto kern = dense_scan_kernel<NCHUNK, QB, RW, true>;
+    SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.scan_smem));
+    kern<<<pl.grid, kScanThreads, pl.scan_smem, st>>>(sp);
+  } else {
+    auto kern = dense_scan_kernel<NCHUNK, QB, RW, false>;
+    SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.scan_smem));
+    kern<<<pl.grid, kScanThreads, pl.scan_smem, st>>>(sp);
+  }
   SB_CUDA(cudaGetLastError());
   return SB_OK;
 }
@@ -542,57 +637,66 @@ int dispatch_scan(int qb, const ScanParams& sp, const ScanPlan& pl, cudaStream_t
   return SB_ERR_UNSUPPORTED;
 }
 
-// q_pad: [B][d_pad] fp32 device, zero padded.  Enqueues all passes on `st`.
+// q_pad: [B][d_pad] fp32 device, zero padded.  Enqueues all scan passes of a chunk of queries, then ONE merge launch
+// (one CTA per query) for the whole chunk.
+constexpr int kMergeChunk = 256;
+
 int dense_topk_enqueue(sb_ctx* ctx, const DenseIndex& ix, const float* q_pad, int B, int k, int64_t* out_ids,
                        double* out_scores, int32_t* out_counts, cudaStream_t st) {
   ScanPlan pl;
   int rc = make_plan(ctx, ix, k, &pl);
   if (rc) return rc;
-  rc = ctx->cand_dev.reserve((size_t)pl.qb_max * pl.grid * pl.kprime * 8);
+  const int chunk = B < kMergeChunk ? B : kMergeChunk;
+  const size_t per_q = (size_t)pl.grid * pl.kprime;
+  rc = ctx->cand_dev.reserve((size_t)chunk * per_q * 8);
   if (rc) return rc;
   SB_CUDA(cudaFuncSetAttribute(dense_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.merge_smem));
-  int b0 = 0;
-  while (b0 < B) {
-    int qb = pl.qb_max;
-    while (qb > B - b0) qb >>= 1;
-    ScanParams sp;
-    sp.rows = ix.rows;
-    sp.inv_norm = ix.inv_norm;
-    sp.q = q_pad + (size_t)b0 * ix.d_pad;
-    sp.cand = ctx->cand_dev.as<unsigned long long>();
-    sp.n = ix.n;
-    sp.d_pad = ix.d_pad;
-    sp.ch = ix.d_pad / 8;
-    sp.num_tiles = pl.num_tiles;
-    sp.kprime = pl.kprime;
-    sp.cap = pl.cap;
-    sp.stages = pl.stages;
-    sp.tile_bytes = pl.tile_bytes;
-    {
-      ProfScope ps(ctx, SB_PROF_DENSE_SCAN, st);
-      rc = dispatch_scan(qb, sp, pl, st);
+  for (int c0 = 0; c0 < B; c0 += chunk) {
+    const int nq = std::min(chunk, B - c0);
+    int b0 = 0;
+    while (b0 < nq) {
+      int qb = pl.qb_max;
+      while (qb > nq - b0) qb >>= 1;
+      ScanParams sp;
+      sp.rows = ix.rows;
+      sp.inv_norm = ix.inv_norm;
+      sp.q = q_pad + (size_t)(c0 + b0) * ix.d_pad;
+      sp.cand = ctx->cand_dev.as<unsigned long long>() + (size_t)b0 * per_q;
+      sp.n = ix.n;
+      sp.d_pad = ix.d_pad;
+      sp.ch = ix.d_pad / 8;
+      sp.num_tiles = pl.num_tiles;
+      sp.kprime = pl.kprime;
+      sp.cap = pl.cap;
+      sp.stages = pl.stages;
+      sp.tile_bytes = pl.tile_bytes;
+      {
+        ProfScope ps(ctx, SB_PROF_DENSE_SCAN, st);
+        rc = dispatch_scan(qb, sp, pl, st);
+      }
+      if (rc) return rc;
+      b0 += qb;
     }
-    if (rc) return rc;
     MergeParams mp;
-    mp.cand = sp.cand;
+    mp.cand = ctx->cand_dev.as<unsigned long long>();
     mp.G = pl.grid;
     mp.kprime = pl.kprime;
+    mp.heads_per_list = pl.heads_per_list;
+    mp.heads_pow2 = pl.heads_pow2;
     mp.rows = ix.rows;
-    mp.q = sp.q;
+    mp.q = q_pad + (size_t)c0 * ix.d_pad;
     mp.d_pad = ix.d_pad;
-    mp.ch = sp.ch;
+    mp.ch = ix.d_pad / 8;
     mp.id_base = ix.id_base;
     mp.k = k;
-    mp.out_ids = out_ids + (size_t)b0 * k;
-    mp.out_scores = out_scores + (size_t)b0 * k;
-    mp.out_counts = out_counts + b0;
-    mp.lists_in_smem = pl.lists_in_smem;
+    mp.out_ids = out_ids + (size_t)c0 * k;
+    mp.out_scores = out_scores + (size_t)c0 * k;
+    mp.out_counts = out_counts + c0;
     {
       ProfScope ps(ctx, SB_PROF_DENSE_MERGE, st);
-      dense_merge_kernel<<<qb, kMergeThreads, pl.merge_smem, st>>>(mp);
+      dense_merge_kernel<<<nq, kMergeThreads, pl.merge_smem, st>>>(mp);
     }
     SB_CUDA(cudaGetLastError());
-    b0 += qb;
   }
   return SB_OK;
 }

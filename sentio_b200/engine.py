@@ -76,7 +76,10 @@ class B200Engine:
     def _stream(self):
         import torch
 
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        # torch's default stream has handle 0, which the C ABI reserves for "the context's own stream": pass the
+        # explicit legacy-default-stream handle (cudaStreamLegacy == 0x1) so our kernels stay ordered with torch ops
+        h = torch.cuda.current_stream(self.device).cuda_stream
+        return C.c_void_p(h if h else 1)
 
     # ------------------------------------------------------------------ K1 dense
     def load_dense(self, vecs: np.ndarray, id_base: int = 0, slot: int = 0) -> None:
