@@ -196,6 +196,14 @@ int sb_ce_score_dev(sb_ctx* ctx, const int32_t* input_ids_dev, const int32_t* to
                     const int32_t* lengths_dev, int32_t P, int32_t S, float* out_logits_dev,
                     float* out_sigmoid_dev, void* stream);
 
+/*
+ * Test hook for the tcgen05 GEMM inside K5: out[M,N] = epilogue(A[M,K] * W[N,K]^T + bias (+ residual)), operands given as
+ * host fp32 and rounded to fp16 on the device; epi 0 = bias (fp16 result), 1 = bias + erf-GELU (fp16 result),
+ * 2 = bias + residual (fp32 result).  N % 128 == 0, K % 64 == 0.
+ */
+int sb_ce_gemm_test(sb_ctx* ctx, const float* a, const float* w, const float* bias, const float* residual, int32_t M,
+                    int32_t N, int32_t K, int32_t epi, float* out);
+
 /* ---------------------------------------------------------------- K6: shard merge ---------------------------- */
 /*
  * Multi-GPU: after ONE all-gather of per-shard top-k records, every rank merges G shard lists per query into the

@@ -1,0 +1,14 @@
+// ce_gemm.cuh -- interface of the tcgen05 GEMM used by the cross-encoder (ce_gemm.cu).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+enum { CE_EPI_BIAS_F16 = 0, CE_EPI_BIAS_GELU_F16 = 1, CE_EPI_BIAS_RES_F32 = 2 };
+
+// 2-D tensor map over a row-major fp16 matrix [rows][cols] (cols contiguous), box 64 x 128, SWIZZLE_128B
+int ce_make_tensor_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols);
+
+// D[M,N] = A[M,K] * W[N,K]^T with one of the fused epilogues; M is padded to 128 by the caller's allocation
+int ce_gemm_launch(int epi, const CUtensorMap& map_a, const CUtensorMap& map_w, int M, int N, int K, const float* bias,
+                   const float* residual, __half* out16, float* out32, cudaStream_t st);

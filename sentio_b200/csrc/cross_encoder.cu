@@ -1,9 +1,506 @@
-// cross_encoder.cu -- K5 placeholder (replaced below in this round)
-#include "common.cuh"
-struct CeModel { int dummy; };
-void ce_model_free(CeModel* m) { delete m; }
-extern "C" {
-int sb_ce_load(sb_ctx*, const float*, int64_t, const sb_ce_config*) { sb_set_error("cross-encoder not built"); return SB_ERR_UNSUPPORTED; }
-int sb_ce_score(sb_ctx*, const int32_t*, const int32_t*, const int32_t*, int32_t, int32_t, float*, float*) { sb_set_error("cross-encoder not built"); return SB_ERR_UNSUPPORTED; }
-int sb_ce_score_dev(sb_ctx*, const int32_t*, const int32_t*, const int32_t*, int32_t, int32_t, float*, float*, void*) { sb_set_error("cross-encoder not built"); return SB_ERR_UNSUPPORTED; }
+// cross_encoder.cu -- K5: BERT-style sequence classifier forward (MiniLM-L6 shape by default) for the reranker.
+//
+// Replaces the remote Jina rerank call behind JinaReranker.rerank (reference src/core/rerankers/jina_reranker.py:139-144).
+// Per layer:  QKV GEMM (tcgen05, bias)  ->  masked softmax attention  ->  out-proj GEMM (+bias +residual, fp32)
+//             -> LayerNorm -> FFN-up GEMM (+bias, erf-GELU) -> FFN-down GEMM (+bias +residual, fp32) -> LayerNorm.
+// The residual stream stays fp32 in HBM; every GEMM operand is an fp16 copy written by the producing kernel; all GEMM
+// accumulation is fp32 in tensor memory (ce_gemm.cu).  Rows beyond a pair's length are padding: they are never read as
+// keys (masked) and their own outputs are never consumed, which is bit-for-bit what the additive -inf mask of the
+// HuggingFace oracle yields for the [CLS] logit.
+//
+// flops per pair = L * (24*S*H^2 + 4*S^2*H)  (2.87 GFLOP at L=6, H=384, S=128); bound: tensor pipe.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "ce_gemm.cuh"
+
+struct CeLayer {
+  __half *wqkv, *wo, *w1, *w2;            // fp16 GEMM weights: [3H,H] [H,H] [I,H] [H,I]
+  float *bqkv, *bo, *b1, *b2;             // fp32 biases
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b;   // fp32 LayerNorm parameters
+  CUtensorMap m_wqkv, m_wo, m_w1, m_w2;
+};
+
+struct CeModel {
+  sb_ce_config cfg;
+  float *word_emb = nullptr, *pos_emb = nullptr, *type_emb = nullptr, *emb_ln_g = nullptr, *emb_ln_b = nullptr;
+  float *pool_w = nullptr, *pool_b = nullptr, *cls_w = nullptr, *cls_b = nullptr;
+  std::vector<CeLayer> layers;
+  std::vector<void*> allocs;
+  // activation workspace (grow-only), sized for m_cap rows
+  int64_t m_cap = 0;
+  float *x32 = nullptr, *pre32 = nullptr;          // residual stream, pre-LayerNorm sums  [M,H]
+  __half *x16 = nullptr, *qkv16 = nullptr, *ctx16 = nullptr, *ffn16 = nullptr;  // [M,H] [M,3H] [M,H] [M,I]
+  CUtensorMap m_x16, m_ctx16, m_ffn16;
+  std::vector<void*> act_allocs;
+};
+
+void ce_model_free(CeModel* m) {
+  if (!m) return;
+  for (void* p : m->allocs) cudaFree(p);
+  for (void* p : m->act_allocs) cudaFree(p);
+  delete m;
 }
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ small kernels
+__global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2half_rn(in[i]);
+}
+
+// One warp per token row: x = LN(word[id] + pos[s] + type[tt]); writes the fp32 residual and its fp16 GEMM copy.
+template <int H>
+__global__ void ce_embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ tts, int M, int S,
+                                   int vocab, int type_vocab, const float* __restrict__ word,
+                                   const float* __restrict__ pos, const float* __restrict__ type,
+                                   const float* __restrict__ g, const float* __restrict__ b, float eps,
+                                   float* __restrict__ x32, __half* __restrict__ x16) {
+  constexpr int PER = H / 32;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= M) return;
+  int id = ids[row], tt = tts[row];
+  id = min(max(id, 0), vocab - 1);
+  tt = min(max(tt, 0), type_vocab - 1);
+  const int s = row % S;
+  float v[PER];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = word[(size_t)id * H + c] + pos[(size_t)s * H + c] + type[(size_t)tt * H + c];
+    sum += v[i];
+  }
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / H;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const float d = v[i] - mean;
+    var += d * d;
+  }
+  for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / H + eps);
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = lane + 32 * i;
+    const float y = (v[i] - mean) * rstd * g[c] + b[c];
+    x32[(size_t)row * H + c] = y;
+    x16[(size_t)row * H + c] = __float2half_rn(y);
+  }
+}
+
+// One warp per row: LayerNorm of the pre-LN sum -> fp32 residual + fp16 GEMM copy.
+template <int H>
+__global__ void ce_ln_kernel(const float* __restrict__ pre, int M, const float* __restrict__ g,
+                             const float* __restrict__ b, float eps, float* __restrict__ x32,
+                             __half* __restrict__ x16) {
+  constexpr int PER = H / 32;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float v[PER];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    v[i] = pre[(size_t)row * H + lane + 32 * i];
+    sum += v[i];
+  }
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / H;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const float d = v[i] - mean;
+    var += d * d;
+  }
+  for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / H + eps);
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = lane + 32 * i;
+    const float y = (v[i] - mean) * rstd * g[c] + b[c];
+    x32[(size_t)row * H + c] = y;
+    x16[(size_t)row * H + c] = __float2half_rn(y);
+  }
+}
+
+// Masked softmax attention, one CTA per (pair, head), one thread per query row; K/V of the head staged in smem as fp32.
+// Single pass online softmax (running max / sum), scores never leave registers.
+template <int DH>
+__global__ void __launch_bounds__(128) ce_attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ lengths,
+                                                           int S, int H, int heads, __half* __restrict__ ctx) {
+  extern __shared__ float att_sm[];
+  const int pair = blockIdx.x / heads, head = blockIdx.x % heads;
+  const int len = min(max(lengths[pair], 1), S);
+  float* Ks = att_sm;                 // [S][DH]
+  float* Vs = att_sm + (size_t)S * DH;
+  const size_t row0 = (size_t)pair * S;
+  const int ld = 3 * H;
+  for (int i = threadIdx.x; i < len * (DH / 2); i += blockDim.x) {
+    const int j = i / (DH / 2), c = (i % (DH / 2)) * 2;
+    const __half2 kk = *reinterpret_cast<const __half2*>(qkv + (row0 + j) * ld + H + head * DH + c);
+    const __half2 vv = *reinterpret_cast<const __half2*>(qkv + (row0 + j) * ld + 2 * H + head * DH + c);
+    const float2 kf = __half22float2(kk), vf = __half22float2(vv);
+    Ks[j * DH + c] = kf.x; Ks[j * DH + c + 1] = kf.y;
+    Vs[j * DH + c] = vf.x; Vs[j * DH + c + 1] = vf.y;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    __half* out = ctx + (row0 + i) * H + head * DH;
+    if (i >= len) {  // padding row: never consumed downstream; keep it finite
+#pragma unroll
+      for (int c = 0; c < DH; c += 2) *reinterpret_cast<__half2*>(out + c) = __floats2half2_rn(0.f, 0.f);
+      continue;
+    }
+    float q[DH];
+    const float scale = rsqrtf((float)DH);
+#pragma unroll
+    for (int c = 0; c < DH; c += 2) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(qkv + (row0 + i) * ld + head * DH + c));
+      q[c] = f.x * scale;
+      q[c + 1] = f.y * scale;
+    }
+    float m = -INFINITY, l = 0.f, acc[DH];
+#pragma unroll
+    for (int c = 0; c < DH; ++c) acc[c] = 0.f;
+    for (int j = 0; j < len; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < DH; ++c) s = fmaf(q[c], Ks[j * DH + c], s);
+      if (s > m) {
+        const float corr = __expf(m - s);
+        l *= corr;
+#pragma unroll
+        for (int c = 0; c < DH; ++c) acc[c] *= corr;
+        m = s;
+      }
+      const float pj = __expf(s - m);
+      l += pj;
+#pragma unroll
+      for (int c = 0; c < DH; ++c) acc[c] = fmaf(pj, Vs[j * DH + c], acc[c]);
+    }
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int c = 0; c < DH; c += 2)
+      *reinterpret_cast<__half2*>(out + c) = __floats2half2_rn(acc[c] * inv, acc[c + 1] * inv);
+  }
+}
+
+// One CTA per pair: pooled = tanh(Wp x_cls + bp); logit = w . pooled + b; relevance = sigmoid(logit).  fp32 throughout.
+__global__ void ce_head_kernel(const float* __restrict__ x32, int S, int H, const float* __restrict__ pool_w,
+                               const float* __restrict__ pool_b, const float* __restrict__ cls_w,
+                               const float* __restrict__ cls_b, float* __restrict__ logits, float* __restrict__ sig) {
+  extern __shared__ float head_sm[];  // x_cls[H], partial[warps]
+  const int pair = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* x = x32 + (size_t)pair * S * H;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) head_sm[i] = x[i];
+  __syncthreads();
+  float part = 0.f;
+  for (int j = warp; j < H; j += nw) {
+    float s = 0.f;
+    for (int c = lane; c < H; c += 32) s = fmaf(pool_w[(size_t)j * H + c], head_sm[c], s);
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    part += cls_w[j] * tanhf(s + pool_b[j]);
+  }
+  if (lane == 0) head_sm[H + warp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float z = cls_b[0];
+    for (int w = 0; w < nw; ++w) z += head_sm[H + w];
+    logits[pair] = z;
+    sig[pair] = 1.f / (1.f + expf(-z));
+  }
+}
+
+int dev_alloc(std::vector<void*>& pool, void** out, size_t bytes) {
+  SB_CUDA(cudaMalloc(out, bytes ? bytes : 16));
+  pool.push_back(*out);
+  return SB_OK;
+}
+
+int upload_f32(CeModel* m, const float*& src, float** dst, size_t n, cudaStream_t st) {
+  int rc = dev_alloc(m->allocs, reinterpret_cast<void**>(dst), n * 4);
+  if (rc) return rc;
+  SB_CUDA(cudaMemcpyAsync(*dst, src, n * 4, cudaMemcpyHostToDevice, st));
+  src += n;
+  return SB_OK;
+}
+
+// upload fp32 host rows to a staging buffer and convert into an fp16 device matrix at dst (+row offset)
+int upload_f16(sb_ctx* ctx, const float*& src, __half* dst, size_t n, cudaStream_t st) {
+  int rc = ctx->misc_dev.reserve(n * 4);
+  if (rc) return rc;
+  SB_CUDA(cudaStreamSynchronize(st));  // staging buffer reuse
+  SB_CUDA(cudaMemcpyAsync(ctx->misc_dev.p, src, n * 4, cudaMemcpyHostToDevice, st));
+  f32_to_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->misc_dev.as<float>(), dst, (int64_t)n);
+  SB_CUDA(cudaGetLastError());
+  src += n;
+  return SB_OK;
+}
+
+int ensure_workspace(CeModel* m, int64_t M) {
+  const int64_t Mp = (M + 127) / 128 * 128;
+  if (Mp <= m->m_cap) return SB_OK;
+  cudaDeviceSynchronize();
+  for (void* p : m->act_allocs) cudaFree(p);
+  m->act_allocs.clear();
+  m->m_cap = 0;
+  const int H = m->cfg.hidden, I = m->cfg.intermediate;
+  int rc;
+  if ((rc = dev_alloc(m->act_allocs, (void**)&m->x32, (size_t)Mp * H * 4))) return rc;
+  if ((rc = dev_alloc(m->act_allocs, (void**)&m->pre32, (size_t)Mp * H * 4))) return rc;
+  if ((rc = dev_alloc(m->act_allocs, (void**)&m->x16, (size_t)Mp * H * 2))) return rc;
+  if ((rc = dev_alloc(m->act_allocs, (void**)&m->qkv16, (size_t)Mp * 3 * H * 2))) return rc;
+  if ((rc = dev_alloc(m->act_allocs, (void**)&m->ctx16, (size_t)Mp * H * 2))) return rc;
+  if ((rc = dev_alloc(m->act_allocs, (void**)&m->ffn16, (size_t)Mp * I * 2))) return rc;
+  // padding rows of the GEMM A operands must be finite
+  SB_CUDA(cudaMemset(m->x16, 0, (size_t)Mp * H * 2));
+  SB_CUDA(cudaMemset(m->ctx16, 0, (size_t)Mp * H * 2));
+  SB_CUDA(cudaMemset(m->ffn16, 0, (size_t)Mp * I * 2));
+  SB_CUDA(cudaMemset(m->x32, 0, (size_t)Mp * H * 4));
+  if ((rc = ce_make_tensor_map(&m->m_x16, m->x16, Mp, H))) return rc;
+  if ((rc = ce_make_tensor_map(&m->m_ctx16, m->ctx16, Mp, H))) return rc;
+  if ((rc = ce_make_tensor_map(&m->m_ffn16, m->ffn16, Mp, I))) return rc;
+  m->m_cap = Mp;
+  return SB_OK;
+}
+
+template <int H>
+int ce_forward(sb_ctx* ctx, CeModel* m, const int32_t* ids, const int32_t* tts, const int32_t* lens, int P, int S,
+               float* logits, float* sig, cudaStream_t st) {
+  const sb_ce_config& c = m->cfg;
+  const int M = P * S, I = c.intermediate, heads = c.heads;
+  const int Mp = (M + 127) / 128 * 128;
+  const int rows_per_block = 8;
+  const unsigned ln_blocks = (unsigned)((M + rows_per_block - 1) / rows_per_block);
+  ProfScope ps(ctx, SB_PROF_CE, st, 2 + (int)m->layers.size() * 7);
+  ce_embed_ln_kernel<H><<<ln_blocks, rows_per_block * 32, 0, st>>>(ids, tts, M, S, c.vocab_size, c.type_vocab,
+                                                                   m->word_emb, m->pos_emb, m->type_emb, m->emb_ln_g,
+                                                                   m->emb_ln_b, c.ln_eps, m->x32, m->x16);
+  SB_CUDA(cudaGetLastError());
+  const size_t att_smem = (size_t)2 * S * 32 * sizeof(float);
+  if (att_smem > 48 * 1024)
+    SB_CUDA(cudaFuncSetAttribute(ce_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
+  int rc;
+  for (CeLayer& L : m->layers) {
+    if ((rc = ce_gemm_launch(CE_EPI_BIAS_F16, m->m_x16, L.m_wqkv, Mp, 3 * H, H, L.bqkv, nullptr, m->qkv16, nullptr, st)))
+      return rc;
+    ce_attention_kernel<32><<<P * heads, 128, att_smem, st>>>(m->qkv16, lens, S, H, heads, m->ctx16);
+    SB_CUDA(cudaGetLastError());
+    if ((rc = ce_gemm_launch(CE_EPI_BIAS_RES_F32, m->m_ctx16, L.m_wo, Mp, H, H, L.bo, m->x32, nullptr, m->pre32, st)))
+      return rc;
+    ce_ln_kernel<H><<<ln_blocks, rows_per_block * 32, 0, st>>>(m->pre32, M, L.ln1_g, L.ln1_b, c.ln_eps, m->x32, m->x16);
+    SB_CUDA(cudaGetLastError());
+    if ((rc = ce_gemm_launch(CE_EPI_BIAS_GELU_F16, m->m_x16, L.m_w1, Mp, I, H, L.b1, nullptr, m->ffn16, nullptr, st)))
+      return rc;
+    if ((rc = ce_gemm_launch(CE_EPI_BIAS_RES_F32, m->m_ffn16, L.m_w2, Mp, H, I, L.b2, m->x32, nullptr, m->pre32, st)))
+      return rc;
+    ce_ln_kernel<H><<<ln_blocks, rows_per_block * 32, 0, st>>>(m->pre32, M, L.ln2_g, L.ln2_b, c.ln_eps, m->x32, m->x16);
+    SB_CUDA(cudaGetLastError());
+  }
+  ce_head_kernel<<<P, 256, (size_t)(H + 32) * sizeof(float), st>>>(m->x32, S, H, m->pool_w, m->pool_b, m->cls_w,
+                                                                  m->cls_b, logits, sig);
+  SB_CUDA(cudaGetLastError());
+  return SB_OK;
+}
+
+int ce_forward_dispatch(sb_ctx* ctx, const int32_t* ids, const int32_t* tts, const int32_t* lens, int P, int S,
+                        float* logits, float* sig, cudaStream_t st) {
+  CeModel* m = ctx->ce;
+  SB_REQUIRE(m != nullptr, SB_ERR_STATE, "sb_ce_score: no cross-encoder loaded (sb_ce_load)");
+  SB_REQUIRE(S > 0 && S <= m->cfg.max_pos, SB_ERR_ARG, "sb_ce_score: sequence length %d exceeds max_pos %d", S,
+             m->cfg.max_pos);
+  SB_REQUIRE(S <= 512, SB_ERR_UNSUPPORTED, "sb_ce_score: sequence length %d > 512", S);
+  int rc = ensure_workspace(m, (int64_t)P * S);
+  if (rc) return rc;
+  switch (m->cfg.hidden) {
+    case 384: return ce_forward<384>(ctx, m, ids, tts, lens, P, S, logits, sig, st);
+    case 128: return ce_forward<128>(ctx, m, ids, tts, lens, P, S, logits, sig, st);
+    case 256: return ce_forward<256>(ctx, m, ids, tts, lens, P, S, logits, sig, st);
+    case 768: return ce_forward<768>(ctx, m, ids, tts, lens, P, S, logits, sig, st);
+  }
+  sb_set_error("sb_ce_score: unsupported hidden size %d", m->cfg.hidden);
+  return SB_ERR_UNSUPPORTED;
+}
+
+__global__ void f16_to_f32_kernel(const __half* __restrict__ in, float* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __half2float(in[i]);
+}
+
+}  // namespace
+
+extern "C" {
+
+// Test hook: run the tcgen05 GEMM of the cross-encoder on host fp32 operands (rounded to fp16 on the device).
+int sb_ce_gemm_test(sb_ctx* ctx, const float* a, const float* w, const float* bias, const float* residual, int32_t M,
+                    int32_t N, int32_t K, int32_t epi, float* out) {
+  SB_REQUIRE(ctx && a && w && bias && out, SB_ERR_ARG, "sb_ce_gemm_test: NULL argument");
+  SB_REQUIRE(M > 0 && N > 0 && K > 0 && N % 128 == 0 && K % 64 == 0, SB_ERR_ARG, "sb_ce_gemm_test: bad shape");
+  SB_REQUIRE(epi != CE_EPI_BIAS_RES_F32 || residual, SB_ERR_ARG, "sb_ce_gemm_test: residual required");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const int Mp = (M + 127) / 128 * 128;
+  std::vector<void*> pool;
+  struct Free { std::vector<void*>& p; ~Free() { for (void* x : p) cudaFree(x); } } fr{pool};
+  float *a32, *w32, *b32, *r32 = nullptr, *o32, *o32b;
+  __half *a16, *w16, *o16;
+  int rc;
+  if ((rc = dev_alloc(pool, (void**)&a32, (size_t)Mp * K * 4))) return rc;
+  if ((rc = dev_alloc(pool, (void**)&w32, (size_t)N * K * 4))) return rc;
+  if ((rc = dev_alloc(pool, (void**)&b32, (size_t)N * 4))) return rc;
+  if ((rc = dev_alloc(pool, (void**)&r32, (size_t)Mp * N * 4))) return rc;
+  if ((rc = dev_alloc(pool, (void**)&o32, (size_t)Mp * N * 4))) return rc;
+  if ((rc = dev_alloc(pool, (void**)&o32b, (size_t)Mp * N * 4))) return rc;
+  if ((rc = dev_alloc(pool, (void**)&a16, (size_t)Mp * K * 2))) return rc;
+  if ((rc = dev_alloc(pool, (void**)&w16, (size_t)N * K * 2))) return rc;
+  if ((rc = dev_alloc(pool, (void**)&o16, (size_t)Mp * N * 2))) return rc;
+  SB_CUDA(cudaMemsetAsync(a32, 0, (size_t)Mp * K * 4, st));
+  SB_CUDA(cudaMemsetAsync(r32, 0, (size_t)Mp * N * 4, st));
+  SB_CUDA(cudaMemcpyAsync(a32, a, (size_t)M * K * 4, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(w32, w, (size_t)N * K * 4, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(b32, bias, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+  if (residual) SB_CUDA(cudaMemcpyAsync(r32, residual, (size_t)M * N * 4, cudaMemcpyHostToDevice, st));
+  f32_to_f16_kernel<<<(unsigned)(((size_t)Mp * K + 255) / 256), 256, 0, st>>>(a32, a16, (int64_t)Mp * K);
+  f32_to_f16_kernel<<<(unsigned)(((size_t)N * K + 255) / 256), 256, 0, st>>>(w32, w16, (int64_t)N * K);
+  CUtensorMap ma, mw;
+  if ((rc = ce_make_tensor_map(&ma, a16, Mp, K))) return rc;
+  if ((rc = ce_make_tensor_map(&mw, w16, N, K))) return rc;
+  if ((rc = ce_gemm_launch(epi, ma, mw, Mp, N, K, b32, r32, o16, o32, st))) return rc;
+  const float* result = o32;
+  if (epi != CE_EPI_BIAS_RES_F32) {
+    f16_to_f32_kernel<<<(unsigned)(((size_t)Mp * N + 255) / 256), 256, 0, st>>>(o16, o32b, (int64_t)Mp * N);
+    result = o32b;
+  }
+  SB_CUDA(cudaGetLastError());
+  SB_CUDA(cudaMemcpyAsync(out, result, (size_t)M * N * 4, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  return SB_OK;
+}
+
+int sb_ce_load(sb_ctx* ctx, const float* weights, int64_t n_floats, const sb_ce_config* cfg) {
+  SB_REQUIRE(ctx && weights && cfg, SB_ERR_ARG, "sb_ce_load: NULL argument");
+  const int V = cfg->vocab_size, H = cfg->hidden, L = cfg->layers, I = cfg->intermediate, Pm = cfg->max_pos,
+            T = cfg->type_vocab;
+  SB_REQUIRE(V > 0 && H > 0 && L > 0 && I > 0 && Pm > 0 && T > 0 && cfg->heads > 0, SB_ERR_ARG, "sb_ce_load: bad config");
+  SB_REQUIRE(H == 128 || H == 256 || H == 384 || H == 768, SB_ERR_UNSUPPORTED,
+             "sb_ce_load: hidden size %d not supported (128/256/384/768)", H);
+  SB_REQUIRE(H / cfg->heads == 32 && H % cfg->heads == 0, SB_ERR_UNSUPPORTED,
+             "sb_ce_load: head dimension must be 32 (hidden %d, heads %d)", H, cfg->heads);
+  SB_REQUIRE(I % 128 == 0 && H % 128 == 0, SB_ERR_UNSUPPORTED, "sb_ce_load: hidden/intermediate must be multiples of 128");
+  const int64_t per_layer = 4ll * H * H + 4ll * H + 2ll * H + (int64_t)I * H + I + (int64_t)H * I + H + 2ll * H;
+  const int64_t expect = (int64_t)V * H + (int64_t)Pm * H + (int64_t)T * H + 2ll * H + L * per_layer + (int64_t)H * H +
+                         H + H + 1;
+  SB_REQUIRE(n_floats == expect, SB_ERR_ARG, "sb_ce_load: blob has %lld floats, config needs %lld", (long long)n_floats,
+             (long long)expect);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = ctx->stream;
+  SB_CUDA(cudaStreamSynchronize(st));
+  if (ctx->ce) {
+    ce_model_free(ctx->ce);
+    ctx->ce = nullptr;
+  }
+  CeModel* m = new CeModel();
+  m->cfg = *cfg;
+  const float* src = weights;
+  int rc = SB_OK;
+#define CE_TRY(expr)            \
+  if ((rc = (expr)) != SB_OK) { \
+    ce_model_free(m);           \
+    return rc;                  \
+  }
+  CE_TRY(upload_f32(m, src, &m->word_emb, (size_t)V * H, st));
+  CE_TRY(upload_f32(m, src, &m->pos_emb, (size_t)Pm * H, st));
+  CE_TRY(upload_f32(m, src, &m->type_emb, (size_t)T * H, st));
+  CE_TRY(upload_f32(m, src, &m->emb_ln_g, H, st));
+  CE_TRY(upload_f32(m, src, &m->emb_ln_b, H, st));
+  m->layers.resize(L);
+  for (int l = 0; l < L; ++l) {
+    CeLayer& Ly = m->layers[l];
+    CE_TRY(dev_alloc(m->allocs, (void**)&Ly.wqkv, (size_t)3 * H * H * 2));
+    CE_TRY(dev_alloc(m->allocs, (void**)&Ly.bqkv, (size_t)3 * H * 4));
+    for (int part = 0; part < 3; ++part) {  // blob order: Wq bq Wk bk Wv bv -> fused [3H,H] weight / [3H] bias
+      CE_TRY(upload_f16(ctx, src, Ly.wqkv + (size_t)part * H * H, (size_t)H * H, st));
+      SB_CUDA(cudaMemcpyAsync(Ly.bqkv + (size_t)part * H, src, (size_t)H * 4, cudaMemcpyHostToDevice, st));
+      src += H;
+    }
+    CE_TRY(dev_alloc(m->allocs, (void**)&Ly.wo, (size_t)H * H * 2));
+    CE_TRY(upload_f16(ctx, src, Ly.wo, (size_t)H * H, st));
+    CE_TRY(upload_f32(m, src, &Ly.bo, H, st));
+    CE_TRY(upload_f32(m, src, &Ly.ln1_g, H, st));
+    CE_TRY(upload_f32(m, src, &Ly.ln1_b, H, st));
+    CE_TRY(dev_alloc(m->allocs, (void**)&Ly.w1, (size_t)I * H * 2));
+    CE_TRY(upload_f16(ctx, src, Ly.w1, (size_t)I * H, st));
+    CE_TRY(upload_f32(m, src, &Ly.b1, I, st));
+    CE_TRY(dev_alloc(m->allocs, (void**)&Ly.w2, (size_t)H * I * 2));
+    CE_TRY(upload_f16(ctx, src, Ly.w2, (size_t)H * I, st));
+    CE_TRY(upload_f32(m, src, &Ly.b2, H, st));
+    CE_TRY(upload_f32(m, src, &Ly.ln2_g, H, st));
+    CE_TRY(upload_f32(m, src, &Ly.ln2_b, H, st));
+    CE_TRY(ce_make_tensor_map(&Ly.m_wqkv, Ly.wqkv, 3 * H, H));
+    CE_TRY(ce_make_tensor_map(&Ly.m_wo, Ly.wo, H, H));
+    CE_TRY(ce_make_tensor_map(&Ly.m_w1, Ly.w1, I, H));
+    CE_TRY(ce_make_tensor_map(&Ly.m_w2, Ly.w2, H, I));
+  }
+  CE_TRY(upload_f32(m, src, &m->pool_w, (size_t)H * H, st));
+  CE_TRY(upload_f32(m, src, &m->pool_b, H, st));
+  CE_TRY(upload_f32(m, src, &m->cls_w, H, st));
+  CE_TRY(upload_f32(m, src, &m->cls_b, 1, st));
+#undef CE_TRY
+  SB_CUDA(cudaStreamSynchronize(st));
+  ctx->ce = m;
+  return SB_OK;
+}
+
+int sb_ce_score_dev(sb_ctx* ctx, const int32_t* input_ids_dev, const int32_t* token_type_dev, const int32_t* lengths_dev,
+                    int32_t P, int32_t S, float* out_logits_dev, float* out_sigmoid_dev, void* stream) {
+  SB_REQUIRE(ctx != nullptr, SB_ERR_ARG, "sb_ce_score_dev: ctx is NULL");
+  SB_REQUIRE(P >= 0 && S > 0, SB_ERR_ARG, "sb_ce_score_dev: bad P=%d S=%d", P, S);
+  if (P == 0) return SB_OK;
+  SB_REQUIRE(input_ids_dev && token_type_dev && lengths_dev && out_logits_dev && out_sigmoid_dev, SB_ERR_ARG,
+             "sb_ce_score_dev: NULL buffer");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  return ce_forward_dispatch(ctx, input_ids_dev, token_type_dev, lengths_dev, P, S, out_logits_dev, out_sigmoid_dev,
+                             pick_stream(ctx, stream));
+}
+
+int sb_ce_score(sb_ctx* ctx, const int32_t* input_ids, const int32_t* token_type, const int32_t* lengths, int32_t P,
+                int32_t S, float* out_logits, float* out_sigmoid) {
+  SB_REQUIRE(ctx != nullptr, SB_ERR_ARG, "sb_ce_score: ctx is NULL");
+  SB_REQUIRE(P >= 0 && S > 0, SB_ERR_ARG, "sb_ce_score: bad P=%d S=%d", P, S);
+  if (P == 0) return SB_OK;
+  SB_REQUIRE(input_ids && token_type && lengths && out_logits && out_sigmoid, SB_ERR_ARG, "sb_ce_score: NULL buffer");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const size_t nb = (size_t)P * S * 4;
+  int rc;
+  if ((rc = ctx->pin_in.reserve(2 * nb + (size_t)P * 4))) return rc;
+  if ((rc = ctx->q_dev.reserve(2 * nb + (size_t)P * 4))) return rc;
+  uint8_t* pi = ctx->pin_in.as<uint8_t>();
+  memcpy(pi, input_ids, nb);
+  memcpy(pi + nb, token_type, nb);
+  memcpy(pi + 2 * nb, lengths, (size_t)P * 4);
+  SB_CUDA(cudaMemcpyAsync(ctx->q_dev.p, pi, 2 * nb + (size_t)P * 4, cudaMemcpyHostToDevice, st));
+  uint8_t* dv = ctx->q_dev.as<uint8_t>();
+  if ((rc = ctx->out_sc_dev.reserve((size_t)P * 8))) return rc;
+  float* dl = ctx->out_sc_dev.as<float>();
+  float* ds = dl + P;
+  if ((rc = ce_forward_dispatch(ctx, (const int32_t*)dv, (const int32_t*)(dv + nb), (const int32_t*)(dv + 2 * nb), P, S,
+                                dl, ds, st)))
+    return rc;
+  if ((rc = ctx->pin_out.reserve((size_t)P * 8))) return rc;
+  SB_CUDA(cudaMemcpyAsync(ctx->pin_out.p, dl, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  memcpy(out_logits, ctx->pin_out.p, (size_t)P * 4);
+  memcpy(out_sigmoid, ctx->pin_out.as<uint8_t>() + (size_t)P * 4, (size_t)P * 4);
+  return SB_OK;
+}
+
+}  // extern "C"

@@ -268,6 +268,18 @@ class B200Engine:
         check(self._lib.sb_ce_load(self._h, _ptr(w), w.size, C.byref(c)), "sb_ce_load")
         self.ce_config = dict(cfg)
 
+    def ce_gemm_test(self, a: np.ndarray, w: np.ndarray, bias: np.ndarray, epi: int, residual: np.ndarray | None = None):
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        w = np.ascontiguousarray(w, dtype=np.float32)
+        bias = np.ascontiguousarray(bias, dtype=np.float32)
+        M, K = a.shape
+        N = w.shape[0]
+        res = None if residual is None else np.ascontiguousarray(residual, dtype=np.float32)
+        out = np.empty((M, N), dtype=np.float32)
+        check(self._lib.sb_ce_gemm_test(self._h, _ptr(a), _ptr(w), _ptr(bias), _ptr(res), M, N, K, int(epi), _ptr(out)),
+              "sb_ce_gemm_test")
+        return out
+
     def ce_score(self, input_ids: np.ndarray, token_type: np.ndarray, lengths: np.ndarray):
         ids = np.ascontiguousarray(input_ids, dtype=np.int32)
         tt = np.ascontiguousarray(token_type, dtype=np.int32)

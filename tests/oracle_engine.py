@@ -107,3 +107,54 @@ class OracleEngine:
         sem = np.asarray(scorers_oracle.semantic(q64, c64, w_sem)) if want_sem else None
         mmr = np.asarray(scorers_oracle.mmr(q64, c64, lambda_, w_mmr)) if want_mmr else None
         return sem, mmr
+
+
+class OracleEngineTorch(OracleEngine):
+    """Adds the `*_dev` methods on CPU torch tensors so HybridPipeline's sharded control flow (record packing, the single
+    all-gather, shard merge, fusion) can run under gloo with world_size 2 on a box without GPUs."""
+
+    def _fill(self, out, arrays):
+        import torch
+
+        for t, a in zip(out, arrays):
+            t.copy_(torch.from_numpy(np.ascontiguousarray(a)).view(t.dtype).reshape(t.shape))
+        return out
+
+    def dense_topk_dev(self, q_t, k, slot=0, out=None):
+        return self._fill(out, self.dense_topk(q_t.numpy(), k, slot))
+
+    def bm25_topk_dev(self, terms_t, off_t, B, n_terms, max_len, k, out=None):
+        terms, off = terms_t.numpy(), off_t.numpy()
+        lists = [terms[off[b]:off[b + 1]] for b in range(B)]
+        return self._fill(out, self.bm25_topk(lists, k))
+
+    def fuse_dev(self, method, rrf_k, w_dense, w_sparse, k, dense, sparse, out=None):
+        d = tuple(x.numpy() for x in dense)
+        s = tuple(x.numpy() for x in sparse)
+        return self._fill(out, self.fuse(method, rrf_k, w_dense, w_sparse, k, dense=d, sparse=s))
+
+    def merge_shards_dev(self, ids0, scores0, counts0, shard_stride_bytes, G, out=None):
+        import torch
+
+        B, k = ids0.shape
+        base = ids0.untyped_storage()
+        raw = torch.tensor([], dtype=torch.uint8).set_(base)  # whole gathered buffer as bytes
+        off_i, off_s, off_c = ids0.storage_offset() * 8, scores0.storage_offset() * 8, counts0.storage_offset() * 4
+        ids = np.full((B, k), -1, np.int64)
+        sc = np.zeros((B, k))
+        cnt = np.zeros(B, np.int32)
+        buf = raw.numpy()
+        for b in range(B):
+            cand = []
+            for g in range(G):
+                o = g * shard_stride_bytes
+                gi = np.frombuffer(buf[o + off_i:o + off_i + B * k * 8].tobytes(), np.int64).reshape(B, k)
+                gs = np.frombuffer(buf[o + off_s:o + off_s + B * k * 8].tobytes(), np.float64).reshape(B, k)
+                gc = np.frombuffer(buf[o + off_c:o + off_c + B * 4].tobytes(), np.int32)
+                cand += [(float(gs[b, j]), int(gi[b, j])) for j in range(int(gc[b]))]
+            cand.sort(key=lambda t: (-t[0], t[1]))
+            cand = cand[:k]
+            ids[b, :len(cand)] = [c[1] for c in cand]
+            sc[b, :len(cand)] = [c[0] for c in cand]
+            cnt[b] = len(cand)
+        return self._fill(out, (ids, sc, cnt))

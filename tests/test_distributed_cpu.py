@@ -1,0 +1,81 @@
+"""world_size-2 gloo test of the sharded path (HybridPipeline): corpus partitioned by contiguous doc range, per-shard
+top-k, ONE all-gather of the packed records, shard merge, fusion on GLOBAL ranks == the unsharded result.
+Runs on CPU with the oracle-backed engine double (the GPU arithmetic has its own parity tests)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, tmpdir):
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, HERE)
+    import torch.distributed as dist
+
+    from oracle_engine import OracleEngineTorch
+    from sentio_b200 import synth
+    from sentio_b200.index import build_bm25_from_token_ids
+    from sentio_b200.pipeline import HybridPipeline
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, d, k, B = 3001, 32, 20, 7
+    x = synth.dense_corpus(n, d)
+    flat, off = synth.text_corpus_tokens(n, vocab=300)
+    idx = build_bm25_from_token_ids(flat, off)
+    q = synth.query_vectors(B, d)
+    terms = [idx.term_ids(t) for t in synth.query_tokens(B, vocab=300)]
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    pipe = HybridPipeline(device=None, rank=rank, world=world, engine=OracleEngineTorch())
+    pipe.load_dense(x[lo:hi], id_base=lo)
+    pipe.load_bm25(idx.shard(lo, hi), id_base=lo)
+    d_ids, d_sc, d_cnt = pipe.search_dense(q, k)
+    f_ids, f_sc, f_src, f_cnt = pipe.search_hybrid(q, terms, k, method="rrf", rrf_k=60)
+    c_ids, c_sc, _, c_cnt = pipe.search_hybrid(q, terms, k, method="comb_sum", rrf_k=60, w_dense=0.7, w_sparse=0.3)
+    np.savez(os.path.join(tmpdir, f"rank{rank}.npz"), d_ids=d_ids, d_sc=d_sc, d_cnt=d_cnt, f_ids=f_ids, f_sc=f_sc,
+             f_cnt=f_cnt, c_ids=c_ids, c_sc=c_sc, c_cnt=c_cnt)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_shards_equal_unsharded(tmp_path):
+    import torch.multiprocessing as mp
+
+    sys.path.insert(0, HERE)
+    from oracle_engine import OracleEngineTorch
+    from sentio_b200 import synth
+    from sentio_b200.index import build_bm25_from_token_ids
+    from sentio_b200.pipeline import HybridPipeline
+
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    n, d, k, B = 3001, 32, 20, 7
+    x = synth.dense_corpus(n, d)
+    flat, off = synth.text_corpus_tokens(n, vocab=300)
+    idx = build_bm25_from_token_ids(flat, off)
+    q = synth.query_vectors(B, d)
+    terms = [idx.term_ids(t) for t in synth.query_tokens(B, vocab=300)]
+    single = HybridPipeline(device=None, engine=OracleEngineTorch())
+    single.load_dense(x)
+    single.load_bm25(idx)
+    d_ref = single.search_dense(q, k)
+    f_ref = single.search_hybrid(q, terms, k, method="rrf", rrf_k=60)
+    c_ref = single.search_hybrid(q, terms, k, method="comb_sum", rrf_k=60, w_dense=0.7, w_sparse=0.3)
+    for rank in range(2):
+        r = np.load(os.path.join(tmp_path, f"rank{rank}.npz"))
+        assert np.array_equal(r["d_ids"], d_ref[0]) and np.array_equal(r["d_sc"], d_ref[1])
+        assert np.array_equal(r["f_ids"], f_ref[0]) and np.array_equal(r["f_sc"], f_ref[1])
+        assert np.array_equal(r["c_ids"], c_ref[0]) and np.array_equal(r["c_sc"], c_ref[1])
+        assert np.array_equal(r["f_cnt"], f_ref[3])
