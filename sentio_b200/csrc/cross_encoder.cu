@@ -241,7 +241,7 @@ int upload_f16(sb_ctx* ctx, const float*& src, __half* dst, size_t n, cudaStream
   return SB_OK;
 }
 
-int ensure_workspace(CeModel* m, int64_t M) {
+int ensure_workspace(CeModel* m, int64_t M, cudaStream_t st) {
   const int64_t Mp = (M + 127) / 128 * 128;
   if (Mp <= m->m_cap) return SB_OK;
   cudaDeviceSynchronize();
@@ -256,11 +256,11 @@ int ensure_workspace(CeModel* m, int64_t M) {
   if ((rc = dev_alloc(m->act_allocs, (void**)&m->qkv16, (size_t)Mp * 3 * H * 2))) return rc;
   if ((rc = dev_alloc(m->act_allocs, (void**)&m->ctx16, (size_t)Mp * H * 2))) return rc;
   if ((rc = dev_alloc(m->act_allocs, (void**)&m->ffn16, (size_t)Mp * I * 2))) return rc;
-  // padding rows of the GEMM A operands must be finite
-  SB_CUDA(cudaMemset(m->x16, 0, (size_t)Mp * H * 2));
-  SB_CUDA(cudaMemset(m->ctx16, 0, (size_t)Mp * H * 2));
-  SB_CUDA(cudaMemset(m->ffn16, 0, (size_t)Mp * I * 2));
-  SB_CUDA(cudaMemset(m->x32, 0, (size_t)Mp * H * 4));
+  // padding rows of the GEMM A operands must be finite; stream-ordered with the forward pass that follows
+  SB_CUDA(cudaMemsetAsync(m->x16, 0, (size_t)Mp * H * 2, st));
+  SB_CUDA(cudaMemsetAsync(m->ctx16, 0, (size_t)Mp * H * 2, st));
+  SB_CUDA(cudaMemsetAsync(m->ffn16, 0, (size_t)Mp * I * 2, st));
+  SB_CUDA(cudaMemsetAsync(m->x32, 0, (size_t)Mp * H * 4, st));
   if ((rc = ce_make_tensor_map(&m->m_x16, m->x16, Mp, H))) return rc;
   if ((rc = ce_make_tensor_map(&m->m_ctx16, m->ctx16, Mp, H))) return rc;
   if ((rc = ce_make_tensor_map(&m->m_ffn16, m->ffn16, Mp, I))) return rc;
@@ -314,7 +314,7 @@ int ce_forward_dispatch(sb_ctx* ctx, const int32_t* ids, const int32_t* tts, con
   SB_REQUIRE(S > 0 && S <= m->cfg.max_pos, SB_ERR_ARG, "sb_ce_score: sequence length %d exceeds max_pos %d", S,
              m->cfg.max_pos);
   SB_REQUIRE(S <= 512, SB_ERR_UNSUPPORTED, "sb_ce_score: sequence length %d > 512", S);
-  int rc = ensure_workspace(m, (int64_t)P * S);
+  int rc = ensure_workspace(m, (int64_t)P * S, st);
   if (rc) return rc;
   switch (m->cfg.hidden) {
     case 384: return ce_forward<384>(ctx, m, ids, tts, lens, P, S, logits, sig, st);

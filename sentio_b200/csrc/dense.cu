@@ -23,7 +23,7 @@ namespace {
 
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kScanThreads = kConsumerThreads + 32;  // + 1 producer warp
+constexpr int kScanThreads = kConsumerThreads + 64;  // + 1 TMA producer warp + 1 compaction warp
 constexpr int kMergeThreads = 512;
 constexpr int kRowPad = 32;  // n_pad granularity (max tile rows)
 
@@ -75,7 +75,7 @@ struct ScanParams {
   int32_t ch;                // 16-byte chunks per row = d_pad / 8
   int32_t num_tiles;
   int32_t kprime;
-  int32_t cap;               // candidate buffer capacity per query (power of two, >= 2*kprime, > kprime + tile rows)
+  int32_t bcap;              // capacity of each of the two append batches per query (kprime + bcap = sort size)
   int32_t stages;
   uint32_t tile_bytes;
 };
@@ -100,24 +100,106 @@ __device__ __forceinline__ float warp_reduce_multi(float (&v)[V], int lane) {
   return r;
 }
 
-// Descending bitonic sort of `len` (power of two) 64-bit keys in shared memory by the 256 consumer threads.
-__device__ __forceinline__ void consumer_bitonic_sort_desc(unsigned long long* buf, int len, int t) {
-  for (int k = 2; k <= len; k <<= 1) {
+// ---- asynchronous compaction (runs on its own warp, off the FMA warps' critical path) -------------------------------
+// Descending bitonic sort of T = 32 * NPER 64-bit keys held in registers across one warp; element e = lane * NPER + r.
+template <int NPER>
+__device__ __forceinline__ void warp_sort_desc(unsigned long long (&v)[NPER], int lane) {
+  constexpr int T = NPER * 32;
+#pragma unroll
+  for (int k = 2; k <= T; k <<= 1) {
+#pragma unroll
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = t; i < len; i += kConsumerThreads) {
-        int ixj = i ^ j;
+      if (j < NPER) {
+#pragma unroll
+        for (int r = 0; r < NPER; ++r) {
+          const int pr = r ^ j;
+          if (pr > r) {
+            const bool desc = (k < NPER) ? ((r & k) == 0) : ((lane & (k / NPER)) == 0);
+            const unsigned long long x = v[r], y = v[pr];
+            const bool sw = desc ? (x < y) : (x > y);
+            v[r] = sw ? y : x;
+            v[pr] = sw ? x : y;
+          }
+        }
+      } else {
+        const int lj = j / NPER;
+        const bool lower = (lane & lj) == 0;
+        const bool desc = (lane & (k / NPER)) == 0;
+        const bool keep_max = lower == desc;
+#pragma unroll
+        for (int r = 0; r < NPER; ++r) {
+          const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[r], lj);
+          const unsigned long long x = v[r];
+          v[r] = keep_max ? (x > o ? x : o) : (x < o ? x : o);
+        }
+      }
+    }
+  }
+}
+
+// best[0..nbest) U batch[0..nbatch)  ->  best[0..min(K', nbest+nbatch))  (sorted descending); returns the new count.
+template <int NPER>
+__device__ __noinline__ int compact_into_best(unsigned long long* best, int nbest, const unsigned long long* batch,
+                                              int nbatch, int kprime, int lane) {
+  unsigned long long v[NPER];
+#pragma unroll
+  for (int r = 0; r < NPER; ++r) {
+    const int e = lane * NPER + r;
+    unsigned long long x = 0ull;
+    if (e < nbest) x = best[e];
+    else if (e - nbest < nbatch) x = batch[e - nbest];
+    v[r] = x;
+  }
+  __syncwarp();
+  warp_sort_desc<NPER>(v, lane);
+#pragma unroll
+  for (int r = 0; r < NPER; ++r) {
+    const int e = lane * NPER + r;
+    if (e < kprime) best[e] = v[r];
+  }
+  __syncwarp();
+  const int total = nbest + nbatch;
+  return total < kprime ? total : kprime;
+}
+
+// Generic (k > 100) path: same result through a shared-memory scratch of T keys, loop-based warp bitonic sort.
+__device__ __noinline__ int compact_into_best_smem(unsigned long long* best, int nbest, const unsigned long long* batch,
+                                                   int nbatch, int kprime, int T, unsigned long long* scratch,
+                                                   int lane) {
+  for (int e = lane; e < T; e += 32) {
+    unsigned long long x = 0ull;
+    if (e < nbest) x = best[e];
+    else if (e - nbest < nbatch) x = batch[e - nbest];
+    scratch[e] = x;
+  }
+  __syncwarp();
+  for (int k = 2; k <= T; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < T; i += 32) {
+        const int ixj = i ^ j;
         if (ixj > i) {
-          unsigned long long a = buf[i], b = buf[ixj];
-          bool desc = (i & k) == 0;
-          if (desc ? (a < b) : (a > b)) {
-            buf[i] = b;
-            buf[ixj] = a;
+          const unsigned long long x = scratch[i], y = scratch[ixj];
+          const bool desc = (i & k) == 0;
+          if (desc ? (x < y) : (x > y)) {
+            scratch[i] = y;
+            scratch[ixj] = x;
           }
         }
       }
-      named_bar_sync(1, kConsumerThreads);
+      __syncwarp();
     }
   }
+  for (int e = lane; e < kprime; e += 32) best[e] = scratch[e];
+  __syncwarp();
+  const int total = nbest + nbatch;
+  return total < kprime ? total : kprime;
+}
+
+__device__ __forceinline__ int compact_dispatch(int T, unsigned long long* best, int nbest,
+                                                const unsigned long long* batch, int nbatch, int kprime,
+                                                unsigned long long* scratch, int lane) {
+  if (T == 512) return compact_into_best<16>(best, nbest, batch, nbatch, kprime, lane);
+  return compact_into_best_smem(best, nbest, batch, nbatch, kprime, T, scratch, lane);
 }
 
 // two fp32 FMAs per instruction (SASS FFMA2): the 3-register FFMA issues at half rate on sm_100, FFMA2 restores
@@ -142,10 +224,18 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
   constexpr int LPV = 32 / V;             // lanes per value after the reduction
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* tiles = smem;
+  // per query: best[K'] (sorted, owned by the compaction warp) + two append batches of bcap keys (ping / pong)
+  const int qstride = p.kprime + 2 * p.bcap;
   unsigned long long* cbuf = reinterpret_cast<unsigned long long*>(smem + (size_t)p.stages * p.tile_bytes);
-  unsigned long long* bars = cbuf + (size_t)QB * p.cap;  // full[stages], empty[stages]
-  volatile int* cnt = reinterpret_cast<volatile int*>(bars + 2 * p.stages);
-  volatile float* thr = reinterpret_cast<volatile float*>(const_cast<int*>(cnt) + QB);
+  const int scratch_keys = (p.kprime + p.bcap == 512) ? 0 : (p.kprime + p.bcap);
+  unsigned long long* bars = cbuf + (size_t)QB * qstride + scratch_keys;  // full[stages], empty[stages]
+  volatile int* cnt = reinterpret_cast<volatile int*>(bars + 2 * p.stages);        // [QB][2] appended per batch
+  volatile float* thr = reinterpret_cast<volatile float*>(const_cast<int*>(cnt) + 2 * QB);
+  volatile int* active = reinterpret_cast<volatile int*>(const_cast<float*>(thr) + QB);   // [QB] batch being appended
+  volatile int* pending = active + QB;   // [QB] 0 = idle, 1 = batch (1 - active) waits for compaction
+  volatile int* frozen = pending + QB;   // [QB] entry count of the batch handed to the compaction warp
+  volatile int* nbest = frozen + QB;     // [QB]
+  volatile int* done_flag = nbest + QB;  // [1] consumers finished streaming
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int stages = p.stages;
@@ -159,9 +249,15 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
     mbar_fence_init();
   }
   if (tid < QB) {
-    cnt[tid] = 0;
+    cnt[2 * tid] = 0;
+    cnt[2 * tid + 1] = 0;
     thr[tid] = -INFINITY;
+    active[tid] = 0;
+    pending[tid] = 0;
+    frozen[tid] = 0;
+    nbest[tid] = 0;
   }
+  if (tid == 0) done_flag[0] = 0;
   __syncthreads();
 
   const int grid = gridDim.x;
@@ -182,6 +278,46 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
         mbar_expect_tx(bar_full0 + 8 * s, p.tile_bytes);
         bulk_g2s(tiles_s + (uint32_t)s * p.tile_bytes, src, p.tile_bytes, bar_full0 + 8 * s, policy);
       }
+    }
+    return;
+  }
+
+  if (warp == kConsumerWarps + 1) {
+    // ------------------------------------------------------------ compaction warp: folds full batches into best[],
+    // publishes the rising threshold, and emits the final sorted top-K' lists.  Never blocks the FMA warps.
+    const int T = p.kprime + p.bcap;
+    unsigned long long* scratch = cbuf + (size_t)QB * qstride;  // only present when T != 512
+    for (;;) {
+      const bool fin = done_flag[0] != 0;
+      __threadfence_block();
+      bool any = false;
+      for (int q = 0; q < QB; ++q) {
+        if (pending[q]) {
+          __threadfence_block();
+          unsigned long long* best = cbuf + (size_t)q * qstride;
+          const unsigned long long* batch = best + p.kprime + (size_t)(1 - active[q]) * p.bcap;
+          const int nb = compact_dispatch(T, best, nbest[q], batch, frozen[q], p.kprime, scratch, lane);
+          if (lane == 0) {
+            nbest[q] = nb;
+            if (nb >= p.kprime) thr[q] = key32_score(best[p.kprime - 1]);
+            __threadfence_block();
+            pending[q] = 0;
+          }
+          __syncwarp();
+          any = true;
+        }
+      }
+      if (fin && !any) break;
+      if (!any) __nanosleep(200);
+    }
+    // final: fold the batch still being appended, then write the sorted list of every query
+    for (int q = 0; q < QB; ++q) {
+      unsigned long long* best = cbuf + (size_t)q * qstride;
+      const int a = active[q];
+      const unsigned long long* batch = best + p.kprime + (size_t)a * p.bcap;
+      const int nb = compact_dispatch(T, best, nbest[q], batch, min((int)cnt[2 * q + a], p.bcap), p.kprime, scratch, lane);
+      unsigned long long* out = p.cand + ((size_t)q * grid + blockIdx.x) * p.kprime;
+      for (int z = lane; z < p.kprime; z += 32) out[z] = z < nb ? best[z] : 0ull;
     }
     return;
   }
@@ -211,7 +347,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
   const int vi = lane / LPV;          // which (row, query) this lane owns after the reduction
   const int ri = vi / QB, qi = vi % QB;
   const bool leader = (lane % LPV) == 0;
-  const int trigger = p.cap - R;
+  const int trigger = p.bcap - R;  // a batch is handed over while it still has room for one more tile
 
   for (int i = 0; i < my_tiles; ++i) {
     const int s = i % stages;
@@ -275,26 +411,29 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
     if (leader) {
       const float score = dot * invn;
       if (grow < p.n && score > thr[qi]) {
-        const int pos = atomicAdd(const_cast<int*>(&cnt[qi]), 1);
-        if (pos < p.cap) cbuf[(size_t)qi * p.cap + pos] = make_key32(score, (uint32_t)grow);
+        const int a = active[qi];
+        const int pos = atomicAdd(const_cast<int*>(&cnt[2 * qi + a]), 1);
+        if (pos < p.bcap) cbuf[(size_t)qi * qstride + p.kprime + (size_t)a * p.bcap + pos] = make_key32(score, (uint32_t)grow);
       }
     }
     bool need = false;
 #pragma unroll
-    for (int q = 0; q < QB; ++q) need |= (cnt[q] > trigger);
+    for (int q = 0; q < QB; ++q) need |= (cnt[2 * q + active[q]] > trigger);
     need = named_bar_or(2, kConsumerThreads, need);
     if (need) {
-      for (int q = 0; q < QB; ++q) {
-        const int c = cnt[q];
-        if (c > trigger) {  // uniform: read after the barrier, nobody appends until the next tile
-          unsigned long long* buf = cbuf + (size_t)q * p.cap;
-          const int nvalid = min(c, p.cap);
-          for (int z = nvalid + tid; z < p.cap; z += kConsumerThreads) buf[z] = 0ull;
-          named_bar_sync(1, kConsumerThreads);
-          consumer_bitonic_sort_desc(buf, p.cap, tid);
-          if (tid == 0) {
-            cnt[q] = min(nvalid, p.kprime);
-            if (nvalid >= p.kprime) thr[q] = key32_score(buf[p.kprime - 1]);
+      // hand the nearly full batch of every such query to the compaction warp and continue on the other batch
+      if (tid == 0) {
+        for (int q = 0; q < QB; ++q) {
+          const int a = active[q];
+          const int c = cnt[2 * q + a];
+          if (c > trigger) {
+            while (pending[q]) __nanosleep(64);  // previous hand-over still being folded (practically never)
+            __threadfence_block();
+            frozen[q] = min(c, p.bcap);
+            cnt[2 * q + (1 - a)] = 0;
+            active[q] = 1 - a;
+            __threadfence_block();
+            pending[q] = 1;
           }
         }
       }
@@ -302,16 +441,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
     }
   }
 
-  // -------------------------------------------------------------- final: sort every buffer, emit the top-K' list
+  // -------------------------------------------------------------- streaming finished: the compaction warp finalises
   named_bar_sync(1, kConsumerThreads);
-  for (int q = 0; q < QB; ++q) {
-    unsigned long long* buf = cbuf + (size_t)q * p.cap;
-    const int nvalid = min((int)cnt[q], p.cap);
-    for (int z = nvalid + tid; z < p.cap; z += kConsumerThreads) buf[z] = 0ull;
-    named_bar_sync(1, kConsumerThreads);
-    consumer_bitonic_sort_desc(buf, p.cap, tid);
-    unsigned long long* out = p.cand + ((size_t)q * grid + blockIdx.x) * p.kprime;
-    for (int z = tid; z < p.kprime; z += kConsumerThreads) out[z] = buf[z];
+  if (tid == 0) {
+    __threadfence_block();
+    done_flag[0] = 1;
   }
 }
 
@@ -541,7 +675,7 @@ int next_pow2(int v) {
 }
 
 struct ScanPlan {
-  int nchunk, rw, qb_max, kprime, cap, stages, grid, num_tiles;
+  int nchunk, rw, qb_max, kprime, bcap, stages, grid, num_tiles;
   uint32_t tile_bytes;
   size_t scan_smem, merge_smem;
   int heads_per_list, heads_pow2;
@@ -563,30 +697,27 @@ int make_plan(sb_ctx* ctx, const DenseIndex& ix, int k, ScanPlan* pl) {
   pl->qb_max = pl->nchunk <= 4 ? 4 : (pl->nchunk <= 8 ? 2 : 1);
   const int slack = 28;
   pl->kprime = next_pow2(k + slack);
-  if (pl->kprime < 32) pl->kprime = 32;
+  if (pl->kprime < 128) pl->kprime = 128;
   SB_REQUIRE(pl->kprime <= 1024, SB_ERR_UNSUPPORTED, "dense: top_k %d too large (max %d)", k, 1024 - slack);
   const int R = kConsumerWarps * pl->rw;
-  pl->cap = pl->kprime * 4;
-  if (pl->cap < 256) pl->cap = 256;
+  // compaction sorts best[K'] + one batch in registers across one warp: 512 / 1024 / 1024 / 2048 keys
+  pl->bcap = pl->kprime <= 256 ? 3 * pl->kprime : pl->kprime;
   pl->tile_bytes = (uint32_t)R * (uint32_t)ix.d_pad * 2u;
   pl->num_tiles = (int)(ix.n_pad / R);
   const size_t budget = ctx->smem_optin;
-  // shrink the candidate buffers / query batch until at least 2 stages fit
-  for (;;) {
-    const size_t fixed = (size_t)pl->qb_max * pl->cap * 8 + 2 * 8 * 8 + 64 + 128;
-    if (fixed + 2 * (size_t)pl->tile_bytes <= budget) break;
-    if (pl->cap > 2 * pl->kprime && pl->cap - R > pl->kprime) { pl->cap >>= 1; continue; }
+  const size_t per_q = (size_t)(pl->kprime + 2 * pl->bcap) * 8;
+  const size_t scratch = (pl->kprime + pl->bcap == 512) ? 0 : (size_t)(pl->kprime + pl->bcap) * 8;
+  while ((size_t)pl->qb_max * per_q + scratch + 1024 + 2 * (size_t)pl->tile_bytes > budget) {
     if (pl->qb_max > 1) { pl->qb_max >>= 1; continue; }
     sb_set_error("dense: configuration does not fit shared memory (d=%d, k=%d)", ix.d, k);
     return SB_ERR_UNSUPPORTED;
   }
-  SB_REQUIRE(pl->cap - R >= pl->kprime, SB_ERR_UNSUPPORTED, "dense: internal cap/trigger invariant violated");
-  const size_t fixed = (size_t)pl->qb_max * pl->cap * 8;
-  int stages = (int)((budget - fixed - 512) / pl->tile_bytes);
+  const size_t fixed = (size_t)pl->qb_max * per_q + scratch;
+  int stages = (int)((budget - fixed - 1024) / pl->tile_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   pl->stages = stages;
-  pl->scan_smem = (size_t)stages * pl->tile_bytes + fixed + 2 * 8 * (size_t)stages + 64;
+  pl->scan_smem = (size_t)stages * pl->tile_bytes + fixed + 2 * 8 * (size_t)stages + 256;
   pl->grid = ctx->num_sms < pl->num_tiles ? ctx->num_sms : pl->num_tiles;
   if (pl->grid < 1) pl->grid = 1;
   pl->heads_per_list = (pl->kprime + pl->grid - 1) / pl->grid;
@@ -667,7 +798,7 @@ int dense_topk_enqueue(sb_ctx* ctx, const DenseIndex& ix, const float* q_pad, in
       sp.ch = ix.d_pad / 8;
       sp.num_tiles = pl.num_tiles;
       sp.kprime = pl.kprime;
-      sp.cap = pl.cap;
+      sp.bcap = pl.bcap;
       sp.stages = pl.stages;
       sp.tile_bytes = pl.tile_bytes;
       {
