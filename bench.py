@@ -307,10 +307,11 @@ def main():
     alg_bytes = n_pad * d_pad * 2 + n_pad * 4
     avg_ms = scan_ms / max(n_scan, 1)
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if n_scan else 0.0
-    roofline = {"bound": "hbm", "kernel": "dense_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    scan_kernel = "dense_scan_mma_kernel (tcgen05, batched queries)" if B >= 16 else "dense_scan_kernel (FFMA2)"
+    roofline = {"bound": "hbm", "kernel": scan_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms, "launches_timed": n_scan,
-                "queries_per_launch": 4, "share_of_step": scan_ms / ms_total}
+                "queries_per_launch": (B * args.steps) / max(n_scan, 1), "share_of_step": scan_ms / ms_total}
     prof = os.path.join(ROOT, "profiles", "r01_dense_scan_ncu.json")
     if os.path.exists(prof):
         try:

@@ -37,6 +37,7 @@ SIGNATURES = {
     "sb_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "sb_profile_read": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "sb_dense_load": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64]),
+    "sb_dense_set_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "sb_dense_count": (C.c_int64, [C.c_void_p, C.c_int]),
     "sb_dense_dim": (C.c_int32, [C.c_void_p, C.c_int]),
     "sb_dense_topk": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,

@@ -93,6 +93,9 @@ struct DenseIndex {
   int64_t id_base = 0;
   __half* rows = nullptr;    // [n_pad][d_pad]
   float* inv_norm = nullptr; // [n_pad], 1/||row|| of the STORED fp16 row (0 for zero rows)
+  // cached CUtensorMap (128 bytes, 64-byte aligned) over rows[] for the tcgen05 batched scan; valid iff tm_rows_ptr == rows
+  alignas(64) unsigned char tm_rows[128] = {0};
+  const void* tm_rows_ptr = nullptr;
 };
 
 struct Bm25Index {
@@ -119,6 +122,7 @@ struct sb_ctx {
   DenseIndex dense[SB_MAX_DENSE_SLOTS];
   Bm25Index bm25;
   CeModel* ce = nullptr;
+  int dense_mode = 0;  // 0 = auto, 1 = CUDA-core scan only, 2 = tcgen05 batched scan whenever eligible
   // bookkeeping: kernels launched by this library, optional per-kernel CUDA-event timing (bench.py roofline leg)
   uint64_t launches = 0;
   bool prof_on = false;

@@ -17,7 +17,8 @@
 #include <string.h>
 #include <algorithm>
 
-#include "common.cuh"
+#include "dense_common.cuh"
+#include "dense_mma.cuh"
 
 namespace {
 
@@ -25,7 +26,7 @@ constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kScanThreads = kConsumerThreads + 64;  // + 1 TMA producer warp + 1 compaction warp
 constexpr int kMergeThreads = 512;
-constexpr int kRowPad = 32;  // n_pad granularity (max tile rows)
+constexpr int kRowPad = 128;  // n_pad granularity (tile rows of the tcgen05 scan; multiple of the CUDA-core tiles)
 
 // ------------------------------------------------------------------------------------------------ load kernels
 // One warp per row.  f32 input: x16 = fp16(x / ||x||) (division in fp64, single rounding); f16 input: verbatim.
@@ -579,92 +580,18 @@ __global__ void __launch_bounds__(kMergeThreads, 1) dense_merge_kernel(const Mer
     __syncthreads();
   }
 
-  // (4) exact fp64 re-score of the K survivors against the stored fp16 rows
-  const float* q = p.q + (size_t)qi * p.d_pad;
-  if (warp == 0) {
-    double s = 0.0;
-    for (int i = lane; i < p.d_pad; i += 32) {
-      const double v = (double)q[i];
-      s += v * v;
-    }
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) qq_s = s;
-  }
-  __syncthreads();
-  const double qn = sqrt(qq_s);
-  for (int c = warp; c < K; c += nw) {
-    const unsigned long long key = sel[c];
-    unsigned long long okey = 0ull;
-    uint32_t idx = 0xffffffffu;
-    if (key != 0ull) {
-      idx = key32_idx(key);
-      const uint4* row = reinterpret_cast<const uint4*>(p.rows + (size_t)idx * p.d_pad);
-      double dot = 0.0, xx = 0.0;
-      for (int ch = lane; ch < p.ch; ch += 32) {
-        const uint4 raw = __ldg(row + ch);
-        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-        const float4 qa = *reinterpret_cast<const float4*>(q + (size_t)ch * 8);
-        const float4 qb = *reinterpret_cast<const float4*>(q + (size_t)ch * 8 + 4);
-        const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 xf = __half22float2(h2[e]);
-          const double x0 = (double)xf.x, x1 = (double)xf.y;
-          dot += x0 * (double)qv[2 * e];
-          dot += x1 * (double)qv[2 * e + 1];
-          xx += x0 * x0;
-          xx += x1 * x1;
-        }
-      }
-      for (int o = 16; o; o >>= 1) {
-        dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        xx += __shfl_xor_sync(0xffffffffu, xx, o);
-      }
-      const double den = qn * sqrt(xx);
-      const double score = den > 0.0 ? dot / den : 0.0;
-      okey = f64_orderable(score);
-      if (okey == 0ull) okey = 1ull;  // keep 0 reserved for "empty"
-    }
-    if (lane == 0) {
-      ek[c] = okey;
-      ei[c] = idx;
-    }
-  }
-  __syncthreads();
-  // (5) final sort by (exact score desc, row index asc)
-  for (int kk = 2; kk <= K; kk <<= 1) {
-    for (int j = kk >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < K; i += nt) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const unsigned long long a = ek[i], b = ek[ixj];
-          const uint32_t ia = ei[i], ib = ei[ixj];
-          const bool a_before_b = (a > b) || (a == b && ia < ib);
-          const bool desc = (i & kk) == 0;
-          if ((desc ? !a_before_b : a_before_b) && !(a == b && ia == ib)) {
-            ek[i] = b; ek[ixj] = a;
-            ei[i] = ib; ei[ixj] = ia;
-          }
-        }
-      }
-      __syncthreads();
-    }
-  }
-  int64_t* oid = p.out_ids + (size_t)qi * p.k;
-  double* osc = p.out_scores + (size_t)qi * p.k;
-  for (int i = tid; i < p.k; i += nt) {
-    const bool valid = (i < K) && ek[i] != 0ull;
-    oid[i] = valid ? p.id_base + (int64_t)ei[i] : -1;
-    osc[i] = valid ? orderable_f64(ek[i]) : 0.0;
-  }
-  if (tid == 0) {
-    int lo = 0, hi = min(p.k, K);  // valid entries are a prefix (empty keys sort last)
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (ek[mid] != 0ull) lo = mid + 1; else hi = mid;
-    }
-    p.out_counts[qi] = lo;
-  }
+  // (4)+(5) exact fp64 re-score, final order, emit
+  RescoreArgs ra;
+  ra.rows = p.rows;
+  ra.q = p.q + (size_t)qi * p.d_pad;
+  ra.d_pad = p.d_pad;
+  ra.ch = p.ch;
+  ra.id_base = p.id_base;
+  ra.k = p.k;
+  ra.out_ids = p.out_ids + (size_t)qi * p.k;
+  ra.out_scores = p.out_scores + (size_t)qi * p.k;
+  ra.out_count = p.out_counts + qi;
+  rescore_and_emit(sel, K, ek, ei, &qq_s, ra);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -772,11 +699,14 @@ int dispatch_scan(int qb, const ScanParams& sp, const ScanPlan& pl, cudaStream_t
 // (one CTA per query) for the whole chunk.
 constexpr int kMergeChunk = 256;
 
-int dense_topk_enqueue(sb_ctx* ctx, const DenseIndex& ix, const float* q_pad, int B, int k, int64_t* out_ids,
+int dense_topk_enqueue(sb_ctx* ctx, DenseIndex& ix, const float* q_pad, int B, int k, int64_t* out_ids,
                        double* out_scores, int32_t* out_counts, cudaStream_t st) {
   ScanPlan pl;
   int rc = make_plan(ctx, ix, k, &pl);
   if (rc) return rc;
+  // batches of >= 16 queries ride the tensor cores: one HBM pass per 64 queries instead of one per 4
+  if (ctx->dense_mode != 1 && dense_mma_eligible(ctx, ix, B))
+    return dense_mma_topk_enqueue(ctx, ix, q_pad, B, k, pl.kprime, out_ids, out_scores, out_counts, st);
   const int chunk = B < kMergeChunk ? B : kMergeChunk;
   const size_t per_q = (size_t)pl.grid * pl.kprime;
   rc = ctx->cand_dev.reserve((size_t)chunk * per_q * 8);
@@ -915,6 +845,13 @@ int sb_dense_load(sb_ctx* ctx, int slot, const void* vecs, int64_t n, int32_t d,
   return SB_OK;
 }
 
+int sb_dense_set_mode(sb_ctx* ctx, int mode) {
+  SB_REQUIRE(ctx != nullptr && mode >= 0 && mode <= 2, SB_ERR_ARG, "sb_dense_set_mode: bad arguments");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->dense_mode = mode;
+  return SB_OK;
+}
+
 int64_t sb_dense_count(sb_ctx* ctx, int slot) {
   if (!ctx || slot < 0 || slot >= SB_MAX_DENSE_SLOTS) return -1;
   return ctx->dense[slot].n;
@@ -935,7 +872,7 @@ int sb_dense_topk_dev(sb_ctx* ctx, int slot, const float* q_dev, int32_t B, int3
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
   cudaStream_t st = pick_stream(ctx, stream);
-  const DenseIndex& ix = ctx->dense[slot];
+  DenseIndex& ix = ctx->dense[slot];
   SB_REQUIRE(ix.d > 0, SB_ERR_STATE, "sb_dense_topk: dense slot %d has no index loaded", slot);
   if (ix.n == 0) {
     fill_empty_topk_kernel<<<(B * k + 255) / 256, 256, 0, st>>>(out_ids_dev, out_scores_dev, out_counts_dev, B, k);
@@ -958,7 +895,7 @@ int sb_dense_topk(sb_ctx* ctx, int slot, const float* q, int32_t B, int32_t k, i
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
   cudaStream_t st = ctx->stream;
-  const DenseIndex& ix = ctx->dense[slot];
+  DenseIndex& ix = ctx->dense[slot];
   SB_REQUIRE(ix.d > 0, SB_ERR_STATE, "sb_dense_topk: dense slot %d has no index loaded", slot);
   if (ix.n == 0) {
     for (int i = 0; i < B * k; ++i) { out_ids[i] = -1; out_scores[i] = 0.0; }

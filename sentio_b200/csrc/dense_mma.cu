@@ -1,0 +1,500 @@
+// dense_mma.cu -- K1b: batched-query dense scan on the 5th-gen tensor cores (tcgen05 / TMEM / TMA).
+//
+// One HBM pass over the fp16 corpus serves QBN = 16 / 32 / 64 queries at once: the scores of a 128-row corpus tile against
+// all QBN queries are one UMMA accumulator  D[128, QBN] = A[128, D] * Q[QBN, D]^T  (A = corpus tile, K-major fp16,
+// streamed by TMA in 64-column SWIZZLE_128B boxes; B = the query block, K-major fp16, resident in shared memory for the
+// whole kernel; D in tensor memory, double buffered).  The pass stays HBM bound: per 16 KB of corpus the tensor pipe
+// needs 4 MMAs of 128 x QBN x 16, a few percent of its capacity.
+//
+// Exactness is kept by construction, not by luck:
+//   * every query gets a SAFE initial threshold from a sampling pass (the K'-th best approximate score over a sample of
+//     corpus tiles is <= the global K'-th best), so only ~1 % of the rows survive the epilogue compare;
+//   * survivors are appended to a per-(CTA, query) global buffer that is sized for the worst case (every row of the
+//     CTA's share) -- nothing is ever dropped, an adversarial corpus order only costs time in the select kernel;
+//   * dense_select_kernel reduces each query's survivors to the K' best approximate keys (chunked bitonic sort) and the
+//     shared exact stage (dense_common.cuh) re-scores them in fp64 against the stored rows and the fp32 query.
+//
+// Warp roles (192 threads, 1 CTA / SM, persistent): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (tcgen05.ld 32x32b, one corpus row per thread, QBN scores in registers).
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "dense_common.cuh"
+#include "dense_mma.cuh"
+
+namespace {
+
+constexpr int kTileRows = 128;
+constexpr int kBK = 64;                       // fp16 elements per 128-byte swizzle row
+constexpr uint32_t kATileBytes = kTileRows * kBK * 2;   // 16 KB
+constexpr int kMmaThreads = 192;
+constexpr int kSelectThreads = 1024;
+constexpr int kSelChunk = 8192;               // keys sorted per round in dense_select_kernel (64 KB of smem)
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;             // LBO (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;   // SBO: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+template <int N>
+struct TmemLd;
+template <>
+struct TmemLd<16> {
+  static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+  }
+};
+
+struct MmaScanParams {
+  const float* inv_norm;
+  const float* thr_init;        // [QBN] safe initial thresholds (NULL = -inf: sampling pass)
+  unsigned long long* cand;     // [QBN][grid][capg]
+  int32_t* counts;              // [QBN][grid]
+  int64_t n;                    // valid rows
+  int32_t kb_count;             // d_pad / 64
+  int32_t num_tiles;            // tiles visited by this launch
+  int32_t tile_first, tile_step; // global tile index = tile_first + t * tile_step,  t in [0, num_tiles)
+  int32_t capg;
+  int32_t stages;
+};
+
+template <int QBN>
+__global__ void __launch_bounds__(kMmaThreads, 1)
+dense_scan_mma_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_q,
+                      const MmaScanParams p) {
+  extern __shared__ uint8_t msm_raw[];
+  const uint32_t raw = smem_u32(msm_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B operands need 1024-byte alignment
+  uint8_t* sm = msm_raw + (base - raw);
+  constexpr uint32_t kQBlockBytes = QBN * kBK * 2;      // one 64-column block of the query operand
+  const uint32_t q_bytes = (uint32_t)p.kb_count * kQBlockBytes;
+  const uint32_t a0 = base + q_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + q_bytes + (size_t)p.stages * kATileBytes);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + p.stages);
+  const uint32_t bar_q = smem_u32(bars + 2 * p.stages);
+  const uint32_t bar_acc_full = smem_u32(bars + 2 * p.stages + 1), bar_acc_empty = smem_u32(bars + 2 * p.stages + 3);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 5);
+  volatile float* thr = reinterpret_cast<volatile float*>(tmem_slot + 2);   // [QBN]
+  int* cnt = reinterpret_cast<int*>(const_cast<float*>(thr) + QBN);        // [QBN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grid = gridDim.x, cta = blockIdx.x;
+  const int my_tiles = cta < p.num_tiles ? (p.num_tiles - 1 - cta) / grid + 1 : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_acc_full + 8 * s, 1);
+      mbar_init(bar_acc_empty + 8 * s, 4);  // one arrival per epilogue warp
+    }
+    mbar_fence_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_rows) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_q) : "memory");
+  }
+  for (int i = threadIdx.x; i < QBN; i += blockDim.x) {
+    thr[i] = p.thr_init ? p.thr_init[i] : -INFINITY;
+    cnt[i] = 0;
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(2 * QBN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(bar_q, q_bytes);
+      for (int kb = 0; kb < p.kb_count; ++kb) tma_load_2d(base + (uint32_t)kb * kQBlockBytes, &tm_q, kb * kBK, 0, bar_q);
+      int it = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int tile = p.tile_first + (cta + t * grid) * p.tile_step;
+        for (int kb = 0; kb < p.kb_count; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t use = (uint32_t)(it / p.stages);
+          if (it >= p.stages) mbar_wait(bar_empty + 8 * s, (use & 1u) ^ 1u);
+          mbar_expect_tx(bar_full + 8 * s, kATileBytes);
+          tma_load_2d(a0 + (uint32_t)s * kATileBytes, &tm_rows, kb * kBK, tile * kTileRows, bar_full + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      // kind::f16: D = f32, A = B = f16 K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(QBN >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
+      mbar_wait(bar_q, 0);
+      int it = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int as = t & 1;
+        if (t >= 2) mbar_wait(bar_acc_empty + 8 * as, (((uint32_t)t >> 1) & 1u) ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * QBN);
+        for (int kb = 0; kb < p.kb_count; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t use = (uint32_t)(it / p.stages);
+          mbar_wait(bar_full + 8 * s, use & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = make_smem_desc_sw128(a0 + (uint32_t)s * kATileBytes);
+          const uint64_t db = make_smem_desc_sw128(base + (uint32_t)kb * kQBlockBytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(bar_empty + 8 * s);
+        }
+        umma_commit(bar_acc_full + 8 * as);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue warps 2..5: one corpus row per thread
+    const int quad = warp & 3;
+    unsigned long long* my_cand = p.cand + (size_t)cta * p.capg;
+    const size_t q_stride = (size_t)grid * p.capg;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int as = t & 1;
+      const int tile = p.tile_first + (cta + t * grid) * p.tile_step;
+      const int64_t row = (int64_t)tile * kTileRows + quad * 32 + lane;
+      const float invn = row < p.n ? __ldg(p.inv_norm + row) : 0.f;
+      mbar_wait(bar_acc_full + 8 * as, ((uint32_t)t >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int c0 = 0; c0 < QBN; c0 += 16) {
+        uint32_t v[16];
+        TmemLd<16>::ld(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * QBN + c0), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < p.n) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float score = __uint_as_float(v[j]) * invn;
+            if (score >= thr[c0 + j]) {
+              const int pos = atomicAdd(&cnt[c0 + j], 1);
+              if (pos < p.capg) my_cand[(size_t)(c0 + j) * q_stride + pos] = make_key32(score, (uint32_t)row);
+            }
+          }
+        }
+      }
+      // the accumulator stage has been read into registers by this warp -> give it back to the MMA issuer
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  for (int i = threadIdx.x; i < QBN; i += blockDim.x) p.counts[(size_t)i * grid + cta] = min(cnt[i], p.capg);
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * QBN) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ select kernel
+struct SelectParams {
+  const unsigned long long* cand;   // [nq][grid][capg]
+  const int32_t* counts;            // [nq][grid]
+  int32_t grid, capg, kprime;
+  int32_t nq;                       // real queries in this block (padded operand rows get a +inf threshold)
+  int32_t mode;                     // 0 = write the K'-th best approximate score (threshold pass), 1 = exact stage + emit
+  float* thr_out;                   // [nq]  (mode 0)
+  const __half* rows;               // mode 1
+  const float* q;                   // [nq][d_pad]
+  int32_t d_pad, ch;
+  int64_t id_base;
+  int32_t k;
+  int64_t* out_ids;
+  double* out_scores;
+  int32_t* out_counts;
+};
+
+__device__ __forceinline__ void select_sort_desc(unsigned long long* a, int len, int tid, int nt) {
+  for (int k = 2; k <= len; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < len; i += nt) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long x = a[i], y = a[ixj];
+          const bool desc = (i & k) == 0;
+          if (desc ? (x < y) : (x > y)) {
+            a[i] = y;
+            a[ixj] = x;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// One CTA per query: running best[K'] (kept at the head of the sort buffer) + as many unseen survivors as fit, sort,
+// repeat until every survivor of every CTA has been seen.  Typical: 1-2 rounds; adversarial corpora: more rounds, still exact.
+__global__ void __launch_bounds__(kSelectThreads, 1) dense_select_kernel(const SelectParams p) {
+  extern __shared__ __align__(16) uint8_t ssm[];
+  unsigned long long* buf = reinterpret_cast<unsigned long long*>(ssm);   // [kSelChunk]
+  unsigned long long* ek = buf + kSelChunk;                               // [K]
+  uint32_t* ei = reinterpret_cast<uint32_t*>(ek + p.kprime);              // [K]
+  __shared__ double qq_s;
+  __shared__ int s_prefix[1024 + 1];
+  const int tid = threadIdx.x, nt = blockDim.x, qi = blockIdx.x;
+  const int K = p.kprime, G = p.grid;
+  const int32_t* counts = p.counts + (size_t)qi * G;
+  const unsigned long long* cand = p.cand + (size_t)qi * G * p.capg;
+  if (tid == 0) {
+    int run = 0;
+    for (int g = 0; g < G; ++g) {
+      s_prefix[g] = run;
+      run += counts[g];
+    }
+    s_prefix[G] = run;
+  }
+  __syncthreads();
+  const int total = s_prefix[G];
+  int nbest = 0;
+  int consumed = 0;
+  do {
+    const int room = kSelChunk - nbest;
+    const int take = min(room, total - consumed);
+    // gather survivors [consumed, consumed + take) of the concatenated per-CTA buffers behind the current best
+    for (int i = tid; i < take; i += nt) {
+      const int pos = consumed + i;
+      int lo = 0, hi = G;  // largest g with s_prefix[g] <= pos
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_prefix[mid] <= pos) lo = mid; else hi = mid;
+      }
+      buf[nbest + i] = cand[(size_t)lo * p.capg + (pos - s_prefix[lo])];
+    }
+    const int filled = nbest + take;
+    int P = 32;
+    while (P < filled) P <<= 1;
+    for (int i = filled + tid; i < P; i += nt) buf[i] = 0ull;
+    __syncthreads();
+    select_sort_desc(buf, P, tid, nt);
+    nbest = min(filled, K);
+    consumed += take;
+  } while (consumed < total);
+  for (int i = nbest + tid; i < K; i += nt) buf[i] = 0ull;
+  __syncthreads();
+  if (p.mode == 0) {
+    if (tid == 0) p.thr_out[qi] = qi >= p.nq ? INFINITY : (nbest >= K ? key32_score(buf[K - 1]) : -INFINITY);
+    return;
+  }
+  RescoreArgs ra;
+  ra.rows = p.rows;
+  ra.q = p.q + (size_t)qi * p.d_pad;
+  ra.d_pad = p.d_pad;
+  ra.ch = p.ch;
+  ra.id_base = p.id_base;
+  ra.k = p.k;
+  ra.out_ids = p.out_ids + (size_t)qi * p.k;
+  ra.out_scores = p.out_scores + (size_t)qi * p.k;
+  ra.out_count = p.out_counts + qi;
+  rescore_and_emit(buf, K, ek, ei, &qq_s, ra);
+}
+
+// fp32 padded queries -> fp16 operand block [QBN][d_pad] (rows beyond nq are zero)
+__global__ void queries_to_f16_kernel(const float* __restrict__ q_pad, int nq, int qbn, int d_pad, __half* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)qbn * d_pad) return;
+  const int r = (int)(i / d_pad);
+  out[i] = r < nq ? __float2half_rn(q_pad[i]) : __float2half_rn(0.f);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int box_rows) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* pfn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &pfn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(pfn);
+  }
+  SB_REQUIRE(fn != nullptr, SB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SB_REQUIRE(r == CUDA_SUCCESS, SB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return SB_OK;
+}
+
+template <int QBN>
+int launch_mma(const CUtensorMap& tm_rows, const CUtensorMap& tm_q, const MmaScanParams& mp, int grid, size_t smem,
+               cudaStream_t st) {
+  auto kern = dense_scan_mma_kernel<QBN>;
+  SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kMmaThreads, smem, st>>>(tm_rows, tm_q, mp);
+  SB_CUDA(cudaGetLastError());
+  return SB_OK;
+}
+
+int dispatch_mma(int qbn, const CUtensorMap& tm_rows, const CUtensorMap& tm_q, const MmaScanParams& mp, int grid,
+                 size_t smem, cudaStream_t st) {
+  switch (qbn) {
+    case 16: return launch_mma<16>(tm_rows, tm_q, mp, grid, smem, st);
+    case 32: return launch_mma<32>(tm_rows, tm_q, mp, grid, smem, st);
+    case 64: return launch_mma<64>(tm_rows, tm_q, mp, grid, smem, st);
+  }
+  sb_set_error("dense_mma: unsupported query block %d", qbn);
+  return SB_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+bool dense_mma_eligible(const sb_ctx* ctx, const DenseIndex& ix, int B) {
+  if (B < 16) return false;
+  if (ix.d_pad % kBK != 0 || ix.n_pad % kTileRows != 0) return false;
+  if (ix.n < 64 * kTileRows) return false;  // tiny corpora: the CUDA-core scan is already launch bound
+  const size_t need = (size_t)ix.d_pad * 16 * 2 + 3 * (size_t)kATileBytes + 4096;
+  return need <= ctx->smem_optin;
+}
+
+int dense_mma_topk_enqueue(sb_ctx* ctx, DenseIndex& ix, const float* q_pad, int B, int k, int kprime, int64_t* out_ids,
+                           double* out_scores, int32_t* out_counts, cudaStream_t st) {
+  const int kb_count = ix.d_pad / kBK;
+  const int total_tiles = (int)(ix.n_pad / kTileRows);
+  // largest query block whose resident operand leaves >= 3 pipeline stages
+  int qbn_max = 64;
+  while (qbn_max > 16 && (size_t)qbn_max * ix.d_pad * 2 + 3 * (size_t)kATileBytes + 4096 > ctx->smem_optin) qbn_max >>= 1;
+  const int grid = std::min(ctx->num_sms, total_tiles);
+  const int capg = ((total_tiles + grid - 1) / grid) * kTileRows;  // worst case: every row of the CTA's share survives
+  int rc;
+  // scratch: fp16 query block | thresholds | counts | survivors
+  const size_t q16_bytes = (size_t)qbn_max * ix.d_pad * 2;
+  const size_t cand_bytes = (size_t)qbn_max * grid * capg * 8;
+  if ((rc = ctx->misc2_dev.reserve(q16_bytes + 256))) return rc;
+  if ((rc = ctx->misc3_dev.reserve((size_t)qbn_max * 4 + (size_t)qbn_max * grid * 4 + 256))) return rc;
+  if ((rc = ctx->cand_dev.reserve(cand_bytes))) return rc;
+  __half* q16 = ctx->misc2_dev.as<__half>();
+  float* thr = ctx->misc3_dev.as<float>();
+  int32_t* counts = reinterpret_cast<int32_t*>(thr + qbn_max);
+  unsigned long long* cand = ctx->cand_dev.as<unsigned long long>();
+  if (ix.tm_rows_ptr != ix.rows) {  // (re)build the corpus tensor map once per loaded index
+    if ((rc = encode_map(reinterpret_cast<CUtensorMap*>(ix.tm_rows), ix.rows, ix.n_pad, ix.d_pad, kTileRows))) return rc;
+    ix.tm_rows_ptr = ix.rows;
+  }
+  const CUtensorMap& tm_rows = *reinterpret_cast<const CUtensorMap*>(ix.tm_rows);
+  const size_t sel_smem = (size_t)kSelChunk * 8 + (size_t)kprime * 12 + 64;
+  SB_CUDA(cudaFuncSetAttribute(dense_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+  // sampling pass geometry: ~64 tiles spread evenly over the corpus
+  const int sample_tiles = std::min(64, total_tiles);
+  const int sample_step = total_tiles / sample_tiles;
+  for (int b0 = 0; b0 < B;) {
+    int qbn = qbn_max;
+    while (qbn > 16 && qbn / 2 >= B - b0) qbn >>= 1;
+    const int nq = std::min(qbn, B - b0);
+    CUtensorMap tm_q;
+    if ((rc = encode_map(&tm_q, q16, qbn, ix.d_pad, qbn))) return rc;
+    const int64_t nconv = (int64_t)qbn * ix.d_pad;
+    queries_to_f16_kernel<<<(unsigned)((nconv + 255) / 256), 256, 0, st>>>(q_pad + (size_t)b0 * ix.d_pad, nq, qbn,
+                                                                           ix.d_pad, q16);
+    SB_CUDA(cudaGetLastError());
+    const size_t q_bytes = (size_t)qbn * ix.d_pad * 2;
+    int stages = (int)((ctx->smem_optin - q_bytes - 4096) / kATileBytes);
+    stages = std::max(3, std::min(stages, 8));
+    const size_t smem = q_bytes + (size_t)stages * kATileBytes + 2048 + 1024;
+    MmaScanParams mp;
+    mp.inv_norm = ix.inv_norm;
+    mp.cand = cand;
+    mp.counts = counts;
+    mp.n = ix.n;
+    mp.kb_count = kb_count;
+    mp.capg = capg;
+    mp.stages = stages;
+    SelectParams sp;
+    sp.cand = cand;
+    sp.counts = counts;
+    sp.capg = capg;
+    sp.kprime = kprime;
+    sp.nq = nq;
+    sp.thr_out = thr;
+    sp.rows = ix.rows;
+    sp.q = q_pad + (size_t)b0 * ix.d_pad;
+    sp.d_pad = ix.d_pad;
+    sp.ch = ix.d_pad / 8;
+    sp.id_base = ix.id_base;
+    sp.k = k;
+    sp.out_ids = out_ids + (size_t)b0 * k;
+    sp.out_scores = out_scores + (size_t)b0 * k;
+    sp.out_counts = out_counts + b0;
+    // (1) sampling pass -> safe thresholds
+    {
+      const int sgrid = std::min(grid, sample_tiles);
+      mp.thr_init = nullptr;
+      mp.num_tiles = sample_tiles;
+      mp.tile_first = 0;
+      mp.tile_step = sample_step;
+      ctx->launches += 2;
+      if ((rc = dispatch_mma(qbn, tm_rows, tm_q, mp, sgrid, smem, st))) return rc;
+      sp.grid = sgrid;
+      sp.mode = 0;
+      dense_select_kernel<<<qbn, kSelectThreads, sel_smem, st>>>(sp);
+      SB_CUDA(cudaGetLastError());
+    }
+    // (2) the full pass
+    {
+      mp.thr_init = thr;
+      mp.num_tiles = total_tiles;
+      mp.tile_first = 0;
+      mp.tile_step = 1;
+      {
+        ProfScope ps(ctx, SB_PROF_DENSE_SCAN, st);
+        rc = dispatch_mma(qbn, tm_rows, tm_q, mp, grid, smem, st);
+      }
+      if (rc) return rc;
+      sp.grid = grid;
+      sp.mode = 1;
+      {
+        ProfScope ps(ctx, SB_PROF_DENSE_MERGE, st);
+        dense_select_kernel<<<nq, kSelectThreads, sel_smem, st>>>(sp);
+      }
+      SB_CUDA(cudaGetLastError());
+    }
+    b0 += nq;
+  }
+  return SB_OK;
+}

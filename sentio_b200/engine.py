@@ -96,6 +96,10 @@ class B200Engine:
         self.dense_dim[slot] = d
         self.dense_count[slot] = n
 
+    def dense_set_mode(self, mode: int) -> None:
+        """0 = auto, 1 = CUDA-core scan only, 2 = tcgen05 batched scan whenever eligible."""
+        check(self._lib.sb_dense_set_mode(self._h, int(mode)), "sb_dense_set_mode")
+
     def dense_topk(self, q: np.ndarray, k: int, slot: int = 0):
         q = np.ascontiguousarray(np.atleast_2d(q), dtype=np.float32)
         B, d = q.shape

@@ -31,6 +31,27 @@ def test_dense_topk_matches_oracle_f16_corpus(engine, n, d, k, B):
     _check(engine, x.astype(np.float16), q, k, id_base=1000)
 
 
+@pytest.mark.parametrize("n,d,k,B", [(9000, 1024, 10, 16), (20000, 256, 100, 40), (30000, 768, 100, 70),
+                                     (200000, 128, 228, 33), (12000, 64, 5, 130)])
+def test_dense_batched_tcgen05_path_matches_oracle(engine, n, d, k, B):
+    """B >= 16 queries take the tcgen05 batched-query scan (dense_mma.cu); results must equal the oracle AND be
+    bit-identical to the CUDA-core scan."""
+    rng = np.random.default_rng(n + d + B)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    x16 = x.astype(np.float16)
+    x16[100:140] = x16[50]          # a block of exact duplicates
+    q = rng.standard_normal((B, d)).astype(np.float32)
+    q[3] = x16[50].astype(np.float32)   # hits the duplicate block -> exact ties
+    q[5] = 0.0                          # zero query -> all scores 0
+    engine.dense_set_mode(0)
+    ids, sc, cnt = _check(engine, x16, q, k, id_base=7)
+    engine.dense_set_mode(1)
+    ids1, sc1, cnt1 = engine.dense_topk(q, k)
+    engine.dense_set_mode(0)
+    assert np.array_equal(ids, ids1) and np.array_equal(sc, sc1) and np.array_equal(cnt, cnt1)
+
+
 def test_dense_f32_input_is_normalised_then_rounded(engine):
     rng = np.random.default_rng(5)
     x = (rng.standard_normal((3000, 200)) * rng.uniform(0.1, 50, size=(3000, 1))).astype(np.float32)
@@ -106,3 +127,12 @@ def test_dense_full_size_1m_x_1024(engine):
     for b in range(2):
         wi, ws = dense_oracle.dense_topk(x16, q[b], k)
         assert_topk_matches(ids[b], sc[b], cnt[b], wi, ws, what=f"1M b={b}")
+    # (e) a 64-query batch takes the tcgen05 batched scan: identical to the CUDA-core scan, bit for bit
+    q64 = np.concatenate([synth.query_vectors(61, d, seed=99), x16[probe].astype(np.float32)])
+    engine.dense_set_mode(0)
+    a = engine.dense_topk(q64, k)
+    engine.dense_set_mode(1)
+    b_ = engine.dense_topk(q64, k)
+    engine.dense_set_mode(0)
+    assert np.array_equal(a[0], b_[0]) and np.array_equal(a[1], b_[1]) and np.array_equal(a[2], b_[2])
+    assert list(a[0][61:, 0]) == list(probe)
