@@ -40,7 +40,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="dense", choices=["dense", "hybrid"])
+    ap.add_argument("--workload", default="dense", choices=["dense", "hybrid", "rerank"])
+    ap.add_argument("--rerank-k", type=int, default=10, help="documents kept after the cross-encoder (config 4: 100 -> 10)")
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--n-docs", type=int, default=1_000_000)
     ap.add_argument("--dim", type=int, default=1024)
@@ -112,7 +113,7 @@ def make_workload(args, need_f32_host=False):
     x16 = synth.dense_corpus(args.n_docs, args.dim)
     queries = synth.query_vectors(1024, args.dim)
     wl = {"x16": x16, "q": queries, "gen_s": None}
-    if args.workload == "hybrid":
+    if args.workload in ("hybrid", "rerank"):
         flat, off = synth.text_corpus_tokens(args.n_docs)
         wl["flat"], wl["off"] = flat, off
         wl["q_tokens"] = synth.query_tokens(1024)
@@ -131,7 +132,8 @@ def cpu_reference(args, wl, n_queries):
     x32 /= np.linalg.norm(x32, axis=1, keepdims=True)  # Qdrant normalises at upsert; the scan is then a plain dot
     q = wl["q"]
     fast = None
-    if args.workload == "hybrid":
+    ce_model = None
+    if args.workload in ("hybrid", "rerank"):
         from oracle import fusion as fusion_oracle
         from oracle.rank_bm25_port import FastBM25
         from sentio_b200.index import build_bm25_from_token_ids
@@ -139,6 +141,13 @@ def cpu_reference(args, wl, n_queries):
         idx = build_bm25_from_token_ids(wl["flat"], wl["off"])
         fast = FastBM25(idx.indptr, idx.post_doc, idx.post_tf, idx.doc_len, idx.idf, idx.avgdl)
         terms = [idx.term_ids(t) for t in wl["q_tokens"]]
+    if args.workload == "rerank":
+        from oracle import cross_encoder as ce_oracle
+        from sentio_b200.cross_encoder import MINILM_L6
+        from sentio_b200.index import hash_tokenize_pairs
+        from sentio_b200 import synth
+
+        ce_model = ce_oracle.hf_model(MINILM_L6, seed=0)
     for i in range(2):  # warm-up
         dense_oracle.fast_topk_f32(x32, q[i], args.top_k)
     t0 = time.perf_counter()
@@ -148,11 +157,20 @@ def cpu_reference(args, wl, n_queries):
             s = fast.get_scores(list(terms[i % len(terms)]))
             order = np.argsort(-s)[: args.top_k]
             sp = [(int(j), float(s[j])) for j in order if s[j] > 0]
-            fusion_oracle.fuse("rrf", 60, 0.5, 0.5, [(int(a), float(b)) for a, b in zip(di, ds)], sp, [], args.top_k)
+            fused = fusion_oracle.fuse("rrf", 60, 0.5, 0.5, [(int(a), float(b)) for a, b in zip(di, ds)], sp, [],
+                                       args.top_k)
+            if ce_model is not None:
+                qtext = synth.token_text(wl["q_tokens"][i % len(terms)])
+                texts = [synth.token_text(wl["flat"][wl["off"][d]:wl["off"][d + 1]]) for d, _, _ in fused]
+                ids, tt, lens = hash_tokenize_pairs(qtext, texts, 128)
+                _, sig = ce_oracle.hf_scores(ce_model, ids, tt, lens, batch=len(texts))
+                sorted(range(len(sig)), key=lambda j: -sig[j])[: args.rerank_k]
     dt = time.perf_counter() - t0
     kind = "port"
     sample = (f"{n_queries} queries of the same workload; dense = fp32 X@q (NumPy/BLAS, {cores} threads) + np.argsort"
-              + ("; BM25 = CSR restatement of rank_bm25 get_scores + np.argsort; rrf fusion in Python" if fast else ""))
+              + ("; BM25 = CSR restatement of rank_bm25 get_scores + np.argsort; rrf fusion in Python" if fast else "")
+              + ("; rerank = HuggingFace BertForSequenceClassification (MiniLM-L6 shape) fp32 on CPU, 100 pairs/query"
+                 if ce_model is not None else ""))
     return {"value": n_queries / dt, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}, dt / n_queries
 
 
@@ -163,8 +181,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     workload_name = (f"{args.n_docs}-doc synthetic, {args.dim}-d, "
-                     + ("dense-only cosine" if args.workload == "dense" else "hybrid dense+BM25 rrf")
-                     + f" top_k={args.top_k}")
+                     + {"dense": "dense-only cosine", "hybrid": "hybrid dense+BM25 rrf",
+                        "rerank": "hybrid dense+BM25 rrf + cross-encoder rerank (MiniLM-L6 random-init)"}[args.workload]
+                     + f" top_k={args.top_k}" + (f"->{args.rerank_k}" if args.workload == "rerank" else ""))
     config = {"workload": workload_name, "batch_queries_per_step": args.batch, "store_dtype": "fp16",
               "shards": max(world, 1), "l2_policy": "corpus (2.05 GB) is larger than L2 (126 MB); no flush needed",
               "query_set": "1024 seeded unit vectors, cycled"}
@@ -200,11 +219,22 @@ def main():
     pipe = HybridPipeline(local_rank, rank=rank, world=world)
     pipe.load_dense(wl["x16"][lo:hi], id_base=lo)
     idx = None
-    if args.workload == "hybrid":
+    rerank = args.workload == "rerank"
+    if args.workload in ("hybrid", "rerank"):
         from sentio_b200.index import build_bm25_from_token_ids
 
         idx = build_bm25_from_token_ids(wl["flat"], wl["off"])
         pipe.load_bm25(idx.shard(lo, hi) if world > 1 else idx, id_base=lo)
+    if rerank:
+        from sentio_b200 import synth
+        from sentio_b200.cross_encoder import MINILM_L6, CrossEncoderWeights
+        from sentio_b200.index import doc_token_matrix, hash_vocab_ids
+
+        vocab_ids = hash_vocab_ids(synth.VOCAB)
+        doc_tok, doc_len = doc_token_matrix(wl["flat"], wl["off"], vocab_ids, ld=120)
+        pipe.load_cross_encoder(CrossEncoderWeights.random(MINILM_L6, seed=0))
+        pipe.load_doc_tokens(doc_tok, doc_len, id_base=0)  # replicated on every rank (240 MB at 1 M docs)
+        q_tok_all = vocab_ids[wl["q_tokens"]].astype(np.int32)
     eng = pipe.engine
     B, k = args.batch, args.top_k
     dev = f"cuda:{local_rank}"
@@ -225,12 +255,20 @@ def main():
         if idx is None:
             return (qt,)
         flat, off = eng.pack_queries([term_lists[i] for i in ids])
-        return (qt, torch.from_numpy(flat).to(dev), torch.from_numpy(off).to(dev), int(off[-1]),
+        base = (qt, torch.from_numpy(flat).to(dev), torch.from_numpy(off).to(dev), int(off[-1]),
                 int(np.diff(off).max()))
+        if not rerank:
+            return base
+        qtok = torch.from_numpy(q_tok_all[ids]).to(dev)
+        qlen = torch.full((B,), q_tok_all.shape[1], dtype=torch.int32, device=dev)
+        return base + (qtok, qlen)
 
     def run_dev(inp):
         if idx is None:
             return pipe.dense_dev(inp[0], k)
+        if rerank:
+            return pipe.hybrid_rerank_dev(inp[0], inp[1], inp[2], inp[3], inp[4], inp[5], inp[6], k, args.rerank_k, 128,
+                                          "rrf", 60, 0.5, 0.5)
         return pipe.hybrid_dev(inp[0], inp[1], inp[2], inp[3], inp[4], k, "rrf", 60, 0.5, 0.5)
 
     def barrier():
@@ -259,6 +297,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     launches = eng.launch_count() - launches0
     n_scan, scan_ms = eng.profile_read("dense_scan")
+    n_ce, ce_ms = eng.profile_read("ce")
     eng.profile(False)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -275,6 +314,11 @@ def main():
     def run_host(s):
         if idx is None:
             return pipe.search_dense(host_batches[s], k)
+        if rerank:
+            sl = batch_slice(s)
+            return pipe.search_hybrid_rerank(host_batches[s], host_terms[s], q_tok_all[sl],
+                                             np.full(B, q_tok_all.shape[1], np.int32), k, args.rerank_k, 128, "rrf", 60,
+                                             0.5, 0.5)
         return pipe.search_hybrid(host_batches[s], host_terms[s], k, "rrf", 60, 0.5, 0.5)
 
     for s in range(args.warmup):
@@ -291,6 +335,9 @@ def main():
     e2e_s = float(te.item())
     h2d = B * args.dim * 4 + (0 if idx is None else sum(len(x) for x in host_terms[0]) * 4 + (B + 1) * 4)
     d2h = B * k * 16 + B * 4 + (B * k * 4 if idx is not None else 0)
+    if rerank:
+        h2d += B * q_tok_all.shape[1] * 4 + B * 4
+        d2h = B * args.rerank_k * 12 + B * 4
     e2e = {"value": B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "timer": "host wall clock around the public host-buffer call (includes H2D, kernels, D2H, sync)"}
 
@@ -318,6 +365,16 @@ def main():
             roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:
             pass
+
+    if rerank and n_ce:
+        # second roofline: the cross-encoder forward (tensor pipe), 2.87 GFLOP per pair at S = 128
+        flops = B * k * args.steps * 6 * (24 * 128 * 384 * 384 + 4 * 128 * 128 * 384)
+        tf = flops / (ce_ms * 1e-3) / 1e12
+        tpeak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1429.5) \
+            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1400.0
+        roofline["cross_encoder"] = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s",
+                                     "frac": tf / tpeak, "ms_total": ce_ms, "forward_calls": n_ce,
+                                     "share_of_step": ce_ms / ms_total}
 
     # ---------------- bounded CPU baseline on this box's host cores (rank 0, N=1 only)
     cpu = None

@@ -202,6 +202,20 @@ int sb_ce_score_dev(sb_ctx* ctx, const int32_t* input_ids_dev, const int32_t* to
                     float* out_sigmoid_dev, void* stream);
 
 /*
+ * Batched rerank (retrieve -> rerank without leaving the device): sb_ce_tokens_load stores the shard's pre-tokenised
+ * documents (doc i = doc_tok[i][0..doc_len[i]), word-piece ids < 65536, id = id_base + i).  sb_rerank_dev frames
+ * `[CLS] query [SEP] doc [SEP]` for every (query b, candidate j < cand_cnt[b]) pair on the device, runs the cross-encoder
+ * and emits, per query, the k_out candidates with the highest relevance (stable on the incoming order, like the
+ * reference's sorted(..., reverse=True) at jina_reranker.py:279-283): out_ids[B*k_out], out_scores[B*k_out] (sigmoid),
+ * out_counts[B].
+ */
+int sb_ce_tokens_load(sb_ctx* ctx, const uint16_t* doc_tok, const int32_t* doc_len, int64_t n_docs, int32_t ld,
+                      int64_t id_base);
+int sb_rerank_dev(sb_ctx* ctx, const int32_t* q_tok_dev, const int32_t* q_len_dev, int32_t lq,
+                  const int64_t* cand_ids_dev, const int32_t* cand_cnt_dev, int32_t B, int32_t k, int32_t S,
+                  int32_t k_out, int64_t* out_ids_dev, float* out_scores_dev, int32_t* out_counts_dev, void* stream);
+
+/*
  * Test hook for the tcgen05 GEMM inside K5: out[M,N] = epilogue(A[M,K] * W[N,K]^T + bias (+ residual)), operands given as
  * host fp32 and rounded to fp16 on the device; epi 0 = bias (fp16 result), 1 = bias + erf-GELU (fp16 result),
  * 2 = bias + residual (fp32 result).  N % 128 == 0, K % 64 == 0.

@@ -12,7 +12,8 @@ void sb_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-void ce_model_free(CeModel* m);  // cross_encoder.cu
+void ce_model_free(CeModel* m);        // cross_encoder.cu
+void ce_tokens_free(CeDocTokens* t);   // cross_encoder.cu
 
 extern "C" {
 
@@ -66,6 +67,7 @@ void sb_destroy(sb_ctx* ctx) {
   if (b.dnorm) cudaFree(b.dnorm);
   if (b.idf) cudaFree(b.idf);
   if (ctx->ce) ce_model_free(ctx->ce);
+  if (ctx->ce_tokens) ce_tokens_free(ctx->ce_tokens);
   ctx->q_dev.release();
   ctx->cand_dev.release();
   ctx->out_ids_dev.release();

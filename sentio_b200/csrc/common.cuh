@@ -111,7 +111,8 @@ struct Bm25Index {
   std::vector<int64_t> h_indptr;  // host copy for planning in the host-buffer entry point
 };
 
-struct CeModel;  // cross_encoder.cu
+struct CeModel;      // cross_encoder.cu
+struct CeDocTokens;  // cross_encoder.cu
 
 struct sb_ctx {
   int device = 0;
@@ -122,6 +123,7 @@ struct sb_ctx {
   DenseIndex dense[SB_MAX_DENSE_SLOTS];
   Bm25Index bm25;
   CeModel* ce = nullptr;
+  CeDocTokens* ce_tokens = nullptr;
   int dense_mode = 0;  // 0 = auto, 1 = CUDA-core scan only, 2 = tcgen05 batched scan whenever eligible
   // bookkeeping: kernels launched by this library, optional per-kernel CUDA-event timing (bench.py roofline leg)
   uint64_t launches = 0;

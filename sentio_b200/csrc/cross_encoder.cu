@@ -12,6 +12,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "ce_gemm.cuh"
@@ -36,6 +37,21 @@ struct CeModel {
   CUtensorMap m_x16, m_ctx16, m_ffn16;
   std::vector<void*> act_allocs;
 };
+
+// Per-shard store of pre-tokenised documents for the batched rerank path: doc i -> tok[i][0..len[i])
+struct CeDocTokens {
+  uint16_t* tok = nullptr;   // [n][ld]
+  int32_t* len = nullptr;    // [n]
+  int64_t n = 0, id_base = 0;
+  int32_t ld = 0;
+};
+
+void ce_tokens_free(CeDocTokens* t) {
+  if (!t) return;
+  if (t->tok) cudaFree(t->tok);
+  if (t->len) cudaFree(t->len);
+  delete t;
+}
 
 void ce_model_free(CeModel* m) {
   if (!m) return;
@@ -331,6 +347,64 @@ __global__ void f16_to_f32_kernel(const __half* __restrict__ in, float* __restri
   if (i < n) out[i] = __half2float(in[i]);
 }
 
+// [CLS] query [SEP] doc [SEP] framing on the device for every (query, candidate) pair of a batch.
+__global__ void ce_build_pairs_kernel(const int32_t* __restrict__ q_tok, const int32_t* __restrict__ q_len, int lq,
+                                      const int64_t* __restrict__ cand_ids, const int32_t* __restrict__ cand_cnt, int k,
+                                      int pair0, int n_pairs, const uint16_t* __restrict__ doc_tok,
+                                      const int32_t* __restrict__ doc_len, int ld, int64_t n_docs, int64_t id_base, int S,
+                                      int32_t* __restrict__ ids, int32_t* __restrict__ tts, int32_t* __restrict__ lens) {
+  const int pl = blockIdx.x;  // pair index inside this chunk
+  if (pl >= n_pairs) return;
+  const int pair = pair0 + pl, b = pair / k, j = pair % k;
+  const bool valid = j < cand_cnt[b];
+  const int64_t row = valid ? cand_ids[(size_t)b * k + j] - id_base : -1;
+  const int nq = min(max(q_len[b], 0), min(lq, S / 2 - 2 > 0 ? S / 2 - 2 : 1));
+  int nd = (valid && row >= 0 && row < n_docs) ? min(doc_len[row], ld) : 0;
+  nd = min(nd, S - nq - 3);
+  if (nd < 0) nd = 0;
+  const int total = valid ? nq + nd + 3 : 2;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    int id = 0, tt = 0;
+    if (valid) {
+      if (s == 0) id = 101;
+      else if (s <= nq) id = q_tok[(size_t)b * lq + s - 1];
+      else if (s == nq + 1) id = 102;
+      else if (s < nq + 2 + nd) { id = doc_tok[(size_t)row * ld + (s - nq - 2)]; tt = 1; }
+      else if (s == nq + 2 + nd) { id = 102; tt = 1; }
+    } else {
+      if (s == 0) id = 101;
+      else if (s == 1) id = 102;
+    }
+    ids[(size_t)pl * S + s] = id;
+    tts[(size_t)pl * S + s] = tt;
+  }
+  if (threadIdx.x == 0) lens[pl] = total;
+}
+
+// One CTA per query: order the k candidates by relevance (desc, stable on the incoming rank) and emit the best k_out.
+__global__ void ce_rank_kernel(const float* __restrict__ sig, const int64_t* __restrict__ cand_ids,
+                               const int32_t* __restrict__ cand_cnt, int k, int k_out, int64_t* __restrict__ out_ids,
+                               float* __restrict__ out_scores, int32_t* __restrict__ out_counts) {
+  extern __shared__ float rk_sm[];
+  const int b = blockIdx.x, n = min(cand_cnt[b], k);
+  for (int j = threadIdx.x; j < n; j += blockDim.x) rk_sm[j] = sig[(size_t)b * k + j];
+  __syncthreads();
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const float s = rk_sm[j];
+    int pos = 0;
+    for (int i = 0; i < n; ++i) pos += (rk_sm[i] > s) || (rk_sm[i] == s && i < j);
+    if (pos < k_out) {
+      out_ids[(size_t)b * k_out + pos] = cand_ids[(size_t)b * k + j];
+      out_scores[(size_t)b * k_out + pos] = s;
+    }
+  }
+  for (int j = n + threadIdx.x; j < k_out; j += blockDim.x) {
+    out_ids[(size_t)b * k_out + j] = -1;
+    out_scores[(size_t)b * k_out + j] = 0.f;
+  }
+  if (threadIdx.x == 0) out_counts[b] = min(n, k_out);
+}
+
 }  // namespace
 
 extern "C" {
@@ -500,6 +574,75 @@ int sb_ce_score(sb_ctx* ctx, const int32_t* input_ids, const int32_t* token_type
   SB_CUDA(cudaStreamSynchronize(st));
   memcpy(out_logits, ctx->pin_out.p, (size_t)P * 4);
   memcpy(out_sigmoid, ctx->pin_out.as<uint8_t>() + (size_t)P * 4, (size_t)P * 4);
+  return SB_OK;
+}
+
+
+int sb_ce_tokens_load(sb_ctx* ctx, const uint16_t* doc_tok, const int32_t* doc_len, int64_t n_docs, int32_t ld,
+                      int64_t id_base) {
+  SB_REQUIRE(ctx && (n_docs == 0 || (doc_tok && doc_len)) && n_docs >= 0 && ld > 0, SB_ERR_ARG,
+             "sb_ce_tokens_load: bad arguments");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  SB_CUDA(cudaStreamSynchronize(ctx->stream));
+  CeDocTokens*& dt = ctx->ce_tokens;
+  if (dt) {
+    if (dt->tok) cudaFree(dt->tok);
+    if (dt->len) cudaFree(dt->len);
+    delete dt;
+    dt = nullptr;
+  }
+  dt = new CeDocTokens();
+  dt->n = n_docs;
+  dt->ld = ld;
+  dt->id_base = id_base;
+  if (n_docs) {
+    SB_CUDA(cudaMalloc(&dt->tok, (size_t)n_docs * ld * 2));
+    SB_CUDA(cudaMalloc(&dt->len, (size_t)n_docs * 4));
+    SB_CUDA(cudaMemcpy(dt->tok, doc_tok, (size_t)n_docs * ld * 2, cudaMemcpyHostToDevice));
+    SB_CUDA(cudaMemcpy(dt->len, doc_len, (size_t)n_docs * 4, cudaMemcpyHostToDevice));
+  }
+  return SB_OK;
+}
+
+int sb_rerank_dev(sb_ctx* ctx, const int32_t* q_tok_dev, const int32_t* q_len_dev, int32_t lq,
+                  const int64_t* cand_ids_dev, const int32_t* cand_cnt_dev, int32_t B, int32_t k, int32_t S,
+                  int32_t k_out, int64_t* out_ids_dev, float* out_scores_dev, int32_t* out_counts_dev, void* stream) {
+  SB_REQUIRE(ctx != nullptr, SB_ERR_ARG, "sb_rerank_dev: ctx is NULL");
+  SB_REQUIRE(B >= 0 && k > 0 && k_out > 0 && lq > 0 && S >= 8, SB_ERR_ARG, "sb_rerank_dev: bad sizes");
+  if (B == 0) return SB_OK;
+  SB_REQUIRE(q_tok_dev && q_len_dev && cand_ids_dev && cand_cnt_dev && out_ids_dev && out_scores_dev && out_counts_dev,
+             SB_ERR_ARG, "sb_rerank_dev: NULL buffer");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  SB_REQUIRE(ctx->ce != nullptr, SB_ERR_STATE, "sb_rerank_dev: no cross-encoder loaded (sb_ce_load)");
+  SB_REQUIRE(ctx->ce_tokens != nullptr && ctx->ce_tokens->n > 0, SB_ERR_STATE,
+             "sb_rerank_dev: no document tokens loaded (sb_ce_tokens_load)");
+  cudaStream_t st = pick_stream(ctx, stream);
+  const CeDocTokens& dt = *ctx->ce_tokens;
+  const int total = B * k;
+  const int chunk = 2048;  // pairs per forward pass: bounds the activation workspace (~2.6 GB at S = 128)
+  int rc;
+  const size_t per_pair = (size_t)S * 8 + 4;
+  if ((rc = ctx->misc_dev.reserve((size_t)std::min(total, chunk) * per_pair + 64))) return rc;
+  if ((rc = ctx->out_sc_dev.reserve((size_t)total * 8))) return rc;
+  int32_t* ids = ctx->misc_dev.as<int32_t>();
+  int32_t* tts = ids + (size_t)std::min(total, chunk) * S;
+  int32_t* lens = tts + (size_t)std::min(total, chunk) * S;
+  float* logits = ctx->out_sc_dev.as<float>();
+  float* sig = logits + total;
+  for (int p0 = 0; p0 < total; p0 += chunk) {
+    const int np = std::min(chunk, total - p0);
+    ctx->launches += 1;
+    ce_build_pairs_kernel<<<np, 128, 0, st>>>(q_tok_dev, q_len_dev, lq, cand_ids_dev, cand_cnt_dev, k, p0, np, dt.tok,
+                                              dt.len, dt.ld, dt.n, dt.id_base, S, ids, tts, lens);
+    SB_CUDA(cudaGetLastError());
+    if ((rc = ce_forward_dispatch(ctx, ids, tts, lens, np, S, logits + p0, sig + p0, st))) return rc;
+  }
+  ctx->launches += 1;
+  ce_rank_kernel<<<B, 128, (size_t)k * 4, st>>>(sig, cand_ids_dev, cand_cnt_dev, k, k_out, out_ids_dev, out_scores_dev,
+                                               out_counts_dev);
+  SB_CUDA(cudaGetLastError());
   return SB_OK;
 }
 

@@ -355,50 +355,39 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
     const uint32_t use = (uint32_t)(i / stages);
     const int64_t tile = (int64_t)blockIdx.x + (int64_t)i * grid;
     const int64_t grow = tile * R + warp * RW + ri;
-    float invn = 0.f;
-    if (leader) invn = __ldg(p.inv_norm + grow);  // issued before the wait: latency overlaps the TMA wait
-
     mbar_wait(bar_full0 + 8 * s, use & 1u);
+    float invn = 0.f;
+    if (leader) invn = __ldg(p.inv_norm + grow);  // consumed after the reduction: latency hides under the FMAs
 
     unsigned long long acc[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[v] = 0ull;
     const uint8_t* wbase = tiles + (size_t)s * p.tile_bytes + (size_t)(warp * RW) * row_bytes + (size_t)lane * 16;
-    // software pipeline: the 16-byte chunks of step j+1 are in flight while step j is multiplied
-    uint4 cur[RW], nxt[RW];
+    // software pipeline at (chunk, row) granularity: the 16 bytes of the next step are in flight while this step is
+    // converted and multiplied (one uint4 of look-ahead keeps the register budget under the 200-register ceiling)
+    uint4 cur = make_uint4(0u, 0u, 0u, 0u);
+    if (EXACT || lane < p.ch) cur = *reinterpret_cast<const uint4*>(wbase);
 #pragma unroll
-    for (int r = 0; r < RW; ++r) {
-      cur[r] = make_uint4(0u, 0u, 0u, 0u);
-      if (EXACT || lane < p.ch) cur[r] = *reinterpret_cast<const uint4*>(wbase + (size_t)r * row_bytes);
-    }
-#pragma unroll
-    for (int j = 0; j < NCHUNK; ++j) {
-      if (j + 1 < NCHUNK) {
-#pragma unroll
-        for (int r = 0; r < RW; ++r) {
-          nxt[r] = make_uint4(0u, 0u, 0u, 0u);
-          if (EXACT || lane + 32 * (j + 1) < p.ch)
-            nxt[r] = *reinterpret_cast<const uint4*>(wbase + (size_t)r * row_bytes + (size_t)(j + 1) * 512);
-        }
+    for (int step = 0; step < NCHUNK * RW; ++step) {
+      const int j = step / RW, r = step % RW;
+      uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+      if (step + 1 < NCHUNK * RW) {
+        const int jn = (step + 1) / RW, rn = (step + 1) % RW;
+        if (EXACT || lane + 32 * jn < p.ch)
+          nxt = *reinterpret_cast<const uint4*>(wbase + (size_t)rn * row_bytes + (size_t)jn * 512);
       }
+      const unsigned long long x0 = h2_to_f2(cur.x), x1 = h2_to_f2(cur.y);
+      const unsigned long long x2 = h2_to_f2(cur.z), x3 = h2_to_f2(cur.w);
 #pragma unroll
-      for (int r = 0; r < RW; ++r) {
-        const unsigned long long x0 = h2_to_f2(cur[r].x), x1 = h2_to_f2(cur[r].y);
-        const unsigned long long x2 = h2_to_f2(cur[r].z), x3 = h2_to_f2(cur[r].w);
-#pragma unroll
-        for (int q = 0; q < QB; ++q) {
-          unsigned long long a = acc[r * QB + q];
-          a = ffma2(x0, qr[q][j][0], a);
-          a = ffma2(x1, qr[q][j][1], a);
-          a = ffma2(x2, qr[q][j][2], a);
-          a = ffma2(x3, qr[q][j][3], a);
-          acc[r * QB + q] = a;
-        }
+      for (int q = 0; q < QB; ++q) {
+        unsigned long long a = acc[r * QB + q];
+        a = ffma2(x0, qr[q][j][0], a);
+        a = ffma2(x1, qr[q][j][1], a);
+        a = ffma2(x2, qr[q][j][2], a);
+        a = ffma2(x3, qr[q][j][3], a);
+        acc[r * QB + q] = a;
       }
-      if (j + 1 < NCHUNK) {
-#pragma unroll
-        for (int r = 0; r < RW; ++r) cur[r] = nxt[r];
-      }
+      cur = nxt;
     }
     // all smem reads of this stage are consumed (their values fed the FMAs above) -> release the slot
     __syncwarp();

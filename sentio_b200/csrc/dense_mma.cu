@@ -30,7 +30,8 @@ constexpr int kBK = 64;                       // fp16 elements per 128-byte swiz
 constexpr uint32_t kATileBytes = kTileRows * kBK * 2;   // 16 KB
 constexpr int kMmaThreads = 192;
 constexpr int kSelectThreads = 1024;
-constexpr int kSelChunk = 8192;               // keys sorted per round in dense_select_kernel (64 KB of smem)
+constexpr int kSelStage = 20480;              // survivors staged in shared memory by dense_select_kernel (160 KB)
+constexpr int kSelTop = 2048;                 // winner buffer: < K' keys above the selected bucket + the bucket
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile(
@@ -263,16 +264,21 @@ __device__ __forceinline__ void select_sort_desc(unsigned long long* a, int len,
   }
 }
 
-// One CTA per query: running best[K'] (kept at the head of the sort buffer) + as many unseen survivors as fit, sort,
-// repeat until every survivor of every CTA has been seen.  Typical: 1-2 rounds; adversarial corpora: more rounds, still exact.
+// One CTA per query: the K' best approximate keys among the survivors of all CTAs by an MSB-first RADIX SELECT
+// (8-bit digits, shared-memory histogram; the pass loop stops as soon as the bucket holding the K'-th key is small),
+// then a small sort of {keys above the bucket} U {bucket}.  Survivors are staged in shared memory when they fit
+// (the normal case: ~1.5 % of the corpus); otherwise every pass streams them from HBM/L2 -- slower, still exact.
 __global__ void __launch_bounds__(kSelectThreads, 1) dense_select_kernel(const SelectParams p) {
   extern __shared__ __align__(16) uint8_t ssm[];
-  unsigned long long* buf = reinterpret_cast<unsigned long long*>(ssm);   // [kSelChunk]
-  unsigned long long* ek = buf + kSelChunk;                               // [K]
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(ssm);  // [kSelStage] staged survivors
+  unsigned long long* top = keys + kSelStage;                             // [kSelTop]   gathered winners
+  unsigned long long* ek = top + kSelTop;                                 // [K]
   uint32_t* ei = reinterpret_cast<uint32_t*>(ek + p.kprime);              // [K]
   __shared__ double qq_s;
   __shared__ int s_prefix[1024 + 1];
-  const int tid = threadIdx.x, nt = blockDim.x, qi = blockIdx.x;
+  __shared__ int s_hist[256];
+  __shared__ int s_sel, s_need, s_bucket, s_ntop;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5, qi = blockIdx.x;
   const int K = p.kprime, G = p.grid;
   const int32_t* counts = p.counts + (size_t)qi * G;
   const unsigned long long* cand = p.cand + (size_t)qi * G * p.capg;
@@ -283,37 +289,86 @@ __global__ void __launch_bounds__(kSelectThreads, 1) dense_select_kernel(const S
       run += counts[g];
     }
     s_prefix[G] = run;
+    s_ntop = 0;
   }
   __syncthreads();
   const int total = s_prefix[G];
-  int nbest = 0;
-  int consumed = 0;
-  do {
-    const int room = kSelChunk - nbest;
-    const int take = min(room, total - consumed);
-    // gather survivors [consumed, consumed + take) of the concatenated per-CTA buffers behind the current best
-    for (int i = tid; i < take; i += nt) {
-      const int pos = consumed + i;
-      int lo = 0, hi = G;  // largest g with s_prefix[g] <= pos
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (s_prefix[mid] <= pos) lo = mid; else hi = mid;
-      }
-      buf[nbest + i] = cand[(size_t)lo * p.capg + (pos - s_prefix[lo])];
+  const bool staged = total <= kSelStage;
+  if (staged) {
+    for (int g = warp; g < G; g += nw) {
+      const int c = s_prefix[g + 1] - s_prefix[g];
+      const unsigned long long* src = cand + (size_t)g * p.capg;
+      unsigned long long* dst = keys + s_prefix[g];
+      for (int i = lane; i < c; i += 32) dst[i] = src[i];
     }
-    const int filled = nbest + take;
-    int P = 32;
-    while (P < filled) P <<= 1;
-    for (int i = filled + tid; i < P; i += nt) buf[i] = 0ull;
     __syncthreads();
-    select_sort_desc(buf, P, tid, nt);
-    nbest = min(filled, K);
-    consumed += take;
-  } while (consumed < total);
-  for (int i = nbest + tid; i < K; i += nt) buf[i] = 0ull;
+  }
+  // visit every survivor once: `body(key)`
+#define SB_FOR_EACH_KEY(BODY)                                                       \
+  if (staged) {                                                                     \
+    for (int i_ = tid; i_ < total; i_ += nt) {                                      \
+      const unsigned long long key = keys[i_];                                      \
+      BODY                                                                          \
+    }                                                                               \
+  } else {                                                                          \
+    for (int g_ = warp; g_ < G; g_ += nw) {                                         \
+      const int c_ = s_prefix[g_ + 1] - s_prefix[g_];                               \
+      const unsigned long long* src_ = cand + (size_t)g_ * p.capg;                  \
+      for (int i_ = lane; i_ < c_; i_ += 32) {                                      \
+        const unsigned long long key = src_[i_];                                    \
+        BODY                                                                        \
+      }                                                                             \
+    }                                                                               \
+  }
+
+  unsigned long long prefix = 0ull, mask = 0ull;
+  if (total > K) {
+    int need = K;  // rank (from the top) of the key we are looking for inside the current bucket
+    for (int shift = 56; shift >= 0; shift -= 8) {
+      for (int i = tid; i < 256; i += nt) s_hist[i] = 0;
+      __syncthreads();
+      SB_FOR_EACH_KEY(if ((key & mask) == prefix) atomicAdd(&s_hist[(int)((key >> shift) & 0xffull)], 1);)
+      __syncthreads();
+      if (tid == 0) {
+        int cum = 0, sel = 0, cnt_b = 0;
+        for (int b = 255; b >= 0; --b) {
+          const int c = s_hist[b];
+          if (cum + c >= need) {
+            sel = b;
+            cnt_b = c;
+            break;
+          }
+          cum += c;
+        }
+        s_sel = sel;
+        s_need = need - cum;
+        s_bucket = cnt_b;
+      }
+      __syncthreads();
+      prefix |= (unsigned long long)s_sel << shift;
+      mask |= 0xffull << shift;
+      need = s_need;
+      const int bucket = s_bucket;
+      __syncthreads();
+      if (bucket <= kSelTop - K) break;  // {above} (< K keys) + bucket fit the winner buffer
+    }
+  }
+  // winners: every key whose decided digits are >= the selected bucket's (at most K - 1 + bucket <= kSelTop keys)
+  SB_FOR_EACH_KEY(if ((key & mask) >= prefix) {
+    const int at = atomicAdd(&s_ntop, 1);
+    if (at < kSelTop) top[at] = key;
+  })
+#undef SB_FOR_EACH_KEY
   __syncthreads();
+  const int ntop = min(s_ntop, kSelTop);
+  int P = 32;
+  while (P < ntop || P < K) P <<= 1;
+  for (int i = ntop + tid; i < P; i += nt) top[i] = 0ull;
+  __syncthreads();
+  select_sort_desc(top, P, tid, nt);
+  const int nbest = min(ntop, K);
   if (p.mode == 0) {
-    if (tid == 0) p.thr_out[qi] = qi >= p.nq ? INFINITY : (nbest >= K ? key32_score(buf[K - 1]) : -INFINITY);
+    if (tid == 0) p.thr_out[qi] = qi >= p.nq ? INFINITY : (nbest >= K ? key32_score(top[K - 1]) : -INFINITY);
     return;
   }
   RescoreArgs ra;
@@ -326,7 +381,7 @@ __global__ void __launch_bounds__(kSelectThreads, 1) dense_select_kernel(const S
   ra.out_ids = p.out_ids + (size_t)qi * p.k;
   ra.out_scores = p.out_scores + (size_t)qi * p.k;
   ra.out_count = p.out_counts + qi;
-  rescore_and_emit(buf, K, ek, ei, &qq_s, ra);
+  rescore_and_emit(top, K, ek, ei, &qq_s, ra);
 }
 
 // fp32 padded queries -> fp16 operand block [QBN][d_pad] (rows beyond nq are zero)
@@ -418,7 +473,7 @@ int dense_mma_topk_enqueue(sb_ctx* ctx, DenseIndex& ix, const float* q_pad, int 
     ix.tm_rows_ptr = ix.rows;
   }
   const CUtensorMap& tm_rows = *reinterpret_cast<const CUtensorMap*>(ix.tm_rows);
-  const size_t sel_smem = (size_t)kSelChunk * 8 + (size_t)kprime * 12 + 64;
+  const size_t sel_smem = (size_t)(kSelStage + kSelTop) * 8 + (size_t)kprime * 12 + 64;
   SB_CUDA(cudaFuncSetAttribute(dense_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
   // sampling pass geometry: ~64 tiles spread evenly over the corpus
   const int sample_tiles = std::min(64, total_tiles);

@@ -272,6 +272,26 @@ class B200Engine:
         check(self._lib.sb_ce_load(self._h, _ptr(w), w.size, C.byref(c)), "sb_ce_load")
         self.ce_config = dict(cfg)
 
+    def ce_tokens_load(self, doc_tok: np.ndarray, doc_len: np.ndarray, id_base: int = 0) -> None:
+        t = np.ascontiguousarray(doc_tok, dtype=np.uint16)
+        ln = np.ascontiguousarray(doc_len, dtype=np.int32)
+        check(self._lib.sb_ce_tokens_load(self._h, _ptr(t), _ptr(ln), t.shape[0], t.shape[1], int(id_base)),
+              "sb_ce_tokens_load")
+
+    def rerank_dev(self, q_tok_t, q_len_t, cand_ids_t, cand_cnt_t, S: int, k_out: int, out=None):
+        import torch
+
+        B, k = cand_ids_t.shape
+        if out is None:
+            dev = cand_ids_t.device
+            out = (torch.empty((B, k_out), dtype=torch.int64, device=dev),
+                   torch.empty((B, k_out), dtype=torch.float32, device=dev),
+                   torch.empty((B,), dtype=torch.int32, device=dev))
+        check(self._lib.sb_rerank_dev(self._h, _tptr(q_tok_t), _tptr(q_len_t), q_tok_t.shape[1], _tptr(cand_ids_t),
+                                      _tptr(cand_cnt_t), B, k, int(S), int(k_out), _tptr(out[0]), _tptr(out[1]),
+                                      _tptr(out[2]), self._stream()), "sb_rerank_dev")
+        return out
+
     def ce_gemm_test(self, a: np.ndarray, w: np.ndarray, bias: np.ndarray, epi: int, residual: np.ndarray | None = None):
         a = np.ascontiguousarray(a, dtype=np.float32)
         w = np.ascontiguousarray(w, dtype=np.float32)

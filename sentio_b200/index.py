@@ -188,6 +188,25 @@ def _hash_token(tok: str) -> int:
     return 1000 + zlib.crc32(tok.encode("utf-8")) % 29522
 
 
+def hash_vocab_ids(n_vocab: int, prefix: str = "w") -> np.ndarray:
+    """Hashed word-piece id of every synthetic vocabulary token ``w0 .. w{n-1}`` (uint16; same hash as below)."""
+    return np.fromiter((_hash_token(f"{prefix}{t}") for t in range(n_vocab)), dtype=np.uint16, count=n_vocab)
+
+
+def doc_token_matrix(flat_tokens: np.ndarray, doc_offsets: np.ndarray, vocab_ids: np.ndarray, ld: int = 120):
+    """Pre-tokenised documents for the batched rerank path: (tok uint16 [N, ld], len int32 [N]) from an integer token
+    stream (doc i = flat_tokens[off[i]:off[i+1]], truncated to ld)."""
+    off = np.asarray(doc_offsets, dtype=np.int64)
+    n = len(off) - 1
+    lens = np.minimum(np.diff(off), ld).astype(np.int32)
+    tok = np.zeros((n, ld), dtype=np.uint16)
+    col = np.arange(ld)[None, :]
+    mask = col < lens[:, None]
+    src = (off[:-1, None] + col)[mask]
+    tok[mask] = vocab_ids[np.asarray(flat_tokens)[src]]
+    return tok, lens
+
+
 def hash_tokenize_pairs(query: str, docs: Sequence[str], seq_len: int = 128):
     """``[CLS] q [SEP] d [SEP]`` framing with crc32-hashed word ids, padded/truncated to ``seq_len``.
 

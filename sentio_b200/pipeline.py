@@ -48,6 +48,15 @@ class HybridPipeline:
     def load_bm25(self, data: Bm25IndexData, id_base: int = 0) -> None:
         self.engine.load_bm25(data, id_base=id_base)
 
+    def load_cross_encoder(self, weights) -> None:
+        """weights: sentio_b200.cross_encoder.CrossEncoderWeights"""
+        self.engine.ce_load(weights.blob(), weights.config)
+
+    def load_doc_tokens(self, doc_tok: np.ndarray, doc_len: np.ndarray, id_base: int = 0) -> None:
+        """Pre-tokenised documents for the rerank stage.  Sharded runs replicate the (small) token matrix on every
+        rank (id_base = 0, all docs), so any global candidate id can be framed locally without a second collective."""
+        self.engine.ce_tokens_load(doc_tok, doc_len, id_base)
+
     # ------------------------------------------------------------------ helpers
     def _buf(self, name, shape, dtype):
         t = self._bufs.get(name)
@@ -129,6 +138,17 @@ class HybridPipeline:
                self._buf("f_src", (B, k), t.int32), self._buf("f_cnt", (B,), t.int32))
         return self.engine.fuse_dev(method, rrf_k, w_dense, w_sparse, k, dv, sv, out=out)
 
+    def hybrid_rerank_dev(self, q_t, terms_t, off_t, n_terms: int, max_len: int, q_tok_t, q_len_t, k: int, k_out: int,
+                          seq_len: int = 128, method: str = "rrf", rrf_k: float = 60, w_dense: float = 0.5,
+                          w_sparse: float = 0.5):
+        """retrieve (dense + BM25 + fusion, top k) -> cross-encoder rerank (top k_out), all on the device."""
+        t = self.torch
+        ids, sc, src, cnt = self.hybrid_dev(q_t, terms_t, off_t, n_terms, max_len, k, method, rrf_k, w_dense, w_sparse)
+        B = q_t.shape[0]
+        out = (self._buf("r_ids", (B, k_out), t.int64), self._buf("r_sc", (B, k_out), t.float32),
+               self._buf("r_cnt", (B,), t.int32))
+        return self.engine.rerank_dev(q_tok_t, q_len_t, ids, cnt, seq_len, k_out, out=out)
+
     # ------------------------------------------------------------------ host (e2e) path
     def search_dense(self, q: np.ndarray, k: int):
         """Host in / host out.  world == 1: straight through the C-ABI host entry point."""
@@ -149,3 +169,16 @@ class HybridPipeline:
         ids, sc, src, cnt = self.hybrid_dev(q_t, terms_t, off_t, int(off[-1]), max_len, k, method, rrf_k, w_dense,
                                             w_sparse)
         return ids.cpu().numpy(), sc.cpu().numpy(), src.cpu().numpy(), cnt.cpu().numpy()
+
+    def search_hybrid_rerank(self, q: np.ndarray, term_lists, q_tok: np.ndarray, q_len: np.ndarray, k: int, k_out: int,
+                             seq_len: int = 128, method: str = "rrf", rrf_k: float = 60, w_dense: float = 0.5,
+                             w_sparse: float = 0.5):
+        flat, off = B200Engine.pack_queries(term_lists)
+        max_len = int(np.diff(off).max()) if len(off) > 1 else 0
+        q_t = self._to_dev(np.ascontiguousarray(q, dtype=np.float32))
+        terms_t, off_t = self._to_dev(flat), self._to_dev(off)
+        qt_t = self._to_dev(np.ascontiguousarray(q_tok, dtype=np.int32))
+        ql_t = self._to_dev(np.ascontiguousarray(q_len, dtype=np.int32))
+        ids, sc, cnt = self.hybrid_rerank_dev(q_t, terms_t, off_t, int(off[-1]), max_len, qt_t, ql_t, k, k_out, seq_len,
+                                              method, rrf_k, w_dense, w_sparse)
+        return ids.cpu().numpy(), sc.cpu().numpy(), cnt.cpu().numpy()

@@ -99,3 +99,39 @@ def test_reranker_control_flow_matches_reference(engine):
     rr._engine = None  # force a failure inside rerank -> default ranking, no exception
     out = rr.rerank("w3 w4", docs, top_k=3)
     assert [d.id for d in out] == ["0", "1", "2"] and [d.metadata["rerank_score"] for d in out] == [1.0, 0.9, 0.8]
+
+
+def test_batched_rerank_pipeline_equals_per_query_reranker(engine):
+    """sb_rerank_dev (device-side pair framing + cross-encoder + ranking) == hash_tokenize_pairs + sb_ce_score per query."""
+    from sentio_b200.index import build_bm25_from_token_ids, doc_token_matrix, hash_vocab_ids
+    from sentio_b200.pipeline import HybridPipeline
+
+    n, d, k, k_out, B, V = 9000, 128, 40, 10, 5, 3000
+    x = synth.dense_corpus(n, d)
+    flat, off = synth.text_corpus_tokens(n, vocab=V)
+    idx = build_bm25_from_token_ids(flat, off)
+    vocab_ids = hash_vocab_ids(V)
+    doc_tok, doc_len = doc_token_matrix(flat, off, vocab_ids, ld=120)
+    cfg = dict(vocab_size=30522, hidden=128, layers=2, heads=4, intermediate=256, max_pos=128, type_vocab=2, ln_eps=1e-12)
+    w = CrossEncoderWeights.random(cfg, seed=5, std=0.05)
+    pipe = HybridPipeline(0)
+    pipe.load_dense(x)
+    pipe.load_bm25(idx)
+    pipe.load_cross_encoder(w)
+    pipe.load_doc_tokens(doc_tok, doc_len)
+    q = synth.query_vectors(B, d)
+    q_raw = synth.query_tokens(B, vocab=V)
+    terms = [idx.term_ids(t) for t in q_raw]
+    q_tok = vocab_ids[q_raw].astype(np.int32)
+    q_len = np.full(B, q_raw.shape[1], np.int32)
+    ids, sc, cnt = pipe.search_hybrid_rerank(q, terms, q_tok, q_len, k, k_out, seq_len=128)
+    f_ids, f_sc, f_src, f_cnt = pipe.search_hybrid(q, terms, k)
+    engine.ce_load(w.blob(), cfg)
+    texts = synth.texts_from_tokens(flat, off)
+    for b in range(B):
+        cand = [int(i) for i in f_ids[b, :f_cnt[b]]]
+        pi, pt, pl = hash_tokenize_pairs(synth.token_text(q_raw[b]), [texts[i] for i in cand], 128)
+        _, sig = engine.ce_score(pi, pt, pl)
+        order = sorted(range(len(cand)), key=lambda j: -sig[j])[:k_out]  # stable, like the reference's sorted()
+        assert [int(i) for i in ids[b, :cnt[b]]] == [cand[j] for j in order]
+        assert np.allclose(sc[b, :cnt[b]], sig[order], rtol=1e-5, atol=1e-6)
