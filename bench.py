@@ -2,7 +2,7 @@
 """bench.py -- retrieval queries/sec on BASELINE.json's configurations.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--workload dense|hybrid] [--batch B] [--n-docs N] [--dim D] [--top-k K]
+                    [--workload dense|hybrid|rerank] [--batch B] [--n-docs N] [--dim D] [--top-k K] [--rerank-k K2]
 
 A "step" = one batch of B synthetic queries through the hot path.  Default workload = BASELINE.json configs[1]:
 1 M docs x 1024-d, dense-only cosine top_k=100 on 1 x B200.  For --gpus N > 1 the SAME corpus is partitioned N ways
@@ -378,7 +378,7 @@ def main():
 
     # ---------------- bounded CPU baseline on this box's host cores (rank 0, N=1 only)
     cpu = None
-    if world == 1:
+    if world == 1 and args.cpu_sample > 0:
         cpu, _ = cpu_reference(args, wl, args.cpu_sample)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
