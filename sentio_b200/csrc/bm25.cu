@@ -23,8 +23,6 @@ namespace {
 constexpr int kScoreThreads = 256;
 constexpr int kPostPerThread = 8;
 constexpr int kChunk = kScoreThreads * kPostPerThread;  // postings per work chunk
-constexpr int kSelThreads = 1024;
-constexpr int kSelPerIter = 2 * kSelThreads;  // scores examined per CTA iteration
 
 // ------------------------------------------------------------------------------------------------ load kernels
 __global__ void bm25_dnorm_kernel(const int32_t* __restrict__ doc_len, int64_t n, double k1, double b, double omb,
@@ -167,113 +165,235 @@ __device__ __forceinline__ void block_bitonic_sort_pairs(unsigned long long* key
   }
 }
 
-struct SelectParams {
-  const double* acc;  // [nq][n]
-  int64_t n;
-  int cq;             // slices (CTAs) per query
-  int kprime;         // power of two >= k
-  int cap;            // smem candidate capacity (power of two, >= kprime + kSelPerIter)
-  unsigned long long* list_key;  // [nq][cq][kprime]
-  uint32_t* list_idx;            // [nq][cq][kprime]
-};
+// ------------------------------------------------------------------------------------------------ top-k select v2
+// sample threshold -> collect -> radix select.  (1) per query, the k-th best positive score among the first 8192 docs is a
+// safe lower bound of the global k-th best; (2) one streaming pass collects every doc with score > 0 and >= bound
+// (~ N * k / 8192 docs) into a per-query buffer sized for the worst case; (3) one CTA per query finds the k-th largest
+// score by MSB-first radix select, breaks exact ties by ascending doc index with a second radix select, sorts the k
+// winners.  Exact for any score distribution (an unrepresentative sample only enlarges step 2's output).
+constexpr int kBmSample = 8192;
+constexpr int kBmStage = 12288;  // (key, idx) pairs staged in shared memory by the final kernel (144 KB)
+constexpr unsigned long long kPosZero = 0x8000000000000000ull;  // f64_orderable(+0.0)
 
-// Each CTA streams one contiguous slice of one query's scores in ascending doc order and keeps the K' best
-// (score desc, doc asc) among scores > 0.  Strict '>' against the running K'-th best is exact: a later doc that ties
-// with the K'-th best has a larger index and loses the tie-break anyway.
-__global__ void __launch_bounds__(kSelThreads, 1) bm25_select_kernel(const SelectParams p) {
-  extern __shared__ __align__(16) uint8_t ssm[];
-  unsigned long long* bkey = reinterpret_cast<unsigned long long*>(ssm);
-  uint32_t* bidx = reinterpret_cast<uint32_t*>(bkey + p.cap);
-  __shared__ int s_cnt;
-  __shared__ unsigned long long s_thr;  // orderable key of the K'-th best so far (0 = none)
-  const int tid = threadIdx.x;
-  const int slice = blockIdx.x, qi = blockIdx.y;
-  const int64_t per = (p.n + p.cq - 1) / p.cq;
-  const int64_t lo = (int64_t)slice * per, hi = min(p.n, lo + per);
-  const double* acc = p.acc + (size_t)qi * p.n;
-  if (tid == 0) {
-    s_cnt = 0;
-    s_thr = f64_orderable(0.0);  // only scores strictly greater than +0.0 qualify
-  }
-  __syncthreads();
-  const int trigger = p.cap - kSelPerIter;
-  for (int64_t base = lo; base < hi; base += kSelPerIter) {
-    const unsigned long long thr = s_thr;
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int64_t i = base + (int64_t)u * kSelThreads + tid;
-      if (i < hi) {
-        const double s = acc[i];
-        const unsigned long long ok = f64_orderable(s);
-        if (ok > thr && s == s) {
-          const int pos = atomicAdd(&s_cnt, 1);
-          bkey[pos] = ok;
-          bidx[pos] = (uint32_t)i;
-        }
-      }
+// K-th largest value among keys[0..n) (shared memory, every thread of the CTA participates); n >= K >= 1.
+__device__ unsigned long long block_kth_largest(const unsigned long long* keys, int n, int K, int* hist, int* scal) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  unsigned long long prefix = 0ull, mask = 0ull;
+  int need = K;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    for (int i = tid; i < 256; i += nt) hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+      const unsigned long long key = keys[i];
+      if ((key & mask) == prefix) atomicAdd(&hist[(int)((key >> shift) & 0xffull)], 1);
     }
     __syncthreads();
-    const int c = s_cnt;
-    if (c > trigger) {
-      for (int z = c + tid; z < p.cap; z += kSelThreads) {
-        bkey[z] = 0ull;
-        bidx[z] = 0xffffffffu;
+    if (tid == 0) {
+      int cum = 0, sel = 0;
+      for (int b = 255; b >= 0; --b) {
+        const int c = hist[b];
+        if (cum + c >= need) {
+          sel = b;
+          break;
+        }
+        cum += c;
       }
-      __syncthreads();
-      block_bitonic_sort_pairs<kSelThreads>(bkey, bidx, p.cap, tid);
-      if (tid == 0) {
-        s_cnt = min(c, p.kprime);
-        if (c >= p.kprime) s_thr = bkey[p.kprime - 1];
-      }
-      __syncthreads();
+      scal[0] = sel;
+      scal[1] = need - cum;
     }
+    __syncthreads();
+    prefix |= (unsigned long long)scal[0] << shift;
+    mask |= 0xffull << shift;
+    need = scal[1];
+    __syncthreads();
   }
+  return prefix;
+}
+
+__global__ void __launch_bounds__(1024, 1) bm25_sample_thr_kernel(const double* __restrict__ acc, int64_t n, int k,
+                                                                  unsigned long long* __restrict__ thr,
+                                                                  int32_t* __restrict__ cnt) {
+  extern __shared__ __align__(16) uint8_t ssm2[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(ssm2);
+  __shared__ int hist[256];
+  __shared__ int scal[2];
+  __shared__ int npos;
+  const int qi = blockIdx.x, tid = threadIdx.x;
+  const int ns = (int)min((int64_t)kBmSample, n);
+  if (tid == 0) npos = 0;
   __syncthreads();
-  const int c = s_cnt;
-  for (int z = c + tid; z < p.cap; z += kSelThreads) {
-    bkey[z] = 0ull;
-    bidx[z] = 0xffffffffu;
+  int local = 0;
+  for (int i = tid; i < ns; i += blockDim.x) {
+    const double s = acc[(size_t)qi * n + i];
+    const unsigned long long key = (s > 0.0) ? f64_orderable(s) : 0ull;
+    keys[i] = key;
+    local += key != 0ull;
   }
+  atomicAdd(&npos, local);
   __syncthreads();
-  block_bitonic_sort_pairs<kSelThreads>(bkey, bidx, p.cap, tid);
-  unsigned long long* ok = p.list_key + ((size_t)qi * p.cq + slice) * p.kprime;
-  uint32_t* oi = p.list_idx + ((size_t)qi * p.cq + slice) * p.kprime;
-  for (int z = tid; z < p.kprime; z += kSelThreads) {
-    ok[z] = bkey[z];
-    oi[z] = bidx[z];
+  unsigned long long t = kPosZero + 1ull;  // "every positive score"
+  if (npos >= k) t = block_kth_largest(keys, ns, k, hist, scal);
+  if (tid == 0) {
+    thr[qi] = t;
+    cnt[qi] = 0;
   }
 }
 
-// One CTA per query: sort the cq * K' surviving pairs, emit the first k (ids = id_base + doc, fp64 scores, count).
-__global__ void __launch_bounds__(kSelThreads, 1) bm25_final_kernel(const unsigned long long* list_key,
-                                                                    const uint32_t* list_idx, int cq, int kprime,
-                                                                    int len_pow2, int k, int64_t id_base,
-                                                                    int64_t* out_ids, double* out_scores,
-                                                                    int32_t* out_counts) {
-  extern __shared__ __align__(16) uint8_t fsm[];
-  unsigned long long* key = reinterpret_cast<unsigned long long*>(fsm);
-  uint32_t* idx = reinterpret_cast<uint32_t*>(key + len_pow2);
-  const int tid = threadIdx.x, qi = blockIdx.x;
-  const int total = cq * kprime;
-  for (int i = tid; i < len_pow2; i += kSelThreads) {
-    key[i] = i < total ? list_key[(size_t)qi * total + i] : 0ull;
-    idx[i] = i < total ? list_idx[(size_t)qi * total + i] : 0xffffffffu;
+__global__ void __launch_bounds__(256) bm25_collect_kernel(const double* __restrict__ acc, int64_t n,
+                                                           const unsigned long long* __restrict__ thr,
+                                                           int32_t* __restrict__ cnt,
+                                                           unsigned long long* __restrict__ ckey,
+                                                           uint32_t* __restrict__ cidx) {
+  const int qi = blockIdx.y, lane = threadIdx.x & 31;
+  const unsigned long long t = thr[qi];
+  const double* a = acc + (size_t)qi * n;
+  unsigned long long* ok = ckey + (size_t)qi * n;
+  uint32_t* oi = cidx + (size_t)qi * n;
+  const int64_t base = (int64_t)blockIdx.x * (256 * 8);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int64_t i = base + (int64_t)u * 256 + threadIdx.x;
+    unsigned long long key = 0ull;
+    if (i < n) key = f64_orderable(a[i]);
+    const bool pass = i < n && key > kPosZero && key >= t && key != 0xffffffffffffffffull;
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (m) {
+      int pos = 0;
+      if (lane == 0) pos = atomicAdd(&cnt[qi], __popc(m));
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+      if (pass) {
+        const int at = pos + __popc(m & ((1u << lane) - 1u));
+        ok[at] = key;
+        oi[at] = (uint32_t)i;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024, 1) bm25_final_select_kernel(const unsigned long long* __restrict__ ckey,
+                                                                    const uint32_t* __restrict__ cidx,
+                                                                    const int32_t* __restrict__ cnt, int64_t n_docs,
+                                                                    int k, int kpow2, int64_t id_base,
+                                                                    int64_t* __restrict__ out_ids,
+                                                                    double* __restrict__ out_scores,
+                                                                    int32_t* __restrict__ out_counts) {
+  extern __shared__ __align__(16) uint8_t fsm2[];
+  unsigned long long* skey = reinterpret_cast<unsigned long long*>(fsm2);   // [kBmStage]
+  uint32_t* sidx = reinterpret_cast<uint32_t*>(skey + kBmStage);            // [kBmStage]
+  unsigned long long* wkey = reinterpret_cast<unsigned long long*>(sidx + kBmStage);  // [kpow2]
+  uint32_t* widx = reinterpret_cast<uint32_t*>(wkey + kpow2);                           // [kpow2]
+  __shared__ int hist[256];
+  __shared__ int scal[4];
+  const int qi = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int n = cnt[qi];
+  const unsigned long long* gk = ckey + (size_t)qi * n_docs;
+  const uint32_t* gi = cidx + (size_t)qi * n_docs;
+  const bool staged = n <= kBmStage;
+  if (staged) {
+    for (int i = tid; i < n; i += nt) {
+      skey[i] = gk[i];
+      sidx[i] = gi[i];
+    }
+  }
+  const unsigned long long* K_ = staged ? skey : gk;
+  const uint32_t* I_ = staged ? sidx : gi;
+  __syncthreads();
+  unsigned long long T = 0ull;        // k-th largest score key; winners: key > T, or key == T with idx <= Icut
+  uint32_t Icut = 0xffffffffu;
+  if (n > k) {
+    // (a) k-th largest key
+    unsigned long long prefix = 0ull, mask = 0ull;
+    int need = k;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+      for (int i = tid; i < 256; i += nt) hist[i] = 0;
+      __syncthreads();
+      for (int i = tid; i < n; i += nt) {
+        const unsigned long long key = K_[i];
+        if ((key & mask) == prefix) atomicAdd(&hist[(int)((key >> shift) & 0xffull)], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int cum = 0, sel = 0;
+        for (int b = 255; b >= 0; --b) {
+          const int c = hist[b];
+          if (cum + c >= need) {
+            sel = b;
+            break;
+          }
+          cum += c;
+        }
+        scal[0] = sel;
+        scal[1] = need - cum;
+      }
+      __syncthreads();
+      prefix |= (unsigned long long)scal[0] << shift;
+      mask |= 0xffull << shift;
+      need = scal[1];
+      __syncthreads();
+    }
+    T = prefix;
+    const int m = need;  // how many docs with key == T belong to the top k (1 <= m <= #equal)
+    // (b) m-th smallest doc index among key == T
+    uint32_t ipre = 0u, imask = 0u;
+    int ineed = m;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      for (int i = tid; i < 256; i += nt) hist[i] = 0;
+      __syncthreads();
+      for (int i = tid; i < n; i += nt) {
+        if (K_[i] == T) {
+          const uint32_t ix = I_[i];
+          if ((ix & imask) == ipre) atomicAdd(&hist[(int)((ix >> shift) & 0xffu)], 1);
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int cum = 0, sel = 255;
+        for (int b = 0; b < 256; ++b) {
+          const int c = hist[b];
+          if (cum + c >= ineed) {
+            sel = b;
+            break;
+          }
+          cum += c;
+        }
+        scal[0] = sel;
+        scal[1] = ineed - cum;
+      }
+      __syncthreads();
+      ipre |= (uint32_t)scal[0] << shift;
+      imask |= 0xffu << shift;
+      ineed = scal[1];
+      __syncthreads();
+    }
+    Icut = ipre;
+  }
+  // gather the winners, then order them (score desc, doc asc)
+  if (tid == 0) scal[2] = 0;
+  for (int i = tid; i < kpow2; i += nt) {
+    wkey[i] = 0ull;
+    widx[i] = 0xffffffffu;
   }
   __syncthreads();
-  if (cq > 1) block_bitonic_sort_pairs<kSelThreads>(key, idx, len_pow2, tid);
-  for (int i = tid; i < k; i += kSelThreads) {
-    const bool valid = i < len_pow2 && key[i] != 0ull;
-    out_ids[(size_t)qi * k + i] = valid ? id_base + (int64_t)idx[i] : -1;
-    out_scores[(size_t)qi * k + i] = valid ? orderable_f64(key[i]) : 0.0;
-  }
-  if (tid == 0) {
-    int lo = 0, hi = min(k, len_pow2);
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (key[mid] != 0ull) lo = mid + 1; else hi = mid;
+  for (int i = tid; i < n; i += nt) {
+    const unsigned long long key = K_[i];
+    const uint32_t ix = I_[i];
+    if (key > T || (key == T && ix <= Icut)) {
+      const int at = atomicAdd(&scal[2], 1);
+      if (at < kpow2) {
+        wkey[at] = key;
+        widx[at] = ix;
+      }
     }
-    out_counts[qi] = lo;
   }
+  __syncthreads();
+  block_bitonic_sort_pairs<1024>(wkey, widx, kpow2, tid);
+  const int nw = min(min(scal[2], k), kpow2);
+  for (int i = tid; i < k; i += nt) {
+    const bool valid = i < nw;
+    out_ids[(size_t)qi * k + i] = valid ? id_base + (int64_t)widx[i] : -1;
+    out_scores[(size_t)qi * k + i] = valid ? orderable_f64(wkey[i]) : 0.0;
+  }
+  if (tid == 0) out_counts[qi] = nw;
 }
 
 int pow2_at_least(int v) {
@@ -347,39 +467,33 @@ int bm25_topk_enqueue(sb_ctx* ctx, const int32_t* q_terms_dev, const int32_t* q_
   if (rc) return rc;
   if (ix.variant == SB_BM25_PLUS)
     SB_CUDA(cudaMemsetAsync(ctx->acc_dev.p, 0, per_q * sbq, st));  // ratio scratch must start at zero
-  const int kprime = std::max(32, pow2_at_least(k));
-  SB_REQUIRE(kprime <= 1024, SB_ERR_UNSUPPORTED, "bm25: top_k %d too large (max 1024)", k);
-  const int cap = std::max(2 * kSelPerIter, pow2_at_least(kprime + kSelPerIter));
-  int cq = (2 * ctx->num_sms + sbq - 1) / sbq;
-  cq = std::max(1, std::min(cq, 16));
-  while (cq > 1 && (int64_t)cq * kSelPerIter > ix.n_docs) cq >>= 1;
-  while (cq * kprime > 8192) cq >>= 1;
-  const int len_pow2 = pow2_at_least(cq * kprime);
-  if ((rc = ctx->misc2_dev.reserve((size_t)sbq * cq * kprime * 8))) return rc;
-  if ((rc = ctx->misc3_dev.reserve((size_t)sbq * cq * kprime * 4))) return rc;
-  const size_t sel_smem = (size_t)cap * 12;
-  const size_t fin_smem = (size_t)len_pow2 * 12;
-  SB_CUDA(cudaFuncSetAttribute(bm25_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
-  SB_CUDA(cudaFuncSetAttribute(bm25_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+  const int kpow2 = std::max(32, pow2_at_least(k));
+  SB_REQUIRE(kpow2 <= 1024, SB_ERR_UNSUPPORTED, "bm25: top_k %d too large (max 1024)", k);
+  // select v2 scratch: thresholds + counters + worst-case (key, idx) buffers of the sub-batch
+  if ((rc = ctx->misc2_dev.reserve((size_t)sbq * ix.n_docs * 8 + (size_t)sbq * 16 + 64))) return rc;
+  if ((rc = ctx->misc3_dev.reserve((size_t)sbq * ix.n_docs * 4 + 64))) return rc;
+  unsigned long long* ckey = ctx->misc2_dev.as<unsigned long long>();
+  unsigned long long* thr = ckey + (size_t)sbq * ix.n_docs;
+  int32_t* cnt = reinterpret_cast<int32_t*>(thr + sbq);
+  uint32_t* cidx = ctx->misc3_dev.as<uint32_t>();
+  const size_t samp_smem = (size_t)kBmSample * 8;
+  const size_t fin_smem = (size_t)kBmStage * 12 + (size_t)kpow2 * 12 + 64;
+  SB_CUDA(cudaFuncSetAttribute(bm25_sample_thr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)samp_smem));
+  SB_CUDA(cudaFuncSetAttribute(bm25_final_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
   for (int b0 = 0; b0 < B; b0 += sbq) {
     const int nq = std::min(sbq, B - b0);
     double* acc = ctx->acc_dev.as<double>();
     double* scratch = acc + (size_t)sbq * ix.n_docs;  // Plus only; fixed offset so it is always all-zero on entry
     if ((rc = bm25_score_subbatch(ctx, q_terms_dev, q_off_dev + b0, nq, max_len, acc, scratch, st))) return rc;
-    SelectParams sp;
-    sp.acc = ctx->acc_dev.as<double>();
-    sp.n = ix.n_docs;
-    sp.cq = cq;
-    sp.kprime = kprime;
-    sp.cap = cap;
-    sp.list_key = ctx->misc2_dev.as<unsigned long long>();
-    sp.list_idx = ctx->misc3_dev.as<uint32_t>();
-    ProfScope ps(ctx, SB_PROF_BM25_SELECT, st, 2);
-    bm25_select_kernel<<<dim3(cq, nq), kSelThreads, sel_smem, st>>>(sp);
+    ProfScope ps(ctx, SB_PROF_BM25_SELECT, st, 3);
+    bm25_sample_thr_kernel<<<nq, 1024, samp_smem, st>>>(acc, ix.n_docs, k, thr, cnt);
     SB_CUDA(cudaGetLastError());
-    bm25_final_kernel<<<nq, kSelThreads, fin_smem, st>>>(sp.list_key, sp.list_idx, cq, kprime, len_pow2, k,
-                                                         ix.id_base, out_ids + (size_t)b0 * k,
-                                                         out_scores + (size_t)b0 * k, out_counts + b0);
+    dim3 cg((unsigned)((ix.n_docs + 2047) / 2048), (unsigned)nq);
+    bm25_collect_kernel<<<cg, 256, 0, st>>>(acc, ix.n_docs, thr, cnt, ckey, cidx);
+    SB_CUDA(cudaGetLastError());
+    bm25_final_select_kernel<<<nq, 1024, fin_smem, st>>>(ckey, cidx, cnt, ix.n_docs, k, kpow2, ix.id_base,
+                                                         out_ids + (size_t)b0 * k, out_scores + (size_t)b0 * k,
+                                                         out_counts + b0);
     SB_CUDA(cudaGetLastError());
   }
   return SB_OK;

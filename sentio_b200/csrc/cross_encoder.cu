@@ -143,7 +143,7 @@ __global__ void ce_ln_kernel(const float* __restrict__ pre, int M, const float* 
   }
 }
 
-// Masked softmax attention, one CTA per (pair, head), one thread per query row; K/V of the head staged in smem as fp32.
+// Long-sequence fallback (S > 256): masked softmax attention, one CTA per (pair, head), one thread per query row; K/V of the head staged in smem as fp32.
 // Single pass online softmax (running max / sum), scores never leave registers.
 template <int DH>
 __global__ void __launch_bounds__(128) ce_attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ lengths,
@@ -202,6 +202,140 @@ __global__ void __launch_bounds__(128) ce_attention_kernel(const __half* __restr
 #pragma unroll
     for (int c = 0; c < DH; c += 2)
       *reinterpret_cast<__half2*>(out + c) = __floats2half2_rn(acc[c] * inv, acc[c + 1] * inv);
+  }
+}
+
+// Masked softmax attention on the tensor cores.  One CTA per (pair, head), 4 warps x 32 query rows; the head's K and V
+// (S x 32 fp16) are staged in shared memory (rows padded to 80 B: conflict-free fragment loads / ldmatrix), scores
+// S = Q K^T and O = P V are mma.sync.m16n8k16 (fp16 in, fp32 accumulate), the softmax runs on the accumulator fragments
+// in registers and the probabilities are re-used directly as the A operand of the second product (no smem round trip).
+// Rows >= len are padding (never consumed downstream): they are written as zeros.
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int S_MAX>
+__global__ void __launch_bounds__(128) ce_attention_mma_kernel(const __half* __restrict__ qkv,
+                                                                const int32_t* __restrict__ lengths, int S, int H,
+                                                                int heads, __half* __restrict__ ctx) {
+  constexpr int DH = 32, LDS_ROW = 40;  // halves per padded smem row (80 B)
+  constexpr int NT = S_MAX / 8;         // key tiles of 8
+  __shared__ __align__(16) __half Ks[S_MAX * LDS_ROW];
+  __shared__ __align__(16) __half Vs[S_MAX * LDS_ROW];
+  const int pair = blockIdx.x / heads, head = blockIdx.x % heads;
+  const int len = min(max(lengths[pair], 1), S);
+  const size_t row0 = (size_t)pair * S;
+  const int ld = 3 * H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  // stage K and V (rows >= len as zeros so that masked products stay finite)
+  for (int i = tid; i < S_MAX * 4; i += 128) {
+    const int j = i >> 2, c = (i & 3) * 8;
+    uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = make_uint4(0u, 0u, 0u, 0u);
+    if (j < len) {
+      kv = *reinterpret_cast<const uint4*>(qkv + (row0 + j) * ld + H + head * DH + c);
+      vv = *reinterpret_cast<const uint4*>(qkv + (row0 + j) * ld + 2 * H + head * DH + c);
+    }
+    *reinterpret_cast<uint4*>(Ks + j * LDS_ROW + c) = kv;
+    *reinterpret_cast<uint4*>(Vs + j * LDS_ROW + c) = vv;
+  }
+  __syncthreads();
+  const float scale = rsqrtf((float)DH);
+#pragma unroll 1
+  for (int mt = 0; mt < 2; ++mt) {
+    const int r0 = warp * 32 + mt * 16;  // first query row of this 16-row tile
+    if (r0 >= S) break;
+    __half* out_lo = ctx + (row0 + r0 + g) * H + head * DH;
+    __half* out_hi = ctx + (row0 + r0 + g + 8) * H + head * DH;
+    if (r0 >= len) {  // whole tile is padding
+      if (r0 + g < S) for (int c = 2 * t; c < DH; c += 8) *reinterpret_cast<uint32_t*>(out_lo + c) = 0u;
+      if (r0 + g + 8 < S) for (int c = 2 * t; c < DH; c += 8) *reinterpret_cast<uint32_t*>(out_hi + c) = 0u;
+      continue;
+    }
+    // Q fragments (A operand) for the two k-steps of 16: rows g / g+8, columns 2t.. and 2t+8..
+    uint32_t qa[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const __half* qlo = qkv + (row0 + min(r0 + g, S - 1)) * ld + head * DH + ks * 16 + 2 * t;
+      const __half* qhi = qkv + (row0 + min(r0 + g + 8, S - 1)) * ld + head * DH + ks * 16 + 2 * t;
+      qa[ks][0] = *reinterpret_cast<const uint32_t*>(qlo);
+      qa[ks][1] = *reinterpret_cast<const uint32_t*>(qhi);
+      qa[ks][2] = *reinterpret_cast<const uint32_t*>(qlo + 8);
+      qa[ks][3] = *reinterpret_cast<const uint32_t*>(qhi + 8);
+    }
+    float sc[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const __half* kp = Ks + (nt * 8 + g) * LDS_ROW + ks * 16 + 2 * t;
+        mma_16816(sc[nt], qa[ks], *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 8));
+      }
+    }
+    // masked softmax over the keys; a row's values live in the 4 lanes sharing g
+    float mlo = -INFINITY, mhi = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int key = nt * 8 + 2 * t;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool ok = key + e < len;
+        sc[nt][e] = ok ? sc[nt][e] * scale : -INFINITY;
+        sc[nt][2 + e] = ok ? sc[nt][2 + e] * scale : -INFINITY;
+        mlo = fmaxf(mlo, sc[nt][e]);
+        mhi = fmaxf(mhi, sc[nt][2 + e]);
+      }
+    }
+    mlo = fmaxf(mlo, __shfl_xor_sync(0xffffffffu, mlo, 1));
+    mlo = fmaxf(mlo, __shfl_xor_sync(0xffffffffu, mlo, 2));
+    mhi = fmaxf(mhi, __shfl_xor_sync(0xffffffffu, mhi, 1));
+    mhi = fmaxf(mhi, __shfl_xor_sync(0xffffffffu, mhi, 2));
+    float llo = 0.f, lhi = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        sc[nt][e] = __expf(sc[nt][e] - mlo);
+        sc[nt][2 + e] = __expf(sc[nt][2 + e] - mhi);
+        llo += sc[nt][e];
+        lhi += sc[nt][2 + e];
+      }
+    }
+    llo += __shfl_xor_sync(0xffffffffu, llo, 1);
+    llo += __shfl_xor_sync(0xffffffffu, llo, 2);
+    lhi += __shfl_xor_sync(0xffffffffu, lhi, 1);
+    lhi += __shfl_xor_sync(0xffffffffu, lhi, 2);
+    // O = P V : P fragments come straight from the score accumulators, V fragments via ldmatrix.trans
+    float oc[DH / 8][4];
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) oc[n][0] = oc[n][1] = oc[n][2] = oc[n][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < NT / 2; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack_h2(sc[2 * kk][0], sc[2 * kk][1]);
+      pa[1] = pack_h2(sc[2 * kk][2], sc[2 * kk][3]);
+      pa[2] = pack_h2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+      pa[3] = pack_h2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+#pragma unroll
+      for (int n = 0; n < DH / 8; ++n) {
+        uint32_t b0, b1;
+        const uint32_t addr = smem_u32(Vs + (kk * 16 + (lane & 15)) * LDS_ROW + n * 8);
+        asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(addr));
+        mma_16816(oc[n], pa, b0, b1);
+      }
+    }
+    const float ilo = 1.f / llo, ihi = 1.f / lhi;
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) {
+      if (r0 + g < S) *reinterpret_cast<uint32_t*>(out_lo + n * 8 + 2 * t) = pack_h2(oc[n][0] * ilo, oc[n][1] * ilo);
+      if (r0 + g + 8 < S) *reinterpret_cast<uint32_t*>(out_hi + n * 8 + 2 * t) = pack_h2(oc[n][2] * ihi, oc[n][3] * ihi);
+    }
   }
 }
 
@@ -297,14 +431,19 @@ int ce_forward(sb_ctx* ctx, CeModel* m, const int32_t* ids, const int32_t* tts, 
                                                                    m->word_emb, m->pos_emb, m->type_emb, m->emb_ln_g,
                                                                    m->emb_ln_b, c.ln_eps, m->x32, m->x16);
   SB_CUDA(cudaGetLastError());
-  const size_t att_smem = (size_t)2 * S * 32 * sizeof(float);
-  if (att_smem > 48 * 1024)
-    SB_CUDA(cudaFuncSetAttribute(ce_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
   int rc;
   for (CeLayer& L : m->layers) {
     if ((rc = ce_gemm_launch(CE_EPI_BIAS_F16, m->m_x16, L.m_wqkv, Mp, 3 * H, H, L.bqkv, nullptr, m->qkv16, nullptr, st)))
       return rc;
-    ce_attention_kernel<32><<<P * heads, 128, att_smem, st>>>(m->qkv16, lens, S, H, heads, m->ctx16);
+    if (S <= 128)
+      ce_attention_mma_kernel<128><<<P * heads, 128, 0, st>>>(m->qkv16, lens, S, H, heads, m->ctx16);
+    else if (S <= 256)
+      ce_attention_mma_kernel<256><<<P * heads, 128, 0, st>>>(m->qkv16, lens, S, H, heads, m->ctx16);
+    else {
+      const size_t att_smem = (size_t)2 * S * 32 * sizeof(float);
+      SB_CUDA(cudaFuncSetAttribute(ce_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
+      ce_attention_kernel<32><<<P * heads, 128, att_smem, st>>>(m->qkv16, lens, S, H, heads, m->ctx16);
+    }
     SB_CUDA(cudaGetLastError());
     if ((rc = ce_gemm_launch(CE_EPI_BIAS_RES_F32, m->m_ctx16, L.m_wo, Mp, H, H, L.bo, m->x32, nullptr, m->pre32, st)))
       return rc;

@@ -149,12 +149,13 @@ class B200Engine:
 
     @staticmethod
     def pack_queries(term_id_lists: Sequence[Sequence[int]]):
+        """-> (flat int32 term ids (at least one slot), CSR offsets int32 [B+1])"""
+        lens = np.fromiter((len(t) for t in term_id_lists), dtype=np.int32, count=len(term_id_lists))
         off = np.zeros(len(term_id_lists) + 1, dtype=np.int32)
-        for i, t in enumerate(term_id_lists):
-            off[i + 1] = off[i] + len(t)
-        flat = np.zeros(max(int(off[-1]), 1), dtype=np.int32)
-        for i, t in enumerate(term_id_lists):
-            flat[off[i]:off[i + 1]] = np.asarray(t, dtype=np.int32)
+        np.cumsum(lens, out=off[1:])
+        if int(off[-1]) == 0:
+            return np.zeros(1, dtype=np.int32), off
+        flat = np.concatenate([np.asarray(t, dtype=np.int32) for t in term_id_lists])
         return flat, off
 
     def bm25_topk(self, term_id_lists: Sequence[Sequence[int]], k: int):

@@ -65,11 +65,18 @@ class HybridPipeline:
             self._bufs[name] = t
         return t
 
-    def _to_dev(self, arr: np.ndarray):
+    def _to_dev(self, arr: np.ndarray, name: str = "in"):
+        """host array -> device tensor through a cached pinned staging buffer (one per call-site name and shape)."""
         t = self.torch.from_numpy(arr)
         if self.device is None:
             return t
-        return t.pin_memory().to(self._torch_device, non_blocking=True)
+        key = ("pin", name, tuple(arr.shape), arr.dtype.str)
+        pin = self._bufs.get(key)
+        if pin is None:
+            pin = self.torch.empty(arr.shape, dtype=t.dtype, pin_memory=True)
+            self._bufs[key] = pin
+        pin.copy_(t)
+        return pin.to(self._torch_device, non_blocking=True)
 
     def _record_layout(self, B: int, k: int, signals: int):
         """Byte layout of one rank's all-gather record: per signal ids[B,k] i64 | scores[B,k] f64 | counts[B] i32."""
@@ -155,7 +162,7 @@ class HybridPipeline:
         if self.world == 1:
             return self.engine.dense_topk(q, k)
         t = self.torch
-        q_t = self._to_dev(np.ascontiguousarray(q, dtype=np.float32))
+        q_t = self._to_dev(np.ascontiguousarray(q, dtype=np.float32), "q")
         ids, sc, cnt = self.dense_dev(q_t, k)
         return ids.cpu().numpy(), sc.cpu().numpy(), cnt.cpu().numpy()
 
@@ -163,9 +170,9 @@ class HybridPipeline:
                       rrf_k: float = 60, w_dense: float = 0.5, w_sparse: float = 0.5):
         flat, off = B200Engine.pack_queries(term_lists)
         max_len = int(np.diff(off).max()) if len(off) > 1 else 0
-        q_t = self._to_dev(np.ascontiguousarray(q, dtype=np.float32))
-        terms_t = self._to_dev(flat)
-        off_t = self._to_dev(off)
+        q_t = self._to_dev(np.ascontiguousarray(q, dtype=np.float32), "q")
+        terms_t = self._to_dev(flat, "terms")
+        off_t = self._to_dev(off, "off")
         ids, sc, src, cnt = self.hybrid_dev(q_t, terms_t, off_t, int(off[-1]), max_len, k, method, rrf_k, w_dense,
                                             w_sparse)
         return ids.cpu().numpy(), sc.cpu().numpy(), src.cpu().numpy(), cnt.cpu().numpy()
@@ -175,10 +182,10 @@ class HybridPipeline:
                              w_sparse: float = 0.5):
         flat, off = B200Engine.pack_queries(term_lists)
         max_len = int(np.diff(off).max()) if len(off) > 1 else 0
-        q_t = self._to_dev(np.ascontiguousarray(q, dtype=np.float32))
-        terms_t, off_t = self._to_dev(flat), self._to_dev(off)
-        qt_t = self._to_dev(np.ascontiguousarray(q_tok, dtype=np.int32))
-        ql_t = self._to_dev(np.ascontiguousarray(q_len, dtype=np.int32))
+        q_t = self._to_dev(np.ascontiguousarray(q, dtype=np.float32), "q")
+        terms_t, off_t = self._to_dev(flat, "terms"), self._to_dev(off, "off")
+        qt_t = self._to_dev(np.ascontiguousarray(q_tok, dtype=np.int32), "qtok")
+        ql_t = self._to_dev(np.ascontiguousarray(q_len, dtype=np.int32), "qlen")
         ids, sc, cnt = self.hybrid_rerank_dev(q_t, terms_t, off_t, int(off[-1]), max_len, qt_t, ql_t, k, k_out, seq_len,
                                               method, rrf_k, w_dense, w_sparse)
         return ids.cpu().numpy(), sc.cpu().numpy(), cnt.cpu().numpy()
