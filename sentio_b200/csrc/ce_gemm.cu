@@ -13,6 +13,8 @@
 // Bound: tensor pipe (2*M*N*K flops); see DESIGN.md for the per-pair flop count.
 #include <cuda.h>
 
+#include <algorithm>
+
 #include "ce_gemm.cuh"
 
 namespace {
@@ -209,6 +211,202 @@ ce_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------------ weight-stationary
+// Persistent variant for K <= 384 (QKV / attention-out / FFN-up): the 128 x K weight tile of this CTA's n-tile stays in
+// shared memory for the whole kernel and only activation tiles stream through the TMA ring, which halves the L2 -> SM
+// traffic per output tile (the 128 x 128 x 384 tiles of the plain kernel are L2-bandwidth bound at ~64 flop/B); the
+// accumulator is double buffered in tensor memory so the epilogue of tile i overlaps the MMAs of tile i + 1.
+constexpr int kWsStages = 5;
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_store_32(const uint32_t (&v)[32], int row, int col, int N,
+                                                  const float* __restrict__ bias, const float* __restrict__ residual,
+                                                  __half* __restrict__ out16, float* __restrict__ out32) {
+  if (EPI == CE_EPI_BIAS_RES_F32) {
+    float* o = out32 + (size_t)row * N + col;
+    const float* r = residual + (size_t)row * N + col;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 rb = *reinterpret_cast<const float4*>(r + j);
+      const float4 bb = *reinterpret_cast<const float4*>(bias + col + j);
+      float4 w;
+      w.x = __uint_as_float(v[j + 0]) + bb.x + rb.x;
+      w.y = __uint_as_float(v[j + 1]) + bb.y + rb.y;
+      w.z = __uint_as_float(v[j + 2]) + bb.z + rb.z;
+      w.w = __uint_as_float(v[j + 3]) + bb.w + rb.w;
+      *reinterpret_cast<float4*>(o + j) = w;
+    }
+  } else {
+    __half* o = out16 + (size_t)row * N + col;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float x = __uint_as_float(v[j + e]) + __ldg(bias + col + j + e);
+        f[e] = (EPI == CE_EPI_BIAS_GELU_F16) ? gelu_erf(x) : x;
+      }
+      uint4 pk;
+      const __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
+      const __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
+      pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+      pk.z = *reinterpret_cast<const uint32_t*>(&h2);
+      pk.w = *reinterpret_cast<const uint32_t*>(&h3);
+      *reinterpret_cast<uint4*>(o + j) = pk;
+    }
+  }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N,
+                  int K, const float* __restrict__ bias, const float* __restrict__ residual, __half* __restrict__ out16,
+                  float* __restrict__ out32) {
+  extern __shared__ uint8_t wsm_raw[];
+  const uint32_t raw = smem_u32(wsm_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = wsm_raw + (base - raw);
+  const int num_k = K / BK;
+  const uint32_t w_bytes = (uint32_t)num_k * kTileBBytes;
+  const uint32_t a0 = base + w_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + w_bytes + kWsStages * kTileABytes);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kWsStages), bar_w = smem_u32(bars + 2 * kWsStages);
+  const uint32_t bar_acc_full = smem_u32(bars + 2 * kWsStages + 1), bar_acc_empty = smem_u32(bars + 2 * kWsStages + 3);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWsStages + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = N / BN, m_tiles = (M + BM - 1) / BM;
+  // this CTA's n-tile and its share of the m-tiles
+  const int n_tile = blockIdx.x % n_tiles;
+  const int peer = blockIdx.x / n_tiles;                                   // index among the CTAs of this n-tile
+  const int peers = ((int)gridDim.x - n_tile + n_tiles - 1) / n_tiles;     // CTAs that own this n-tile
+  const int my_tiles = peer < m_tiles ? (m_tiles - 1 - peer) / peers + 1 : 0;
+  const int n0 = n_tile * BN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWsStages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_w, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_acc_full + 8 * s, 1);
+      mbar_init(bar_acc_empty + 8 * s, 4);
+    }
+    mbar_fence_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(2 * BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_w, w_bytes);
+      for (int kb = 0; kb < num_k; ++kb) tma_load_2d(base + (uint32_t)kb * kTileBBytes, &map_w, kb * BK, n0, bar_w);
+      int it = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int m0 = (peer + t * peers) * BM;
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const int s = it % kWsStages;
+          const uint32_t use = (uint32_t)(it / kWsStages);
+          if (it >= kWsStages) mbar_wait(bar_empty + 8 * s, (use & 1u) ^ 1u);
+          mbar_expect_tx(bar_full + 8 * s, kTileABytes);
+          tma_load_2d(a0 + (uint32_t)s * kTileABytes, &map_a, kb * BK, m0, bar_full + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc();
+      mbar_wait(bar_w, 0);
+      int it = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int as = t & 1;
+        if (t >= 2) mbar_wait(bar_acc_empty + 8 * as, (((uint32_t)t >> 1) & 1u) ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const int s = it % kWsStages;
+          const uint32_t use = (uint32_t)(it / kWsStages);
+          mbar_wait(bar_full + 8 * s, use & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = make_smem_desc(a0 + (uint32_t)s * kTileABytes);
+          const uint64_t db = make_smem_desc(base + (uint32_t)kb * kTileBBytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(bar_empty + 8 * s);
+        }
+        umma_commit(bar_acc_full + 8 * as);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int as = t & 1;
+      const int row = (peer + t * peers) * BM + quad * 32 + lane;
+      mbar_wait(bar_acc_full + 8 * as, ((uint32_t)t >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c0 + 32 >= BN) {  // last read of this accumulator stage: hand it back before the (long) stores
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+        }
+        if (row < M) epilogue_store_32<EPI>(v, row, n0 + c0, N, bias, residual, out16, out32);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
+  }
+}
+
+template <int EPI>
+int launch_ws(const CUtensorMap& map_a, const CUtensorMap& map_w, int M, int N, int K, const float* bias,
+              const float* residual, __half* out16, float* out32, cudaStream_t st) {
+  const size_t smem = (size_t)(K / BK) * kTileBBytes + (size_t)kWsStages * kTileABytes + 1024 + 256;
+  static bool once = false;
+  if (!once) {
+    SB_CUDA(cudaFuncSetAttribute(ce_gemm_ws_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    once = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = (N / BN) * ((M + BM - 1) / BM);
+  const int grid = std::max(N / BN, std::min(sms, tiles));
+  ce_gemm_ws_kernel<EPI><<<grid, kGemmThreads, smem, st>>>(map_a, map_w, M, N, K, bias, residual, out16, out32);
+  SB_CUDA(cudaGetLastError());
+  return SB_OK;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -246,6 +444,15 @@ int ce_make_tensor_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t 
 int ce_gemm_launch(int epi, const CUtensorMap& map_a, const CUtensorMap& map_w, int M, int N, int K, const float* bias,
                    const float* residual, __half* out16, float* out32, cudaStream_t st) {
   SB_REQUIRE(N % BN == 0 && K % BK == 0, SB_ERR_ARG, "ce_gemm: N=%d / K=%d must be multiples of %d / %d", N, K, BN, BK);
+  if (K <= 384 && (M + BM - 1) / BM >= 4) {  // weight-stationary persistent kernel
+    switch (epi) {
+      case CE_EPI_BIAS_F16: return launch_ws<CE_EPI_BIAS_F16>(map_a, map_w, M, N, K, bias, residual, out16, out32, st);
+      case CE_EPI_BIAS_GELU_F16:
+        return launch_ws<CE_EPI_BIAS_GELU_F16>(map_a, map_w, M, N, K, bias, residual, out16, out32, st);
+      case CE_EPI_BIAS_RES_F32:
+        return launch_ws<CE_EPI_BIAS_RES_F32>(map_a, map_w, M, N, K, bias, residual, out16, out32, st);
+    }
+  }
   dim3 grid(N / BN, (M + BM - 1) / BM);
   switch (epi) {
     case CE_EPI_BIAS_F16: {

@@ -18,7 +18,10 @@ _erf = np.vectorize(math.erf)
 
 
 @pytest.mark.parametrize("M,N,K,epi", [(128, 128, 64, 0), (200, 256, 384, 0), (1000, 1152, 384, 0), (333, 1536, 384, 1),
-                                       (512, 384, 1536, 2), (77, 128, 128, 2)])
+                                       (512, 384, 1536, 2), (77, 128, 128, 2),
+                                       # >= 4 row tiles and K <= 384 -> weight-stationary persistent kernel
+                                       (2048, 384, 384, 2), (5000, 1536, 384, 1), (700, 128, 64, 0), (25600, 1152, 384, 0),
+                                       (513, 256, 192, 2)])
 def test_tcgen05_gemm_matches_numpy(engine, M, N, K, epi):
     rng = np.random.default_rng(M + N + K + epi)
     a = rng.standard_normal((M, K)).astype(np.float32)
