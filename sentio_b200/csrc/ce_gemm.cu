@@ -217,6 +217,10 @@ ce_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // traffic per output tile (the 128 x 128 x 384 tiles of the plain kernel are L2-bandwidth bound at ~64 flop/B); the
 // accumulator is double buffered in tensor memory so the epilogue of tile i overlaps the MMAs of tile i + 1.
 constexpr int kWsStages = 5;
+constexpr int kWsEpiWarps = 8;                      // 2 per TMEM lane quadrant, 64 accumulator columns each
+constexpr int kWsThreads = 64 + 32 * kWsEpiWarps;   // TMA warp + MMA warp + epilogue warps
+constexpr uint32_t kStageRow = 144;                 // bytes per staged row (128 B of payload + 16 B pad: conflict-free 128-bit stores)
+constexpr uint32_t kStageWarpBytes = 32 * kStageRow; // one epilogue warp's staging tile (32 rows)
 
 template <int EPI>
 __device__ __forceinline__ void epilogue_store_32(const uint32_t (&v)[32], int row, int col, int N,
@@ -258,8 +262,8 @@ __device__ __forceinline__ void epilogue_store_32(const uint32_t (&v)[32], int r
   }
 }
 
-template <int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int EPI, bool RESIDENT>
+__global__ void __launch_bounds__(kWsThreads, 1)
 ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N,
                   int K, const float* __restrict__ bias, const float* __restrict__ residual, __half* __restrict__ out16,
                   float* __restrict__ out32) {
@@ -268,21 +272,33 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = wsm_raw + (base - raw);
   const int num_k = K / BK;
-  const uint32_t w_bytes = (uint32_t)num_k * kTileBBytes;
+  // RESIDENT: [W: num_k x 16 KB][A ring: stages x 16 KB]      streaming: [ring: stages x (A 16 KB + W 16 KB)]
+  constexpr uint32_t kRingStage = RESIDENT ? kTileABytes : kStageBytes;
+  const uint32_t w_bytes = RESIDENT ? (uint32_t)num_k * kTileBBytes : 0u;
   const uint32_t a0 = base + w_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + w_bytes + kWsStages * kTileABytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + w_bytes + kWsStages * kRingStage);
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kWsStages), bar_w = smem_u32(bars + 2 * kWsStages);
   const uint32_t bar_acc_full = smem_u32(bars + 2 * kWsStages + 1), bar_acc_empty = smem_u32(bars + 2 * kWsStages + 3);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWsStages + 5);
+  float* bias_s = reinterpret_cast<float*>(tmem_slot + 2);                        // [BN] bias of the current n-tile (x2)
+  uint8_t* stage_s = reinterpret_cast<uint8_t*>(bias_s + 2 * BN);                 // [kWsEpiWarps][32 rows][144 B]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = N / BN, m_tiles = (M + BM - 1) / BM;
-  // this CTA's n-tile and its share of the m-tiles
-  const int n_tile = blockIdx.x % n_tiles;
-  const int peer = blockIdx.x / n_tiles;                                   // index among the CTAs of this n-tile
-  const int peers = ((int)gridDim.x - n_tile + n_tiles - 1) / n_tiles;     // CTAs that own this n-tile
-  const int my_tiles = peer < m_tiles ? (m_tiles - 1 - peer) / peers + 1 : 0;
-  const int n0 = n_tile * BN;
+  // RESIDENT: this CTA owns one n-tile for its lifetime and a strided share of the m-tiles.
+  // streaming: tiles are enumerated n-fastest (consecutive CTAs share the same activation rows in L2).
+  const int n_tile_fixed = blockIdx.x % n_tiles;
+  const int peer = blockIdx.x / n_tiles;                                        // index among the CTAs of this n-tile
+  const int peers = ((int)gridDim.x - n_tile_fixed + n_tiles - 1) / n_tiles;    // CTAs that own this n-tile
+  const int total_tiles = n_tiles * m_tiles;
+  const int my_tiles = RESIDENT ? (peer < m_tiles ? (m_tiles - 1 - peer) / peers + 1 : 0)
+                                : ((int)blockIdx.x < total_tiles ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0);
+  auto tile_m0 = [&](int t) -> int {
+    return RESIDENT ? (peer + t * peers) * BM : (((int)blockIdx.x + t * (int)gridDim.x) / n_tiles) * BM;
+  };
+  auto tile_n0 = [&](int t) -> int {
+    return RESIDENT ? n_tile_fixed * BN : (((int)blockIdx.x + t * (int)gridDim.x) % n_tiles) * BN;
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWsStages; ++s) {
@@ -292,7 +308,7 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     mbar_init(bar_w, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_acc_full + 8 * s, 1);
-      mbar_init(bar_acc_empty + 8 * s, 4);
+      mbar_init(bar_acc_empty + 8 * s, kWsEpiWarps);
     }
     mbar_fence_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -311,24 +327,28 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(bar_w, w_bytes);
-      for (int kb = 0; kb < num_k; ++kb) tma_load_2d(base + (uint32_t)kb * kTileBBytes, &map_w, kb * BK, n0, bar_w);
+      if (RESIDENT) {
+        mbar_expect_tx(bar_w, w_bytes);
+        for (int kb = 0; kb < num_k; ++kb)
+          tma_load_2d(base + (uint32_t)kb * kTileBBytes, &map_w, kb * BK, n_tile_fixed * BN, bar_w);
+      }
       int it = 0;
       for (int t = 0; t < my_tiles; ++t) {
-        const int m0 = (peer + t * peers) * BM;
+        const int m0 = tile_m0(t), n0 = tile_n0(t);
         for (int kb = 0; kb < num_k; ++kb, ++it) {
           const int s = it % kWsStages;
           const uint32_t use = (uint32_t)(it / kWsStages);
           if (it >= kWsStages) mbar_wait(bar_empty + 8 * s, (use & 1u) ^ 1u);
-          mbar_expect_tx(bar_full + 8 * s, kTileABytes);
-          tma_load_2d(a0 + (uint32_t)s * kTileABytes, &map_a, kb * BK, m0, bar_full + 8 * s);
+          mbar_expect_tx(bar_full + 8 * s, kRingStage);
+          tma_load_2d(a0 + (uint32_t)s * kRingStage, &map_a, kb * BK, m0, bar_full + 8 * s);
+          if (!RESIDENT) tma_load_2d(a0 + (uint32_t)s * kRingStage + kTileABytes, &map_w, kb * BK, n0, bar_full + 8 * s);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc();
-      mbar_wait(bar_w, 0);
+      if (RESIDENT) mbar_wait(bar_w, 0);
       int it = 0;
       for (int t = 0; t < my_tiles; ++t) {
         const int as = t & 1;
@@ -340,8 +360,9 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const uint32_t use = (uint32_t)(it / kWsStages);
           mbar_wait(bar_full + 8 * s, use & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t da = make_smem_desc(a0 + (uint32_t)s * kTileABytes);
-          const uint64_t db = make_smem_desc(base + (uint32_t)kb * kTileBBytes);
+          const uint64_t da = make_smem_desc(a0 + (uint32_t)s * kRingStage);
+          const uint64_t db = make_smem_desc(RESIDENT ? base + (uint32_t)kb * kTileBBytes
+                                                       : a0 + (uint32_t)s * kRingStage + kTileABytes);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
@@ -351,16 +372,34 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
     }
   } else {
-    const int quad = warp & 3;
+    // ---------------------------------------------------------------- epilogue: 8 warps, warp e covers TMEM lane quadrant
+    // (warp & 3) and accumulator columns [64 * (e >> 2), +64).  Accumulator rows are transposed through a padded
+    // shared-memory tile so that every global access is a fully coalesced row segment (the thread-per-row direct
+    // stores of the simple kernel are LSU / latency bound, see profiles/).
+    const int e = warp - 2, quad = warp & 3, half = e >> 2;
+    uint8_t* st = stage_s + (size_t)e * kStageWarpBytes;
+    const uint32_t st_u32 = smem_u32(st);
+    int bias_n0 = -1;
     for (int t = 0; t < my_tiles; ++t) {
       const int as = t & 1;
-      const int row = (peer + t * peers) * BM + quad * 32 + lane;
+      const int row0 = tile_m0(t) + quad * 32;
+      const int n0 = tile_n0(t);
+      const int colw = n0 + half * 64;  // first global column of this warp
+      // bias of this n-tile in shared memory: loaded once when RESIDENT, per tile (parity double buffer) when streaming.
+      // The four quadrant-warps of one column half fill disjoint quarters and meet on a named barrier; because they
+      // meet at every reload, a warp can never run two tiles ahead of a reader of the buffer it overwrites.
+      float* bias_buf = bias_s + (RESIDENT ? 0 : (t & 1) * BN);
+      if (!RESIDENT || bias_n0 < 0) {
+        bias_buf[half * 64 + quad * 16 + (lane & 15)] = __ldg(bias + colw + quad * 16 + (lane & 15));
+        bias_n0 = n0;
+        asm volatile("bar.sync %0, %1;" ::"r"(3 + half), "r"(128) : "memory");
+      }
       mbar_wait(bar_acc_full + 8 * as, ((uint32_t)t >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int cc = 0; cc < 64; cc += 32) {
         uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c0);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + half * 64 + cc);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -372,14 +411,71 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             : "r"(taddr)
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c0 + 32 >= BN) {  // last read of this accumulator stage: hand it back before the (long) stores
+        if (cc == 32) {  // last read of this accumulator stage by this warp: hand it back to the MMA issuer
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
         }
-        if (row < M) epilogue_store_32<EPI>(v, row, n0 + c0, N, bias, residual, out16, out32);
+        const float* bs = bias_buf + half * 64 + cc;
+        if (EPI == CE_EPI_BIAS_RES_F32) {
+          // phase 1: acc + bias as fp32, this thread's row -> 128 B of the staging tile
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 w;
+            w.x = __uint_as_float(v[j + 0]) + bs[j + 0];
+            w.y = __uint_as_float(v[j + 1]) + bs[j + 1];
+            w.z = __uint_as_float(v[j + 2]) + bs[j + 2];
+            w.w = __uint_as_float(v[j + 3]) + bs[j + 3];
+            *reinterpret_cast<float4*>(st + (size_t)lane * kStageRow + (size_t)j * 4) = w;
+          }
+          __syncwarp();
+          // phase 2: one 128-byte row segment per instruction: + residual, fp32 out
+#pragma unroll 4
+          for (int r = 0; r < 32; ++r) {
+            const int row = row0 + r;
+            if (row < M) {
+              const size_t g = (size_t)row * N + colw + cc + lane;
+              const float x = *reinterpret_cast<const float*>(st + (size_t)r * kStageRow + (size_t)lane * 4);
+              out32[g] = x + __ldg(residual + g);
+            }
+          }
+          __syncwarp();
+        } else {
+          // phase 1: bias (+ GELU), fp16, this thread's row -> 64 B (half of a 128-B staged row per 32-column chunk)
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float f[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float x = __uint_as_float(v[j + q]) + bs[j + q];
+              f[q] = (EPI == CE_EPI_BIAS_GELU_F16) ? gelu_erf(x) : x;
+            }
+            uint4 pk;
+            const __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
+            const __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
+            pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+            pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<const uint32_t*>(&h2);
+            pk.w = *reinterpret_cast<const uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(st + (size_t)lane * kStageRow + (size_t)(cc + j) * 2) = pk;
+          }
+          if (cc == 32) {
+            __syncwarp();
+            // phase 2: 64 fp16 columns = one 128-byte row segment per instruction
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) {
+              const int row = row0 + r;
+              if (row < M) {
+                const uint32_t x = *reinterpret_cast<const uint32_t*>(st + (size_t)r * kStageRow + (size_t)lane * 4);
+                *reinterpret_cast<uint32_t*>(out16 + (size_t)row * N + colw + 2 * lane) = x;
+              }
+            }
+            __syncwarp();
+          }
+        }
       }
     }
+    (void)st_u32;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -388,21 +484,23 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   }
 }
 
-template <int EPI>
+template <int EPI, bool RESIDENT>
 int launch_ws(const CUtensorMap& map_a, const CUtensorMap& map_w, int M, int N, int K, const float* bias,
               const float* residual, __half* out16, float* out32, cudaStream_t st) {
-  const size_t smem = (size_t)(K / BK) * kTileBBytes + (size_t)kWsStages * kTileABytes + 1024 + 256;
-  static bool once = false;
-  if (!once) {
-    SB_CUDA(cudaFuncSetAttribute(ce_gemm_ws_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    once = true;
+  const size_t extra = 1024 /*align*/ + 256 /*barriers*/ + 2 * BN * 4 /*bias*/ + (size_t)kWsEpiWarps * kStageWarpBytes;
+  const size_t smem = RESIDENT ? (size_t)(K / BK) * kTileBBytes + (size_t)kWsStages * kTileABytes + extra
+                               : (size_t)kWsStages * kStageBytes + extra;
+  static size_t configured = 0;
+  if (configured < smem) {
+    SB_CUDA(cudaFuncSetAttribute(ce_gemm_ws_kernel<EPI, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = (N / BN) * ((M + BM - 1) / BM);
   const int grid = std::max(N / BN, std::min(sms, tiles));
-  ce_gemm_ws_kernel<EPI><<<grid, kGemmThreads, smem, st>>>(map_a, map_w, M, N, K, bias, residual, out16, out32);
+  ce_gemm_ws_kernel<EPI, RESIDENT><<<grid, kWsThreads, smem, st>>>(map_a, map_w, M, N, K, bias, residual, out16, out32);
   SB_CUDA(cudaGetLastError());
   return SB_OK;
 }
@@ -444,13 +542,25 @@ int ce_make_tensor_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t 
 int ce_gemm_launch(int epi, const CUtensorMap& map_a, const CUtensorMap& map_w, int M, int N, int K, const float* bias,
                    const float* residual, __half* out16, float* out32, cudaStream_t st) {
   SB_REQUIRE(N % BN == 0 && K % BK == 0, SB_ERR_ARG, "ce_gemm: N=%d / K=%d must be multiples of %d / %d", N, K, BN, BK);
-  if (K <= 384 && (M + BM - 1) / BM >= 4) {  // weight-stationary persistent kernel
-    switch (epi) {
-      case CE_EPI_BIAS_F16: return launch_ws<CE_EPI_BIAS_F16>(map_a, map_w, M, N, K, bias, residual, out16, out32, st);
-      case CE_EPI_BIAS_GELU_F16:
-        return launch_ws<CE_EPI_BIAS_GELU_F16>(map_a, map_w, M, N, K, bias, residual, out16, out32, st);
-      case CE_EPI_BIAS_RES_F32:
-        return launch_ws<CE_EPI_BIAS_RES_F32>(map_a, map_w, M, N, K, bias, residual, out16, out32, st);
+  if ((M + BM - 1) / BM >= 4) {  // persistent kernels: weight-stationary when the weight tile fits, streaming otherwise
+    if (K <= 384) {
+      switch (epi) {
+        case CE_EPI_BIAS_F16:
+          return launch_ws<CE_EPI_BIAS_F16, true>(map_a, map_w, M, N, K, bias, residual, out16, out32, st);
+        case CE_EPI_BIAS_GELU_F16:
+          return launch_ws<CE_EPI_BIAS_GELU_F16, true>(map_a, map_w, M, N, K, bias, residual, out16, out32, st);
+        case CE_EPI_BIAS_RES_F32:
+          return launch_ws<CE_EPI_BIAS_RES_F32, true>(map_a, map_w, M, N, K, bias, residual, out16, out32, st);
+      }
+    } else {
+      switch (epi) {
+        case CE_EPI_BIAS_F16:
+          return launch_ws<CE_EPI_BIAS_F16, false>(map_a, map_w, M, N, K, bias, residual, out16, out32, st);
+        case CE_EPI_BIAS_GELU_F16:
+          return launch_ws<CE_EPI_BIAS_GELU_F16, false>(map_a, map_w, M, N, K, bias, residual, out16, out32, st);
+        case CE_EPI_BIAS_RES_F32:
+          return launch_ws<CE_EPI_BIAS_RES_F32, false>(map_a, map_w, M, N, K, bias, residual, out16, out32, st);
+      }
     }
   }
   dim3 grid(N / BN, (M + BM - 1) / BM);
