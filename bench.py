@@ -360,7 +360,7 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms, "launches_timed": n_scan,
                 "queries_per_launch": (B * args.steps) / max(n_scan, 1), "share_of_step": scan_ms / ms_total}
     prof = os.path.join(ROOT, "profiles", "r01_dense_scan_ncu.json")
-    if os.path.exists(prof):
+    if os.path.exists(prof) and world == 1:
         try:
             roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:

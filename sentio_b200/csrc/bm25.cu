@@ -185,7 +185,11 @@ __device__ unsigned long long block_kth_largest(const unsigned long long* keys, 
     __syncthreads();
     for (int i = tid; i < n; i += nt) {
       const unsigned long long key = keys[i];
-      if ((key & mask) == prefix) atomicAdd(&hist[(int)((key >> shift) & 0xffull)], 1);
+      if ((key & mask) == prefix) {  // warp-aggregated: equal digits elect one lane (concentrated digits serialise)
+        const int dgt = (int)((key >> shift) & 0xffull);
+        const unsigned grp = __match_any_sync(__activemask(), dgt);
+        if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&hist[dgt], __popc(grp));
+      }
     }
     __syncthreads();
     if (tid == 0) {
@@ -309,7 +313,11 @@ __global__ void __launch_bounds__(1024, 1) bm25_final_select_kernel(const unsign
       __syncthreads();
       for (int i = tid; i < n; i += nt) {
         const unsigned long long key = K_[i];
-        if ((key & mask) == prefix) atomicAdd(&hist[(int)((key >> shift) & 0xffull)], 1);
+        if ((key & mask) == prefix) {
+          const int dgt = (int)((key >> shift) & 0xffull);
+          const unsigned grp = __match_any_sync(__activemask(), dgt);
+          if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&hist[dgt], __popc(grp));
+        }
       }
       __syncthreads();
       if (tid == 0) {

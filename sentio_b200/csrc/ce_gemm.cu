@@ -229,9 +229,9 @@ ce_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // traffic per output tile (the 128 x 128 x 384 tiles of the plain kernel are L2-bandwidth bound at ~64 flop/B); the
 // accumulator is double buffered in tensor memory so the epilogue of tile i overlaps the MMAs of tile i + 1.
 constexpr int kWsStages = 5;
-constexpr int kWsEpiWarps = 8;                      // 2 per TMEM lane quadrant, 64 accumulator columns each
+constexpr int kWsEpiWarps = 16;                     // 4 per TMEM lane quadrant, 32 accumulator columns each
 constexpr int kWsThreads = 64 + 32 * kWsEpiWarps;   // TMA warp + MMA warp + epilogue warps
-constexpr uint32_t kStageRow = 144;                 // bytes per staged row (128 B of payload + 16 B pad: conflict-free 128-bit stores)
+constexpr uint32_t kStageRow = 80;                  // bytes per staged row (64 B of payload + 16 B pad: conflict-free 128-bit stores)
 constexpr uint32_t kStageWarpBytes = 32 * kStageRow; // one epilogue warp's staging tile (32 rows)
 
 template <int EPI>
@@ -292,8 +292,7 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kWsStages), bar_w = smem_u32(bars + 2 * kWsStages);
   const uint32_t bar_acc_full = smem_u32(bars + 2 * kWsStages + 1), bar_acc_empty = smem_u32(bars + 2 * kWsStages + 3);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWsStages + 5);
-  float* bias_s = reinterpret_cast<float*>(tmem_slot + 2);                        // [BN] bias of the current n-tile (x2)
-  uint8_t* stage_s = reinterpret_cast<uint8_t*>(bias_s + 2 * BN);                 // [kWsEpiWarps][32 rows][144 B]
+  uint8_t* stage_s = reinterpret_cast<uint8_t*>(tmem_slot + 2);                   // [kWsEpiWarps][32 rows][80 B]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = N / BN, m_tiles = (M + BM - 1) / BM;
@@ -384,34 +383,29 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
     }
   } else {
-    // ---------------------------------------------------------------- epilogue: 8 warps, warp e covers TMEM lane quadrant
-    // (warp & 3) and accumulator columns [64 * (e >> 2), +64).  Accumulator rows are transposed through a padded
-    // shared-memory tile so that every global access is a fully coalesced row segment (the thread-per-row direct
-    // stores of the simple kernel are LSU / latency bound, see profiles/).
-    const int e = warp - 2, quad = warp & 3, half = e >> 2;
+    // ---------------------------------------------------------------- epilogue: 16 warps; warp e reads TMEM lane quadrant
+    // (warp & 3), accumulator columns [32 * (e >> 2), +32).  Phase 1: thread = accumulator row, bias (+GELU) applied,
+    // 64 bytes of the row parked in a padded shared-memory tile.  Phase 2: the tile is drained two rows per instruction
+    // so that every global access is a full, coalesced 64-byte row segment (thread-per-row stores straight to global are
+    // LSU / latency bound; see profiles/r01_run5_ce_gemm_ncu.md vs r01_run8_ce_gemm_ws_ncu.md).
+    const int e = warp - 2, quad = warp & 3, colgrp = e >> 2;
     uint8_t* st = stage_s + (size_t)e * kStageWarpBytes;
-    const uint32_t st_u32 = smem_u32(st);
-    int bias_n0 = -1;
+    const int sub = lane >> 4, c16 = lane & 15;
+    float bias_lane = 0.f;  // bias of column (col0 + lane); broadcast with shuffles in phase 1
+    int bias_col0 = -1;
     for (int t = 0; t < my_tiles; ++t) {
       const int as = t & 1;
       const int row0 = tile_m0(t) + quad * 32;
-      const int n0 = tile_n0(t);
-      const int colw = n0 + half * 64;  // first global column of this warp
-      // bias of this n-tile in shared memory: loaded once when RESIDENT, per tile (parity double buffer) when streaming.
-      // The four quadrant-warps of one column half fill disjoint quarters and meet on a named barrier; because they
-      // meet at every reload, a warp can never run two tiles ahead of a reader of the buffer it overwrites.
-      float* bias_buf = bias_s + (RESIDENT ? 0 : (t & 1) * BN);
-      if (!RESIDENT || bias_n0 < 0) {
-        bias_buf[half * 64 + quad * 16 + (lane & 15)] = __ldg(bias + colw + quad * 16 + (lane & 15));
-        bias_n0 = n0;
-        asm volatile("bar.sync %0, %1;" ::"r"(3 + half), "r"(128) : "memory");
+      const int col0 = tile_n0(t) + colgrp * 32;
+      if (col0 != bias_col0) {
+        bias_lane = __ldg(bias + col0 + lane);
+        bias_col0 = col0;
       }
       mbar_wait(bar_acc_full + 8 * as, ((uint32_t)t >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-      for (int cc = 0; cc < 64; cc += 32) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + half * 64 + cc);
+      uint32_t v[32];
+      {
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + colgrp * 32);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -423,77 +417,72 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             : "r"(taddr)
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (cc == 32) {  // last read of this accumulator stage by this warp: hand it back to the MMA issuer
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
-        }
-        const float* bs = bias_buf + half * 64 + cc;
-        if (EPI == CE_EPI_BIAS_RES_F32) {
-          // phase 1: acc + bias as fp32, this thread's row -> 128 B of the staging tile
+      }
+      // the accumulator stage is in registers now: hand it back to the MMA issuer before the stores
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+      float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
+      for (int j = 0; j < 32; ++j) {
+        const float x = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bias_lane, j);
+        f[j] = (EPI == CE_EPI_BIAS_GELU_F16) ? gelu_erf(x) : x;
+      }
+      if (EPI == CE_EPI_BIAS_RES_F32) {
+#pragma unroll 1
+        for (int p2 = 0; p2 < 2; ++p2) {  // two passes of 16 fp32 columns (64 bytes per staged row)
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
             float4 w;
-            w.x = __uint_as_float(v[j + 0]) + bs[j + 0];
-            w.y = __uint_as_float(v[j + 1]) + bs[j + 1];
-            w.z = __uint_as_float(v[j + 2]) + bs[j + 2];
-            w.w = __uint_as_float(v[j + 3]) + bs[j + 3];
+            w.x = p2 ? f[16 + j + 0] : f[j + 0];
+            w.y = p2 ? f[16 + j + 1] : f[j + 1];
+            w.z = p2 ? f[16 + j + 2] : f[j + 2];
+            w.w = p2 ? f[16 + j + 3] : f[j + 3];
             *reinterpret_cast<float4*>(st + (size_t)lane * kStageRow + (size_t)j * 4) = w;
           }
           __syncwarp();
-          // phase 2: one 128-byte row segment per instruction: + residual, fp32 out
+          const int col = col0 + 16 * p2 + c16;
 #pragma unroll 1
-          for (int r0 = 0; r0 < 32; r0 += 8) {
+          for (int r0 = 0; r0 < 32; r0 += 16) {
             float res[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {  // eight independent residual loads in flight per lane
-              const int row = row0 + r0 + u;
-              res[u] = row < M ? __ldg(residual + (size_t)row * N + colw + cc + lane) : 0.f;
+              const int row = row0 + r0 + 2 * u + sub;
+              res[u] = row < M ? __ldg(residual + (size_t)row * N + col) : 0.f;
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-              const int row = row0 + r0 + u;
-              const float x = *reinterpret_cast<const float*>(st + (size_t)(r0 + u) * kStageRow + (size_t)lane * 4);
-              if (row < M) out32[(size_t)row * N + colw + cc + lane] = x + res[u];
+              const int rr = r0 + 2 * u + sub, row = row0 + rr;
+              const float x = *reinterpret_cast<const float*>(st + (size_t)rr * kStageRow + (size_t)c16 * 4);
+              if (row < M) out32[(size_t)row * N + col] = x + res[u];
             }
           }
           __syncwarp();
-        } else {
-          // phase 1: bias (+ GELU), fp16, this thread's row -> 64 B (half of a 128-B staged row per 32-column chunk)
+        }
+      } else {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float f[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float x = __uint_as_float(v[j + q]) + bs[j + q];
-              f[q] = (EPI == CE_EPI_BIAS_GELU_F16) ? gelu_erf(x) : x;
-            }
-            uint4 pk;
-            const __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
-            const __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
-            pk.x = *reinterpret_cast<const uint32_t*>(&h0);
-            pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-            pk.z = *reinterpret_cast<const uint32_t*>(&h2);
-            pk.w = *reinterpret_cast<const uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(st + (size_t)lane * kStageRow + (size_t)(cc + j) * 2) = pk;
-          }
-          if (cc == 32) {
-            __syncwarp();
-            // phase 2: 64 fp16 columns = one 128-byte row segment per instruction
+        for (int j = 0; j < 32; j += 8) {
+          uint4 pk;
+          const __half2 h0 = __floats2half2_rn(f[j + 0], f[j + 1]), h1 = __floats2half2_rn(f[j + 2], f[j + 3]);
+          const __half2 h2 = __floats2half2_rn(f[j + 4], f[j + 5]), h3 = __floats2half2_rn(f[j + 6], f[j + 7]);
+          pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+          pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+          pk.z = *reinterpret_cast<const uint32_t*>(&h2);
+          pk.w = *reinterpret_cast<const uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(st + (size_t)lane * kStageRow + (size_t)j * 2) = pk;
+        }
+        __syncwarp();
 #pragma unroll 4
-            for (int r = 0; r < 32; ++r) {
-              const int row = row0 + r;
-              if (row < M) {
-                const uint32_t x = *reinterpret_cast<const uint32_t*>(st + (size_t)r * kStageRow + (size_t)lane * 4);
-                *reinterpret_cast<uint32_t*>(out16 + (size_t)row * N + colw + 2 * lane) = x;
-              }
-            }
-            __syncwarp();
+        for (int r = 0; r < 32; r += 2) {  // two 64-byte row segments (32 fp16 columns each) per instruction
+          const int rr = r + sub, row = row0 + rr;
+          if (row < M) {
+            const uint32_t x = *reinterpret_cast<const uint32_t*>(st + (size_t)rr * kStageRow + (size_t)c16 * 4);
+            *reinterpret_cast<uint32_t*>(out16 + (size_t)row * N + col0 + 2 * c16) = x;
           }
         }
+        __syncwarp();
       }
     }
-    (void)st_u32;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -505,7 +494,7 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 template <int EPI, bool RESIDENT>
 int launch_ws(const CUtensorMap& map_a, const CUtensorMap& map_w, int M, int N, int K, const float* bias,
               const float* residual, __half* out16, float* out32, cudaStream_t st) {
-  const size_t extra = 1024 /*align*/ + 256 /*barriers*/ + 2 * BN * 4 /*bias*/ + (size_t)kWsEpiWarps * kStageWarpBytes;
+  const size_t extra = 1024 /*align*/ + 256 /*barriers*/ + (size_t)kWsEpiWarps * kStageWarpBytes;
   const size_t smem = RESIDENT ? (size_t)(K / BK) * kTileBBytes + (size_t)kWsStages * kTileABytes + extra
                                : (size_t)kWsStages * kStageBytes + extra;
   static size_t configured = 0;

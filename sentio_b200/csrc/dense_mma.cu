@@ -327,7 +327,13 @@ __global__ void __launch_bounds__(kSelectThreads, 1) dense_select_kernel(const S
     for (int shift = 56; shift >= 0; shift -= 8) {
       for (int i = tid; i < 256; i += nt) s_hist[i] = 0;
       __syncthreads();
-      SB_FOR_EACH_KEY(if ((key & mask) == prefix) atomicAdd(&s_hist[(int)((key >> shift) & 0xffull)], 1);)
+      // warp-aggregated histogram update: in the leading passes nearly all keys share a digit, and per-key shared
+      // atomics on one bin serialise; lanes with equal digits elect one lane to add their count
+      SB_FOR_EACH_KEY(if ((key & mask) == prefix) {
+        const int dgt = (int)((key >> shift) & 0xffull);
+        const unsigned grp = __match_any_sync(__activemask(), dgt);
+        if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&s_hist[dgt], __popc(grp));
+      })
       __syncthreads();
       if (tid == 0) {
         int cum = 0, sel = 0, cnt_b = 0;
@@ -350,7 +356,7 @@ __global__ void __launch_bounds__(kSelectThreads, 1) dense_select_kernel(const S
       need = s_need;
       const int bucket = s_bucket;
       __syncthreads();
-      if (bucket <= kSelTop - K) break;  // {above} (< K keys) + bucket fit the winner buffer
+      if (bucket <= 256 && bucket <= kSelTop - K) break;  // {above} (< K keys) + a small bucket: finish by sorting
     }
   }
   // winners: every key whose decided digits are >= the selected bucket's (at most K - 1 + bucket <= kSelTop keys)
