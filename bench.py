@@ -30,7 +30,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "retrieval queries/sec @1M docs,1024-d,top_k=100"
+METRIC = "retrieval queries/sec @1M docs,1024-d,top_k=100"  # BASELINE.json metric (the workload actually run is in config)
 UNIT = "queries/s"
 
 
@@ -106,11 +106,18 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- synthetic workload
-def make_workload(args, need_f32_host=False):
+def make_workload(args, lo=None, hi=None):
+    """Synthetic corpus / queries.  Corpora above 2 M docs are generated shard-locally from
+    independently seeded chunks (synth.dense_corpus_range), so a rank only ever materialises its own rows."""
     from sentio_b200 import synth
 
     t0 = time.time()
-    x16 = synth.dense_corpus(args.n_docs, args.dim)
+    if args.n_docs > 2_000_000 and lo is not None:
+        x16 = synth.dense_corpus_range(lo, hi, args.dim)
+    else:
+        x16 = synth.dense_corpus(args.n_docs, args.dim)
+        if lo is not None:
+            x16 = x16[lo:hi]
     queries = synth.query_vectors(1024, args.dim)
     wl = {"x16": x16, "q": queries, "gen_s": None}
     if args.workload in ("hybrid", "rerank"):
@@ -213,11 +220,11 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-    wl = make_workload(args)
     n = args.n_docs
     lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    wl = make_workload(args, lo, hi)
     pipe = HybridPipeline(local_rank, rank=rank, world=world)
-    pipe.load_dense(wl["x16"][lo:hi], id_base=lo)
+    pipe.load_dense(wl["x16"], id_base=lo)
     idx = None
     rerank = args.workload == "rerank"
     if args.workload in ("hybrid", "rerank"):
@@ -378,7 +385,7 @@ def main():
 
     # ---------------- bounded CPU baseline on this box's host cores (rank 0, N=1 only)
     cpu = None
-    if world == 1 and args.cpu_sample > 0:
+    if world == 1 and args.cpu_sample > 0 and args.n_docs <= 2_000_000:
         cpu, _ = cpu_reference(args, wl, args.cpu_sample)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -26,6 +26,22 @@ def dense_corpus(n: int, d: int, seed: int = 1234, chunk: int = 65536) -> np.nda
     return out
 
 
+def dense_corpus_range(lo: int, hi: int, d: int, seed: int = 1234, chunk: int = 65536) -> np.ndarray:
+    """Rows [lo, hi) of a corpus whose 65536-row chunks are seeded independently (SeedSequence([seed, chunk_index])):
+    any shard can be generated without generating the rows before it (used for the 8 M-doc sharded runs).
+    NOTE: a different stream than ``dense_corpus`` (which advances one generator sequentially)."""
+    out = np.empty((hi - lo, d), dtype=np.float16)
+    c = lo // chunk
+    while c * chunk < hi:
+        rng = np.random.default_rng(np.random.SeedSequence([seed, c]))
+        x = rng.standard_normal((chunk, d), dtype=np.float32)
+        x /= np.linalg.norm(x, axis=1, keepdims=True)
+        a, b = max(lo, c * chunk), min(hi, (c + 1) * chunk)
+        out[a - lo:b - lo] = x[a - c * chunk:b - c * chunk].astype(np.float16)
+        c += 1
+    return out
+
+
 def query_vectors(b: int, d: int, seed: int = 4321) -> np.ndarray:
     rng = np.random.default_rng(seed)
     q = rng.standard_normal((b, d), dtype=np.float32)
