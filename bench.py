@@ -5,9 +5,12 @@
                     [--workload dense|hybrid|rerank] [--batch B] [--n-docs N] [--dim D] [--top-k K] [--rerank-k K2]
 
 A "step" = one batch of B synthetic queries through the hot path.  Default workload = BASELINE.json configs[1]:
-1 M docs x 1024-d, dense-only cosine top_k=100 on 1 x B200.  For --gpus N > 1 the SAME corpus is partitioned N ways
-(contiguous doc ranges), every rank scans its shard and ONE NCCL all-gather of the per-shard top-k is followed by the
-merge kernel -> strong scaling (total work fixed).
+1 M docs x 1024-d, dense-only cosine top_k=100 on 1 x B200.  --batch is the number of queries per step PER GPU: a step
+on N GPUs carries N x batch queries.  --shard corpus (default, north_star): the SAME corpus is partitioned N ways
+(contiguous doc ranges), every rank scores all N x batch queries against its shard, ONE NCCL all-gather of the per-shard
+top-k is followed by the merge kernel.  --shard queries: the corpus is replicated, every rank answers its own batch,
+no collective.  Either way per-GPU work per step is constant in N -> "scaling": "weak"; the corpus of the metric
+(1 M docs) never changes.
 
 value   : whole-job queries/sec, inputs already resident in HBM (device entry points, CUDA-event timed, max over ranks)
 e2e     : the same metric through the host-buffer C-ABI entry point (pinned host queries -> H2D -> kernels -> D2H results)
@@ -47,6 +50,9 @@ def parse_args():
     ap.add_argument("--dim", type=int, default=1024)
     ap.add_argument("--top-k", type=int, default=100)
     ap.add_argument("--cpu-sample", type=int, default=24, help="queries in the bounded CPU-baseline sample")
+    ap.add_argument("--shard", default="corpus", choices=["corpus", "queries"],
+                    help="--gpus N > 1: 'corpus' = contiguous doc ranges + ONE NCCL all-gather of per-shard top-k "
+                         "(north_star); 'queries' = corpus replicated on every GPU, queries split, no collective")
     return ap.parse_args()
 
 
@@ -191,8 +197,15 @@ def main():
                      + {"dense": "dense-only cosine", "hybrid": "hybrid dense+BM25 rrf",
                         "rerank": "hybrid dense+BM25 rrf + cross-encoder rerank (MiniLM-L6 random-init)"}[args.workload]
                      + f" top_k={args.top_k}" + (f"->{args.rerank_k}" if args.workload == "rerank" else ""))
-    config = {"workload": workload_name, "batch_queries_per_step": args.batch, "store_dtype": "fp16",
-              "shards": max(world, 1), "l2_policy": "corpus (2.05 GB) is larger than L2 (126 MB); no flush needed",
+    sharded = world > 1 and args.shard == "corpus"
+    replicated = world > 1 and args.shard == "queries"
+    B_gpu = args.batch
+    B_total = args.batch * world
+    config = {"workload": workload_name, "batch_queries_per_step": B_total, "queries_per_gpu_per_step": B_gpu,
+              "store_dtype": "fp16", "shards": world if sharded else 1,
+              "multi_gpu": ("corpus partition + one NCCL all-gather of per-shard top-k" if sharded else
+                            "corpus replicated, queries split, no collective" if replicated else "single GPU"),
+              "l2_policy": "corpus (2.05 GB) is larger than L2 (126 MB); no flush needed",
               "query_set": "1024 seeded unit vectors, cycled"}
 
     if args.impl == "reference":
@@ -204,7 +217,7 @@ def main():
         base, per_q = cpu_reference(args, wl, total)
         line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_q * per_step * 1e3,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": {**config, "batch_queries_per_step": per_step},
                 "cpu_baseline": {**base, "sample": f"{per_step} queries per step; " + base["sample"]},
                 "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -221,9 +234,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     n = args.n_docs
-    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    if sharded:
+        lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    else:
+        lo, hi = 0, n
     wl = make_workload(args, lo, hi)
-    pipe = HybridPipeline(local_rank, rank=rank, world=world)
+    pipe = HybridPipeline(local_rank, rank=rank if sharded else 0, world=world if sharded else 1)
     pipe.load_dense(wl["x16"], id_base=lo)
     idx = None
     rerank = args.workload == "rerank"
@@ -231,7 +247,7 @@ def main():
         from sentio_b200.index import build_bm25_from_token_ids
 
         idx = build_bm25_from_token_ids(wl["flat"], wl["off"])
-        pipe.load_bm25(idx.shard(lo, hi) if world > 1 else idx, id_base=lo)
+        pipe.load_bm25(idx.shard(lo, hi) if sharded else idx, id_base=lo)
     if rerank:
         from sentio_b200 import synth
         from sentio_b200.cross_encoder import MINILM_L6, CrossEncoderWeights
@@ -243,7 +259,9 @@ def main():
         pipe.load_doc_tokens(doc_tok, doc_len, id_base=0)  # replicated on every rank (240 MB at 1 M docs)
         q_tok_all = vocab_ids[wl["q_tokens"]].astype(np.int32)
     eng = pipe.engine
-    B, k = args.batch, args.top_k
+    # queries this rank handles per step: all of them when the corpus is partitioned, its own slice when replicated
+    B, k = (B_total if sharded else B_gpu), args.top_k
+    q_shift = rank * B_gpu if replicated else 0
     dev = f"cuda:{local_rank}"
     q_all = torch.from_numpy(wl["q"]).to(dev)
     n_q = q_all.shape[0]
@@ -252,7 +270,7 @@ def main():
         term_lists = [idx.term_ids(t) for t in wl["q_tokens"]]
 
     def batch_slice(step):
-        s = (step * B) % n_q
+        s = (step * B_total + q_shift) % n_q
         idxs = [(s + i) % n_q for i in range(B)]
         return idxs
 
@@ -289,6 +307,8 @@ def main():
         run_dev(inputs[s])
     barrier()
     eng.profile(True)
+    if rerank:
+        eng.ce_stats(reset=True)
     launches0 = eng.launch_count()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -305,12 +325,13 @@ def main():
     launches = eng.launch_count() - launches0
     n_scan, scan_ms = eng.profile_read("dense_scan")
     n_ce, ce_ms = eng.profile_read("ce")
+    ce_pairs, ce_rows, ce_sq = eng.ce_stats() if rerank else (0, 0, 0)
     eng.profile(False)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    value = B * args.steps / (ms_total / 1e3)
+    value = B_total * args.steps / (ms_total / 1e3)
 
     # ---------------- e2e leg: host (pinned by the library) buffers in, host results out, every step
     host_batches = [wl["q"][batch_slice(s)] for s in range(args.warmup + args.steps)]
@@ -344,9 +365,11 @@ def main():
     d2h = B * k * 16 + B * 4 + (B * k * 4 if idx is not None else 0)
     if rerank:
         h2d += B * q_tok_all.shape[1] * 4 + B * 4
-        d2h = B * args.rerank_k * 12 + B * 4
-    e2e = {"value": B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "timer": "host wall clock around the public host-buffer call (includes H2D, kernels, D2H, sync)"}
+        d2h = B_gpu * args.rerank_k * 12 + B_gpu * 4  # every rank returns the rows of the queries it reranked
+    e2e = {"value": B_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+           "d2h_bytes_per_step": d2h * world,
+           "timer": "host wall clock around the public host-buffer call (includes H2D, kernels, D2H, sync); "
+                    "bytes are summed over ranks"}
 
     if rank != 0:
         if world > 1:
@@ -374,13 +397,16 @@ def main():
             pass
 
     if rerank and n_ce:
-        # second roofline: the cross-encoder forward (tensor pipe), 2.87 GFLOP per pair at S = 128
-        flops = B * k * args.steps * 6 * (24 * 128 * 384 * 384 + 4 * 128 * 128 * 384)
+        # second roofline: the cross-encoder forward (tensor pipe).  Flops of the work actually done: the packed-token
+        # forward computes sum(len) token rows, not P x 128 (library counters); 2.87 GFLOP per pair only at len = 128.
+        flops = 6 * (24 * 384 * 384 * ce_rows + 4 * 384 * ce_sq)
         tf = flops / (ce_ms * 1e-3) / 1e12
         tpeak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1429.5) \
             if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1400.0
         roofline["cross_encoder"] = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s",
                                      "frac": tf / tpeak, "ms_total": ce_ms, "forward_calls": n_ce,
+                                     "pairs": ce_pairs, "mean_pair_len": ce_rows / max(ce_pairs, 1),
+                                     "flops_counted": "L*(24*H^2*sum(len) + 4*H*sum(len^2)), padding excluded",
                                      "share_of_step": ce_ms / ms_total}
 
     # ---------------- bounded CPU baseline on this box's host cores (rank 0, N=1 only)
@@ -390,7 +416,7 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f16 store / f32 scan / f64 exact re-score",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16 store / f32 scan / f64 exact re-score",
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "corpus_gen_s": wl["gen_s"]}
     print(json.dumps(line))

@@ -192,7 +192,8 @@ typedef struct sb_ce_config {
  */
 int sb_ce_load(sb_ctx* ctx, const float* weights, int64_t n_floats, const sb_ce_config* cfg);
 /*
- * input_ids / token_type: P x S int32 (host), lengths[P] = number of real tokens per pair (attention mask).
+ * input_ids / token_type: P x S int32 (host), lengths[P] = number of real tokens per pair (attention mask); positions
+ * >= lengths[p] are padding and are skipped entirely (tokens are packed on the device; same [CLS] logit as masking).
  * out_logits[P], out_sigmoid[P] (relevance in [0,1], reference test_jina_reranker.py:283-300).
  */
 int sb_ce_score(sb_ctx* ctx, const int32_t* input_ids, const int32_t* token_type, const int32_t* lengths,
@@ -200,6 +201,13 @@ int sb_ce_score(sb_ctx* ctx, const int32_t* input_ids, const int32_t* token_type
 int sb_ce_score_dev(sb_ctx* ctx, const int32_t* input_ids_dev, const int32_t* token_type_dev,
                     const int32_t* lengths_dev, int32_t P, int32_t S, float* out_logits_dev,
                     float* out_sigmoid_dev, void* stream);
+
+/*
+ * Work counters of the packed-token forward since the last reset: out3 = {pairs scored, sum of pair lengths (token rows
+ * actually computed), sum of squared pair lengths}.  flops = layers * (24 * H^2 * out3[1] + 4 * H * out3[2]) -- used by
+ * bench.py so the tensor-pipe roofline counts the work done, not the padding skipped.  Synchronises the device.
+ */
+int sb_ce_stats(sb_ctx* ctx, int64_t* out3, int32_t reset);
 
 /*
  * Batched rerank (retrieve -> rerank without leaving the device): sb_ce_tokens_load stores the shard's pre-tokenised

@@ -73,6 +73,7 @@ SIGNATURES = {
                               C.c_void_p]),
     "sb_ce_score_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
+    "sb_ce_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "sb_ce_tokens_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64]),
     "sb_rerank_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                 C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -20,10 +20,6 @@
 
 namespace {
 
-constexpr int kScoreThreads = 256;
-constexpr int kPostPerThread = 8;
-constexpr int kChunk = kScoreThreads * kPostPerThread;  // postings per work chunk
-
 // ------------------------------------------------------------------------------------------------ load kernels
 __global__ void bm25_dnorm_kernel(const int32_t* __restrict__ doc_len, int64_t n, double k1, double b, double omb,
                                   double avgdl, double* __restrict__ dnorm) {
@@ -46,94 +42,235 @@ __global__ void bm25_ratio_kernel(const int32_t* __restrict__ post_doc, const ui
   ratio[i] = __ddiv_rn(num, den);
 }
 
-// ------------------------------------------------------------------------------------------------ plan kernel
-// For the sub-batch of nq queries: for every term position j < max_len, the exclusive prefix of work chunks per query.
-// chunk_prefix[j * (nq + 1) + b]; term id < 0 or idf == 0 -> no work (adds exactly +-0.0 in the reference).
-__global__ void bm25_plan_kernel(const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_off, int nq,
-                                 int max_len, const int64_t* __restrict__ indptr, const double* __restrict__ idf,
-                                 int64_t n_terms, int32_t* __restrict__ chunk_prefix) {
-  const int j = blockIdx.x;
-  if (j >= max_len || threadIdx.x != 0) return;
-  int32_t run = 0;
-  int32_t* out = chunk_prefix + (size_t)j * (nq + 1);
-  for (int b = 0; b < nq; ++b) {
-    out[b] = run;
-    const int len = q_off[b + 1] - q_off[b];
-    if (j < len) {
-      const int t = q_terms[q_off[b] + j];
-      if (t >= 0 && t < n_terms && idf[t] != 0.0) {
-        const int64_t df = indptr[t + 1] - indptr[t];
-        run += (int32_t)((df + kChunk - 1) / kChunk);
-      }
-    }
-  }
-  out[nq] = run;
-}
+// ------------------------------------------------------------------------------------------------ range scoring
+// One CTA scores ONE query over a run of consecutive doc ranges of kRange docs.  The fp64 accumulators of the range live
+// in shared memory (64 KB), so the only HBM traffic of scoring is the postings themselves (4 B doc + 8 B ratio each):
+// no N x 8 B zero fill, no accumulator read-modify-write through L2, no N x 8 B re-read for the top-k.
+//
+//  * postings of a term are sorted by doc, so the slice of a posting list that falls into [r0, r1) is contiguous; its
+//    start is found once per (CTA, term) with a warp-cooperative 32-ary search and then carried from range to range
+//    (the end of range i is the start of range i + 1);
+//  * terms are processed strictly in QUERY ORDER with a block barrier between them, and a doc occurs at most once per
+//    posting list, so the per-doc addition order equals NumPy's `score += ...` loop order without any atomics
+//    => bit-identical fp64;
+//  * what happens to the finished range depends on MODE:
+//      kModeSample : (S ranges spread over the corpus) ceil(k/S)-th best positive score of the range, min over the S
+//                    ranges -> thr[q], a lower bound of the global k-th best score
+//      kModeCollect: every doc with score > 0 and >= thr[q] is appended to the query's candidate list
+//      kModeDump   : the accumulators are written to out[q][doc] (sb_bm25_scores, the bit-exactness hook)
+constexpr int kRange = 8192;            // docs per range
+constexpr unsigned long long kPosZero = 0x8000000000000000ull;  // f64_orderable(+0.0)
+constexpr int kRsThreads = 512;
+constexpr int kRsPost = 4;              // postings per thread per chunk
+enum { kModeSample = 0, kModeCollect = 1, kModeDump = 2 };
 
-// ------------------------------------------------------------------------------------------------ scoring kernels
-struct ScoreParams {
+struct RangeParams {
   const int32_t* q_terms;
   const int32_t* q_off;  // offsets of THIS sub-batch (q_off[0] may be > 0)
-  int nq;
-  int j;                 // term position handled by this launch
-  const int32_t* chunk_prefix;  // [nq + 1] for this j
+  int max_len;           // longest query of the sub-batch (sizes the per-term state in shared memory)
+  int ranges_per_cta;
   const int64_t* indptr;
   const int32_t* post_doc;
   const double* ratio;
   const double* idf;
-  double* acc;   // [nq][n_docs]   (Okapi: accumulators; Plus: per-term ratio scratch)
+  int64_t n_terms;
   int64_t n_docs;
+  double delta;          // BM25Plus
+  int k;                 // kModeSample: rank inside one sample range = ceil(top_k / number of sample ranges)
+  unsigned long long* thr;   // [nq]
+  int32_t* cnt;              // [nq]
+  unsigned long long* ckey;  // [nq][n_docs]   kModeCollect
+  uint32_t* cidx;            // [nq][n_docs]
+  double* dump;              // [nq][n_docs]   kModeDump
 };
 
-// Okapi: acc[b][doc] += idf * ratio.   Plus (scatter phase): scratch[b][doc] = ratio.
-template <bool PLUS>
-__global__ void __launch_bounds__(kScoreThreads) bm25_score_kernel(const ScoreParams p) {
-  __shared__ int s_pref[64 + 1];
-  const int nq = p.nq;
-  for (int i = threadIdx.x; i <= nq; i += blockDim.x) s_pref[i] = p.chunk_prefix[i];
-  __syncthreads();
-  const int total = s_pref[nq];
-  for (int c = blockIdx.x; c < total; c += gridDim.x) {
-    int b = 0;
-    while (b + 1 < nq && s_pref[b + 1] <= c) ++b;  // nq <= 64: linear scan
-    const int t = p.q_terms[p.q_off[b] + p.j];
-    const int64_t lo = p.indptr[t], hi = p.indptr[t + 1];
-    const double idf = p.idf[t];
-    const int64_t base = lo + (int64_t)(c - s_pref[b]) * kChunk;
-    double* acc = p.acc + (size_t)b * p.n_docs;
-#pragma unroll
-    for (int it = 0; it < kPostPerThread; ++it) {
-      const int64_t pidx = base + (int64_t)it * kScoreThreads + threadIdx.x;
-      if (pidx < hi) {
-        const int32_t doc = __ldg(p.post_doc + pidx);
-        const double r = __ldg(p.ratio + pidx);
-        if (PLUS) {
-          acc[doc] = r;
-        } else {
-          acc[doc] = __dadd_rn(acc[doc], __dmul_rn(idf, r));
-        }
+// first p in [lo, hi) with a[p] >= target (hi if none); all 32 lanes of the warp participate and return the same value
+__device__ __forceinline__ int64_t warp_lower_bound(const int32_t* __restrict__ a, int64_t lo, int64_t hi, int32_t target,
+                                                    int lane) {
+  while (hi - lo > 32) {
+    const int64_t step = (hi - lo + 31) / 32;  // >= 2
+    const int64_t p = lo + (int64_t)lane * step;
+    const bool ge = (p >= hi) || (__ldg(a + p) >= target);
+    const unsigned m = __ballot_sync(0xffffffffu, ge);
+    if (m == 0u) {
+      lo = lo + 31 * step + 1;
+    } else {
+      const int f = __ffs(m) - 1;
+      if (f == 0) {
+        hi = lo;
+      } else {
+        hi = min(hi, lo + (int64_t)f * step);  // lane f may have probed past the end of the list
+        lo = lo + (int64_t)(f - 1) * step + 1;
       }
     }
   }
+  const int64_t p = lo + lane;
+  const bool ge = (p >= hi) || (__ldg(a + p) >= target);
+  const unsigned m = __ballot_sync(0xffffffffu, ge);
+  return m ? lo + (__ffs(m) - 1) : hi;
 }
 
-// Plus (dense phase): for every query whose term j is scored: acc[b][d] += idf * (delta + scratch[b][d]); scratch = 0.
-__global__ void bm25_plus_dense_kernel(const int32_t* q_terms, const int32_t* q_off, int nq, int j,
-                                       const double* __restrict__ idf, int64_t n_terms, double delta,
-                                       double* __restrict__ acc, double* __restrict__ scratch, int64_t n_docs) {
-  const int b = blockIdx.y;
-  const int len = q_off[b + 1] - q_off[b];
-  if (j >= len) return;
-  const int t = q_terms[q_off[b] + j];
-  if (t < 0 || t >= n_terms) return;
-  const double w = idf[t];
-  if (w == 0.0) return;
-  double* a = acc + (size_t)b * n_docs;
-  double* s = scratch + (size_t)b * n_docs;
-  for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < n_docs; d += (int64_t)gridDim.x * blockDim.x) {
-    const double r = s[d];
-    a[d] = __dadd_rn(a[d], __dmul_rn(w, __dadd_rn(delta, r)));
-    if (r != 0.0) s[d] = 0.0;
+__device__ unsigned long long block_kth_largest(const unsigned long long* keys, int n, int K, int* hist, int* scal);
+
+template <int MODE, bool PLUS>
+__global__ void __launch_bounds__(kRsThreads, 3) bm25_range_kernel(const RangeParams p) {
+  extern __shared__ __align__(16) uint8_t rsm[];
+  double* acc = reinterpret_cast<double*>(rsm);                               // [kRange]
+  int64_t* s_cur = reinterpret_cast<int64_t*>(acc + kRange);                  // [2][max_len]  posting cursor per term
+  int64_t* s_hi = s_cur + 2 * (size_t)p.max_len;                              // [max_len]     end of the posting list
+  double* s_idf = reinterpret_cast<double*>(s_hi + p.max_len);                // [max_len]     0.0 = term contributes nothing
+  int32_t* s_wid = reinterpret_cast<int32_t*>(s_idf + p.max_len);            // [max_len]     loads per thread per chunk
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_wid + p.max_len);          // [kRange / 32] PLUS: doc had a posting
+  __shared__ int hist[256];
+  __shared__ int scal[2];
+  __shared__ int npos;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int qi = blockIdx.x;
+  const int64_t n_ranges = (p.n_docs + kRange - 1) / kRange;
+  // kModeSample: gridDim.y sample ranges spread evenly over the corpus, one per CTA
+  const int64_t first = MODE == kModeSample ? ((int64_t)blockIdx.y * n_ranges) / gridDim.y
+                                            : (int64_t)blockIdx.y * p.ranges_per_cta;
+  const int64_t last = MODE == kModeSample ? first + 1 : min(first + (int64_t)p.ranges_per_cta, n_ranges);  // exclusive
+  const int q0 = p.q_off[qi];
+  const int len = min(p.q_off[qi + 1] - q0, p.max_len);
+  // per-term state: posting cursor at the first range's lower doc bound
+  for (int j = warp; j < len; j += kRsThreads / 32) {
+    const int t = p.q_terms[q0 + j];
+    double w = 0.0;
+    int64_t pos = 0, hi = 0;
+    int wid = 1;
+    if (t >= 0 && t < p.n_terms) {
+      w = p.idf[t];
+      if (w != 0.0) {
+        const int64_t lo = p.indptr[t];
+        hi = p.indptr[t + 1];
+        pos = first == 0 ? lo : warp_lower_bound(p.post_doc, lo, hi, (int32_t)(first * kRange), lane);
+        // expected postings per range -> how many postings a thread fetches per chunk (rare terms: do not over-read)
+        const int64_t per_range = ((hi - lo) * kRange) / max(p.n_docs, (int64_t)1);
+        wid = (int)min((int64_t)kRsPost, per_range / kRsThreads + 1);
+      }
+    }
+    if (lane == 0) {
+      s_cur[j] = pos;
+      s_hi[j] = hi;
+      s_idf[j] = w;
+      s_wid[j] = wid;
+    }
+  }
+  for (int i = tid; i < kRange; i += kRsThreads) acc[i] = 0.0;
+  if (PLUS)
+    for (int i = tid; i < kRange / 32; i += kRsThreads) s_bits[i] = 0u;
+  __syncthreads();
+
+  for (int64_t r = first; r < last; ++r) {
+    const int32_t r0 = (int32_t)(r * kRange);
+    const int32_t r1 = (int32_t)min((int64_t)r0 + kRange, p.n_docs);
+    const int nd = r1 - r0;
+    const int par = (int)((r - first) & 1);
+    const int64_t* cur_in = s_cur + (size_t)par * p.max_len;
+    int64_t* cur_out = s_cur + (size_t)(par ^ 1) * p.max_len;
+    for (int j = 0; j < len; ++j) {
+      const double w = s_idf[j];
+      if (w == 0.0) continue;  // block-uniform
+      const int64_t pos0 = cur_in[j], hi = s_hi[j];
+      const int wid = s_wid[j];
+      const double wd = PLUS ? __dmul_rn(w, __dadd_rn(p.delta, 0.0)) : 0.0;
+      int64_t pos = pos0;
+      for (;;) {
+        int32_t doc[kRsPost];
+        double rat[kRsPost];
+#pragma unroll
+        for (int u = 0; u < kRsPost; ++u) {
+          const int64_t idx = pos + (int64_t)u * kRsThreads + tid;
+          doc[u] = 0x7fffffff;
+          rat[u] = 0.0;
+          if (u < wid && idx < hi) {
+            doc[u] = __ldg(p.post_doc + idx);
+            rat[u] = __ldg(p.ratio + idx);
+          }
+        }
+        bool any_out = false;
+#pragma unroll
+        for (int u = 0; u < kRsPost; ++u) {
+          const int64_t idx = pos + (int64_t)u * kRsThreads + tid;
+          if (u >= wid) {
+          } else if (doc[u] < r1) {
+            const int d = doc[u] - r0;
+            if (PLUS) {
+              acc[d] = __dadd_rn(acc[d], __dmul_rn(w, __dadd_rn(p.delta, rat[u])));
+              atomicOr(&s_bits[d >> 5], 1u << (d & 31));
+            } else {
+              acc[d] = __dadd_rn(acc[d], __dmul_rn(w, rat[u]));
+            }
+          } else {
+            any_out = true;
+            // the unique boundary idx b in [pos0, hi]: doc(b) >= r1 (doc(hi) = +inf) and (b == pos0 or doc(b-1) < r1)
+            if (idx <= hi && (idx == pos0 || __ldg(p.post_doc + idx - 1) < r1)) cur_out[j] = idx;
+          }
+        }
+        if (__syncthreads_or(any_out)) break;
+        pos += (int64_t)wid * kRsThreads;
+      }
+      if (PLUS) {
+        // every doc of the range WITHOUT a posting of this term gets idf * (delta + 0.0); a warp owns one bit word
+        for (int i = tid; i < kRange; i += kRsThreads) {
+          const uint32_t word = s_bits[i >> 5];
+          if (i < nd && !((word >> (i & 31)) & 1u)) acc[i] = __dadd_rn(acc[i], wd);
+          __syncwarp();
+          if (lane == 0 && word) s_bits[i >> 5] = 0u;
+        }
+        __syncthreads();
+      }
+    }
+    // the barrier that ended the last term's loop (or the initial one) ordered all accumulator updates before this point
+    if (MODE == kModeDump) {
+      double* out = p.dump + (size_t)qi * p.n_docs + r0;
+      for (int i = tid; i < nd; i += kRsThreads) out[i] = acc[i];
+      for (int i = tid; i < kRange; i += kRsThreads) acc[i] = 0.0;
+    } else if (MODE == kModeCollect) {
+      const unsigned long long t = p.thr[qi];
+      unsigned long long* ok = p.ckey + (size_t)qi * p.n_docs;
+      uint32_t* oi = p.cidx + (size_t)qi * p.n_docs;
+      for (int i = tid; i < kRange; i += kRsThreads) {
+        unsigned long long key = 0ull;
+        if (i < nd) key = f64_orderable(acc[i]);
+        acc[i] = 0.0;
+        const bool pass = i < nd && key > kPosZero && key >= t && key != 0xffffffffffffffffull;
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+          int at = 0;
+          if (lane == 0) at = atomicAdd(&p.cnt[qi], __popc(m));
+          at = __shfl_sync(0xffffffffu, at, 0);
+          if (pass) {
+            at += __popc(m & ((1u << lane) - 1u));
+            ok[at] = key;
+            oi[at] = (uint32_t)(r0 + i);
+          }
+        }
+      }
+    } else {  // kModeSample: the accumulators become sort keys in place
+      unsigned long long* keys = reinterpret_cast<unsigned long long*>(acc);
+      if (tid == 0) npos = 0;
+      __syncthreads();
+      int local = 0;
+      for (int i = tid; i < kRange; i += kRsThreads) {
+        const double s = acc[i];
+        const unsigned long long key = (i < nd && s > 0.0) ? f64_orderable(s) : 0ull;
+        keys[i] = key;
+        local += key != 0ull;
+      }
+      local = __reduce_add_sync(0xffffffffu, local);
+      if (lane == 0 && local) atomicAdd(&npos, local);
+      __syncthreads();
+      // S sample ranges each report their ceil(k / S)-th best positive score; at least k docs score >= the MINIMUM of
+      // those, so it is a lower bound of the global k-th best (a range with too few positives degrades the bound to
+      // "every positive score", never below).  thr[] was preset to all-ones by the host.
+      unsigned long long t = kPosZero + 1ull;
+      if (npos >= p.k) t = block_kth_largest(keys, kRange, p.k, hist, scal);
+      if (tid == 0) atomicMin(p.thr + qi, t);
+      return;
+    }
+    __syncthreads();
   }
 }
 
@@ -171,9 +308,7 @@ __device__ __forceinline__ void block_bitonic_sort_pairs(unsigned long long* key
 // (~ N * k / 8192 docs) into a per-query buffer sized for the worst case; (3) one CTA per query finds the k-th largest
 // score by MSB-first radix select, breaks exact ties by ascending doc index with a second radix select, sorts the k
 // winners.  Exact for any score distribution (an unrepresentative sample only enlarges step 2's output).
-constexpr int kBmSample = 8192;
 constexpr int kBmStage = 12288;  // (key, idx) pairs staged in shared memory by the final kernel (144 KB)
-constexpr unsigned long long kPosZero = 0x8000000000000000ull;  // f64_orderable(+0.0)
 
 // K-th largest value among keys[0..n) (shared memory, every thread of the CTA participates); n >= K >= 1.
 __device__ unsigned long long block_kth_largest(const unsigned long long* keys, int n, int K, int* hist, int* scal) {
@@ -212,66 +347,6 @@ __device__ unsigned long long block_kth_largest(const unsigned long long* keys, 
     __syncthreads();
   }
   return prefix;
-}
-
-__global__ void __launch_bounds__(1024, 1) bm25_sample_thr_kernel(const double* __restrict__ acc, int64_t n, int k,
-                                                                  unsigned long long* __restrict__ thr,
-                                                                  int32_t* __restrict__ cnt) {
-  extern __shared__ __align__(16) uint8_t ssm2[];
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(ssm2);
-  __shared__ int hist[256];
-  __shared__ int scal[2];
-  __shared__ int npos;
-  const int qi = blockIdx.x, tid = threadIdx.x;
-  const int ns = (int)min((int64_t)kBmSample, n);
-  if (tid == 0) npos = 0;
-  __syncthreads();
-  int local = 0;
-  for (int i = tid; i < ns; i += blockDim.x) {
-    const double s = acc[(size_t)qi * n + i];
-    const unsigned long long key = (s > 0.0) ? f64_orderable(s) : 0ull;
-    keys[i] = key;
-    local += key != 0ull;
-  }
-  atomicAdd(&npos, local);
-  __syncthreads();
-  unsigned long long t = kPosZero + 1ull;  // "every positive score"
-  if (npos >= k) t = block_kth_largest(keys, ns, k, hist, scal);
-  if (tid == 0) {
-    thr[qi] = t;
-    cnt[qi] = 0;
-  }
-}
-
-__global__ void __launch_bounds__(256) bm25_collect_kernel(const double* __restrict__ acc, int64_t n,
-                                                           const unsigned long long* __restrict__ thr,
-                                                           int32_t* __restrict__ cnt,
-                                                           unsigned long long* __restrict__ ckey,
-                                                           uint32_t* __restrict__ cidx) {
-  const int qi = blockIdx.y, lane = threadIdx.x & 31;
-  const unsigned long long t = thr[qi];
-  const double* a = acc + (size_t)qi * n;
-  unsigned long long* ok = ckey + (size_t)qi * n;
-  uint32_t* oi = cidx + (size_t)qi * n;
-  const int64_t base = (int64_t)blockIdx.x * (256 * 8);
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const int64_t i = base + (int64_t)u * 256 + threadIdx.x;
-    unsigned long long key = 0ull;
-    if (i < n) key = f64_orderable(a[i]);
-    const bool pass = i < n && key > kPosZero && key >= t && key != 0xffffffffffffffffull;
-    const unsigned m = __ballot_sync(0xffffffffu, pass);
-    if (m) {
-      int pos = 0;
-      if (lane == 0) pos = atomicAdd(&cnt[qi], __popc(m));
-      pos = __shfl_sync(0xffffffffu, pos, 0);
-      if (pass) {
-        const int at = pos + __popc(m & ((1u << lane) - 1u));
-        ok[at] = key;
-        oi[at] = (uint32_t)i;
-      }
-    }
-  }
 }
 
 __global__ void __launch_bounds__(1024, 1) bm25_final_select_kernel(const unsigned long long* __restrict__ ckey,
@@ -410,95 +485,95 @@ int pow2_at_least(int v) {
   return p;
 }
 
-// Score queries [0, nq) of a sub-batch into ctx->acc_dev ([nq][n_docs]); q_off points at the sub-batch's offsets.
-int bm25_score_subbatch(sb_ctx* ctx, const int32_t* q_terms_dev, const int32_t* q_off_dev, int nq, int max_len,
-                        double* acc, double* scratch, cudaStream_t st) {
-  Bm25Index& ix = ctx->bm25;
-  const size_t acc_bytes = (size_t)nq * ix.n_docs * sizeof(double);
-  SB_CUDA(cudaMemsetAsync(acc, 0, acc_bytes, st));
-  if (max_len <= 0) return SB_OK;
-  int rc = ctx->misc_dev.reserve((size_t)max_len * (nq + 1) * sizeof(int32_t));
-  if (rc) return rc;
-  int32_t* chunk_prefix = ctx->misc_dev.as<int32_t>();
-  ctx->launches += 1;
-  bm25_plan_kernel<<<max_len, 32, 0, st>>>(q_terms_dev, q_off_dev, nq, max_len, ix.indptr, ix.idf, ix.n_terms,
-                                           chunk_prefix);
+size_t range_smem_bytes(int max_len) {
+  return (size_t)kRange * 8 + (size_t)std::max(max_len, 1) * (16 + 8 + 8 + 4) + (kRange / 32) * 4 + 16;
+}
+
+template <int MODE, bool PLUS>
+int launch_range_kernel(sb_ctx* ctx, const RangeParams& rp, int nq, int n_chunks, cudaStream_t st) {
+  const size_t smem = range_smem_bytes(rp.max_len);
+  SB_REQUIRE(smem <= ctx->smem_optin, SB_ERR_UNSUPPORTED, "bm25: a query of %d terms does not fit the per-CTA term state",
+             rp.max_len);
+  SB_CUDA(cudaFuncSetAttribute(bm25_range_kernel<MODE, PLUS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  bm25_range_kernel<MODE, PLUS><<<dim3((unsigned)nq, (unsigned)n_chunks), kRsThreads, smem, st>>>(rp);
   SB_CUDA(cudaGetLastError());
-  const int grid = ctx->num_sms * 8;
-  for (int j = 0; j < max_len; ++j) {
-    ScoreParams sp;
-    sp.q_terms = q_terms_dev;
-    sp.q_off = q_off_dev;
-    sp.nq = nq;
-    sp.j = j;
-    sp.chunk_prefix = chunk_prefix + (size_t)j * (nq + 1);
-    sp.indptr = ix.indptr;
-    sp.post_doc = ix.post_doc;
-    sp.ratio = ix.post_ratio;
-    sp.idf = ix.idf;
-    sp.n_docs = ix.n_docs;
-    ProfScope ps(ctx, SB_PROF_BM25_SCORE, st, ix.variant == SB_BM25_PLUS ? 2 : 1);
-    if (ix.variant == SB_BM25_PLUS) {
-      sp.acc = scratch;
-      bm25_score_kernel<true><<<grid, kScoreThreads, 0, st>>>(sp);
-      SB_CUDA(cudaGetLastError());
-      dim3 g((unsigned)std::min<int64_t>((ix.n_docs + 255) / 256, (int64_t)ctx->num_sms * 4), (unsigned)nq);
-      bm25_plus_dense_kernel<<<g, 256, 0, st>>>(q_terms_dev, q_off_dev, nq, j, ix.idf, ix.n_terms, ix.delta, acc,
-                                                scratch, ix.n_docs);
-      SB_CUDA(cudaGetLastError());
-    } else {
-      sp.acc = acc;
-      bm25_score_kernel<false><<<grid, kScoreThreads, 0, st>>>(sp);
-      SB_CUDA(cudaGetLastError());
-    }
-  }
   return SB_OK;
 }
 
-int bm25_subbatch_size(sb_ctx* ctx, int B) {
+template <int MODE>
+int launch_range(sb_ctx* ctx, const RangeParams& rp, int nq, int n_chunks, cudaStream_t st) {
+  return ctx->bm25.variant == SB_BM25_PLUS ? launch_range_kernel<MODE, true>(ctx, rp, nq, n_chunks, st)
+                                           : launch_range_kernel<MODE, false>(ctx, rp, nq, n_chunks, st);
+}
+
+RangeParams range_params(sb_ctx* ctx, const int32_t* q_terms_dev, const int32_t* q_off_dev, int max_len) {
   const Bm25Index& ix = ctx->bm25;
-  // keep the fp64 accumulators of a sub-batch L2 resident (~96 MB of the 126 MB L2)
-  const size_t per_q = (size_t)ix.n_docs * sizeof(double) * (ix.variant == SB_BM25_PLUS ? 2 : 1);
-  int64_t sbq = (int64_t)((96ull << 20) / (per_q ? per_q : 1));
-  if (sbq < 1) sbq = 1;
-  if (sbq > 64) sbq = 64;
-  if (sbq > B) sbq = B;
-  return (int)sbq;
+  RangeParams rp;
+  memset(&rp, 0, sizeof(rp));
+  rp.q_terms = q_terms_dev;
+  rp.q_off = q_off_dev;
+  rp.max_len = std::max(max_len, 1);
+  rp.ranges_per_cta = 1;
+  rp.indptr = ix.indptr;
+  rp.post_doc = ix.post_doc;
+  rp.ratio = ix.post_ratio;
+  rp.idf = ix.idf;
+  rp.n_terms = ix.n_terms;
+  rp.n_docs = ix.n_docs;
+  rp.delta = ix.delta;
+  return rp;
+}
+
+// consecutive ranges per CTA: long runs amortise the per-term posting-list search, short runs fill the machine
+int ranges_per_cta(sb_ctx* ctx, int nq, int64_t n_ranges) {
+  const int64_t resident = (int64_t)ctx->num_sms * 3;
+  int64_t r = ((int64_t)nq * n_ranges) / (resident * 4);
+  if (r < 1) r = 1;
+  if (r > 8) r = 8;
+  return (int)r;
 }
 
 int bm25_topk_enqueue(sb_ctx* ctx, const int32_t* q_terms_dev, const int32_t* q_off_dev, int B, int max_len, int k,
                       int64_t* out_ids, double* out_scores, int32_t* out_counts, cudaStream_t st) {
   Bm25Index& ix = ctx->bm25;
-  const int sbq = bm25_subbatch_size(ctx, B);
-  const size_t per_q = (size_t)ix.n_docs * sizeof(double) * (ix.variant == SB_BM25_PLUS ? 2 : 1);
-  int rc = ctx->acc_dev.reserve(per_q * sbq);
-  if (rc) return rc;
-  if (ix.variant == SB_BM25_PLUS)
-    SB_CUDA(cudaMemsetAsync(ctx->acc_dev.p, 0, per_q * sbq, st));  // ratio scratch must start at zero
   const int kpow2 = std::max(32, pow2_at_least(k));
   SB_REQUIRE(kpow2 <= 1024, SB_ERR_UNSUPPORTED, "bm25: top_k %d too large (max 1024)", k);
-  // select v2 scratch: thresholds + counters + worst-case (key, idx) buffers of the sub-batch
+  // sub-batch: the worst-case candidate lists ((key, idx) per doc per query) of a sub-batch stay under 1.5 GB
+  int64_t sbq = (int64_t)((1536ull << 20) / ((size_t)ix.n_docs * 12 + 1));
+  sbq = std::max<int64_t>(1, std::min<int64_t>(sbq, B));
+  int rc;
   if ((rc = ctx->misc2_dev.reserve((size_t)sbq * ix.n_docs * 8 + (size_t)sbq * 16 + 64))) return rc;
   if ((rc = ctx->misc3_dev.reserve((size_t)sbq * ix.n_docs * 4 + 64))) return rc;
   unsigned long long* ckey = ctx->misc2_dev.as<unsigned long long>();
   unsigned long long* thr = ckey + (size_t)sbq * ix.n_docs;
   int32_t* cnt = reinterpret_cast<int32_t*>(thr + sbq);
   uint32_t* cidx = ctx->misc3_dev.as<uint32_t>();
-  const size_t samp_smem = (size_t)kBmSample * 8;
   const size_t fin_smem = (size_t)kBmStage * 12 + (size_t)kpow2 * 12 + 64;
-  SB_CUDA(cudaFuncSetAttribute(bm25_sample_thr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)samp_smem));
   SB_CUDA(cudaFuncSetAttribute(bm25_final_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
-  for (int b0 = 0; b0 < B; b0 += sbq) {
-    const int nq = std::min(sbq, B - b0);
-    double* acc = ctx->acc_dev.as<double>();
-    double* scratch = acc + (size_t)sbq * ix.n_docs;  // Plus only; fixed offset so it is always all-zero on entry
-    if ((rc = bm25_score_subbatch(ctx, q_terms_dev, q_off_dev + b0, nq, max_len, acc, scratch, st))) return rc;
-    ProfScope ps(ctx, SB_PROF_BM25_SELECT, st, 3);
-    bm25_sample_thr_kernel<<<nq, 1024, samp_smem, st>>>(acc, ix.n_docs, k, thr, cnt);
-    SB_CUDA(cudaGetLastError());
-    dim3 cg((unsigned)((ix.n_docs + 2047) / 2048), (unsigned)nq);
-    bm25_collect_kernel<<<cg, 256, 0, st>>>(acc, ix.n_docs, thr, cnt, ckey, cidx);
-    SB_CUDA(cudaGetLastError());
+  const int64_t n_ranges = (ix.n_docs + kRange - 1) / kRange;
+  for (int b0 = 0; b0 < B; b0 += (int)sbq) {
+    const int nq = (int)std::min<int64_t>(sbq, B - b0);
+    RangeParams rp = range_params(ctx, q_terms_dev, q_off_dev + b0, max_len);
+    rp.k = k;
+    rp.thr = thr;
+    rp.cnt = cnt;
+    rp.ckey = ckey;
+    rp.cidx = cidx;
+    {
+      ProfScope ps(ctx, SB_PROF_BM25_SCORE, st, 2);
+      // (1) safe per-query lower bound of the k-th best score from S sample ranges (exact k-th best when S == 1)
+      const int S = (int)std::min<int64_t>(8, n_ranges);
+      rp.k = (k + S - 1) / S;
+      SB_CUDA(cudaMemsetAsync(thr, 0xff, (size_t)nq * 8, st));
+      SB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nq * 4, st));
+      if ((rc = launch_range<kModeSample>(ctx, rp, nq, S, st))) return rc;
+      // (2) score every range in shared memory, keep only docs that can still reach the top k
+      rp.ranges_per_cta = ranges_per_cta(ctx, nq, n_ranges);
+      const int n_chunks = (int)((n_ranges + rp.ranges_per_cta - 1) / rp.ranges_per_cta);
+      if ((rc = launch_range<kModeCollect>(ctx, rp, nq, n_chunks, st))) return rc;
+    }
+    ProfScope ps(ctx, SB_PROF_BM25_SELECT, st, 1);
+    // (3) exact k-th largest by radix select over the (few) candidates, ties by ascending doc index, sort the winners
     bm25_final_select_kernel<<<nq, 1024, fin_smem, st>>>(ckey, cidx, cnt, ix.n_docs, k, kpow2, ix.id_base,
                                                          out_ids + (size_t)b0 * k, out_scores + (size_t)b0 * k,
                                                          out_counts + b0);
@@ -668,12 +743,14 @@ int sb_bm25_scores(sb_ctx* ctx, const int32_t* q_terms, int32_t n_q, double* out
   int32_t off[2] = {0, n_q};
   if (n_q) SB_CUDA(cudaMemcpyAsync(ctx->q_dev.p, q_terms, (size_t)n_q * 4, cudaMemcpyHostToDevice, st));
   SB_CUDA(cudaMemcpyAsync(ctx->q_dev.as<uint8_t>() + tb, off, 8, cudaMemcpyHostToDevice, st));
-  const size_t per_q = (size_t)ix.n_docs * sizeof(double) * (ix.variant == SB_BM25_PLUS ? 2 : 1);
-  if ((rc = ctx->acc_dev.reserve(per_q))) return rc;
-  if (ix.variant == SB_BM25_PLUS) SB_CUDA(cudaMemsetAsync(ctx->acc_dev.p, 0, per_q, st));
-  if ((rc = bm25_score_subbatch(ctx, ctx->q_dev.as<int32_t>(),
-                                reinterpret_cast<const int32_t*>(ctx->q_dev.as<uint8_t>() + tb), 1, n_q,
-                                ctx->acc_dev.as<double>(), ctx->acc_dev.as<double>() + ix.n_docs, st)))
+  if ((rc = ctx->acc_dev.reserve((size_t)ix.n_docs * sizeof(double)))) return rc;
+  RangeParams rp = range_params(ctx, ctx->q_dev.as<int32_t>(),
+                                reinterpret_cast<const int32_t*>(ctx->q_dev.as<uint8_t>() + tb), n_q);
+  rp.dump = ctx->acc_dev.as<double>();
+  const int64_t n_ranges = (ix.n_docs + kRange - 1) / kRange;
+  rp.ranges_per_cta = ranges_per_cta(ctx, 1, n_ranges);
+  ctx->launches += 1;
+  if ((rc = launch_range<kModeDump>(ctx, rp, 1, (int)((n_ranges + rp.ranges_per_cta - 1) / rp.ranges_per_cta), st)))
     return rc;
   SB_CUDA(cudaMemcpyAsync(out_scores, ctx->acc_dev.p, (size_t)ix.n_docs * 8, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));

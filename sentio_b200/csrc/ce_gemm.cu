@@ -88,9 +88,10 @@ __device__ __forceinline__ float gelu_erf(float x) {
 
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 2)
-ce_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N, int K,
+ce_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M_cap, int N, int K,
                const float* __restrict__ bias, const float* __restrict__ residual, __half* __restrict__ out16,
-               float* __restrict__ out32) {
+               float* __restrict__ out32, const int* __restrict__ m_dev) {
+  const int M = m_dev ? min(M_cap, __ldg(m_dev)) : M_cap;
   extern __shared__ uint8_t gsm_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t raw = smem_u32(gsm_raw);
@@ -276,9 +277,10 @@ __device__ __forceinline__ void epilogue_store_32(const uint32_t (&v)[32], int r
 
 template <int EPI, bool RESIDENT>
 __global__ void __launch_bounds__(kWsThreads, 1)
-ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N,
+ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M_cap, int N,
                   int K, const float* __restrict__ bias, const float* __restrict__ residual, __half* __restrict__ out16,
-                  float* __restrict__ out32) {
+                  float* __restrict__ out32, const int* __restrict__ m_dev) {
+  const int M = m_dev ? min(M_cap, __ldg(m_dev)) : M_cap;
   extern __shared__ uint8_t wsm_raw[];
   const uint32_t raw = smem_u32(wsm_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -493,7 +495,7 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
 template <int EPI, bool RESIDENT>
 int launch_ws(const CUtensorMap& map_a, const CUtensorMap& map_w, int M, int N, int K, const float* bias,
-              const float* residual, __half* out16, float* out32, cudaStream_t st) {
+              const float* residual, __half* out16, float* out32, cudaStream_t st, const int* m_dev) {
   const size_t extra = 1024 /*align*/ + 256 /*barriers*/ + (size_t)kWsEpiWarps * kStageWarpBytes;
   const size_t smem = RESIDENT ? (size_t)(K / BK) * kTileBBytes + (size_t)kWsStages * kTileABytes + extra
                                : (size_t)kWsStages * kStageBytes + extra;
@@ -507,7 +509,8 @@ int launch_ws(const CUtensorMap& map_a, const CUtensorMap& map_w, int M, int N, 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = (N / BN) * ((M + BM - 1) / BM);
   const int grid = std::max(N / BN, std::min(sms, tiles));
-  ce_gemm_ws_kernel<EPI, RESIDENT><<<grid, kWsThreads, smem, st>>>(map_a, map_w, M, N, K, bias, residual, out16, out32);
+  ce_gemm_ws_kernel<EPI, RESIDENT><<<grid, kWsThreads, smem, st>>>(map_a, map_w, M, N, K, bias, residual, out16, out32,
+                                                                   m_dev);
   SB_CUDA(cudaGetLastError());
   return SB_OK;
 }
@@ -547,26 +550,26 @@ int ce_make_tensor_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t 
 }
 
 int ce_gemm_launch(int epi, const CUtensorMap& map_a, const CUtensorMap& map_w, int M, int N, int K, const float* bias,
-                   const float* residual, __half* out16, float* out32, cudaStream_t st) {
+                   const float* residual, __half* out16, float* out32, cudaStream_t st, const int* m_dev) {
   SB_REQUIRE(N % BN == 0 && K % BK == 0, SB_ERR_ARG, "ce_gemm: N=%d / K=%d must be multiples of %d / %d", N, K, BN, BK);
   if ((M + BM - 1) / BM >= 4) {  // persistent kernels: weight-stationary when the weight tile fits, streaming otherwise
     if (K <= 384) {
       switch (epi) {
         case CE_EPI_BIAS_F16:
-          return launch_ws<CE_EPI_BIAS_F16, true>(map_a, map_w, M, N, K, bias, residual, out16, out32, st);
+          return launch_ws<CE_EPI_BIAS_F16, true>(map_a, map_w, M, N, K, bias, residual, out16, out32, st, m_dev);
         case CE_EPI_BIAS_GELU_F16:
-          return launch_ws<CE_EPI_BIAS_GELU_F16, true>(map_a, map_w, M, N, K, bias, residual, out16, out32, st);
+          return launch_ws<CE_EPI_BIAS_GELU_F16, true>(map_a, map_w, M, N, K, bias, residual, out16, out32, st, m_dev);
         case CE_EPI_BIAS_RES_F32:
-          return launch_ws<CE_EPI_BIAS_RES_F32, true>(map_a, map_w, M, N, K, bias, residual, out16, out32, st);
+          return launch_ws<CE_EPI_BIAS_RES_F32, true>(map_a, map_w, M, N, K, bias, residual, out16, out32, st, m_dev);
       }
     } else {
       switch (epi) {
         case CE_EPI_BIAS_F16:
-          return launch_ws<CE_EPI_BIAS_F16, false>(map_a, map_w, M, N, K, bias, residual, out16, out32, st);
+          return launch_ws<CE_EPI_BIAS_F16, false>(map_a, map_w, M, N, K, bias, residual, out16, out32, st, m_dev);
         case CE_EPI_BIAS_GELU_F16:
-          return launch_ws<CE_EPI_BIAS_GELU_F16, false>(map_a, map_w, M, N, K, bias, residual, out16, out32, st);
+          return launch_ws<CE_EPI_BIAS_GELU_F16, false>(map_a, map_w, M, N, K, bias, residual, out16, out32, st, m_dev);
         case CE_EPI_BIAS_RES_F32:
-          return launch_ws<CE_EPI_BIAS_RES_F32, false>(map_a, map_w, M, N, K, bias, residual, out16, out32, st);
+          return launch_ws<CE_EPI_BIAS_RES_F32, false>(map_a, map_w, M, N, K, bias, residual, out16, out32, st, m_dev);
       }
     }
   }
@@ -580,7 +583,7 @@ int ce_gemm_launch(int epi, const CUtensorMap& map_a, const CUtensorMap& map_w, 
         once = true;
       }
       ce_gemm_kernel<CE_EPI_BIAS_F16><<<grid, kGemmThreads, kGemmSmem, st>>>(map_a, map_w, M, N, K, bias, residual,
-                                                                             out16, out32);
+                                                                             out16, out32, m_dev);
       break;
     }
     case CE_EPI_BIAS_GELU_F16: {
@@ -590,8 +593,7 @@ int ce_gemm_launch(int epi, const CUtensorMap& map_a, const CUtensorMap& map_w, 
                                      (int)kGemmSmem));
         once = true;
       }
-      ce_gemm_kernel<CE_EPI_BIAS_GELU_F16><<<grid, kGemmThreads, kGemmSmem, st>>>(map_a, map_w, M, N, K, bias,
-                                                                                  residual, out16, out32);
+      ce_gemm_kernel<CE_EPI_BIAS_GELU_F16><<<grid, kGemmThreads, kGemmSmem, st>>>(map_a, map_w, M, N, K, bias, residual, out16, out32, m_dev);
       break;
     }
     case CE_EPI_BIAS_RES_F32: {
@@ -602,7 +604,7 @@ int ce_gemm_launch(int epi, const CUtensorMap& map_a, const CUtensorMap& map_w, 
         once = true;
       }
       ce_gemm_kernel<CE_EPI_BIAS_RES_F32><<<grid, kGemmThreads, kGemmSmem, st>>>(map_a, map_w, M, N, K, bias, residual,
-                                                                                 out16, out32);
+                                                                                 out16, out32, m_dev);
       break;
     }
     default:

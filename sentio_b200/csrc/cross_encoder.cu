@@ -4,11 +4,16 @@
 // Per layer:  QKV GEMM (tcgen05, bias)  ->  masked softmax attention  ->  out-proj GEMM (+bias +residual, fp32)
 //             -> LayerNorm -> FFN-up GEMM (+bias, erf-GELU) -> FFN-down GEMM (+bias +residual, fp32) -> LayerNorm.
 // The residual stream stays fp32 in HBM; every GEMM operand is an fp16 copy written by the producing kernel; all GEMM
-// accumulation is fp32 in tensor memory (ce_gemm.cu).  Rows beyond a pair's length are padding: they are never read as
-// keys (masked) and their own outputs are never consumed, which is bit-for-bit what the additive -inf mask of the
-// HuggingFace oracle yields for the [CLS] logit.
+// accumulation is fp32 in tensor memory (ce_gemm.cu).
 //
-// flops per pair = L * (24*S*H^2 + 4*S^2*H)  (2.87 GFLOP at L=6, H=384, S=128); bound: tensor pipe.
+// PACKED TOKENS: positions beyond a pair's length are padding -- never read as keys (masked) and never consumed, which is
+// what the additive -inf mask of the HuggingFace oracle yields for the [CLS] logit -- so they are not computed at all: the
+// tokens of all pairs of a forward pass are packed back to back (pair p occupies rows [cu[p], cu[p] + len[p])), every
+// GEMM / LayerNorm runs over sum(len) rows instead of P*S, attention only visits the key tiles below len.  The packed row
+// count only exists on the device (cu[P]); grids are sized for P*S and the kernels clamp to it (ce_gemm.cuh m_dev), so
+// the forward stays a pure enqueue with no host synchronisation.
+//
+// flops per pair = L * (24*len*H^2 + 4*len^2*H)  (2.87 GFLOP at L=6, H=384, len=S=128); bound: tensor pipe.
 #include <math.h>
 #include <string.h>
 
@@ -36,6 +41,14 @@ struct CeModel {
   __half *x16 = nullptr, *qkv16 = nullptr, *ctx16 = nullptr, *ffn16 = nullptr;  // [M,H] [M,3H] [M,H] [M,I]
   CUtensorMap m_x16, m_ctx16, m_ffn16;
   std::vector<void*> act_allocs;
+  int32_t* cu = nullptr;   // [cu_cap + 1] first packed row of every pair; cu[P] = packed row count of the pass
+  int64_t cu_cap = 0;
+  unsigned long long* stats = nullptr;  // device: {pairs, sum len, sum len^2} since the last reset (sb_ce_stats)
+  // last layer: only the [CLS] row of a pair reaches the head -> P-row buffers for everything after its K/V projection
+  float *xcls32 = nullptr, *precls32 = nullptr;                       // [P,H]
+  __half *xcls16 = nullptr, *ctxcls16 = nullptr, *ffncls16 = nullptr;  // [P,H] [P,H] [P,I]
+  CUtensorMap m_xcls16, m_ctxcls16, m_ffncls16;
+  std::vector<void*> cls_allocs;
 };
 
 // Per-shard store of pre-tokenised documents for the batched rerank path: doc i -> tok[i][0..len[i])
@@ -57,6 +70,9 @@ void ce_model_free(CeModel* m) {
   if (!m) return;
   for (void* p : m->allocs) cudaFree(p);
   for (void* p : m->act_allocs) cudaFree(p);
+  if (m->cu) cudaFree(m->cu);
+  if (m->stats) cudaFree(m->stats);
+  for (void* p : m->cls_allocs) cudaFree(p);
   delete m;
 }
 
@@ -68,20 +84,70 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restri
   if (i < n) out[i] = __float2half_rn(in[i]);
 }
 
-// One warp per token row: x = LN(word[id] + pos[s] + type[tt]); writes the fp32 residual and its fp16 GEMM copy.
+// cu[p] = sum_{i<p} clamp(len[i], 1, S): first packed row of pair p; cu[P] = packed row count.  One CTA.
+__global__ void __launch_bounds__(1024) ce_cu_kernel(const int32_t* __restrict__ lens, int P, int S,
+                                                     int32_t* __restrict__ cu, unsigned long long* __restrict__ stats) {
+  __shared__ int warp_sum[32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < P; base += 1024) {
+    const int i = base + tid;
+    const int v = i < P ? min(max(lens[i], 1), S) : 0;
+    int x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_sum[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      warp_sum[lane] = w;  // inclusive
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int excl = carry + (warp ? warp_sum[warp - 1] : 0) + x - v;
+    if (i < P) cu[i] = excl;
+    {
+      unsigned long long sq = (unsigned long long)v * (unsigned long long)v;
+      for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      if (lane == 0 && sq) atomicAdd(stats + 2, sq);
+    }
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + warp_sum[31];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    cu[P] = carry_s;
+    atomicAdd(stats + 0, (unsigned long long)P);
+    atomicAdd(stats + 1, (unsigned long long)carry_s);
+  }
+}
+
+// One warp per (pair, position): x = LN(word[id] + pos[s] + type[tt]); writes the fp32 residual and its fp16 GEMM copy
+// to the PACKED row cu[pair] + s.  M = P * S padded positions are enumerated, positions >= len produce nothing.
 template <int H>
-__global__ void ce_embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ tts, int M, int S,
+__global__ void ce_embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ tts,
+                                   const int32_t* __restrict__ lens, const int32_t* __restrict__ cu, int M, int S,
                                    int vocab, int type_vocab, const float* __restrict__ word,
                                    const float* __restrict__ pos, const float* __restrict__ type,
                                    const float* __restrict__ g, const float* __restrict__ b, float eps,
                                    float* __restrict__ x32, __half* __restrict__ x16) {
   constexpr int PER = H / 32;
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (row >= M) return;
-  int id = ids[row], tt = tts[row];
+  const int prow = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (prow >= M) return;
+  const int pair = prow / S, s = prow % S;
+  if (s >= min(max(lens[pair], 1), S)) return;
+  const int row = cu[pair] + s;
+  int id = ids[prow], tt = tts[prow];
   id = min(max(id, 0), vocab - 1);
   tt = min(max(tt, 0), type_vocab - 1);
-  const int s = row % S;
   float v[PER];
   float sum = 0.f;
 #pragma unroll
@@ -111,12 +177,12 @@ __global__ void ce_embed_ln_kernel(const int32_t* __restrict__ ids, const int32_
 
 // One warp per row: LayerNorm of the pre-LN sum -> fp32 residual + fp16 GEMM copy.
 template <int H>
-__global__ void ce_ln_kernel(const float* __restrict__ pre, int M, const float* __restrict__ g,
-                             const float* __restrict__ b, float eps, float* __restrict__ x32,
-                             __half* __restrict__ x16) {
+__global__ void ce_ln_kernel(const float* __restrict__ pre, int M_host, const int32_t* __restrict__ m_dev,
+                             const float* __restrict__ g, const float* __restrict__ b, float eps,
+                             float* __restrict__ x32, __half* __restrict__ x16) {
   constexpr int PER = H / 32;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (row >= M) return;
+  if (row >= (m_dev ? __ldg(m_dev) : M_host)) return;
   float v[PER];
   float sum = 0.f;
 #pragma unroll
@@ -147,13 +213,14 @@ __global__ void ce_ln_kernel(const float* __restrict__ pre, int M, const float* 
 // Single pass online softmax (running max / sum), scores never leave registers.
 template <int DH>
 __global__ void __launch_bounds__(128) ce_attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ lengths,
-                                                           int S, int H, int heads, __half* __restrict__ ctx) {
+                                                           const int32_t* __restrict__ cu, int S, int H, int heads,
+                                                           __half* __restrict__ ctx) {
   extern __shared__ float att_sm[];
   const int pair = blockIdx.x / heads, head = blockIdx.x % heads;
   const int len = min(max(lengths[pair], 1), S);
   float* Ks = att_sm;                 // [S][DH]
   float* Vs = att_sm + (size_t)S * DH;
-  const size_t row0 = (size_t)pair * S;
+  const size_t row0 = (size_t)cu[pair];
   const int ld = 3 * H;
   for (int i = threadIdx.x; i < len * (DH / 2); i += blockDim.x) {
     const int j = i / (DH / 2), c = (i % (DH / 2)) * 2;
@@ -164,13 +231,8 @@ __global__ void __launch_bounds__(128) ce_attention_kernel(const __half* __restr
     Vs[j * DH + c] = vf.x; Vs[j * DH + c + 1] = vf.y;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
     __half* out = ctx + (row0 + i) * H + head * DH;
-    if (i >= len) {  // padding row: never consumed downstream; keep it finite
-#pragma unroll
-      for (int c = 0; c < DH; c += 2) *reinterpret_cast<__half2*>(out + c) = __floats2half2_rn(0.f, 0.f);
-      continue;
-    }
     float q[DH];
     const float scale = rsqrtf((float)DH);
 #pragma unroll
@@ -209,7 +271,7 @@ __global__ void __launch_bounds__(128) ce_attention_kernel(const __half* __restr
 // (S x 32 fp16) are staged in shared memory (rows padded to 80 B: conflict-free fragment loads / ldmatrix), scores
 // S = Q K^T and O = P V are mma.sync.m16n8k16 (fp16 in, fp32 accumulate), the softmax runs on the accumulator fragments
 // in registers and the probabilities are re-used directly as the A operand of the second product (no smem round trip).
-// Rows >= len are padding (never consumed downstream): they are written as zeros.
+// Packed layout: the pair's rows are [cu[pair], cu[pair] + len); key tiles at or beyond len are skipped.
 __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
@@ -222,19 +284,21 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 
 template <int S_MAX>
 __global__ void __launch_bounds__(128) ce_attention_mma_kernel(const __half* __restrict__ qkv,
-                                                                const int32_t* __restrict__ lengths, int S, int H,
+                                                                const int32_t* __restrict__ lengths,
+                                                                const int32_t* __restrict__ cu, int S, int H,
                                                                 int heads, __half* __restrict__ ctx) {
   constexpr int DH = 32, LDS_ROW = 40;  // halves per padded smem row (80 B)
   constexpr int NT = S_MAX / 8;         // key tiles of 8
   __shared__ __align__(16) __half Ks[S_MAX * LDS_ROW];
   __shared__ __align__(16) __half Vs[S_MAX * LDS_ROW];
   const int pair = blockIdx.x / heads, head = blockIdx.x % heads;
-  const int len = min(max(lengths[pair], 1), S);
-  const size_t row0 = (size_t)pair * S;
+  const int len = min(min(max(lengths[pair], 1), S), S_MAX);
+  const size_t row0 = (size_t)cu[pair];
   const int ld = 3 * H;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   // stage K and V (rows >= len as zeros so that masked products stay finite)
-  for (int i = tid; i < S_MAX * 4; i += 128) {
+  const int stage_rows = min(S_MAX, (len + 15) & ~15);  // key tiles beyond len are never touched
+  for (int i = tid; i < stage_rows * 4; i += 128) {
     const int j = i >> 2, c = (i & 3) * 8;
     uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = make_uint4(0u, 0u, 0u, 0u);
     if (j < len) {
@@ -249,20 +313,15 @@ __global__ void __launch_bounds__(128) ce_attention_mma_kernel(const __half* __r
 #pragma unroll 1
   for (int mt = 0; mt < 2; ++mt) {
     const int r0 = warp * 32 + mt * 16;  // first query row of this 16-row tile
-    if (r0 >= S) break;
+    if (r0 >= len) break;                // no such rows in the packed layout
     __half* out_lo = ctx + (row0 + r0 + g) * H + head * DH;
     __half* out_hi = ctx + (row0 + r0 + g + 8) * H + head * DH;
-    if (r0 >= len) {  // whole tile is padding
-      if (r0 + g < S) for (int c = 2 * t; c < DH; c += 8) *reinterpret_cast<uint32_t*>(out_lo + c) = 0u;
-      if (r0 + g + 8 < S) for (int c = 2 * t; c < DH; c += 8) *reinterpret_cast<uint32_t*>(out_hi + c) = 0u;
-      continue;
-    }
     // Q fragments (A operand) for the two k-steps of 16: rows g / g+8, columns 2t.. and 2t+8..
     uint32_t qa[2][4];
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
-      const __half* qlo = qkv + (row0 + min(r0 + g, S - 1)) * ld + head * DH + ks * 16 + 2 * t;
-      const __half* qhi = qkv + (row0 + min(r0 + g + 8, S - 1)) * ld + head * DH + ks * 16 + 2 * t;
+      const __half* qlo = qkv + (row0 + min(r0 + g, len - 1)) * ld + head * DH + ks * 16 + 2 * t;
+      const __half* qhi = qkv + (row0 + min(r0 + g + 8, len - 1)) * ld + head * DH + ks * 16 + 2 * t;
       qa[ks][0] = *reinterpret_cast<const uint32_t*>(qlo);
       qa[ks][1] = *reinterpret_cast<const uint32_t*>(qhi);
       qa[ks][2] = *reinterpret_cast<const uint32_t*>(qlo + 8);
@@ -272,6 +331,7 @@ __global__ void __launch_bounds__(128) ce_attention_mma_kernel(const __half* __r
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+      if (nt * 8 >= len) continue;  // CTA-uniform: the whole key tile is masked
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
         const __half* kp = Ks + (nt * 8 + g) * LDS_ROW + ks * 16 + 2 * t;
@@ -317,6 +377,7 @@ __global__ void __launch_bounds__(128) ce_attention_mma_kernel(const __half* __r
     for (int n = 0; n < DH / 8; ++n) oc[n][0] = oc[n][1] = oc[n][2] = oc[n][3] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < NT / 2; ++kk) {
+      if (kk * 16 >= len) continue;  // probabilities of these keys are exactly 0
       uint32_t pa[4];
       pa[0] = pack_h2(sc[2 * kk][0], sc[2 * kk][1]);
       pa[1] = pack_h2(sc[2 * kk][2], sc[2 * kk][3]);
@@ -333,19 +394,86 @@ __global__ void __launch_bounds__(128) ce_attention_mma_kernel(const __half* __r
     const float ilo = 1.f / llo, ihi = 1.f / lhi;
 #pragma unroll
     for (int n = 0; n < DH / 8; ++n) {
-      if (r0 + g < S) *reinterpret_cast<uint32_t*>(out_lo + n * 8 + 2 * t) = pack_h2(oc[n][0] * ilo, oc[n][1] * ilo);
-      if (r0 + g + 8 < S) *reinterpret_cast<uint32_t*>(out_hi + n * 8 + 2 * t) = pack_h2(oc[n][2] * ihi, oc[n][3] * ihi);
+      if (r0 + g < len) *reinterpret_cast<uint32_t*>(out_lo + n * 8 + 2 * t) = pack_h2(oc[n][0] * ilo, oc[n][1] * ilo);
+      if (r0 + g + 8 < len) *reinterpret_cast<uint32_t*>(out_hi + n * 8 + 2 * t) = pack_h2(oc[n][2] * ihi, oc[n][3] * ihi);
     }
   }
 }
 
+// Last layer: the head only consumes the [CLS] row of every pair, so attention is evaluated for that single query row.
+// One warp per (pair, head): lane j scores keys j, j + 32, ... (fp32 dot over the 32 head dims), warp softmax, then lane c
+// accumulates output dim c over all keys.  The warp also gathers its 32 columns of the pair's fp32 residual row into
+// xcls32, the residual operand of the P-row out-projection that follows.
+__global__ void __launch_bounds__(128) ce_attention_cls_kernel(const __half* __restrict__ qkv,
+                                                                const int32_t* __restrict__ lengths,
+                                                                const int32_t* __restrict__ cu, int P, int S, int H,
+                                                                int heads, const float* __restrict__ x32,
+                                                                __half* __restrict__ ctx_cls, float* __restrict__ xcls32) {
+  constexpr int DH = 32, KPL = 16;  // keys per lane: S <= 512
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wg >= P * heads) return;
+  const int pair = wg / heads, head = wg % heads;
+  const int len = min(max(lengths[pair], 1), S);
+  const size_t row0 = (size_t)cu[pair];
+  const int ld = 3 * H;
+  const float qmine = __half2float(qkv[row0 * ld + head * DH + lane]) * rsqrtf((float)DH);
+  float qv[DH];
+#pragma unroll
+  for (int c = 0; c < DH; ++c) qv[c] = __shfl_sync(0xffffffffu, qmine, c);
+  float sc[KPL];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int u = 0; u < KPL; ++u) {
+    const int j = u * 32 + lane;
+    sc[u] = -INFINITY;
+    if (u * 32 < len && j < len) {
+      const uint4* kp = reinterpret_cast<const uint4*>(qkv + (row0 + j) * ld + H + head * DH);
+      float s = 0.f;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const uint4 raw = __ldg(kp + v);
+        const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          s = fmaf(qv[v * 8 + 2 * e], f.x, s);
+          s = fmaf(qv[v * 8 + 2 * e + 1], f.y, s);
+        }
+      }
+      sc[u] = s;
+      mx = fmaxf(mx, s);
+    }
+  }
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float l = 0.f;
+#pragma unroll
+  for (int u = 0; u < KPL; ++u) {
+    sc[u] = (u * 32 < len && u * 32 + lane < len) ? __expf(sc[u] - mx) : 0.f;
+    l += sc[u];
+  }
+  for (int o = 16; o; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  float acc = 0.f;
+#pragma unroll
+  for (int u = 0; u < KPL; ++u) {
+    if (u * 32 >= len) break;  // warp-uniform
+    const int nk = min(32, len - u * 32);
+    for (int jj = 0; jj < nk; ++jj) {
+      const float pj = __shfl_sync(0xffffffffu, sc[u], jj);
+      acc = fmaf(pj, __half2float(qkv[(row0 + u * 32 + jj) * ld + 2 * H + head * DH + lane]), acc);
+    }
+  }
+  ctx_cls[(size_t)pair * H + head * DH + lane] = __float2half_rn(acc / l);
+  xcls32[(size_t)pair * H + head * DH + lane] = x32[row0 * H + head * DH + lane];
+}
+
 // One CTA per pair: pooled = tanh(Wp x_cls + bp); logit = w . pooled + b; relevance = sigmoid(logit).  fp32 throughout.
-__global__ void ce_head_kernel(const float* __restrict__ x32, int S, int H, const float* __restrict__ pool_w,
+__global__ void ce_head_kernel(const float* __restrict__ x32, const int32_t* __restrict__ cu, int H,
+                               const float* __restrict__ pool_w,
                                const float* __restrict__ pool_b, const float* __restrict__ cls_w,
                                const float* __restrict__ cls_b, float* __restrict__ logits, float* __restrict__ sig) {
   extern __shared__ float head_sm[];  // x_cls[H], partial[warps]
   const int pair = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const float* x = x32 + (size_t)pair * S * H;
+  const float* x = x32 + (size_t)(cu ? cu[pair] : pair) * H;  // the pair's [CLS] row (cu == NULL: x32 is [P,H])
   for (int i = threadIdx.x; i < H; i += blockDim.x) head_sm[i] = x[i];
   __syncthreads();
   float part = 0.f;
@@ -391,7 +519,36 @@ int upload_f16(sb_ctx* ctx, const float*& src, __half* dst, size_t n, cudaStream
   return SB_OK;
 }
 
-int ensure_workspace(CeModel* m, int64_t M, cudaStream_t st) {
+int ensure_workspace(CeModel* m, int64_t P, int64_t M, cudaStream_t st) {
+  if (!m->stats) {
+    SB_CUDA(cudaMalloc(&m->stats, 3 * sizeof(unsigned long long)));
+    SB_CUDA(cudaMemsetAsync(m->stats, 0, 3 * sizeof(unsigned long long), st));
+  }
+  if (P > m->cu_cap) {
+    cudaDeviceSynchronize();
+    if (m->cu) cudaFree(m->cu);
+    m->cu = nullptr;
+    m->cu_cap = 0;
+    SB_CUDA(cudaMalloc(&m->cu, (size_t)(P + P / 4 + 2) * 4));
+    m->cu_cap = P + P / 4 + 1;
+    for (void* p : m->cls_allocs) cudaFree(p);
+    m->cls_allocs.clear();
+    const int64_t Pp = (m->cu_cap + 127) / 128 * 128;
+    const int Hc = m->cfg.hidden, Ic = m->cfg.intermediate;
+    int rc;
+    if ((rc = dev_alloc(m->cls_allocs, (void**)&m->xcls32, (size_t)Pp * Hc * 4))) return rc;
+    if ((rc = dev_alloc(m->cls_allocs, (void**)&m->precls32, (size_t)Pp * Hc * 4))) return rc;
+    if ((rc = dev_alloc(m->cls_allocs, (void**)&m->xcls16, (size_t)Pp * Hc * 2))) return rc;
+    if ((rc = dev_alloc(m->cls_allocs, (void**)&m->ctxcls16, (size_t)Pp * Hc * 2))) return rc;
+    if ((rc = dev_alloc(m->cls_allocs, (void**)&m->ffncls16, (size_t)Pp * Ic * 2))) return rc;
+    SB_CUDA(cudaMemsetAsync(m->xcls32, 0, (size_t)Pp * Hc * 4, st));
+    SB_CUDA(cudaMemsetAsync(m->xcls16, 0, (size_t)Pp * Hc * 2, st));
+    SB_CUDA(cudaMemsetAsync(m->ctxcls16, 0, (size_t)Pp * Hc * 2, st));
+    SB_CUDA(cudaMemsetAsync(m->ffncls16, 0, (size_t)Pp * Ic * 2, st));
+    if ((rc = ce_make_tensor_map(&m->m_xcls16, m->xcls16, Pp, Hc))) return rc;
+    if ((rc = ce_make_tensor_map(&m->m_ctxcls16, m->ctxcls16, Pp, Hc))) return rc;
+    if ((rc = ce_make_tensor_map(&m->m_ffncls16, m->ffncls16, Pp, Ic))) return rc;
+  }
   const int64_t Mp = (M + 127) / 128 * 128;
   if (Mp <= m->m_cap) return SB_OK;
   cudaDeviceSynchronize();
@@ -426,37 +583,75 @@ int ce_forward(sb_ctx* ctx, CeModel* m, const int32_t* ids, const int32_t* tts, 
   const int Mp = (M + 127) / 128 * 128;
   const int rows_per_block = 8;
   const unsigned ln_blocks = (unsigned)((M + rows_per_block - 1) / rows_per_block);
-  ProfScope ps(ctx, SB_PROF_CE, st, 2 + (int)m->layers.size() * 7);
-  ce_embed_ln_kernel<H><<<ln_blocks, rows_per_block * 32, 0, st>>>(ids, tts, M, S, c.vocab_size, c.type_vocab,
+  ProfScope ps(ctx, SB_PROF_CE, st, 3 + (int)m->layers.size() * 7);
+  int32_t* cu = m->cu;
+  const int32_t* m_dev = cu + P;  // packed row count of this pass (device side only)
+  ce_cu_kernel<<<1, 1024, 0, st>>>(lens, P, S, cu, m->stats);
+  SB_CUDA(cudaGetLastError());
+  ce_embed_ln_kernel<H><<<ln_blocks, rows_per_block * 32, 0, st>>>(ids, tts, lens, cu, M, S, c.vocab_size, c.type_vocab,
                                                                    m->word_emb, m->pos_emb, m->type_emb, m->emb_ln_g,
                                                                    m->emb_ln_b, c.ln_eps, m->x32, m->x16);
   SB_CUDA(cudaGetLastError());
   int rc;
-  for (CeLayer& L : m->layers) {
-    if ((rc = ce_gemm_launch(CE_EPI_BIAS_F16, m->m_x16, L.m_wqkv, Mp, 3 * H, H, L.bqkv, nullptr, m->qkv16, nullptr, st)))
+  const int Pp = (P + 127) / 128 * 128;
+  const unsigned cls_ln_blocks = (unsigned)((P + rows_per_block - 1) / rows_per_block);
+  for (size_t li = 0; li < m->layers.size(); ++li) {
+    CeLayer& L = m->layers[li];
+    if ((rc = ce_gemm_launch(CE_EPI_BIAS_F16, m->m_x16, L.m_wqkv, Mp, 3 * H, H, L.bqkv, nullptr, m->qkv16, nullptr, st,
+                             m_dev)))
       return rc;
+    if (li + 1 == m->layers.size() && H % 32 == 0 && H / heads == 32) {
+      // last layer: K/V of every token, everything else for the P [CLS] rows only
+      ce_attention_cls_kernel<<<(unsigned)((P * heads + 3) / 4), 128, 0, st>>>(m->qkv16, lens, cu, P, S, H, heads, m->x32,
+                                                                              m->ctxcls16, m->xcls32);
+      SB_CUDA(cudaGetLastError());
+      if ((rc = ce_gemm_launch(CE_EPI_BIAS_RES_F32, m->m_ctxcls16, L.m_wo, Pp, H, H, L.bo, m->xcls32, nullptr,
+                               m->precls32, st)))
+        return rc;
+      ce_ln_kernel<H><<<cls_ln_blocks, rows_per_block * 32, 0, st>>>(m->precls32, P, nullptr, L.ln1_g, L.ln1_b, c.ln_eps,
+                                                                     m->xcls32, m->xcls16);
+      SB_CUDA(cudaGetLastError());
+      if ((rc = ce_gemm_launch(CE_EPI_BIAS_GELU_F16, m->m_xcls16, L.m_w1, Pp, I, H, L.b1, nullptr, m->ffncls16, nullptr,
+                               st)))
+        return rc;
+      if ((rc = ce_gemm_launch(CE_EPI_BIAS_RES_F32, m->m_ffncls16, L.m_w2, Pp, H, I, L.b2, m->xcls32, nullptr,
+                               m->precls32, st)))
+        return rc;
+      ce_ln_kernel<H><<<cls_ln_blocks, rows_per_block * 32, 0, st>>>(m->precls32, P, nullptr, L.ln2_g, L.ln2_b, c.ln_eps,
+                                                                     m->xcls32, m->xcls16);
+      SB_CUDA(cudaGetLastError());
+      ce_head_kernel<<<P, 256, (size_t)(H + 32) * sizeof(float), st>>>(m->xcls32, nullptr, H, m->pool_w, m->pool_b,
+                                                                      m->cls_w, m->cls_b, logits, sig);
+      SB_CUDA(cudaGetLastError());
+      return SB_OK;
+    }
     if (S <= 128)
-      ce_attention_mma_kernel<128><<<P * heads, 128, 0, st>>>(m->qkv16, lens, S, H, heads, m->ctx16);
+      ce_attention_mma_kernel<128><<<P * heads, 128, 0, st>>>(m->qkv16, lens, cu, S, H, heads, m->ctx16);
     else if (S <= 256)
-      ce_attention_mma_kernel<256><<<P * heads, 128, 0, st>>>(m->qkv16, lens, S, H, heads, m->ctx16);
+      ce_attention_mma_kernel<256><<<P * heads, 128, 0, st>>>(m->qkv16, lens, cu, S, H, heads, m->ctx16);
     else {
       const size_t att_smem = (size_t)2 * S * 32 * sizeof(float);
       SB_CUDA(cudaFuncSetAttribute(ce_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
-      ce_attention_kernel<32><<<P * heads, 128, att_smem, st>>>(m->qkv16, lens, S, H, heads, m->ctx16);
+      ce_attention_kernel<32><<<P * heads, 128, att_smem, st>>>(m->qkv16, lens, cu, S, H, heads, m->ctx16);
     }
     SB_CUDA(cudaGetLastError());
-    if ((rc = ce_gemm_launch(CE_EPI_BIAS_RES_F32, m->m_ctx16, L.m_wo, Mp, H, H, L.bo, m->x32, nullptr, m->pre32, st)))
+    if ((rc = ce_gemm_launch(CE_EPI_BIAS_RES_F32, m->m_ctx16, L.m_wo, Mp, H, H, L.bo, m->x32, nullptr, m->pre32, st,
+                             m_dev)))
       return rc;
-    ce_ln_kernel<H><<<ln_blocks, rows_per_block * 32, 0, st>>>(m->pre32, M, L.ln1_g, L.ln1_b, c.ln_eps, m->x32, m->x16);
+    ce_ln_kernel<H><<<ln_blocks, rows_per_block * 32, 0, st>>>(m->pre32, M, m_dev, L.ln1_g, L.ln1_b, c.ln_eps, m->x32,
+                                                               m->x16);
     SB_CUDA(cudaGetLastError());
-    if ((rc = ce_gemm_launch(CE_EPI_BIAS_GELU_F16, m->m_x16, L.m_w1, Mp, I, H, L.b1, nullptr, m->ffn16, nullptr, st)))
+    if ((rc = ce_gemm_launch(CE_EPI_BIAS_GELU_F16, m->m_x16, L.m_w1, Mp, I, H, L.b1, nullptr, m->ffn16, nullptr, st,
+                             m_dev)))
       return rc;
-    if ((rc = ce_gemm_launch(CE_EPI_BIAS_RES_F32, m->m_ffn16, L.m_w2, Mp, H, I, L.b2, m->x32, nullptr, m->pre32, st)))
+    if ((rc = ce_gemm_launch(CE_EPI_BIAS_RES_F32, m->m_ffn16, L.m_w2, Mp, H, I, L.b2, m->x32, nullptr, m->pre32, st,
+                             m_dev)))
       return rc;
-    ce_ln_kernel<H><<<ln_blocks, rows_per_block * 32, 0, st>>>(m->pre32, M, L.ln2_g, L.ln2_b, c.ln_eps, m->x32, m->x16);
+    ce_ln_kernel<H><<<ln_blocks, rows_per_block * 32, 0, st>>>(m->pre32, M, m_dev, L.ln2_g, L.ln2_b, c.ln_eps, m->x32,
+                                                               m->x16);
     SB_CUDA(cudaGetLastError());
   }
-  ce_head_kernel<<<P, 256, (size_t)(H + 32) * sizeof(float), st>>>(m->x32, S, H, m->pool_w, m->pool_b, m->cls_w,
+  ce_head_kernel<<<P, 256, (size_t)(H + 32) * sizeof(float), st>>>(m->x32, cu, H, m->pool_w, m->pool_b, m->cls_w,
                                                                   m->cls_b, logits, sig);
   SB_CUDA(cudaGetLastError());
   return SB_OK;
@@ -469,7 +664,7 @@ int ce_forward_dispatch(sb_ctx* ctx, const int32_t* ids, const int32_t* tts, con
   SB_REQUIRE(S > 0 && S <= m->cfg.max_pos, SB_ERR_ARG, "sb_ce_score: sequence length %d exceeds max_pos %d", S,
              m->cfg.max_pos);
   SB_REQUIRE(S <= 512, SB_ERR_UNSUPPORTED, "sb_ce_score: sequence length %d > 512", S);
-  int rc = ensure_workspace(m, (int64_t)P * S, st);
+  int rc = ensure_workspace(m, P, (int64_t)P * S, st);
   if (rc) return rc;
   switch (m->cfg.hidden) {
     case 384: return ce_forward<384>(ctx, m, ids, tts, lens, P, S, logits, sig, st);
@@ -681,6 +876,20 @@ int sb_ce_score_dev(sb_ctx* ctx, const int32_t* input_ids_dev, const int32_t* to
   DeviceGuard g(ctx->device);
   return ce_forward_dispatch(ctx, input_ids_dev, token_type_dev, lengths_dev, P, S, out_logits_dev, out_sigmoid_dev,
                              pick_stream(ctx, stream));
+}
+
+int sb_ce_stats(sb_ctx* ctx, int64_t* out3, int32_t reset) {
+  SB_REQUIRE(ctx != nullptr && out3 != nullptr, SB_ERR_ARG, "sb_ce_stats: NULL argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  out3[0] = out3[1] = out3[2] = 0;
+  if (!ctx->ce || !ctx->ce->stats) return SB_OK;
+  SB_CUDA(cudaDeviceSynchronize());
+  unsigned long long h[3];
+  SB_CUDA(cudaMemcpy(h, ctx->ce->stats, sizeof(h), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 3; ++i) out3[i] = (int64_t)h[i];
+  if (reset) SB_CUDA(cudaMemset(ctx->ce->stats, 0, sizeof(h)));
+  return SB_OK;
 }
 
 int sb_ce_score(sb_ctx* ctx, const int32_t* input_ids, const int32_t* token_type, const int32_t* lengths, int32_t P,

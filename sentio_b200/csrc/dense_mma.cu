@@ -19,6 +19,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "dense_common.cuh"
 #include "dense_mma.cuh"
@@ -282,16 +283,31 @@ __global__ void __launch_bounds__(kSelectThreads, 1) dense_select_kernel(const S
   const int K = p.kprime, G = p.grid;
   const int32_t* counts = p.counts + (size_t)qi * G;
   const unsigned long long* cand = p.cand + (size_t)qi * G * p.capg;
-  if (tid == 0) {
-    int run = 0;
-    for (int g = 0; g < G; ++g) {
-      s_prefix[g] = run;
-      run += counts[g];
+  // exclusive prefix of the per-CTA survivor counts (G <= 1024): one element per thread, warp scans + a scan of the sums
+  {
+    const int v = tid < G ? counts[tid] : 0;
+    int x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
     }
-    s_prefix[G] = run;
-    s_ntop = 0;
+    if (lane == 31) s_hist[warp] = x;
+    if (tid == 0) s_ntop = 0;
+    __syncthreads();
+    if (warp == 0) {
+      int w = lane < nw ? s_hist[lane] : 0;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      s_hist[32 + lane] = w;  // inclusive warp totals
+    }
+    __syncthreads();
+    const int incl = x + (warp ? s_hist[32 + warp - 1] : 0);
+    if (tid < G) s_prefix[tid] = incl - v;
+    if (tid == G - 1) s_prefix[G] = incl;
+    __syncthreads();
   }
-  __syncthreads();
   const int total = s_prefix[G];
   const bool staged = total <= kSelStage;
   if (staged) {
@@ -464,15 +480,21 @@ int dense_mma_topk_enqueue(sb_ctx* ctx, DenseIndex& ix, const float* q_pad, int 
   const int grid = std::min(ctx->num_sms, total_tiles);
   const int capg = ((total_tiles + grid - 1) / grid) * kTileRows;  // worst case: every row of the CTA's share survives
   int rc;
-  // scratch: fp16 query block | thresholds | counts | survivors
-  const size_t q16_bytes = (size_t)qbn_max * ix.d_pad * 2;
-  const size_t cand_bytes = (size_t)qbn_max * grid * capg * 8;
-  if ((rc = ctx->misc2_dev.reserve(q16_bytes + 256))) return rc;
-  if ((rc = ctx->misc3_dev.reserve((size_t)qbn_max * 4 + (size_t)qbn_max * grid * 4 + 256))) return rc;
-  if ((rc = ctx->cand_dev.reserve(cand_bytes))) return rc;
+  // Query groups of qbn_max (the last one may use a smaller operand block).  Several groups are kept in flight so that
+  // the two select launches (one CTA per query) cover ALL their queries at once instead of qbn at a time: with small
+  // shards the selects, not the scans, would otherwise dominate.  In-flight groups are bounded by the survivor scratch.
+  const int n_groups = (B + qbn_max - 1) / qbn_max;
+  const size_t cand_per_group = (size_t)qbn_max * grid * capg * 8;
+  int gmax = (int)std::max<size_t>(1, (size_t)(2048ull << 20) / cand_per_group);
+  gmax = std::min(gmax, n_groups);
+  // scratch: fp16 query blocks | thresholds | counts | survivors
+  const size_t q16_group = (size_t)qbn_max * ix.d_pad * 2;
+  if ((rc = ctx->misc2_dev.reserve(q16_group * gmax + 256))) return rc;
+  if ((rc = ctx->misc3_dev.reserve(((size_t)qbn_max * 4 + (size_t)qbn_max * grid * 4) * gmax + 256))) return rc;
+  if ((rc = ctx->cand_dev.reserve(cand_per_group * gmax))) return rc;
   __half* q16 = ctx->misc2_dev.as<__half>();
   float* thr = ctx->misc3_dev.as<float>();
-  int32_t* counts = reinterpret_cast<int32_t*>(thr + qbn_max);
+  int32_t* counts = reinterpret_cast<int32_t*>(thr + (size_t)qbn_max * gmax);
   unsigned long long* cand = ctx->cand_dev.as<unsigned long long>();
   if (ix.tm_rows_ptr != ix.rows) {  // (re)build the corpus tensor map once per loaded index
     if ((rc = encode_map(reinterpret_cast<CUtensorMap*>(ix.tm_rows), ix.rows, ix.n_pad, ix.d_pad, kTileRows))) return rc;
@@ -484,78 +506,90 @@ int dense_mma_topk_enqueue(sb_ctx* ctx, DenseIndex& ix, const float* q_pad, int 
   // sampling pass geometry: ~64 tiles spread evenly over the corpus
   const int sample_tiles = std::min(64, total_tiles);
   const int sample_step = total_tiles / sample_tiles;
-  for (int b0 = 0; b0 < B;) {
-    int qbn = qbn_max;
-    while (qbn > 16 && qbn / 2 >= B - b0) qbn >>= 1;
-    const int nq = std::min(qbn, B - b0);
-    CUtensorMap tm_q;
-    if ((rc = encode_map(&tm_q, q16, qbn, ix.d_pad, qbn))) return rc;
-    const int64_t nconv = (int64_t)qbn * ix.d_pad;
-    queries_to_f16_kernel<<<(unsigned)((nconv + 255) / 256), 256, 0, st>>>(q_pad + (size_t)b0 * ix.d_pad, nq, qbn,
-                                                                           ix.d_pad, q16);
-    SB_CUDA(cudaGetLastError());
-    const size_t q_bytes = (size_t)qbn * ix.d_pad * 2;
-    int stages = (int)((ctx->smem_optin - q_bytes - 4096) / kATileBytes);
-    stages = std::max(3, std::min(stages, 8));
-    const size_t smem = q_bytes + (size_t)stages * kATileBytes + 2048 + 1024;
+  const int sgrid = std::min(grid, sample_tiles);
+  for (int c0 = 0; c0 < B; c0 += gmax * qbn_max) {
+    const int nq_chunk = std::min(B - c0, gmax * qbn_max);   // real queries of this chunk of groups
+    const int ng = (nq_chunk + qbn_max - 1) / qbn_max;
+    struct Group { int qbn, nq; CUtensorMap tm_q; size_t smem; int stages; };
+    std::vector<Group> gs((size_t)ng);
+    int rows_total = 0;  // operand rows of the chunk (padding only at the very end)
+    for (int g = 0; g < ng; ++g) {
+      Group& G = gs[(size_t)g];
+      const int left = nq_chunk - g * qbn_max;
+      G.qbn = qbn_max;
+      while (G.qbn > 16 && G.qbn / 2 >= left) G.qbn >>= 1;
+      G.nq = std::min(G.qbn, left);
+      __half* q16g = q16 + (size_t)g * qbn_max * ix.d_pad;
+      if ((rc = encode_map(&G.tm_q, q16g, G.qbn, ix.d_pad, G.qbn))) return rc;
+      const int64_t nconv = (int64_t)G.qbn * ix.d_pad;
+      ctx->launches += 1;
+      queries_to_f16_kernel<<<(unsigned)((nconv + 255) / 256), 256, 0, st>>>(
+          q_pad + (size_t)(c0 + g * qbn_max) * ix.d_pad, G.nq, G.qbn, ix.d_pad, q16g);
+      SB_CUDA(cudaGetLastError());
+      const size_t q_bytes = (size_t)G.qbn * ix.d_pad * 2;
+      G.stages = std::max(3, std::min((int)((ctx->smem_optin - q_bytes - 4096) / kATileBytes), 8));
+      G.smem = q_bytes + (size_t)G.stages * kATileBytes + 2048 + 1024;
+      rows_total = g * qbn_max + G.qbn;
+    }
     MmaScanParams mp;
     mp.inv_norm = ix.inv_norm;
-    mp.cand = cand;
-    mp.counts = counts;
     mp.n = ix.n;
     mp.kb_count = kb_count;
     mp.capg = capg;
-    mp.stages = stages;
     SelectParams sp;
     sp.cand = cand;
     sp.counts = counts;
     sp.capg = capg;
     sp.kprime = kprime;
-    sp.nq = nq;
+    sp.nq = nq_chunk;
     sp.thr_out = thr;
     sp.rows = ix.rows;
-    sp.q = q_pad + (size_t)b0 * ix.d_pad;
+    sp.q = q_pad + (size_t)c0 * ix.d_pad;
     sp.d_pad = ix.d_pad;
     sp.ch = ix.d_pad / 8;
     sp.id_base = ix.id_base;
     sp.k = k;
-    sp.out_ids = out_ids + (size_t)b0 * k;
-    sp.out_scores = out_scores + (size_t)b0 * k;
-    sp.out_counts = out_counts + b0;
-    // (1) sampling pass -> safe thresholds
-    {
-      const int sgrid = std::min(grid, sample_tiles);
-      mp.thr_init = nullptr;
-      mp.num_tiles = sample_tiles;
-      mp.tile_first = 0;
-      mp.tile_step = sample_step;
-      ctx->launches += 2;
-      if ((rc = dispatch_mma(qbn, tm_rows, tm_q, mp, sgrid, smem, st))) return rc;
-      sp.grid = sgrid;
-      sp.mode = 0;
-      dense_select_kernel<<<qbn, kSelectThreads, sel_smem, st>>>(sp);
-      SB_CUDA(cudaGetLastError());
+    sp.out_ids = out_ids + (size_t)c0 * k;
+    sp.out_scores = out_scores + (size_t)c0 * k;
+    sp.out_counts = out_counts + c0;
+    // (1) sampling passes -> safe thresholds for every query of the chunk (one select launch)
+    mp.thr_init = nullptr;
+    mp.num_tiles = sample_tiles;
+    mp.tile_first = 0;
+    mp.tile_step = sample_step;
+    for (int g = 0; g < ng; ++g) {
+      const Group& G = gs[(size_t)g];
+      mp.cand = cand + (size_t)g * qbn_max * sgrid * capg;
+      mp.counts = counts + (size_t)g * qbn_max * sgrid;
+      mp.stages = G.stages;
+      ctx->launches += 1;
+      if ((rc = dispatch_mma(G.qbn, tm_rows, G.tm_q, mp, sgrid, G.smem, st))) return rc;
     }
-    // (2) the full pass
-    {
-      mp.thr_init = thr;
-      mp.num_tiles = total_tiles;
-      mp.tile_first = 0;
-      mp.tile_step = 1;
-      {
-        ProfScope ps(ctx, SB_PROF_DENSE_SCAN, st);
-        rc = dispatch_mma(qbn, tm_rows, tm_q, mp, grid, smem, st);
-      }
-      if (rc) return rc;
-      sp.grid = grid;
-      sp.mode = 1;
-      {
-        ProfScope ps(ctx, SB_PROF_DENSE_MERGE, st);
-        dense_select_kernel<<<nq, kSelectThreads, sel_smem, st>>>(sp);
-      }
-      SB_CUDA(cudaGetLastError());
+    sp.grid = sgrid;
+    sp.mode = 0;
+    ctx->launches += 1;
+    dense_select_kernel<<<rows_total, kSelectThreads, sel_smem, st>>>(sp);
+    SB_CUDA(cudaGetLastError());
+    // (2) the full passes, then one select + exact re-score launch for the chunk
+    mp.num_tiles = total_tiles;
+    mp.tile_first = 0;
+    mp.tile_step = 1;
+    for (int g = 0; g < ng; ++g) {
+      const Group& G = gs[(size_t)g];
+      mp.thr_init = thr + (size_t)g * qbn_max;
+      mp.cand = cand + (size_t)g * qbn_max * grid * capg;
+      mp.counts = counts + (size_t)g * qbn_max * grid;
+      mp.stages = G.stages;
+      ProfScope ps(ctx, SB_PROF_DENSE_SCAN, st);
+      if ((rc = dispatch_mma(G.qbn, tm_rows, G.tm_q, mp, grid, G.smem, st))) return rc;
     }
-    b0 += nq;
+    sp.grid = grid;
+    sp.mode = 1;
+    {
+      ProfScope ps(ctx, SB_PROF_DENSE_MERGE, st);
+      dense_select_kernel<<<nq_chunk, kSelectThreads, sel_smem, st>>>(sp);
+    }
+    SB_CUDA(cudaGetLastError());
   }
   return SB_OK;
 }

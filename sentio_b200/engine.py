@@ -317,6 +317,12 @@ class B200Engine:
                   "sb_ce_score")
         return logits, sig
 
+    def ce_stats(self, reset: bool = False):
+        """(pairs, token rows computed, sum of squared pair lengths) of the packed-token forward since the last reset."""
+        out = np.zeros(3, dtype=np.int64)
+        check(self._lib.sb_ce_stats(self._h, _ptr(out), int(reset)), "sb_ce_stats")
+        return int(out[0]), int(out[1]), int(out[2])
+
     def ce_score_dev(self, ids_t, tt_t, len_t, out=None):
         import torch
 

@@ -148,13 +148,27 @@ class HybridPipeline:
     def hybrid_rerank_dev(self, q_t, terms_t, off_t, n_terms: int, max_len: int, q_tok_t, q_len_t, k: int, k_out: int,
                           seq_len: int = 128, method: str = "rrf", rrf_k: float = 60, w_dense: float = 0.5,
                           w_sparse: float = 0.5):
-        """retrieve (dense + BM25 + fusion, top k) -> cross-encoder rerank (top k_out), all on the device."""
+        """retrieve (dense + BM25 + fusion, top k) -> cross-encoder rerank (top k_out), all on the device.
+
+        Sharded runs: after the all-gather + merge every rank holds the fused candidates of ALL queries; the rerank (the
+        expensive stage) is then split by query -- rank r scores queries ``rerank_slice(B)`` and returns only those rows
+        (no second collective; the caller owns the per-rank result slices)."""
         t = self.torch
         ids, sc, src, cnt = self.hybrid_dev(q_t, terms_t, off_t, n_terms, max_len, k, method, rrf_k, w_dense, w_sparse)
-        B = q_t.shape[0]
+        lo, hi = self.rerank_slice(q_t.shape[0])
+        B = hi - lo
         out = (self._buf("r_ids", (B, k_out), t.int64), self._buf("r_sc", (B, k_out), t.float32),
                self._buf("r_cnt", (B,), t.int32))
-        return self.engine.rerank_dev(q_tok_t, q_len_t, ids, cnt, seq_len, k_out, out=out)
+        if B == 0:
+            return out
+        return self.engine.rerank_dev(q_tok_t[lo:hi], q_len_t[lo:hi], ids[lo:hi], cnt[lo:hi], seq_len, k_out, out=out)
+
+    def rerank_slice(self, B: int):
+        """[lo, hi) of the batch that this rank reranks (the whole batch on a single GPU)."""
+        if self.world == 1:
+            return 0, B
+        per = (B + self.world - 1) // self.world
+        return min(B, self.rank * per), min(B, (self.rank + 1) * per)
 
     # ------------------------------------------------------------------ host (e2e) path
     def search_dense(self, q: np.ndarray, k: int):

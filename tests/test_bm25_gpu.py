@@ -62,6 +62,28 @@ def test_medium_synthetic_corpus_bit_exact_and_topk(engine, variant, n):
         assert np.array_equal(sc[b, :cnt[b]], want[order]), b
 
 
+@pytest.mark.parametrize("variant", ["okapi", "plus"])
+def test_many_queries_multi_range_ctas(engine, variant):
+    """Enough (query, range) work items that one CTA walks SEVERAL consecutive doc ranges and carries the posting
+    cursors from one range to the next (ranges_per_cta > 1 in bm25.cu)."""
+    n, V, B, k = 100_000, 5000, 320, 50
+    flat, off = synth.text_corpus_tokens(n, vocab=V)
+    idx = build_bm25_from_token_ids(flat, off, variant=variant)
+    fast = FastBM25(idx.indptr, idx.post_doc, idx.post_tf, idx.doc_len, idx.idf, idx.avgdl, variant)
+    engine.load_bm25(idx)
+    queries = synth.query_tokens(B, vocab=V)
+    queries[:, -1] = V - 1 - np.arange(B) % 50  # rare tail terms: posting lists that end long before the last range
+    term_lists = [idx.term_ids(q) for q in queries]
+    ids, sc, cnt = engine.bm25_topk(term_lists, k)
+    for b in range(0, B, 9):
+        want = fast.get_scores(list(term_lists[b]))
+        order = np.argsort(-want, kind="stable")[:k]
+        order = order[want[order] > 0]
+        assert int(cnt[b]) == len(order), b
+        assert np.array_equal(ids[b, :cnt[b]], order), b
+        assert np.array_equal(sc[b, :cnt[b]], want[order]), b
+
+
 def test_faithful_port_small_random_corpus_okapi_negative_idf(engine):
     rng = np.random.default_rng(4)
     texts = ["common " + " ".join(f"t{rng.integers(0, 12)}" for _ in range(rng.integers(1, 9))) for _ in range(40)]
