@@ -118,6 +118,27 @@ int sb_bm25_load(sb_ctx* ctx, const int64_t* indptr, const int32_t* post_doc, co
                  const double* idf, int32_t variant, double k1, double b, double delta, int64_t id_base);
 int64_t sb_bm25_count(sb_ctx* ctx);
 /*
+ * GPU index build -- replaces the corpus pass of BM25Retriever.index (reference src/core/retrievers/sparse.py:70-100,
+ * where rank_bm25 builds per-doc frequency dicts, df and doc_len in Python).
+ *
+ * sb_bm25_build_tokens: host token stream flat_tokens[n_tokens] (non-negative raw token ids; doc i is
+ * flat_tokens[doc_off[i] : doc_off[i+1]]).  On the device: sort by (token, position), vocabulary = token runs relabelled
+ * in FIRST-OCCURRENCE order (rank_bm25's dict insertion order, which its idf sum depends on), term-major CSR postings
+ * with docs ascending, tf, doc_len, df.  Returns the number of terms and postings.
+ * sb_bm25_build_read: df[n_terms] (term-id order) and the raw token of every term id, for the host-side idf table
+ * (math.log bit for bit) and token -> term-id map.  sb_bm25_build_export: the CSR arrays themselves (persistence /
+ * sharding); any pointer may be NULL.
+ * sb_bm25_build_finish: installs the built CSR as the context's BM25 index with the host-computed idf (same meaning as
+ * the arguments of sb_bm25_load); no posting array ever crosses to the host unless exported.
+ */
+int sb_bm25_build_tokens(sb_ctx* ctx, const int32_t* flat_tokens, int64_t n_tokens, const int64_t* doc_off,
+                         int64_t n_docs, int64_t* n_terms_out, int64_t* nnz_out);
+int sb_bm25_build_read(sb_ctx* ctx, int64_t* df_out, int32_t* term_token_out);
+int sb_bm25_build_export(sb_ctx* ctx, int64_t* indptr_out, int32_t* post_doc_out, uint16_t* post_tf_out,
+                         int32_t* doc_len_out);
+int sb_bm25_build_finish(sb_ctx* ctx, const double* idf, double avgdl, int32_t variant, double k1, double b,
+                         double delta, int64_t id_base);
+/*
  * sb_bm25_topk: B queries given as term ids (q_terms, CSR offsets q_off[B+1]; -1 = unknown token; duplicates are
  * scored twice exactly like the reference).  Outputs best-first (score desc, id asc), only score > 0:
  * out_ids[B*k], out_scores[B*k] (bit-identical to the fp64 NumPy arithmetic), out_counts[B] (may be < k).

@@ -73,6 +73,11 @@ SIGNATURES = {
                               C.c_void_p]),
     "sb_ce_score_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
+    "sb_bm25_build_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "sb_bm25_build_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sb_bm25_build_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sb_bm25_build_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_double, C.c_double, C.c_double,
+                                       C.c_int64]),
     "sb_ce_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "sb_ce_tokens_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64]),
     "sb_rerank_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,

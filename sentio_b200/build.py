@@ -19,7 +19,7 @@ CSRC = PKG / "csrc"
 OUT = PKG / "libsentio_b200.so"
 OBJ = PKG / "build"
 
-SOURCES = ["api.cu", "dense.cu", "bm25.cu", "fuse.cu", "mmr.cu", "cross_encoder.cu", "ce_gemm.cu", "dense_mma.cu"]
+SOURCES = ["api.cu", "dense.cu", "bm25.cu", "bm25_build.cu", "fuse.cu", "mmr.cu", "cross_encoder.cu", "ce_gemm.cu", "dense_mma.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -14,6 +14,7 @@ void sb_set_error(const char* fmt, ...) {
 
 void ce_model_free(CeModel* m);        // cross_encoder.cu
 void ce_tokens_free(CeDocTokens* t);   // cross_encoder.cu
+void bm25_build_free(Bm25Build* b);    // bm25_build.cu
 
 extern "C" {
 
@@ -68,6 +69,7 @@ void sb_destroy(sb_ctx* ctx) {
   if (b.idf) cudaFree(b.idf);
   if (ctx->ce) ce_model_free(ctx->ce);
   if (ctx->ce_tokens) ce_tokens_free(ctx->ce_tokens);
+  if (ctx->bm25_build) bm25_build_free(ctx->bm25_build);
   ctx->q_dev.release();
   ctx->cand_dev.release();
   ctx->out_ids_dev.release();

@@ -110,10 +110,11 @@ __device__ __forceinline__ int64_t warp_lower_bound(const int32_t* __restrict__ 
   return m ? lo + (__ffs(m) - 1) : hi;
 }
 
-__device__ unsigned long long block_kth_largest(const unsigned long long* keys, int n, int K, int* hist, int* scal);
+__device__ unsigned long long block_kth_largest(const unsigned long long* keys, int n, int K, int* hist, int* scal,
+                                                int passes);
 
 template <int MODE, bool PLUS>
-__global__ void __launch_bounds__(kRsThreads, 3) bm25_range_kernel(const RangeParams p) {
+__global__ void __launch_bounds__(kRsThreads, 2) bm25_range_kernel(const RangeParams p) {
   extern __shared__ __align__(16) uint8_t rsm[];
   double* acc = reinterpret_cast<double*>(rsm);                               // [kRange]
   int64_t* s_cur = reinterpret_cast<int64_t*>(acc + kRange);                  // [2][max_len]  posting cursor per term
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(kRsThreads, 3) bm25_range_kernel(const RangePa
   int32_t* s_wid = reinterpret_cast<int32_t*>(s_idf + p.max_len);            // [max_len]     loads per thread per chunk
   uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_wid + p.max_len);          // [kRange / 32] PLUS: doc had a posting
   __shared__ int hist[256];
-  __shared__ int scal[2];
+  __shared__ int scal[4];
   __shared__ int npos;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int qi = blockIdx.x;
@@ -162,6 +163,26 @@ __global__ void __launch_bounds__(kRsThreads, 3) bm25_range_kernel(const RangePa
     for (int i = tid; i < kRange / 32; i += kRsThreads) s_bits[i] = 0u;
   __syncthreads();
 
+  // Software pipeline: the first kRsThreads postings of each of the leading kPf query terms are fetched into registers one
+  // RANGE ahead (the cursor of (range r + 1, term j) is known as soon as term j of range r is done), so the steady state
+  // never waits for a posting load between two term barriers; only terms with more than kRsThreads postings inside a range
+  // issue further (wide) loads.
+  constexpr int kPf = 8;
+  int32_t pf_doc[kPf];
+  double pf_rat[kPf];
+#pragma unroll
+  for (int j = 0; j < kPf; ++j) {
+    pf_doc[j] = 0x7fffffff;
+    pf_rat[j] = 0.0;
+    if (j < len && s_idf[j] != 0.0) {
+      const int64_t idx = s_cur[j] + tid;
+      if (idx < s_hi[j]) {
+        pf_doc[j] = __ldg(p.post_doc + idx);
+        pf_rat[j] = __ldg(p.ratio + idx);
+      }
+    }
+  }
+
   for (int64_t r = first; r < last; ++r) {
     const int32_t r0 = (int32_t)(r * kRange);
     const int32_t r1 = (int32_t)min((int64_t)r0 + kRange, p.n_docs);
@@ -169,14 +190,42 @@ __global__ void __launch_bounds__(kRsThreads, 3) bm25_range_kernel(const RangePa
     const int par = (int)((r - first) & 1);
     const int64_t* cur_in = s_cur + (size_t)par * p.max_len;
     int64_t* cur_out = s_cur + (size_t)(par ^ 1) * p.max_len;
-    for (int j = 0; j < len; ++j) {
+
+    // one posting: accumulate if its doc is inside the range; returns true when the posting lies beyond the range
+    auto apply = [&](int32_t doc, double rat, double w) -> bool {
+      if (doc >= r1) return true;
+      const int d = doc - r0;
+      if (PLUS) {
+        acc[d] = __dadd_rn(acc[d], __dmul_rn(w, __dadd_rn(p.delta, rat)));
+        atomicOr(&s_bits[d >> 5], 1u << (d & 31));
+      } else {
+        acc[d] = __dadd_rn(acc[d], __dmul_rn(w, rat));
+      }
+      return false;
+    };
+    // the unique boundary idx b in [pos0, hi]: doc(b) >= r1 (doc(hi) = +inf) and (b == pos0 or doc(b - 1) < r1) becomes the
+    // term's cursor for the next range.  doc(idx - 1) comes from the neighbouring lane; lane 0 re-reads it (L1 hit).
+    auto boundary = [&](int j, int64_t idx, int32_t doc, bool out, int64_t pos0, int64_t hi) {
+      int32_t prev = __shfl_up_sync(0xffffffffu, doc, 1);
+      if (out) {
+        if (lane == 0) prev = idx == pos0 ? -1 : (idx - 1 < hi ? __ldg(p.post_doc + idx - 1) : 0x7fffffff);
+        if (idx <= hi && prev < r1) cur_out[j] = idx;
+      }
+    };
+    auto run_term = [&](int j, bool have_pf, int32_t d0, double rt0) {
       const double w = s_idf[j];
-      if (w == 0.0) continue;  // block-uniform
+      if (w == 0.0) return;  // block-uniform
       const int64_t pos0 = cur_in[j], hi = s_hi[j];
-      const int wid = s_wid[j];
-      const double wd = PLUS ? __dmul_rn(w, __dadd_rn(p.delta, 0.0)) : 0.0;
       int64_t pos = pos0;
-      for (;;) {
+      bool done = false;
+      if (have_pf) {  // chunk 0: one posting per thread, already in registers
+        const bool out = apply(d0, rt0, w);
+        boundary(j, pos0 + tid, d0, out, pos0, hi);
+        done = __syncthreads_or(out);
+        pos = pos0 + kRsThreads;
+      }
+      const int wid = s_wid[j];
+      while (!done) {
         int32_t doc[kRsPost];
         double rat[kRsPost];
 #pragma unroll
@@ -192,27 +241,18 @@ __global__ void __launch_bounds__(kRsThreads, 3) bm25_range_kernel(const RangePa
         bool any_out = false;
 #pragma unroll
         for (int u = 0; u < kRsPost; ++u) {
-          const int64_t idx = pos + (int64_t)u * kRsThreads + tid;
-          if (u >= wid) {
-          } else if (doc[u] < r1) {
-            const int d = doc[u] - r0;
-            if (PLUS) {
-              acc[d] = __dadd_rn(acc[d], __dmul_rn(w, __dadd_rn(p.delta, rat[u])));
-              atomicOr(&s_bits[d >> 5], 1u << (d & 31));
-            } else {
-              acc[d] = __dadd_rn(acc[d], __dmul_rn(w, rat[u]));
-            }
-          } else {
-            any_out = true;
-            // the unique boundary idx b in [pos0, hi]: doc(b) >= r1 (doc(hi) = +inf) and (b == pos0 or doc(b-1) < r1)
-            if (idx <= hi && (idx == pos0 || __ldg(p.post_doc + idx - 1) < r1)) cur_out[j] = idx;
+          if (u < wid) {  // block-uniform
+            const bool out = apply(doc[u], rat[u], w);
+            boundary(j, pos + (int64_t)u * kRsThreads + tid, doc[u], out, pos0, hi);
+            any_out |= out;
           }
         }
-        if (__syncthreads_or(any_out)) break;
+        done = __syncthreads_or(any_out);
         pos += (int64_t)wid * kRsThreads;
       }
       if (PLUS) {
         // every doc of the range WITHOUT a posting of this term gets idf * (delta + 0.0); a warp owns one bit word
+        const double wd = __dmul_rn(w, __dadd_rn(p.delta, 0.0));
         for (int i = tid; i < kRange; i += kRsThreads) {
           const uint32_t word = s_bits[i >> 5];
           if (i < nd && !((word >> (i & 31)) & 1u)) acc[i] = __dadd_rn(acc[i], wd);
@@ -221,7 +261,25 @@ __global__ void __launch_bounds__(kRsThreads, 3) bm25_range_kernel(const RangePa
         }
         __syncthreads();
       }
+    };
+
+#pragma unroll
+    for (int j = 0; j < kPf; ++j) {
+      if (j < len) {  // block-uniform
+        run_term(j, true, pf_doc[j], pf_rat[j]);
+        // refill the slot with the term's first chunk of the NEXT range (its cursor was published before the last barrier)
+        pf_doc[j] = 0x7fffffff;
+        pf_rat[j] = 0.0;
+        if (r + 1 < last && s_idf[j] != 0.0) {
+          const int64_t idx = cur_out[j] + tid;
+          if (idx < s_hi[j]) {
+            pf_doc[j] = __ldg(p.post_doc + idx);
+            pf_rat[j] = __ldg(p.ratio + idx);
+          }
+        }
+      }
     }
+    for (int j = kPf; j < len; ++j) run_term(j, false, 0, 0.0);
     // the barrier that ended the last term's loop (or the initial one) ordered all accumulator updates before this point
     if (MODE == kModeDump) {
       double* out = p.dump + (size_t)qi * p.n_docs + r0;
@@ -266,7 +324,7 @@ __global__ void __launch_bounds__(kRsThreads, 3) bm25_range_kernel(const RangePa
       // those, so it is a lower bound of the global k-th best (a range with too few positives degrades the bound to
       // "every positive score", never below).  thr[] was preset to all-ones by the host.
       unsigned long long t = kPosZero + 1ull;
-      if (npos >= p.k) t = block_kth_largest(keys, kRange, p.k, hist, scal);
+      if (npos >= p.k) t = block_kth_largest(keys, kRange, p.k, hist, scal, 3);  // sign + exponent + 12 mantissa bits
       if (tid == 0) atomicMin(p.thr + qi, t);
       return;
     }
@@ -311,11 +369,14 @@ __device__ __forceinline__ void block_bitonic_sort_pairs(unsigned long long* key
 constexpr int kBmStage = 12288;  // (key, idx) pairs staged in shared memory by the final kernel (144 KB)
 
 // K-th largest value among keys[0..n) (shared memory, every thread of the CTA participates); n >= K >= 1.
-__device__ unsigned long long block_kth_largest(const unsigned long long* keys, int n, int K, int* hist, int* scal) {
+// passes < 8 stops after the leading 8 * passes bits and returns the LOWER EDGE of the bucket that holds the K-th largest
+// key (<= the exact answer): all a safe threshold needs.
+__device__ unsigned long long block_kth_largest(const unsigned long long* keys, int n, int K, int* hist, int* scal,
+                                                int passes) {
   const int tid = threadIdx.x, nt = blockDim.x;
   unsigned long long prefix = 0ull, mask = 0ull;
   int need = K;
-  for (int shift = 56; shift >= 0; shift -= 8) {
+  for (int shift = 56; shift >= 0 && passes > 0; shift -= 8, --passes) {
     for (int i = tid; i < 256; i += nt) hist[i] = 0;
     __syncthreads();
     for (int i = tid; i < n; i += nt) {
@@ -327,19 +388,7 @@ __device__ unsigned long long block_kth_largest(const unsigned long long* keys, 
       }
     }
     __syncthreads();
-    if (tid == 0) {
-      int cum = 0, sel = 0;
-      for (int b = 255; b >= 0; --b) {
-        const int c = hist[b];
-        if (cum + c >= need) {
-          sel = b;
-          break;
-        }
-        cum += c;
-      }
-      scal[0] = sel;
-      scal[1] = need - cum;
-    }
+    if (tid < 32) warp_select_bin<true>(hist, need, tid, scal);
     __syncthreads();
     prefix |= (unsigned long long)scal[0] << shift;
     mask |= 0xffull << shift;
@@ -395,19 +444,7 @@ __global__ void __launch_bounds__(1024, 1) bm25_final_select_kernel(const unsign
         }
       }
       __syncthreads();
-      if (tid == 0) {
-        int cum = 0, sel = 0;
-        for (int b = 255; b >= 0; --b) {
-          const int c = hist[b];
-          if (cum + c >= need) {
-            sel = b;
-            break;
-          }
-          cum += c;
-        }
-        scal[0] = sel;
-        scal[1] = need - cum;
-      }
+      if (tid < 32) warp_select_bin<true>(hist, need, tid, scal);
       __syncthreads();
       prefix |= (unsigned long long)scal[0] << shift;
       mask |= 0xffull << shift;
@@ -429,19 +466,7 @@ __global__ void __launch_bounds__(1024, 1) bm25_final_select_kernel(const unsign
         }
       }
       __syncthreads();
-      if (tid == 0) {
-        int cum = 0, sel = 255;
-        for (int b = 0; b < 256; ++b) {
-          const int c = hist[b];
-          if (cum + c >= ineed) {
-            sel = b;
-            break;
-          }
-          cum += c;
-        }
-        scal[0] = sel;
-        scal[1] = ineed - cum;
-      }
+      if (tid < 32) warp_select_bin<false>(hist, ineed, tid, scal);
       __syncthreads();
       ipre |= (uint32_t)scal[0] << shift;
       imask |= 0xffu << shift;
@@ -526,7 +551,7 @@ RangeParams range_params(sb_ctx* ctx, const int32_t* q_terms_dev, const int32_t*
 
 // consecutive ranges per CTA: long runs amortise the per-term posting-list search, short runs fill the machine
 int ranges_per_cta(sb_ctx* ctx, int nq, int64_t n_ranges) {
-  const int64_t resident = (int64_t)ctx->num_sms * 3;
+  const int64_t resident = (int64_t)ctx->num_sms * 2;  // 2 CTAs of bm25_range_kernel per SM
   int64_t r = ((int64_t)nq * n_ranges) / (resident * 4);
   if (r < 1) r = 1;
   if (r > 8) r = 8;
@@ -593,22 +618,15 @@ __global__ void bm25_fill_empty_kernel(int64_t* ids, double* sc, int32_t* cnt, i
 
 }  // namespace
 
-extern "C" {
-
-int sb_bm25_load(sb_ctx* ctx, const int64_t* indptr, const int32_t* post_doc, const uint16_t* post_tf,
-                 int64_t n_terms, int64_t nnz, const int32_t* doc_len, int64_t n_docs, double avgdl,
-                 const double* idf, int32_t variant, double k1, double b, double delta, int64_t id_base) {
-  SB_REQUIRE(ctx != nullptr, SB_ERR_ARG, "sb_bm25_load: ctx is NULL");
-  SB_REQUIRE(n_terms >= 0 && nnz >= 0 && n_docs >= 0, SB_ERR_ARG, "sb_bm25_load: negative size");
-  SB_REQUIRE(n_docs < (1ll << 31), SB_ERR_ARG, "sb_bm25_load: a shard holds at most 2^31-1 docs");
-  SB_REQUIRE(variant == SB_BM25_OKAPI || variant == SB_BM25_PLUS, SB_ERR_ARG, "sb_bm25_load: bad variant %d", variant);
-  SB_REQUIRE(indptr && (nnz == 0 || (post_doc && post_tf)) && (n_docs == 0 || doc_len) && (n_terms == 0 || idf),
-             SB_ERR_ARG, "sb_bm25_load: NULL buffer");
-  SB_REQUIRE(indptr[0] == 0 && indptr[n_terms] == nnz, SB_ERR_ARG, "sb_bm25_load: indptr does not span nnz");
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  DeviceGuard g(ctx->device);
+// Installs a term-major CSR that already lives on the device as the context's BM25 index (sb_bm25_load uploads host
+// arrays first; the GPU builder of bm25_build.cu hands its arrays over directly).  Takes ownership of indptr_dev and
+// post_doc_dev; tf_dev / doc_len_dev are only read (dnorm and the query-independent ratio are derived from them).
+int bm25_install_device_csr(sb_ctx* ctx, int64_t* indptr_dev, int32_t* post_doc_dev, const uint16_t* tf_dev,
+                            const int32_t* doc_len_dev, int64_t n_terms, int64_t nnz, int64_t n_docs, double avgdl,
+                            const double* idf_host, int32_t variant, double k1, double b, double delta, int64_t id_base,
+                            cudaStream_t st) {
   Bm25Index& ix = ctx->bm25;
-  SB_CUDA(cudaStreamSynchronize(ctx->stream));
+  SB_CUDA(cudaStreamSynchronize(st));
   if (ix.indptr) cudaFree(ix.indptr);
   if (ix.post_doc) cudaFree(ix.post_doc);
   if (ix.post_ratio) cudaFree(ix.post_ratio);
@@ -624,37 +642,59 @@ int sb_bm25_load(sb_ctx* ctx, const int64_t* indptr, const int32_t* post_doc, co
   ix.b = b;
   ix.delta = delta;
   ix.avgdl = avgdl;
-  ix.h_indptr.assign(indptr, indptr + n_terms + 1);
-  cudaStream_t st = ctx->stream;
-  SB_CUDA(cudaMalloc(&ix.indptr, (size_t)(n_terms + 1) * 8));
-  SB_CUDA(cudaMemcpyAsync(ix.indptr, indptr, (size_t)(n_terms + 1) * 8, cudaMemcpyHostToDevice, st));
+  ix.indptr = indptr_dev;
+  ix.post_doc = post_doc_dev;
   SB_CUDA(cudaMalloc(&ix.idf, (size_t)std::max<int64_t>(n_terms, 1) * 8));
-  if (n_terms) SB_CUDA(cudaMemcpyAsync(ix.idf, idf, (size_t)n_terms * 8, cudaMemcpyHostToDevice, st));
+  if (n_terms) SB_CUDA(cudaMemcpyAsync(ix.idf, idf_host, (size_t)n_terms * 8, cudaMemcpyHostToDevice, st));
   SB_CUDA(cudaMalloc(&ix.dnorm, (size_t)std::max<int64_t>(n_docs, 1) * 8));
-  SB_CUDA(cudaMalloc(&ix.post_doc, (size_t)std::max<int64_t>(nnz, 1) * 4));
   // query-independent fp64 ratio tf*(k1+1)/(tf+dnorm[doc]) (8 B per posting) replaces the 2 B tf + 8 B dnorm gather
   SB_CUDA(cudaMalloc(&ix.post_ratio, (size_t)std::max<int64_t>(nnz, 1) * 8));
   if (n_docs) {
-    int rc = ctx->misc_dev.reserve((size_t)n_docs * 4);
-    if (rc) return rc;
-    SB_CUDA(cudaMemcpyAsync(ctx->misc_dev.p, doc_len, (size_t)n_docs * 4, cudaMemcpyHostToDevice, st));
     const double omb = 1.0 - b;  // Python evaluates `1 - self.b` first (left-to-right)
-    bm25_dnorm_kernel<<<(unsigned)((n_docs + 255) / 256), 256, 0, st>>>(ctx->misc_dev.as<int32_t>(), n_docs, k1, b,
-                                                                        omb, avgdl, ix.dnorm);
+    bm25_dnorm_kernel<<<(unsigned)((n_docs + 255) / 256), 256, 0, st>>>(doc_len_dev, n_docs, k1, b, omb, avgdl, ix.dnorm);
     SB_CUDA(cudaGetLastError());
   }
   if (nnz) {
-    SB_CUDA(cudaMemcpyAsync(ix.post_doc, post_doc, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
-    int rc = ctx->misc2_dev.reserve((size_t)nnz * 2);
-    if (rc) return rc;
-    SB_CUDA(cudaMemcpyAsync(ctx->misc2_dev.p, post_tf, (size_t)nnz * 2, cudaMemcpyHostToDevice, st));
     const double k1p1 = k1 + 1.0;
-    bm25_ratio_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(ix.post_doc, ctx->misc2_dev.as<uint16_t>(), nnz,
-                                                                     ix.dnorm, k1p1, ix.post_ratio);
+    bm25_ratio_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(ix.post_doc, tf_dev, nnz, ix.dnorm, k1p1,
+                                                                     ix.post_ratio);
     SB_CUDA(cudaGetLastError());
   }
   SB_CUDA(cudaStreamSynchronize(st));
   return SB_OK;
+}
+
+extern "C" {
+
+int sb_bm25_load(sb_ctx* ctx, const int64_t* indptr, const int32_t* post_doc, const uint16_t* post_tf,
+                 int64_t n_terms, int64_t nnz, const int32_t* doc_len, int64_t n_docs, double avgdl,
+                 const double* idf, int32_t variant, double k1, double b, double delta, int64_t id_base) {
+  SB_REQUIRE(ctx != nullptr, SB_ERR_ARG, "sb_bm25_load: ctx is NULL");
+  SB_REQUIRE(n_terms >= 0 && nnz >= 0 && n_docs >= 0, SB_ERR_ARG, "sb_bm25_load: negative size");
+  SB_REQUIRE(n_docs < (1ll << 31), SB_ERR_ARG, "sb_bm25_load: a shard holds at most 2^31-1 docs");
+  SB_REQUIRE(variant == SB_BM25_OKAPI || variant == SB_BM25_PLUS, SB_ERR_ARG, "sb_bm25_load: bad variant %d", variant);
+  SB_REQUIRE(indptr && (nnz == 0 || (post_doc && post_tf)) && (n_docs == 0 || doc_len) && (n_terms == 0 || idf),
+             SB_ERR_ARG, "sb_bm25_load: NULL buffer");
+  SB_REQUIRE(indptr[0] == 0 && indptr[n_terms] == nnz, SB_ERR_ARG, "sb_bm25_load: indptr does not span nnz");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = ctx->stream;
+  SB_CUDA(cudaStreamSynchronize(st));
+  int64_t* indptr_dev = nullptr;
+  int32_t* post_doc_dev = nullptr;
+  SB_CUDA(cudaMalloc(&indptr_dev, (size_t)(n_terms + 1) * 8));
+  SB_CUDA(cudaMemcpyAsync(indptr_dev, indptr, (size_t)(n_terms + 1) * 8, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMalloc(&post_doc_dev, (size_t)std::max<int64_t>(nnz, 1) * 4));
+  int rc;
+  if ((rc = ctx->misc_dev.reserve((size_t)std::max<int64_t>(n_docs, 1) * 4))) return rc;
+  if ((rc = ctx->misc2_dev.reserve((size_t)std::max<int64_t>(nnz, 1) * 2))) return rc;
+  if (n_docs) SB_CUDA(cudaMemcpyAsync(ctx->misc_dev.p, doc_len, (size_t)n_docs * 4, cudaMemcpyHostToDevice, st));
+  if (nnz) {
+    SB_CUDA(cudaMemcpyAsync(post_doc_dev, post_doc, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(ctx->misc2_dev.p, post_tf, (size_t)nnz * 2, cudaMemcpyHostToDevice, st));
+  }
+  return bm25_install_device_csr(ctx, indptr_dev, post_doc_dev, ctx->misc2_dev.as<uint16_t>(), ctx->misc_dev.as<int32_t>(),
+                                 n_terms, nnz, n_docs, avgdl, idf, variant, k1, b, delta, id_base, st);
 }
 
 int64_t sb_bm25_count(sb_ctx* ctx) { return ctx ? ctx->bm25.n_docs : -1; }

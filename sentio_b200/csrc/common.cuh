@@ -108,11 +108,11 @@ struct Bm25Index {
   double* post_ratio = nullptr; // [nnz] query-independent tf*(k1+1)/(tf+dnorm[doc]) (fp64, exact op order)
   double* dnorm = nullptr;     // [n_docs]  k1*(1-b+b*dl/avgdl), same op order as rank_bm25
   double* idf = nullptr;       // [V]
-  std::vector<int64_t> h_indptr;  // host copy for planning in the host-buffer entry point
 };
 
 struct CeModel;      // cross_encoder.cu
 struct CeDocTokens;  // cross_encoder.cu
+struct Bm25Build;    // bm25_build.cu
 
 struct sb_ctx {
   int device = 0;
@@ -124,6 +124,7 @@ struct sb_ctx {
   Bm25Index bm25;
   CeModel* ce = nullptr;
   CeDocTokens* ce_tokens = nullptr;
+  Bm25Build* bm25_build = nullptr;  // GPU index build in progress (sb_bm25_build_tokens .. sb_bm25_build_finish)
   int dense_mode = 0;  // 0 = auto, 1 = CUDA-core scan only, 2 = tcgen05 batched scan whenever eligible
   // bookkeeping: kernels launched by this library, optional per-kernel CUDA-event timing (bench.py roofline leg)
   uint64_t launches = 0;
@@ -214,6 +215,49 @@ __device__ __forceinline__ float key32_score(uint64_t k) { return orderable_f32(
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+
+// Radix-select helper, called by ONE full warp: scan the 256-bin histogram from the top (DESC) or the bottom and find the
+// bin where the running count first reaches `need`.  out[0] = bin, out[1] = rank inside the bin (need - count of the bins
+// before it), out[2] = the bin's count.  Lane l owns 8 consecutive bins in scan order; one shuffle scan across lanes.
+template <bool DESC>
+__device__ __forceinline__ void warp_select_bin(const int* hist, int need, int lane, int* out) {
+  int c[8];
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int b = DESC ? 255 - 8 * lane - i : 8 * lane + i;
+    c[i] = hist[b];
+    s += c[i];
+  }
+  int incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  const int excl = incl - s;
+  const bool mine = excl < need && need <= incl;
+  const unsigned m = __ballot_sync(0xffffffffu, mine);
+  if (mine) {
+    int cum = excl;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (cum + c[i] >= need) {
+        out[0] = DESC ? 255 - 8 * lane - i : 8 * lane + i;
+        out[1] = need - cum;
+        out[2] = c[i];
+        break;
+      }
+      cum += c[i];
+    }
+  }
+  if (m == 0u && lane == 31) {  // fewer than `need` keys in total (callers avoid it): same answer as a full serial scan
+    out[0] = DESC ? 0 : 255;
+    out[1] = need - incl;
+    out[2] = hist[DESC ? 0 : 255];
+  }
 }
 
 // ---- mbarrier / bulk-copy (TMA engine, SASS UBLKCP) wrappers

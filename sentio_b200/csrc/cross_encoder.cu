@@ -283,7 +283,7 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 }
 
 template <int S_MAX>
-__global__ void __launch_bounds__(128) ce_attention_mma_kernel(const __half* __restrict__ qkv,
+__global__ void __launch_bounds__(128, 4) ce_attention_mma_kernel(const __half* __restrict__ qkv,
                                                                 const int32_t* __restrict__ lengths,
                                                                 const int32_t* __restrict__ cu, int S, int H,
                                                                 int heads, __half* __restrict__ ctx) {
@@ -297,7 +297,23 @@ __global__ void __launch_bounds__(128) ce_attention_mma_kernel(const __half* __r
   const int ld = 3 * H;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   // stage K and V (rows >= len as zeros so that masked products stay finite)
-  const int stage_rows = min(S_MAX, (len + 15) & ~15);  // key tiles beyond len are never touched
+  // Q fragments (A operand) of both 16-row tiles of this warp, issued BEFORE the K/V staging so the two global round trips
+  // overlap: rows g / g+8, two k-steps of 16 columns (2t.. and 2t+8..)
+  uint32_t qa_all[2][2][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const int r0 = warp * 32 + mt * 16;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const __half* qlo = qkv + (row0 + min(r0 + g, len - 1)) * ld + head * DH + ks * 16 + 2 * t;
+      const __half* qhi = qkv + (row0 + min(r0 + g + 8, len - 1)) * ld + head * DH + ks * 16 + 2 * t;
+      qa_all[mt][ks][0] = *reinterpret_cast<const uint32_t*>(qlo);
+      qa_all[mt][ks][1] = *reinterpret_cast<const uint32_t*>(qhi);
+      qa_all[mt][ks][2] = *reinterpret_cast<const uint32_t*>(qlo + 8);
+      qa_all[mt][ks][3] = *reinterpret_cast<const uint32_t*>(qhi + 8);
+    }
+  }
+  const int stage_rows = min(S_MAX, (len + 31) & ~31);  // 32-key groups beyond len are never touched
   for (int i = tid; i < stage_rows * 4; i += 128) {
     const int j = i >> 2, c = (i & 3) * 8;
     uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = make_uint4(0u, 0u, 0u, 0u);
@@ -316,26 +332,26 @@ __global__ void __launch_bounds__(128) ce_attention_mma_kernel(const __half* __r
     if (r0 >= len) break;                // no such rows in the packed layout
     __half* out_lo = ctx + (row0 + r0 + g) * H + head * DH;
     __half* out_hi = ctx + (row0 + r0 + g + 8) * H + head * DH;
-    // Q fragments (A operand) for the two k-steps of 16: rows g / g+8, columns 2t.. and 2t+8..
     uint32_t qa[2][4];
 #pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      const __half* qlo = qkv + (row0 + min(r0 + g, len - 1)) * ld + head * DH + ks * 16 + 2 * t;
-      const __half* qhi = qkv + (row0 + min(r0 + g + 8, len - 1)) * ld + head * DH + ks * 16 + 2 * t;
-      qa[ks][0] = *reinterpret_cast<const uint32_t*>(qlo);
-      qa[ks][1] = *reinterpret_cast<const uint32_t*>(qhi);
-      qa[ks][2] = *reinterpret_cast<const uint32_t*>(qlo + 8);
-      qa[ks][3] = *reinterpret_cast<const uint32_t*>(qhi + 8);
-    }
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) qa[ks][e] = mt ? qa_all[1][ks][e] : qa_all[0][ks][e];
     float sc[NT][4];
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
-      if (nt * 8 >= len) continue;  // CTA-uniform: the whole key tile is masked
+    for (int nc = 0; nc < NT / 4; ++nc) {  // groups of 32 keys: 8 independent MMAs per branch keep the tensor pipe fed
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        const __half* kp = Ks + (nt * 8 + g) * LDS_ROW + ks * 16 + 2 * t;
-        mma_16816(sc[nt], qa[ks], *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 8));
+      for (int i = 0; i < 4; ++i) sc[nc * 4 + i][0] = sc[nc * 4 + i][1] = sc[nc * 4 + i][2] = sc[nc * 4 + i][3] = 0.f;
+      if (nc * 32 < len) {  // CTA-uniform: groups at or beyond len are entirely masked
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int nt = nc * 4 + i;
+            const __half* kp = Ks + (nt * 8 + g) * LDS_ROW + ks * 16 + 2 * t;
+            mma_16816(sc[nt], qa[ks], *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 8));
+          }
+        }
       }
     }
     // masked softmax over the keys; a row's values live in the 4 lanes sharing g
@@ -377,7 +393,7 @@ __global__ void __launch_bounds__(128) ce_attention_mma_kernel(const __half* __r
     for (int n = 0; n < DH / 8; ++n) oc[n][0] = oc[n][1] = oc[n][2] = oc[n][3] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < NT / 2; ++kk) {
-      if (kk * 16 >= len) continue;  // probabilities of these keys are exactly 0
+      if ((kk >> 1) * 32 >= len) continue;  // 32-key group entirely beyond len: its probabilities are exactly 0
       uint32_t pa[4];
       pa[0] = pack_h2(sc[2 * kk][0], sc[2 * kk][1]);
       pa[1] = pack_h2(sc[2 * kk][2], sc[2 * kk][3]);

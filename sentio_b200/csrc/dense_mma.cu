@@ -278,7 +278,8 @@ __global__ void __launch_bounds__(kSelectThreads, 1) dense_select_kernel(const S
   __shared__ double qq_s;
   __shared__ int s_prefix[1024 + 1];
   __shared__ int s_hist[256];
-  __shared__ int s_sel, s_need, s_bucket, s_ntop;
+  __shared__ int s_scal[4];
+  __shared__ int s_ntop;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5, qi = blockIdx.x;
   const int K = p.kprime, G = p.grid;
   const int32_t* counts = p.counts + (size_t)qi * G;
@@ -351,26 +352,12 @@ __global__ void __launch_bounds__(kSelectThreads, 1) dense_select_kernel(const S
         if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&s_hist[dgt], __popc(grp));
       })
       __syncthreads();
-      if (tid == 0) {
-        int cum = 0, sel = 0, cnt_b = 0;
-        for (int b = 255; b >= 0; --b) {
-          const int c = s_hist[b];
-          if (cum + c >= need) {
-            sel = b;
-            cnt_b = c;
-            break;
-          }
-          cum += c;
-        }
-        s_sel = sel;
-        s_need = need - cum;
-        s_bucket = cnt_b;
-      }
+      if (warp == 0) warp_select_bin<true>(s_hist, need, lane, s_scal);
       __syncthreads();
-      prefix |= (unsigned long long)s_sel << shift;
+      prefix |= (unsigned long long)s_scal[0] << shift;
       mask |= 0xffull << shift;
-      need = s_need;
-      const int bucket = s_bucket;
+      need = s_scal[1];
+      const int bucket = s_scal[2];
       __syncthreads();
       if (bucket <= 256 && bucket <= kSelTop - K) break;  // {above} (< K keys) + a small bucket: finish by sorting
     }

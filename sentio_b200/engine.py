@@ -147,6 +147,40 @@ class B200Engine:
         self.bm25 = data
         self.bm25_id_base = int(id_base)
 
+    def build_bm25_gpu(self, flat_tokens: np.ndarray, doc_offsets: np.ndarray, variant: str = "okapi", k1: float = 1.5,
+                       b: float = 0.75, epsilon: float = 0.25, delta: float = 1.0, id_base: int = 0,
+                       export: bool = False) -> Bm25IndexData:
+        """Index build on the device (sb_bm25_build_*): sort-based CSR construction from an integer token stream, idf on
+        the host from the device-computed df, index installed without the postings ever visiting the host
+        (``export=True`` additionally copies the CSR back, for ``save`` / ``shard``).  Same index as
+        ``index.build_bm25_from_token_ids`` + ``load_bm25`` (tests/test_bm25_build_gpu.py)."""
+        from .index import finish_gpu_built_index
+
+        variant = variant.lower()
+        flat = np.ascontiguousarray(flat_tokens, dtype=np.int32)
+        off = np.ascontiguousarray(doc_offsets, dtype=np.int64)
+        n_docs = len(off) - 1
+        if n_docs <= 0 or len(flat) == 0:
+            raise ValueError("empty corpus")
+        nt, nnz = C.c_int64(0), C.c_int64(0)
+        check(self._lib.sb_bm25_build_tokens(self._h, _ptr(flat), len(flat), _ptr(off), n_docs, C.byref(nt),
+                                             C.byref(nnz)), "sb_bm25_build_tokens")
+        V, nnz = int(nt.value), int(nnz.value)
+        df = np.empty(V, dtype=np.int64)
+        term_token = np.empty(V, dtype=np.int32)
+        check(self._lib.sb_bm25_build_read(self._h, _ptr(df), _ptr(term_token)), "sb_bm25_build_read")
+        csr = None
+        if export:
+            csr = (np.empty(V + 1, np.int64), np.empty(nnz, np.int32), np.empty(nnz, np.uint16), np.empty(n_docs, np.int32))
+            check(self._lib.sb_bm25_build_export(self._h, *[_ptr(a) for a in csr]), "sb_bm25_build_export")
+        data = finish_gpu_built_index(df, term_token, n_docs, len(flat), variant, k1, b, epsilon, delta, csr)
+        idf = np.ascontiguousarray(data.idf, dtype=np.float64)
+        check(self._lib.sb_bm25_build_finish(self._h, _ptr(idf), float(data.avgdl), 1 if variant == "plus" else 0,
+                                             float(k1), float(b), float(delta), int(id_base)), "sb_bm25_build_finish")
+        self.bm25 = data
+        self.bm25_id_base = int(id_base)
+        return data
+
     @staticmethod
     def pack_queries(term_id_lists: Sequence[Sequence[int]]):
         """-> (flat int32 term ids (at least one slot), CSR offsets int32 [B+1])"""

@@ -17,7 +17,8 @@ from typing import Iterable, Sequence
 
 import numpy as np
 
-__all__ = ["Bm25IndexData", "build_bm25_from_texts", "build_bm25_from_token_ids", "tokenize", "hash_tokenize_pairs"]
+__all__ = ["Bm25IndexData", "build_bm25_from_texts", "build_bm25_from_token_ids", "finish_gpu_built_index",
+           "tokenize", "tokenize_texts", "hash_tokenize_pairs"]
 
 
 def tokenize(text: str) -> list[str]:
@@ -103,6 +104,22 @@ def _idf_table(df: np.ndarray, n_docs: int, variant: str, epsilon: float) -> tup
     return idf, average_idf
 
 
+def finish_gpu_built_index(df: np.ndarray, term_token: np.ndarray, n_docs: int, n_tokens: int, variant: str, k1: float,
+                           b: float, epsilon: float, delta: float, csr=None) -> Bm25IndexData:
+    """Host half of the GPU index build (engine.build_bm25_gpu): idf table from the device-computed df (math.log, bit for
+    bit like rank_bm25) + raw token -> term id map.  ``csr`` = (indptr, post_doc, post_tf, doc_len) when exported."""
+    idf, average_idf = _idf_table(df, n_docs, variant, epsilon)
+    size = int(term_token.max()) + 1 if len(term_token) else 0
+    token_id_map = np.full(size, -1, dtype=np.int32)
+    token_id_map[term_token] = np.arange(len(term_token), dtype=np.int32)
+    empty = (np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros(0, np.uint16), np.zeros(0, np.int32))
+    indptr, post_doc, post_tf, doc_len = csr if csr is not None else empty
+    return Bm25IndexData(variant=variant, k1=float(k1), b=float(b), epsilon=float(epsilon), delta=float(delta),
+                         n_docs=int(n_docs), avgdl=n_tokens / n_docs, indptr=indptr, post_doc=post_doc, post_tf=post_tf,
+                         doc_len=doc_len, idf=idf, vocab=None, token_id_map=token_id_map, average_idf=average_idf,
+                         extras={"built_on": "gpu", "postings_on_host": csr is not None})
+
+
 def build_bm25_from_token_ids(flat_tokens: np.ndarray, doc_offsets: np.ndarray, variant: str = "okapi", k1: float = 1.5,
                               b: float = 0.75, epsilon: float = 0.25, delta: float = 1.0, vocab_tokens=None) -> Bm25IndexData:
     """CSR build from an integer token stream (doc i = flat_tokens[doc_offsets[i]:doc_offsets[i+1]])."""
@@ -155,6 +172,24 @@ def build_bm25_from_token_ids(flat_tokens: np.ndarray, doc_offsets: np.ndarray, 
                          n_docs=n_docs, avgdl=avgdl, indptr=indptr, post_doc=post_doc, post_tf=tf.astype(np.uint16),
                          doc_len=doc_len.astype(np.int32), idf=idf, vocab=vocab, token_id_map=token_id_map,
                          average_idf=average_idf)
+
+
+def tokenize_texts(texts: Iterable[str]):
+    """``text.lower().split()`` (sparse.py:88) over a corpus -> (vocab token->id in first-occurrence order,
+    flat int32 token ids, int64 doc offsets): the string half of index building, which stays on the host."""
+    vocab: dict[str, int] = {}
+    flat: list[int] = []
+    offsets = [0]
+    get = vocab.get
+    for text in texts:
+        for tok in text.lower().split():
+            tid = get(tok)
+            if tid is None:
+                tid = len(vocab)
+                vocab[tok] = tid
+            flat.append(tid)
+        offsets.append(len(flat))
+    return vocab, np.asarray(flat, dtype=np.int32), np.asarray(offsets, dtype=np.int64)
 
 
 def build_bm25_from_texts(texts: Iterable[str], variant: str = "okapi", k1: float = 1.5, b: float = 0.75,
