@@ -224,6 +224,23 @@ int sb_ce_score_dev(sb_ctx* ctx, const int32_t* input_ids_dev, const int32_t* to
                     float* out_sigmoid_dev, void* stream);
 
 /*
+ * Query / document embedder on the device -- replaces the remote `embedder.embed_sync(query)` that
+ * precedes the dense search in DenseRetriever.retrieve (reference src/core/retrievers/dense.py:43; the provider is the
+ * hosted Jina embeddings API, src/core/embeddings/providers/jina.py).  A second BERT-style encoder (same blob layout and
+ * kernels as the cross-encoder; its pooler / classifier tensors are ignored) whose final [CLS] state is optionally
+ * projected (proj_w [out_dim, hidden], proj_b [out_dim], fp32; NULL = identity) and L2-normalised.
+ * sb_enc_embed: input_ids / token_type P x S int32 (host), lengths[P]; out[P * sb_enc_dim()] fp32 (host).
+ * sb_enc_embed_dev: the same on device buffers (chains straight into sb_dense_topk_dev without a host round trip).
+ */
+int sb_enc_load(sb_ctx* ctx, const float* weights, int64_t n_floats, const sb_ce_config* cfg, const float* proj_w,
+                const float* proj_b, int32_t out_dim);
+int32_t sb_enc_dim(sb_ctx* ctx);
+int sb_enc_embed(sb_ctx* ctx, const int32_t* input_ids, const int32_t* token_type, const int32_t* lengths, int32_t P,
+                 int32_t S, int32_t normalize, float* out);
+int sb_enc_embed_dev(sb_ctx* ctx, const int32_t* input_ids_dev, const int32_t* token_type_dev,
+                     const int32_t* lengths_dev, int32_t P, int32_t S, int32_t normalize, float* out_dev, void* stream);
+
+/*
  * Work counters of the packed-token forward since the last reset: out3 = {pairs scored, sum of pair lengths (token rows
  * actually computed), sum of squared pair lengths}.  flops = layers * (24 * H^2 * out3[1] + 4 * H * out3[2]) -- used by
  * bench.py so the tensor-pipe roofline counts the work done, not the padding skipped.  Synchronises the device.
@@ -261,6 +278,24 @@ int sb_ce_gemm_test(sb_ctx* ctx, const float* a, const float* w, const float* bi
 int sb_merge_shards_dev(sb_ctx* ctx, const int64_t* in_ids, const double* in_scores, const int32_t* in_counts,
                         int64_t shard_stride_bytes, int32_t G, int32_t B, int32_t k, int64_t* out_ids,
                         double* out_scores, int32_t* out_counts, void* stream);
+
+/* ---------------------------------------------------------------- K7: document selector ------------------------ */
+/*
+ * Batched form of select_documents_node (reference src/core/graph/nodes.py:272-337), the node that follows the reranker:
+ * per query, stable sort of the candidates by score (descending), repeated ids dropped, the first top_k unique documents
+ * walked, blank documents skipped, documents kept while the running `len(text) // 4` token estimate stays <= max_tokens
+ * (the first document that does not fit ends the walk).
+ * sb_doc_chars_load: n_chars[i] = characters of document (id_base + i)'s usable text -- `doc.text`, else
+ * `metadata["content"]` (nodes.py:296-299) -- and 0 for a blank one.
+ * sb_select_dev: cand_ids [B,k] / cand_scores [B,k] (score_dtype 0 = float32, e.g. sb_rerank_dev's output, 1 = float64,
+ * e.g. sb_fuse_dev's) / cand_cnt [B] -> out_ids [B,top_k] (-1 padded), out_scores [B,top_k] (same dtype),
+ * out_counts [B] (= metadata.selected_count), out_tokens [B] (= metadata.selected_tokens).
+ */
+int sb_doc_chars_load(sb_ctx* ctx, const int32_t* n_chars, int64_t n_docs, int64_t id_base);
+int sb_select_dev(sb_ctx* ctx, const int64_t* cand_ids_dev, const void* cand_scores_dev, int32_t score_dtype,
+                  const int32_t* cand_cnt_dev, int32_t B, int32_t k, int32_t top_k, int32_t max_tokens,
+                  int64_t* out_ids_dev, void* out_scores_dev, int32_t* out_counts_dev, int32_t* out_tokens_dev,
+                  void* stream);
 
 #ifdef __cplusplus
 }

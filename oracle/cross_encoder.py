@@ -86,3 +86,32 @@ def numpy_forward(weights, input_ids, token_type, lengths, dtype=np.float64):
     pooled = np.tanh(x[:, 0] @ t["pool_w"].T + t["pool_b"])
     logits = pooled @ t["cls_w"] + t["cls_b"][0]
     return logits, 1.0 / (1.0 + np.exp(-logits))
+
+
+# ------------------------------------------------------------------------------------------------ embedder oracle
+def hf_cls_states(model, input_ids, token_type, lengths, batch: int = 32):
+    """Final-layer [CLS] hidden states of the BERT encoder inside ``model`` (fp32 CPU), shape [P, H] -- the oracle of the
+    on-device query embedder: the encoder stack is the cross-encoder's, pinned above."""
+    import torch
+
+    ids = torch.as_tensor(np.asarray(input_ids), dtype=torch.long)
+    tt = torch.as_tensor(np.asarray(token_type), dtype=torch.long)
+    S = ids.shape[1]
+    mask = (torch.arange(S)[None, :] < torch.as_tensor(np.asarray(lengths), dtype=torch.long)[:, None]).long()
+    out = []
+    with torch.no_grad():
+        for i in range(0, ids.shape[0], batch):
+            o = model.bert(input_ids=ids[i:i + batch], token_type_ids=tt[i:i + batch], attention_mask=mask[i:i + batch])
+            out.append(o.last_hidden_state[:, 0].double())
+    return torch.cat(out).numpy() if out else np.zeros((0, 0))
+
+
+def embed_from_cls(cls_states, proj_w=None, proj_b=None, normalize=True):
+    """embedding = normalize(W_proj cls + b_proj)  (fp64)."""
+    y = np.asarray(cls_states, dtype=np.float64)
+    if proj_w is not None:
+        y = y @ np.asarray(proj_w, dtype=np.float64).T + np.asarray(proj_b, dtype=np.float64)
+    if normalize:
+        n = np.linalg.norm(y, axis=1, keepdims=True)
+        y = y / np.where(n > 0, n, 1.0)
+    return y

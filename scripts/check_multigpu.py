@@ -50,6 +50,38 @@ def main():
             same = bool(np.array_equal(rs[0], results[method][0]) and np.array_equal(rs[1], results[method][1]))
             print(f"hybrid {method} sharded == single:", same, flush=True)
             ok &= same
+    # rerank: every rank holds the merged candidates of all queries and reranks ITS slice of the queries
+    from sentio_b200.cross_encoder import CrossEncoderWeights
+    from sentio_b200.index import doc_token_matrix, hash_vocab_ids
+
+    cfg = dict(vocab_size=30522, hidden=128, layers=2, heads=4, intermediate=256, max_pos=128, type_vocab=2, ln_eps=1e-12)
+    w = CrossEncoderWeights.random(cfg, seed=5, std=0.05)
+    vocab_ids = hash_vocab_ids(20000)
+    doc_tok, doc_len = doc_token_matrix(flat, off, vocab_ids, ld=120)
+    q_raw = synth.query_tokens(B, vocab=20000)
+    q_tok = vocab_ids[q_raw].astype(np.int32)
+    q_len = np.full(B, q_raw.shape[1], np.int32)
+    pipe.load_cross_encoder(w)
+    pipe.load_doc_tokens(doc_tok, doc_len)
+    r_ids, r_sc, r_cnt = pipe.search_hybrid_rerank(q, terms, q_tok, q_len, 40, 10, seq_len=128)
+    a, b = pipe.rerank_slice(B)
+    mine = torch.zeros(1, device=f"cuda:{local}")
+    if rank == 0:
+        single.load_cross_encoder(w)
+        single.load_doc_tokens(doc_tok, doc_len)
+        s_ids, s_sc, s_cnt = single.search_hybrid_rerank(q, terms, q_tok, q_len, 40, 10, seq_len=128)
+        ref = torch.from_numpy(np.concatenate([s_ids.astype(np.float64), s_sc.astype(np.float64)], axis=1)).to(f"cuda:{local}")
+    else:
+        ref = torch.empty((B, 20), dtype=torch.float64, device=f"cuda:{local}")
+    dist.broadcast(ref, 0)
+    ref = ref.cpu().numpy()
+    same = bool(np.array_equal(ref[a:b, :10], r_ids.astype(np.float64)) and
+                np.allclose(ref[a:b, 10:], r_sc.astype(np.float64), rtol=1e-5, atol=1e-6))
+    print(f"rank {rank}: rerank slice [{a},{b}) == single-GPU rows: {same}", flush=True)
+    mine[0] = 0 if same else 1
+    dist.all_reduce(mine)
+    if rank == 0:
+        ok &= float(mine.item()) == 0
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

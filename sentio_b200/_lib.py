@@ -78,12 +78,21 @@ SIGNATURES = {
     "sb_bm25_build_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sb_bm25_build_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_double, C.c_double, C.c_double,
                                        C.c_int64]),
+    "sb_enc_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(SbCeConfig), C.c_void_p, C.c_void_p, C.c_int32]),
+    "sb_enc_dim": (C.c_int32, [C.c_void_p]),
+    "sb_enc_embed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                               C.c_void_p]),
+    "sb_enc_embed_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_void_p, C.c_void_p]),
     "sb_ce_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "sb_ce_tokens_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64]),
     "sb_rerank_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                 C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sb_ce_gemm_test": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_int32, C.c_void_p]),
+    "sb_doc_chars_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]),
+    "sb_select_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sb_merge_shards_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

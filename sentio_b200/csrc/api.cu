@@ -68,6 +68,7 @@ void sb_destroy(sb_ctx* ctx) {
   if (b.dnorm) cudaFree(b.dnorm);
   if (b.idf) cudaFree(b.idf);
   if (ctx->ce) ce_model_free(ctx->ce);
+  if (ctx->enc) ce_model_free(ctx->enc);
   if (ctx->ce_tokens) ce_tokens_free(ctx->ce_tokens);
   if (ctx->bm25_build) bm25_build_free(ctx->bm25_build);
   ctx->q_dev.release();
@@ -79,6 +80,7 @@ void sb_destroy(sb_ctx* ctx) {
   ctx->misc2_dev.release();
   ctx->misc3_dev.release();
   ctx->acc_dev.release();
+  ctx->doc_chars_dev.release();
   ctx->pin_in.release();
   ctx->pin_out.release();
   for (auto& r : ctx->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

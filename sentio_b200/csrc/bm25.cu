@@ -14,6 +14,7 @@
 // Algorithmic bytes per query: sum_t df(t) * (4 B doc + 8 B ratio + 16 B accumulator RMW) + N * 8 B zero fill
 // + N * 8 B top-k read; the accumulators of a sub-batch are sized to stay L2 resident.
 #include <algorithm>
+#include <type_traits>
 #include <string.h>
 
 #include "common.cuh"
@@ -114,13 +115,14 @@ __device__ unsigned long long block_kth_largest(const unsigned long long* keys, 
                                                 int passes);
 
 template <int MODE, bool PLUS>
-__global__ void __launch_bounds__(kRsThreads, 2) bm25_range_kernel(const RangeParams p) {
+__global__ void __launch_bounds__(kRsThreads, 3) bm25_range_kernel(const RangeParams p) {
   extern __shared__ __align__(16) uint8_t rsm[];
   double* acc = reinterpret_cast<double*>(rsm);                               // [kRange]
-  int64_t* s_cur = reinterpret_cast<int64_t*>(acc + kRange);                  // [2][max_len]  posting cursor per term
-  int64_t* s_hi = s_cur + 2 * (size_t)p.max_len;                              // [max_len]     end of the posting list
-  double* s_idf = reinterpret_cast<double*>(s_hi + p.max_len);                // [max_len]     0.0 = term contributes nothing
-  int32_t* s_wid = reinterpret_cast<int32_t*>(s_idf + p.max_len);            // [max_len]     loads per thread per chunk
+  int64_t* s_lo = reinterpret_cast<int64_t*>(acc + kRange);                   // [max_len] first posting of the term's list
+  double* s_idf = reinterpret_cast<double*>(s_lo + p.max_len);                // [max_len] 0.0 = term contributes nothing
+  int32_t* s_cur = reinterpret_cast<int32_t*>(s_idf + p.max_len);             // [2][max_len] cursor, relative to s_lo
+  int32_t* s_n = s_cur + 2 * (size_t)p.max_len;                               // [max_len] postings in the list (df < 2^31)
+  int32_t* s_wid = s_n + p.max_len;                                           // [max_len] postings per thread per chunk
   uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_wid + p.max_len);          // [kRange / 32] PLUS: doc had a posting
   __shared__ int hist[256];
   __shared__ int scal[4];
@@ -138,24 +140,23 @@ __global__ void __launch_bounds__(kRsThreads, 2) bm25_range_kernel(const RangePa
   for (int j = warp; j < len; j += kRsThreads / 32) {
     const int t = p.q_terms[q0 + j];
     double w = 0.0;
-    int64_t pos = 0, hi = 0;
-    int wid = 1;
+    int64_t lo = 0, pos = 0, hi = 0;
     if (t >= 0 && t < p.n_terms) {
       w = p.idf[t];
       if (w != 0.0) {
-        const int64_t lo = p.indptr[t];
+        lo = p.indptr[t];
         hi = p.indptr[t + 1];
         pos = first == 0 ? lo : warp_lower_bound(p.post_doc, lo, hi, (int32_t)(first * kRange), lane);
-        // expected postings per range -> how many postings a thread fetches per chunk (rare terms: do not over-read)
-        const int64_t per_range = ((hi - lo) * kRange) / max(p.n_docs, (int64_t)1);
-        wid = (int)min((int64_t)kRsPost, per_range / kRsThreads + 1);
       }
     }
     if (lane == 0) {
-      s_cur[j] = pos;
-      s_hi[j] = hi;
+      s_lo[j] = lo;
+      s_cur[j] = (int32_t)(pos - lo);
+      s_n[j] = (int32_t)(hi - lo);
       s_idf[j] = w;
-      s_wid[j] = wid;
+      // expected postings of the term inside one range -> chunk width (rare terms must not over-read)
+      const int64_t per_range = ((hi - lo) * kRange) / max(p.n_docs, (int64_t)1);
+      s_wid[j] = per_range < kRsThreads / 2 ? 1 : kRsPost;
     }
   }
   for (int i = tid; i < kRange; i += kRsThreads) acc[i] = 0.0;
@@ -163,93 +164,68 @@ __global__ void __launch_bounds__(kRsThreads, 2) bm25_range_kernel(const RangePa
     for (int i = tid; i < kRange / 32; i += kRsThreads) s_bits[i] = 0u;
   __syncthreads();
 
-  // Software pipeline: the first kRsThreads postings of each of the leading kPf query terms are fetched into registers one
-  // RANGE ahead (the cursor of (range r + 1, term j) is known as soon as term j of range r is done), so the steady state
-  // never waits for a posting load between two term barriers; only terms with more than kRsThreads postings inside a range
-  // issue further (wide) loads.
-  constexpr int kPf = 8;
-  int32_t pf_doc[kPf];
-  double pf_rat[kPf];
-#pragma unroll
-  for (int j = 0; j < kPf; ++j) {
-    pf_doc[j] = 0x7fffffff;
-    pf_rat[j] = 0.0;
-    if (j < len && s_idf[j] != 0.0) {
-      const int64_t idx = s_cur[j] + tid;
-      if (idx < s_hi[j]) {
-        pf_doc[j] = __ldg(p.post_doc + idx);
-        pf_rat[j] = __ldg(p.ratio + idx);
-      }
-    }
-  }
-
   for (int64_t r = first; r < last; ++r) {
     const int32_t r0 = (int32_t)(r * kRange);
     const int32_t r1 = (int32_t)min((int64_t)r0 + kRange, p.n_docs);
     const int nd = r1 - r0;
     const int par = (int)((r - first) & 1);
-    const int64_t* cur_in = s_cur + (size_t)par * p.max_len;
-    int64_t* cur_out = s_cur + (size_t)(par ^ 1) * p.max_len;
+    const int32_t* cur_in = s_cur + (size_t)par * p.max_len;
+    int32_t* cur_out = s_cur + (size_t)(par ^ 1) * p.max_len;
 
-    // one posting: accumulate if its doc is inside the range; returns true when the posting lies beyond the range
-    auto apply = [&](int32_t doc, double rat, double w) -> bool {
-      if (doc >= r1) return true;
-      const int d = doc - r0;
-      if (PLUS) {
-        acc[d] = __dadd_rn(acc[d], __dmul_rn(w, __dadd_rn(p.delta, rat)));
-        atomicOr(&s_bits[d >> 5], 1u << (d & 31));
-      } else {
-        acc[d] = __dadd_rn(acc[d], __dmul_rn(w, rat));
-      }
-      return false;
-    };
-    // the unique boundary idx b in [pos0, hi]: doc(b) >= r1 (doc(hi) = +inf) and (b == pos0 or doc(b - 1) < r1) becomes the
-    // term's cursor for the next range.  doc(idx - 1) comes from the neighbouring lane; lane 0 re-reads it (L1 hit).
-    auto boundary = [&](int j, int64_t idx, int32_t doc, bool out, int64_t pos0, int64_t hi) {
-      int32_t prev = __shfl_up_sync(0xffffffffu, doc, 1);
-      if (out) {
-        if (lane == 0) prev = idx == pos0 ? -1 : (idx - 1 < hi ? __ldg(p.post_doc + idx - 1) : 0x7fffffff);
-        if (idx <= hi && prev < r1) cur_out[j] = idx;
-      }
-    };
-    auto run_term = [&](int j, bool have_pf, int32_t d0, double rt0) {
+    for (int j = 0; j < len; ++j) {
       const double w = s_idf[j];
-      if (w == 0.0) return;  // block-uniform
-      const int64_t pos0 = cur_in[j], hi = s_hi[j];
-      int64_t pos = pos0;
-      bool done = false;
-      if (have_pf) {  // chunk 0: one posting per thread, already in registers
-        const bool out = apply(d0, rt0, w);
-        boundary(j, pos0 + tid, d0, out, pos0, hi);
-        done = __syncthreads_or(out);
-        pos = pos0 + kRsThreads;
-      }
-      const int wid = s_wid[j];
-      while (!done) {
-        int32_t doc[kRsPost];
-        double rat[kRsPost];
-#pragma unroll
-        for (int u = 0; u < kRsPost; ++u) {
-          const int64_t idx = pos + (int64_t)u * kRsThreads + tid;
-          doc[u] = 0x7fffffff;
-          rat[u] = 0.0;
-          if (u < wid && idx < hi) {
-            doc[u] = __ldg(p.post_doc + idx);
-            rat[u] = __ldg(p.ratio + idx);
+      if (w == 0.0) continue;  // block-uniform
+      const int32_t pos0 = cur_in[j], n = s_n[j];
+      const int wid = s_wid[j];   // postings a thread fetches per chunk: 1 for rare terms (no over-read), else kRsPost
+      const int32_t* __restrict__ pd = p.post_doc + s_lo[j];
+      const double* __restrict__ pr = p.ratio + s_lo[j];
+      // one posting (index i of the list, doc d, ratio rt): accumulate when d is inside the range; otherwise it lies beyond
+      // the range and, if it is the FIRST such posting -- doc(i) >= r1 (doc(n) = +inf) and (i == pos0 or doc(i-1) < r1) --
+      // its index is the term's cursor for the next range.  Returns true for "beyond".
+      auto apply = [&](int32_t i, int32_t d, double rt) -> bool {
+        if (d < r1) {
+          const int x = d - r0;
+          if (PLUS) {
+            acc[x] = __dadd_rn(acc[x], __dmul_rn(w, __dadd_rn(p.delta, rt)));
+            atomicOr(&s_bits[x >> 5], 1u << (x & 31));
+          } else {
+            acc[x] = __dadd_rn(acc[x], __dmul_rn(w, rt));
           }
+          return false;
         }
-        bool any_out = false;
+        if (i <= n && (i == pos0 || __ldg(pd + i - 1) < r1)) cur_out[j] = i;
+        return true;
+      };
+      // chunk loop, specialised on the chunk width (block-uniform) so the unrolled body carries no per-slot predicates
+      auto walk = [&](auto width) {
+        constexpr int W = decltype(width)::value;
+        const int32_t* __restrict__ qd = pd + tid;
+        const double* __restrict__ qr = pr + tid;
+        int32_t pos = pos0;
+        for (;;) {
+          int32_t doc[W];
+          double rat[W];
 #pragma unroll
-        for (int u = 0; u < kRsPost; ++u) {
-          if (u < wid) {  // block-uniform
-            const bool out = apply(doc[u], rat[u], w);
-            boundary(j, pos + (int64_t)u * kRsThreads + tid, doc[u], out, pos0, hi);
-            any_out |= out;
+          for (int u = 0; u < W; ++u) {
+            const int32_t i = pos + u * kRsThreads + tid;
+            doc[u] = 0x7fffffff;
+            rat[u] = 0.0;
+            if (i < n) {
+              doc[u] = __ldg(qd + pos + u * kRsThreads);
+              rat[u] = __ldg(qr + pos + u * kRsThreads);
+            }
           }
+          bool any_out = false;
+#pragma unroll
+          for (int u = 0; u < W; ++u) any_out |= apply(pos + u * kRsThreads + tid, doc[u], rat[u]);
+          if (__syncthreads_or(any_out)) break;
+          pos += W * kRsThreads;
         }
-        done = __syncthreads_or(any_out);
-        pos += (int64_t)wid * kRsThreads;
-      }
+      };
+      if (wid == 1)
+        walk(std::integral_constant<int, 1>());
+      else
+        walk(std::integral_constant<int, kRsPost>());
       if (PLUS) {
         // every doc of the range WITHOUT a posting of this term gets idf * (delta + 0.0); a warp owns one bit word
         const double wd = __dmul_rn(w, __dadd_rn(p.delta, 0.0));
@@ -261,39 +237,23 @@ __global__ void __launch_bounds__(kRsThreads, 2) bm25_range_kernel(const RangePa
         }
         __syncthreads();
       }
-    };
-
-#pragma unroll
-    for (int j = 0; j < kPf; ++j) {
-      if (j < len) {  // block-uniform
-        run_term(j, true, pf_doc[j], pf_rat[j]);
-        // refill the slot with the term's first chunk of the NEXT range (its cursor was published before the last barrier)
-        pf_doc[j] = 0x7fffffff;
-        pf_rat[j] = 0.0;
-        if (r + 1 < last && s_idf[j] != 0.0) {
-          const int64_t idx = cur_out[j] + tid;
-          if (idx < s_hi[j]) {
-            pf_doc[j] = __ldg(p.post_doc + idx);
-            pf_rat[j] = __ldg(p.ratio + idx);
-          }
-        }
-      }
     }
-    for (int j = kPf; j < len; ++j) run_term(j, false, 0, 0.0);
     // the barrier that ended the last term's loop (or the initial one) ordered all accumulator updates before this point
     if (MODE == kModeDump) {
       double* out = p.dump + (size_t)qi * p.n_docs + r0;
       for (int i = tid; i < nd; i += kRsThreads) out[i] = acc[i];
       for (int i = tid; i < kRange; i += kRsThreads) acc[i] = 0.0;
     } else if (MODE == kModeCollect) {
+      // thr is the orderable image of a positive double (or of "every positive score"): for positive scores the key order
+      // is the numeric order, so the filter compares doubles and only survivors are converted
       const unsigned long long t = p.thr[qi];
+      const double td = orderable_f64(t);
       unsigned long long* ok = p.ckey + (size_t)qi * p.n_docs;
       uint32_t* oi = p.cidx + (size_t)qi * p.n_docs;
       for (int i = tid; i < kRange; i += kRsThreads) {
-        unsigned long long key = 0ull;
-        if (i < nd) key = f64_orderable(acc[i]);
+        const double sv = acc[i];
         acc[i] = 0.0;
-        const bool pass = i < nd && key > kPosZero && key >= t && key != 0xffffffffffffffffull;
+        const bool pass = i < nd && sv > 0.0 && sv >= td && sv <= 1.7976931348623157e308;  // finite positive (NaN fails)
         const unsigned m = __ballot_sync(0xffffffffu, pass);
         if (m) {
           int at = 0;
@@ -301,7 +261,7 @@ __global__ void __launch_bounds__(kRsThreads, 2) bm25_range_kernel(const RangePa
           at = __shfl_sync(0xffffffffu, at, 0);
           if (pass) {
             at += __popc(m & ((1u << lane) - 1u));
-            ok[at] = key;
+            ok[at] = f64_orderable(sv);
             oi[at] = (uint32_t)(r0 + i);
           }
         }
@@ -511,7 +471,7 @@ int pow2_at_least(int v) {
 }
 
 size_t range_smem_bytes(int max_len) {
-  return (size_t)kRange * 8 + (size_t)std::max(max_len, 1) * (16 + 8 + 8 + 4) + (kRange / 32) * 4 + 16;
+  return (size_t)kRange * 8 + (size_t)std::max(max_len, 1) * (8 + 8 + 8 + 4 + 4) + (kRange / 32) * 4 + 16;
 }
 
 template <int MODE, bool PLUS>
@@ -551,7 +511,7 @@ RangeParams range_params(sb_ctx* ctx, const int32_t* q_terms_dev, const int32_t*
 
 // consecutive ranges per CTA: long runs amortise the per-term posting-list search, short runs fill the machine
 int ranges_per_cta(sb_ctx* ctx, int nq, int64_t n_ranges) {
-  const int64_t resident = (int64_t)ctx->num_sms * 2;  // 2 CTAs of bm25_range_kernel per SM
+  const int64_t resident = (int64_t)ctx->num_sms * 3;  // 3 CTAs of bm25_range_kernel per SM
   int64_t r = ((int64_t)nq * n_ranges) / (resident * 4);
   if (r < 1) r = 1;
   if (r > 8) r = 8;

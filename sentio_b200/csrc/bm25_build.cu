@@ -114,7 +114,7 @@ __global__ void rank_runs_kernel(const int32_t* __restrict__ sorted_runs, const 
 }
 
 __global__ void scatter_postings_kernel(const int32_t* __restrict__ pair_pos, const int32_t* __restrict__ run_idx,
-                                        const int32_t* __restrict__ docs, const int32_t* __restrict__ rank_of_run,
+                                        const int32_t* __restrict__ run_head, const int32_t* __restrict__ docs, const int32_t* __restrict__ rank_of_run,
                                         const int32_t* __restrict__ run_pair_start, const int64_t* __restrict__ indptr,
                                         int64_t nnz, int64_t T, int32_t* __restrict__ post_doc,
                                         uint16_t* __restrict__ tf, int32_t* __restrict__ err) {
@@ -122,7 +122,7 @@ __global__ void scatter_postings_kernel(const int32_t* __restrict__ pair_pos, co
   if (p >= nnz) return;
   const int64_t i = pair_pos[p];
   const int64_t next = p + 1 < nnz ? (int64_t)pair_pos[p + 1] : T;
-  const int u = run_idx[i];
+  const int u = run_idx[i] + run_head[i] - 1;  // exclusive scan + own flag - 1 = index of the run that contains i
   const int64_t dest = indptr[rank_of_run[u]] + (p - run_pair_start[u]);
   post_doc[dest] = docs[i];
   const int64_t f = next - i;
@@ -289,7 +289,7 @@ int sb_bm25_build_tokens(sb_ctx* ctx, const int32_t* flat_tokens, int64_t n_toke
   }
   SB_CUDA(cudaMemcpyAsync(B->indptr + V, &nnz, 8, cudaMemcpyHostToDevice, st));
   ctx->launches += 1;
-  scatter_postings_kernel<<<blocks_for(nnz), 256, 0, st>>>(pair_pos, run_idx, vals2, rank_of_run, run_pair_start, B->indptr,
+  scatter_postings_kernel<<<blocks_for(nnz), 256, 0, st>>>(pair_pos, run_idx, run_head, vals2, rank_of_run, run_pair_start, B->indptr,
                                                           nnz, T, B->post_doc, B->tf, err_d);
   SB_CUDA(cudaGetLastError());
   SB_CUDA(cudaMemcpyAsync(&err_h, err_d, 4, cudaMemcpyDeviceToHost, st));

@@ -122,7 +122,8 @@ struct sb_ctx {
   std::mutex mu;
   DenseIndex dense[SB_MAX_DENSE_SLOTS];
   Bm25Index bm25;
-  CeModel* ce = nullptr;
+  CeModel* ce = nullptr;   // reranker (sb_ce_load)
+  CeModel* enc = nullptr;  // query / document embedder (sb_enc_load)
   CeDocTokens* ce_tokens = nullptr;
   Bm25Build* bm25_build = nullptr;  // GPU index build in progress (sb_bm25_build_tokens .. sb_bm25_build_finish)
   int dense_mode = 0;  // 0 = auto, 1 = CUDA-core scan only, 2 = tcgen05 batched scan whenever eligible
@@ -134,6 +135,8 @@ struct sb_ctx {
   std::vector<cudaEvent_t> prof_pool;
   // scratch
   DevBuf q_dev, cand_dev, out_ids_dev, out_sc_dev, out_cnt_dev, misc_dev, misc2_dev, misc3_dev, acc_dev;
+  DevBuf doc_chars_dev;  // K7: characters of every document's usable text (0 = blank), sb_doc_chars_load
+  int64_t doc_chars_n = 0, doc_chars_base = 0;
   PinBuf pin_in, pin_out;
 };
 

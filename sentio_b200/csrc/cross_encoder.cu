@@ -49,6 +49,9 @@ struct CeModel {
   __half *xcls16 = nullptr, *ctxcls16 = nullptr, *ffncls16 = nullptr;  // [P,H] [P,H] [P,I]
   CUtensorMap m_xcls16, m_ctxcls16, m_ffncls16;
   std::vector<void*> cls_allocs;
+  // embedder use (sb_enc_*): optional output projection of the final [CLS] state, fp32 [out_dim, H] + [out_dim]
+  float *proj_w = nullptr, *proj_b = nullptr;
+  int out_dim = 0;
 };
 
 // Per-shard store of pre-tokenised documents for the batched rerank path: doc i -> tok[i][0..len[i])
@@ -482,30 +485,54 @@ __global__ void __launch_bounds__(128) ce_attention_cls_kernel(const __half* __r
   xcls32[(size_t)pair * H + head * DH + lane] = x32[row0 * H + head * DH + lane];
 }
 
-// One CTA per pair: pooled = tanh(Wp x_cls + bp); logit = w . pooled + b; relevance = sigmoid(logit).  fp32 throughout.
-__global__ void ce_head_kernel(const float* __restrict__ x32, const int32_t* __restrict__ cu, int H,
-                               const float* __restrict__ pool_w,
-                               const float* __restrict__ pool_b, const float* __restrict__ cls_w,
-                               const float* __restrict__ cls_b, float* __restrict__ logits, float* __restrict__ sig) {
-  extern __shared__ float head_sm[];  // x_cls[H], partial[warps]
-  const int pair = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const float* x = x32 + (size_t)(cu ? cu[pair] : pair) * H;  // the pair's [CLS] row (cu == NULL: x32 is [P,H])
-  for (int i = threadIdx.x; i < H; i += blockDim.x) head_sm[i] = x[i];
-  __syncthreads();
-  float part = 0.f;
-  for (int j = warp; j < H; j += nw) {
-    float s = 0.f;
-    for (int c = lane; c < H; c += 32) s = fmaf(pool_w[(size_t)j * H + c], head_sm[c], s);
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    part += cls_w[j] * tanhf(s + pool_b[j]);
+// pooled = tanh(Wp x_cls + bp); logit = w . pooled + b; relevance = sigmoid(logit).  fp32 throughout.
+// One CTA per kHeadPairs pairs: every row of the pooler weight is read once per CTA and dotted with all of its pairs'
+// [CLS] rows (one CTA per pair re-read the 590 KB matrix P times).
+constexpr int kHeadPairs = 8;
+__global__ void __launch_bounds__(256) ce_head_kernel(const float* __restrict__ x32, const int32_t* __restrict__ cu, int P,
+                                                      int H, const float* __restrict__ pool_w,
+                                                      const float* __restrict__ pool_b, const float* __restrict__ cls_w,
+                                                      const float* __restrict__ cls_b, float* __restrict__ logits,
+                                                      float* __restrict__ sig) {
+  extern __shared__ float head_sm[];  // x_cls[kHeadPairs][H], partial[warps][kHeadPairs]
+  const int pair0 = blockIdx.x * kHeadPairs, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int np = min(kHeadPairs, P - pair0);
+  for (int i = threadIdx.x; i < kHeadPairs * H; i += blockDim.x) {
+    const int q = i / H, c = i % H;
+    // the pair's [CLS] row (cu == NULL: x32 is [P,H])
+    head_sm[i] = q < np ? x32[(size_t)(cu ? cu[pair0 + q] : pair0 + q) * H + c] : 0.f;
   }
-  if (lane == 0) head_sm[H + warp] = part;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  float part[kHeadPairs];
+#pragma unroll
+  for (int q = 0; q < kHeadPairs; ++q) part[q] = 0.f;
+  for (int j = warp; j < H; j += nw) {
+    float s[kHeadPairs];
+#pragma unroll
+    for (int q = 0; q < kHeadPairs; ++q) s[q] = 0.f;
+    for (int c = lane; c < H; c += 32) {
+      const float wv = pool_w[(size_t)j * H + c];
+#pragma unroll
+      for (int q = 0; q < kHeadPairs; ++q) s[q] = fmaf(wv, head_sm[q * H + c], s[q]);
+    }
+    const float cw = cls_w[j], pb = pool_b[j];
+#pragma unroll
+    for (int q = 0; q < kHeadPairs; ++q) {
+      float v = s[q];
+      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      part[q] += cw * tanhf(v + pb);
+    }
+  }
+  float* partial = head_sm + kHeadPairs * H;
+  if (lane == 0)
+#pragma unroll
+    for (int q = 0; q < kHeadPairs; ++q) partial[warp * kHeadPairs + q] = part[q];
+  __syncthreads();
+  if (threadIdx.x < np) {
     float z = cls_b[0];
-    for (int w = 0; w < nw; ++w) z += head_sm[H + w];
-    logits[pair] = z;
-    sig[pair] = 1.f / (1.f + expf(-z));
+    for (int w = 0; w < nw; ++w) z += partial[w * kHeadPairs + threadIdx.x];
+    logits[pair0 + threadIdx.x] = z;
+    sig[pair0 + threadIdx.x] = 1.f / (1.f + expf(-z));
   }
 }
 
@@ -593,7 +620,7 @@ int ensure_workspace(CeModel* m, int64_t P, int64_t M, cudaStream_t st) {
 
 template <int H>
 int ce_forward(sb_ctx* ctx, CeModel* m, const int32_t* ids, const int32_t* tts, const int32_t* lens, int P, int S,
-               float* logits, float* sig, cudaStream_t st) {
+               float* logits, float* sig, float* cls_out, cudaStream_t st) {
   const sb_ce_config& c = m->cfg;
   const int M = P * S, I = c.intermediate, heads = c.heads;
   const int Mp = (M + 127) / 128 * 128;
@@ -636,8 +663,12 @@ int ce_forward(sb_ctx* ctx, CeModel* m, const int32_t* ids, const int32_t* tts, 
       ce_ln_kernel<H><<<cls_ln_blocks, rows_per_block * 32, 0, st>>>(m->precls32, P, nullptr, L.ln2_g, L.ln2_b, c.ln_eps,
                                                                      m->xcls32, m->xcls16);
       SB_CUDA(cudaGetLastError());
-      ce_head_kernel<<<P, 256, (size_t)(H + 32) * sizeof(float), st>>>(m->xcls32, nullptr, H, m->pool_w, m->pool_b,
-                                                                      m->cls_w, m->cls_b, logits, sig);
+      if (cls_out) {  // embedder: hand the final [CLS] states over instead of running the classifier head
+        SB_CUDA(cudaMemcpyAsync(cls_out, m->xcls32, (size_t)P * H * 4, cudaMemcpyDeviceToDevice, st));
+        return SB_OK;
+      }
+      ce_head_kernel<<<(P + kHeadPairs - 1) / kHeadPairs, 256, (size_t)kHeadPairs * (H + 8) * sizeof(float), st>>>(
+          m->xcls32, nullptr, P, H, m->pool_w, m->pool_b, m->cls_w, m->cls_b, logits, sig);
       SB_CUDA(cudaGetLastError());
       return SB_OK;
     }
@@ -667,26 +698,27 @@ int ce_forward(sb_ctx* ctx, CeModel* m, const int32_t* ids, const int32_t* tts, 
                                                                m->x16);
     SB_CUDA(cudaGetLastError());
   }
-  ce_head_kernel<<<P, 256, (size_t)(H + 32) * sizeof(float), st>>>(m->x32, cu, H, m->pool_w, m->pool_b, m->cls_w,
-                                                                  m->cls_b, logits, sig);
+  SB_REQUIRE(cls_out == nullptr, SB_ERR_UNSUPPORTED, "encoder output needs 32-wide attention heads");
+  ce_head_kernel<<<(P + kHeadPairs - 1) / kHeadPairs, 256, (size_t)kHeadPairs * (H + 8) * sizeof(float), st>>>(
+      m->x32, cu, P, H, m->pool_w, m->pool_b, m->cls_w, m->cls_b, logits, sig);
   SB_CUDA(cudaGetLastError());
   return SB_OK;
 }
 
-int ce_forward_dispatch(sb_ctx* ctx, const int32_t* ids, const int32_t* tts, const int32_t* lens, int P, int S,
-                        float* logits, float* sig, cudaStream_t st) {
-  CeModel* m = ctx->ce;
-  SB_REQUIRE(m != nullptr, SB_ERR_STATE, "sb_ce_score: no cross-encoder loaded (sb_ce_load)");
+// m = the reranker (ctx->ce: logits / sigmoid out) or the embedder (ctx->enc: cls_out = final [CLS] states [P,H])
+int ce_forward_dispatch(sb_ctx* ctx, CeModel* m, const int32_t* ids, const int32_t* tts, const int32_t* lens, int P,
+                        int S, float* logits, float* sig, float* cls_out, cudaStream_t st) {
+  SB_REQUIRE(m != nullptr, SB_ERR_STATE, "no model loaded (sb_ce_load / sb_enc_load)");
   SB_REQUIRE(S > 0 && S <= m->cfg.max_pos, SB_ERR_ARG, "sb_ce_score: sequence length %d exceeds max_pos %d", S,
              m->cfg.max_pos);
   SB_REQUIRE(S <= 512, SB_ERR_UNSUPPORTED, "sb_ce_score: sequence length %d > 512", S);
   int rc = ensure_workspace(m, P, (int64_t)P * S, st);
   if (rc) return rc;
   switch (m->cfg.hidden) {
-    case 384: return ce_forward<384>(ctx, m, ids, tts, lens, P, S, logits, sig, st);
-    case 128: return ce_forward<128>(ctx, m, ids, tts, lens, P, S, logits, sig, st);
-    case 256: return ce_forward<256>(ctx, m, ids, tts, lens, P, S, logits, sig, st);
-    case 768: return ce_forward<768>(ctx, m, ids, tts, lens, P, S, logits, sig, st);
+    case 384: return ce_forward<384>(ctx, m, ids, tts, lens, P, S, logits, sig, cls_out, st);
+    case 128: return ce_forward<128>(ctx, m, ids, tts, lens, P, S, logits, sig, cls_out, st);
+    case 256: return ce_forward<256>(ctx, m, ids, tts, lens, P, S, logits, sig, cls_out, st);
+    case 768: return ce_forward<768>(ctx, m, ids, tts, lens, P, S, logits, sig, cls_out, st);
   }
   sb_set_error("sb_ce_score: unsupported hidden size %d", m->cfg.hidden);
   return SB_ERR_UNSUPPORTED;
@@ -806,8 +838,8 @@ int sb_ce_gemm_test(sb_ctx* ctx, const float* a, const float* w, const float* bi
   return SB_OK;
 }
 
-int sb_ce_load(sb_ctx* ctx, const float* weights, int64_t n_floats, const sb_ce_config* cfg) {
-  SB_REQUIRE(ctx && weights && cfg, SB_ERR_ARG, "sb_ce_load: NULL argument");
+// uploads one BERT-style model (blob layout of sentio_b200/cross_encoder.py); the caller holds ctx->mu and owns *out
+static int ce_load_model(sb_ctx* ctx, const float* weights, int64_t n_floats, const sb_ce_config* cfg, CeModel** out) {
   const int V = cfg->vocab_size, H = cfg->hidden, L = cfg->layers, I = cfg->intermediate, Pm = cfg->max_pos,
             T = cfg->type_vocab;
   SB_REQUIRE(V > 0 && H > 0 && L > 0 && I > 0 && Pm > 0 && T > 0 && cfg->heads > 0, SB_ERR_ARG, "sb_ce_load: bad config");
@@ -821,14 +853,8 @@ int sb_ce_load(sb_ctx* ctx, const float* weights, int64_t n_floats, const sb_ce_
                          H + H + 1;
   SB_REQUIRE(n_floats == expect, SB_ERR_ARG, "sb_ce_load: blob has %lld floats, config needs %lld", (long long)n_floats,
              (long long)expect);
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  DeviceGuard g(ctx->device);
   cudaStream_t st = ctx->stream;
   SB_CUDA(cudaStreamSynchronize(st));
-  if (ctx->ce) {
-    ce_model_free(ctx->ce);
-    ctx->ce = nullptr;
-  }
   CeModel* m = new CeModel();
   m->cfg = *cfg;
   const float* src = weights;
@@ -877,9 +903,168 @@ int sb_ce_load(sb_ctx* ctx, const float* weights, int64_t n_floats, const sb_ce_
   CE_TRY(upload_f32(m, src, &m->cls_b, 1, st));
 #undef CE_TRY
   SB_CUDA(cudaStreamSynchronize(st));
+  *out = m;
+  return SB_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// out[p, :] = (normalize) ( W_proj x_cls[p] + b_proj )   (W_proj == NULL: identity on the H-dim [CLS] state).
+// One CTA per kHeadPairs inputs, a warp per output column: every projection row is read once per CTA.
+__global__ void __launch_bounds__(256) enc_project_kernel(const float* __restrict__ cls, int P, int H,
+                                                          const float* __restrict__ pw, const float* __restrict__ pb,
+                                                          int D, int normalize, float* __restrict__ out) {
+  extern __shared__ float ep_sm[];   // x[kHeadPairs][H], y[kHeadPairs][D], norm[kHeadPairs]
+  float* x = ep_sm;
+  float* y = ep_sm + kHeadPairs * H;
+  float* nrm = y + (size_t)kHeadPairs * D;
+  const int p0 = blockIdx.x * kHeadPairs, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int np = min(kHeadPairs, P - p0);
+  for (int i = threadIdx.x; i < kHeadPairs * H; i += blockDim.x) x[i] = (i / H) < np ? cls[(size_t)p0 * H + i] : 0.f;
+  __syncthreads();
+  for (int o = warp; o < D; o += nw) {
+    float acc[kHeadPairs];
+#pragma unroll
+    for (int q = 0; q < kHeadPairs; ++q) acc[q] = 0.f;
+    if (pw) {
+      for (int c = lane; c < H; c += 32) {
+        const float wv = pw[(size_t)o * H + c];
+#pragma unroll
+        for (int q = 0; q < kHeadPairs; ++q) acc[q] = fmaf(wv, x[q * H + c], acc[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < kHeadPairs; ++q)
+        for (int s = 16; s; s >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], s);
+    }
+    if (lane == 0)
+#pragma unroll
+      for (int q = 0; q < kHeadPairs; ++q) y[(size_t)q * D + o] = pw ? acc[q] + pb[o] : x[q * H + o];
+  }
+  __syncthreads();
+  if (warp < kHeadPairs) {  // L2 norm of row `warp`
+    float ss = 0.f;
+    for (int o = lane; o < D; o += 32) ss = fmaf(y[(size_t)warp * D + o], y[(size_t)warp * D + o], ss);
+    for (int s = 16; s; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
+    if (lane == 0) nrm[warp] = (normalize && ss > 0.f) ? rsqrtf(ss) : 1.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < np * D; i += blockDim.x) out[(size_t)p0 * D + i] = y[i] * nrm[i / D];
+}
+
+int enc_embed_enqueue(sb_ctx* ctx, const int32_t* ids, const int32_t* tts, const int32_t* lens, int P, int S, int normalize,
+                      float* out_dev, cudaStream_t st) {
+  CeModel* m = ctx->enc;
+  SB_REQUIRE(m != nullptr, SB_ERR_STATE, "sb_enc_embed: no encoder loaded (sb_enc_load)");
+  const int H = m->cfg.hidden, D = m->proj_w ? m->out_dim : H;
+  int rc = ctx->misc3_dev.reserve((size_t)P * H * 4 + 64);
+  if (rc) return rc;
+  float* cls = ctx->misc3_dev.as<float>();
+  if ((rc = ce_forward_dispatch(ctx, m, ids, tts, lens, P, S, nullptr, nullptr, cls, st))) return rc;
+  const size_t smem = ((size_t)kHeadPairs * (H + D) + kHeadPairs + 8) * sizeof(float);
+  SB_REQUIRE(smem <= ctx->smem_optin, SB_ERR_UNSUPPORTED, "sb_enc_embed: output dimension %d too large", D);
+  SB_CUDA(cudaFuncSetAttribute(enc_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ctx->launches += 1;
+  enc_project_kernel<<<(P + kHeadPairs - 1) / kHeadPairs, 256, smem, st>>>(cls, P, H, m->proj_w, m->proj_b, D, normalize,
+                                                                          out_dev);
+  SB_CUDA(cudaGetLastError());
+  return SB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sb_ce_load(sb_ctx* ctx, const float* weights, int64_t n_floats, const sb_ce_config* cfg) {
+  SB_REQUIRE(ctx && weights && cfg, SB_ERR_ARG, "sb_ce_load: NULL argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  CeModel* m = nullptr;
+  int rc = ce_load_model(ctx, weights, n_floats, cfg, &m);
+  if (rc) return rc;
+  if (ctx->ce) ce_model_free(ctx->ce);
   ctx->ce = m;
   return SB_OK;
 }
+
+int sb_enc_load(sb_ctx* ctx, const float* weights, int64_t n_floats, const sb_ce_config* cfg, const float* proj_w,
+                const float* proj_b, int32_t out_dim) {
+  SB_REQUIRE(ctx && weights && cfg, SB_ERR_ARG, "sb_enc_load: NULL argument");
+  SB_REQUIRE((proj_w == nullptr) == (proj_b == nullptr) && (proj_w == nullptr || out_dim > 0), SB_ERR_ARG,
+             "sb_enc_load: proj_w / proj_b / out_dim must be given together");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  CeModel* m = nullptr;
+  int rc = ce_load_model(ctx, weights, n_floats, cfg, &m);
+  if (rc) return rc;
+  if (proj_w) {
+    const float* src = proj_w;
+    if ((rc = upload_f32(m, src, &m->proj_w, (size_t)out_dim * cfg->hidden, ctx->stream)) == SB_OK) {
+      src = proj_b;
+      rc = upload_f32(m, src, &m->proj_b, (size_t)out_dim, ctx->stream);
+    }
+    if (rc) {
+      ce_model_free(m);
+      return rc;
+    }
+    m->out_dim = out_dim;
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  if (ctx->enc) ce_model_free(ctx->enc);
+  ctx->enc = m;
+  return SB_OK;
+}
+
+int32_t sb_enc_dim(sb_ctx* ctx) {
+  if (!ctx || !ctx->enc) return -1;
+  return ctx->enc->proj_w ? ctx->enc->out_dim : ctx->enc->cfg.hidden;
+}
+
+int sb_enc_embed_dev(sb_ctx* ctx, const int32_t* input_ids_dev, const int32_t* token_type_dev, const int32_t* lengths_dev,
+                     int32_t P, int32_t S, int32_t normalize, float* out_dev, void* stream) {
+  SB_REQUIRE(ctx != nullptr, SB_ERR_ARG, "sb_enc_embed_dev: ctx is NULL");
+  SB_REQUIRE(P >= 0 && S > 0, SB_ERR_ARG, "sb_enc_embed_dev: bad P=%d S=%d", P, S);
+  if (P == 0) return SB_OK;
+  SB_REQUIRE(input_ids_dev && token_type_dev && lengths_dev && out_dev, SB_ERR_ARG, "sb_enc_embed_dev: NULL buffer");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  return enc_embed_enqueue(ctx, input_ids_dev, token_type_dev, lengths_dev, P, S, normalize, out_dev,
+                           pick_stream(ctx, stream));
+}
+
+int sb_enc_embed(sb_ctx* ctx, const int32_t* input_ids, const int32_t* token_type, const int32_t* lengths, int32_t P,
+                 int32_t S, int32_t normalize, float* out) {
+  SB_REQUIRE(ctx != nullptr, SB_ERR_ARG, "sb_enc_embed: ctx is NULL");
+  SB_REQUIRE(P >= 0 && S > 0, SB_ERR_ARG, "sb_enc_embed: bad P=%d S=%d", P, S);
+  if (P == 0) return SB_OK;
+  SB_REQUIRE(input_ids && token_type && lengths && out, SB_ERR_ARG, "sb_enc_embed: NULL buffer");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  SB_REQUIRE(ctx->enc != nullptr, SB_ERR_STATE, "sb_enc_embed: no encoder loaded (sb_enc_load)");
+  cudaStream_t st = ctx->stream;
+  const int D = ctx->enc->proj_w ? ctx->enc->out_dim : ctx->enc->cfg.hidden;
+  const size_t nb = (size_t)P * S * 4;
+  int rc;
+  if ((rc = ctx->pin_in.reserve(2 * nb + (size_t)P * 4))) return rc;
+  if ((rc = ctx->q_dev.reserve(2 * nb + (size_t)P * 4))) return rc;
+  uint8_t* pi = ctx->pin_in.as<uint8_t>();
+  memcpy(pi, input_ids, nb);
+  memcpy(pi + nb, token_type, nb);
+  memcpy(pi + 2 * nb, lengths, (size_t)P * 4);
+  SB_CUDA(cudaMemcpyAsync(ctx->q_dev.p, pi, 2 * nb + (size_t)P * 4, cudaMemcpyHostToDevice, st));
+  uint8_t* dv = ctx->q_dev.as<uint8_t>();
+  if ((rc = ctx->out_sc_dev.reserve((size_t)P * D * 4))) return rc;
+  if ((rc = enc_embed_enqueue(ctx, (const int32_t*)dv, (const int32_t*)(dv + nb), (const int32_t*)(dv + 2 * nb), P, S,
+                              normalize, ctx->out_sc_dev.as<float>(), st)))
+    return rc;
+  if ((rc = ctx->pin_out.reserve((size_t)P * D * 4))) return rc;
+  SB_CUDA(cudaMemcpyAsync(ctx->pin_out.p, ctx->out_sc_dev.p, (size_t)P * D * 4, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  memcpy(out, ctx->pin_out.p, (size_t)P * D * 4);
+  return SB_OK;
+}
+
 
 int sb_ce_score_dev(sb_ctx* ctx, const int32_t* input_ids_dev, const int32_t* token_type_dev, const int32_t* lengths_dev,
                     int32_t P, int32_t S, float* out_logits_dev, float* out_sigmoid_dev, void* stream) {
@@ -890,8 +1075,8 @@ int sb_ce_score_dev(sb_ctx* ctx, const int32_t* input_ids_dev, const int32_t* to
              "sb_ce_score_dev: NULL buffer");
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
-  return ce_forward_dispatch(ctx, input_ids_dev, token_type_dev, lengths_dev, P, S, out_logits_dev, out_sigmoid_dev,
-                             pick_stream(ctx, stream));
+  return ce_forward_dispatch(ctx, ctx->ce, input_ids_dev, token_type_dev, lengths_dev, P, S, out_logits_dev,
+                             out_sigmoid_dev, nullptr, pick_stream(ctx, stream));
 }
 
 int sb_ce_stats(sb_ctx* ctx, int64_t* out3, int32_t reset) {
@@ -930,8 +1115,8 @@ int sb_ce_score(sb_ctx* ctx, const int32_t* input_ids, const int32_t* token_type
   if ((rc = ctx->out_sc_dev.reserve((size_t)P * 8))) return rc;
   float* dl = ctx->out_sc_dev.as<float>();
   float* ds = dl + P;
-  if ((rc = ce_forward_dispatch(ctx, (const int32_t*)dv, (const int32_t*)(dv + nb), (const int32_t*)(dv + 2 * nb), P, S,
-                                dl, ds, st)))
+  if ((rc = ce_forward_dispatch(ctx, ctx->ce, (const int32_t*)dv, (const int32_t*)(dv + nb),
+                                (const int32_t*)(dv + 2 * nb), P, S, dl, ds, nullptr, st)))
     return rc;
   if ((rc = ctx->pin_out.reserve((size_t)P * 8))) return rc;
   SB_CUDA(cudaMemcpyAsync(ctx->pin_out.p, dl, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
@@ -1001,7 +1186,7 @@ int sb_rerank_dev(sb_ctx* ctx, const int32_t* q_tok_dev, const int32_t* q_len_de
     ce_build_pairs_kernel<<<np, 128, 0, st>>>(q_tok_dev, q_len_dev, lq, cand_ids_dev, cand_cnt_dev, k, p0, np, dt.tok,
                                               dt.len, dt.ld, dt.n, dt.id_base, S, ids, tts, lens);
     SB_CUDA(cudaGetLastError());
-    if ((rc = ce_forward_dispatch(ctx, ids, tts, lens, np, S, logits + p0, sig + p0, st))) return rc;
+    if ((rc = ce_forward_dispatch(ctx, ctx->ce, ids, tts, lens, np, S, logits + p0, sig + p0, nullptr, st))) return rc;
   }
   ctx->launches += 1;
   ce_rank_kernel<<<B, 128, (size_t)k * 4, st>>>(sig, cand_ids_dev, cand_cnt_dev, k, k_out, out_ids_dev, out_scores_dev,

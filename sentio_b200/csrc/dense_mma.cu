@@ -359,8 +359,16 @@ __global__ void __launch_bounds__(kSelectThreads, 1) dense_select_kernel(const S
       need = s_scal[1];
       const int bucket = s_scal[2];
       __syncthreads();
-      if (bucket <= 256 && bucket <= kSelTop - K) break;  // {above} (< K keys) + a small bucket: finish by sorting
+      // mode 1: {above} (< K keys) + a small bucket: finish by sorting.  mode 0 only needs a LOWER BOUND of the K-th
+      // best key, so it narrows the bucket a little further and takes the bucket's lower edge -- no gather, no sort.
+      if (p.mode == 0 ? bucket <= 16 : (bucket <= 256 && bucket <= kSelTop - K)) break;
     }
+  }
+  if (p.mode == 0) {
+    // undecided low bits of `prefix` are zero: a key <= the K-th best; its score field (possibly with cleared low bits)
+    // is a safe threshold.  Fewer than K survivors: no threshold.
+    if (tid == 0) p.thr_out[qi] = qi >= p.nq ? INFINITY : (total > K ? key32_score(prefix) : -INFINITY);
+    return;
   }
   // winners: every key whose decided digits are >= the selected bucket's (at most K - 1 + bucket <= kSelTop keys)
   SB_FOR_EACH_KEY(if ((key & mask) >= prefix) {
@@ -375,11 +383,6 @@ __global__ void __launch_bounds__(kSelectThreads, 1) dense_select_kernel(const S
   for (int i = ntop + tid; i < P; i += nt) top[i] = 0ull;
   __syncthreads();
   select_sort_desc(top, P, tid, nt);
-  const int nbest = min(ntop, K);
-  if (p.mode == 0) {
-    if (tid == 0) p.thr_out[qi] = qi >= p.nq ? INFINITY : (nbest >= K ? key32_score(top[K - 1]) : -INFINITY);
-    return;
-  }
   RescoreArgs ra;
   ra.rows = p.rows;
   ra.q = p.q + (size_t)qi * p.d_pad;

@@ -281,6 +281,61 @@ __global__ void __launch_bounds__(256) merge_shards_kernel(const int64_t* in_ids
   }
 }
 
+// ------------------------------------------------------------------------------------------------ K7: document selector
+// Batched form of select_documents_node (reference src/core/graph/nodes.py:272-337): per query, stable sort of the candidates
+// by score (desc), ids seen before are dropped, the first top_k unique documents are walked, blank documents (0 chars) are
+// skipped, a document is kept while the running len(text) // 4 estimate stays <= max_tokens and the first one that does
+// not fit ends the walk.  One CTA per query; the walk itself is sequential by definition (<= top_k steps, one thread).
+template <typename ScoreT>
+__global__ void __launch_bounds__(128) select_docs_kernel(const int64_t* __restrict__ cand_ids,
+                                                          const ScoreT* __restrict__ cand_scores,
+                                                          const int32_t* __restrict__ cand_cnt, int k, int top_k,
+                                                          int max_tokens, const int32_t* __restrict__ doc_chars,
+                                                          int64_t n_docs, int64_t id_base, int64_t* __restrict__ out_ids,
+                                                          ScoreT* __restrict__ out_scores, int32_t* __restrict__ out_counts,
+                                                          int32_t* __restrict__ out_tokens) {
+  extern __shared__ __align__(16) uint8_t sel_sm[];
+  double* sc = reinterpret_cast<double*>(sel_sm);        // [k]
+  int32_t* order = reinterpret_cast<int32_t*>(sc + k);   // [k] candidate index at every sorted position
+  const int b = blockIdx.x, n = min(max(cand_cnt[b], 0), k);
+  for (int j = threadIdx.x; j < n; j += blockDim.x) sc[j] = (double)cand_scores[(size_t)b * k + j];
+  __syncthreads();
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const double s = sc[j];
+    int pos = 0;
+    for (int i = 0; i < n; ++i) pos += (sc[i] > s) || (sc[i] == s && i < j);  // sorted(..., reverse=True) is stable
+    order[pos] = j;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const int64_t* ids = cand_ids + (size_t)b * k;
+  int uniq = 0, nsel = 0, total = 0;
+  for (int p = 0; p < n && uniq < top_k; ++p) {
+    const int j = order[p];
+    const int64_t id = ids[j];
+    bool seen = false;
+    for (int q = 0; q < p && !seen; ++q) seen = ids[order[q]] == id;
+    if (seen) continue;
+    ++uniq;
+    const int64_t row = id - id_base;
+    const int chars = (row >= 0 && row < n_docs) ? doc_chars[row] : 0;
+    if (chars <= 0) continue;  // blank document
+    const int tok = chars / 4;
+    if (total + tok > max_tokens) break;
+    out_ids[(size_t)b * top_k + nsel] = id;
+    out_scores[(size_t)b * top_k + nsel] = cand_scores[(size_t)b * k + j];
+    ++nsel;
+    total += tok;
+  }
+  for (int q = nsel; q < top_k; ++q) {
+    out_ids[(size_t)b * top_k + q] = -1;
+    out_scores[(size_t)b * top_k + q] = (ScoreT)0;
+  }
+  out_counts[b] = nsel;
+  out_tokens[b] = total;
+}
+
+
 }  // namespace
 
 int sb_fuse_enqueue(sb_ctx* ctx, int32_t method, double rrf_k, double w_dense, double w_sparse, int32_t B,
@@ -426,6 +481,50 @@ int sb_merge_shards_dev(sb_ctx* ctx, const int64_t* in_ids, const double* in_sco
   ctx->launches += 1;
   merge_shards_kernel<<<B, 256, (size_t)len * 16, st>>>(in_ids, in_scores, in_counts, shard_stride_bytes, G, B, k, len,
                                                         out_ids, out_scores, out_counts);
+  SB_CUDA(cudaGetLastError());
+  return SB_OK;
+}
+
+int sb_doc_chars_load(sb_ctx* ctx, const int32_t* n_chars, int64_t n_docs, int64_t id_base) {
+  SB_REQUIRE(ctx != nullptr && n_docs >= 0 && (n_docs == 0 || n_chars), SB_ERR_ARG, "sb_doc_chars_load: bad arguments");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  SB_CUDA(cudaStreamSynchronize(ctx->stream));
+  int rc = ctx->doc_chars_dev.reserve((size_t)std::max<int64_t>(n_docs, 1) * 4);
+  if (rc) return rc;
+  if (n_docs) SB_CUDA(cudaMemcpy(ctx->doc_chars_dev.p, n_chars, (size_t)n_docs * 4, cudaMemcpyHostToDevice));
+  ctx->doc_chars_n = n_docs;
+  ctx->doc_chars_base = id_base;
+  return SB_OK;
+}
+
+int sb_select_dev(sb_ctx* ctx, const int64_t* cand_ids_dev, const void* cand_scores_dev, int32_t score_dtype,
+                  const int32_t* cand_cnt_dev, int32_t B, int32_t k, int32_t top_k, int32_t max_tokens,
+                  int64_t* out_ids_dev, void* out_scores_dev, int32_t* out_counts_dev, int32_t* out_tokens_dev,
+                  void* stream) {
+  SB_REQUIRE(ctx != nullptr, SB_ERR_ARG, "sb_select_dev: ctx is NULL");
+  SB_REQUIRE(B >= 0 && k > 0 && top_k > 0 && max_tokens >= 0, SB_ERR_ARG, "sb_select_dev: bad sizes");
+  SB_REQUIRE(score_dtype == 0 || score_dtype == 1, SB_ERR_ARG, "sb_select_dev: score_dtype must be 0 (f32) or 1 (f64)");
+  if (B == 0) return SB_OK;
+  SB_REQUIRE(cand_ids_dev && cand_scores_dev && cand_cnt_dev && out_ids_dev && out_scores_dev && out_counts_dev &&
+                 out_tokens_dev, SB_ERR_ARG, "sb_select_dev: NULL buffer");
+  const size_t smem = (size_t)k * 12 + 16;
+  SB_REQUIRE(smem <= 48 * 1024, SB_ERR_UNSUPPORTED, "sb_select_dev: k=%d too large", k);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  SB_REQUIRE(ctx->doc_chars_dev.p != nullptr, SB_ERR_STATE, "sb_select_dev: no document lengths loaded (sb_doc_chars_load)");
+  cudaStream_t st = pick_stream(ctx, stream);
+  ctx->launches += 1;
+  if (score_dtype == 0)
+    select_docs_kernel<float><<<B, 128, smem, st>>>(cand_ids_dev, (const float*)cand_scores_dev, cand_cnt_dev, k, top_k,
+                                                    max_tokens, ctx->doc_chars_dev.as<int32_t>(), ctx->doc_chars_n,
+                                                    ctx->doc_chars_base, out_ids_dev, (float*)out_scores_dev,
+                                                    out_counts_dev, out_tokens_dev);
+  else
+    select_docs_kernel<double><<<B, 128, smem, st>>>(cand_ids_dev, (const double*)cand_scores_dev, cand_cnt_dev, k, top_k,
+                                                     max_tokens, ctx->doc_chars_dev.as<int32_t>(), ctx->doc_chars_n,
+                                                     ctx->doc_chars_base, out_ids_dev, (double*)out_scores_dev,
+                                                     out_counts_dev, out_tokens_dev);
   SB_CUDA(cudaGetLastError());
   return SB_OK;
 }

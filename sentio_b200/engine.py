@@ -307,6 +307,47 @@ class B200Engine:
         check(self._lib.sb_ce_load(self._h, _ptr(w), w.size, C.byref(c)), "sb_ce_load")
         self.ce_config = dict(cfg)
 
+    def enc_load(self, weights: np.ndarray, cfg: dict, proj_w: np.ndarray | None = None,
+                 proj_b: np.ndarray | None = None) -> None:
+        """Load the on-device embedder (sb_enc_load): encoder blob + optional [out_dim, hidden] output projection."""
+        w = np.ascontiguousarray(weights, dtype=np.float32).reshape(-1)
+        c = SbCeConfig(int(cfg["vocab_size"]), int(cfg["hidden"]), int(cfg["layers"]), int(cfg["heads"]),
+                       int(cfg["intermediate"]), int(cfg["max_pos"]), int(cfg.get("type_vocab", 2)),
+                       float(cfg.get("ln_eps", 1e-12)))
+        pw = pb = None
+        out_dim = 0
+        if proj_w is not None:
+            pw = np.ascontiguousarray(proj_w, dtype=np.float32)
+            pb = np.ascontiguousarray(proj_b, dtype=np.float32)
+            out_dim = int(pw.shape[0])
+            if pw.shape != (out_dim, int(cfg["hidden"])) or pb.shape != (out_dim,):
+                raise ValueError("proj_w must be [out_dim, hidden] and proj_b [out_dim]")
+        check(self._lib.sb_enc_load(self._h, _ptr(w), w.size, C.byref(c), _ptr(pw), _ptr(pb), out_dim), "sb_enc_load")
+        self.enc_config = dict(cfg)
+
+    def enc_dim(self) -> int:
+        return int(self._lib.sb_enc_dim(self._h))
+
+    def enc_embed(self, input_ids: np.ndarray, token_type: np.ndarray, lengths: np.ndarray, normalize: bool = True):
+        ids = np.ascontiguousarray(input_ids, dtype=np.int32)
+        tt = np.ascontiguousarray(token_type, dtype=np.int32)
+        ln = np.ascontiguousarray(lengths, dtype=np.int32)
+        P, S = ids.shape
+        out = np.empty((P, self.enc_dim()), dtype=np.float32)
+        check(self._lib.sb_enc_embed(self._h, _ptr(ids), _ptr(tt), _ptr(ln), P, S, int(normalize), _ptr(out)),
+              "sb_enc_embed")
+        return out
+
+    def enc_embed_dev(self, ids_t, tt_t, len_t, normalize: bool = True, out=None):
+        import torch
+
+        P, S = ids_t.shape
+        if out is None:
+            out = torch.empty((P, self.enc_dim()), dtype=torch.float32, device=ids_t.device)
+        check(self._lib.sb_enc_embed_dev(self._h, _tptr(ids_t), _tptr(tt_t), _tptr(len_t), P, S, int(normalize),
+                                         _tptr(out), self._stream()), "sb_enc_embed_dev")
+        return out
+
     def ce_tokens_load(self, doc_tok: np.ndarray, doc_len: np.ndarray, id_base: int = 0) -> None:
         t = np.ascontiguousarray(doc_tok, dtype=np.uint16)
         ln = np.ascontiguousarray(doc_len, dtype=np.int32)
@@ -325,6 +366,27 @@ class B200Engine:
         check(self._lib.sb_rerank_dev(self._h, _tptr(q_tok_t), _tptr(q_len_t), q_tok_t.shape[1], _tptr(cand_ids_t),
                                       _tptr(cand_cnt_t), B, k, int(S), int(k_out), _tptr(out[0]), _tptr(out[1]),
                                       _tptr(out[2]), self._stream()), "sb_rerank_dev")
+        return out
+
+    def load_doc_chars(self, n_chars: np.ndarray, id_base: int = 0) -> None:
+        """K7 input: characters of every document's usable text (0 = blank); see sentio_b200.selector.selector_chars."""
+        a = np.ascontiguousarray(n_chars, dtype=np.int32)
+        check(self._lib.sb_doc_chars_load(self._h, _ptr(a), len(a), int(id_base)), "sb_doc_chars_load")
+
+    def select_dev(self, cand_ids_t, cand_scores_t, cand_cnt_t, top_k: int, max_tokens: int, out=None):
+        """Batched document selector (sb_select_dev) on device tensors; scores float32 or float64."""
+        import torch
+
+        B, k = cand_ids_t.shape
+        dt = {torch.float32: 0, torch.float64: 1}[cand_scores_t.dtype]
+        if out is None:
+            dev = cand_ids_t.device
+            out = (torch.empty((B, top_k), dtype=torch.int64, device=dev),
+                   torch.empty((B, top_k), dtype=cand_scores_t.dtype, device=dev),
+                   torch.empty((B,), dtype=torch.int32, device=dev), torch.empty((B,), dtype=torch.int32, device=dev))
+        check(self._lib.sb_select_dev(self._h, _tptr(cand_ids_t), _tptr(cand_scores_t), dt, _tptr(cand_cnt_t), B, k,
+                                      int(top_k), int(max_tokens), _tptr(out[0]), _tptr(out[1]), _tptr(out[2]),
+                                      _tptr(out[3]), self._stream()), "sb_select_dev")
         return out
 
     def ce_gemm_test(self, a: np.ndarray, w: np.ndarray, bias: np.ndarray, epi: int, residual: np.ndarray | None = None):

@@ -9,7 +9,7 @@ __all__ = ["BaseRetriever", "ScorerPlugin", "get_retriever", "get_scorer"]
 
 
 def get_retriever(kind: str, **kwargs: Any):
-    """``dense`` | ``hybrid`` | ``bm25``/``sparse`` -> GPU-backed retriever; same argument rules as the reference."""
+    """``dense`` | ``hybrid`` | ``bm25``/``sparse`` | ``pyserini``/``lucene`` -> GPU-backed retriever; same argument rules as the reference."""
     kind = kind.lower()
     if kind == "dense":
         from .dense import DenseRetriever
@@ -27,7 +27,9 @@ def get_retriever(kind: str, **kwargs: Any):
 
         return BM25Retriever(**kwargs)
     if kind in ("pyserini", "lucene"):
-        raise ValueError("Pyserini (JVM) retrieval is out of scope of the B200 hot path; use kind='bm25'")
+        from .sparse import PyseriniBM25Retriever
+
+        return PyseriniBM25Retriever(**kwargs)  # RuntimeError without an index dir / corpus, like the reference
     raise ValueError(f"Unknown retriever kind: {kind}")
 
 

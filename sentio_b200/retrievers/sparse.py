@@ -18,7 +18,7 @@ import numpy as np
 
 from ..document import Document
 from ..engine import B200Engine
-from ..index import Bm25IndexData, build_bm25_from_texts
+from ..index import Bm25IndexData, tokenize_texts
 from .base import BaseRetriever
 
 logger = logging.getLogger(__name__)
@@ -52,9 +52,18 @@ class BM25Retriever(BaseRetriever):
         self.doc_ids = [doc.id for doc in documents]
         self.doc_map = {doc.id: doc for doc in documents}
         variant = "plus" if self.variant == "plus" else "okapi"
-        self.bm25 = build_bm25_from_texts((doc.text for doc in documents), variant=variant, **self._params)
+        # strings -> first-occurrence token ids on the host (sparse.py:88's tokeniser); everything numeric -- sort, df,
+        # tf, CSR -- on the device (sb_bm25_build_*); the CSR is exported once so save() / load() keep working
+        vocab, flat, off = tokenize_texts(doc.text for doc in documents)
+        if len(flat) == 0:
+            logger.warning("BM25 corpus has no tokens")
+            return
+        if self._engine is None:
+            self._engine = B200Engine(self._device)
+        self.bm25 = self._engine.build_bm25_gpu(flat, off, variant=variant, id_base=0, export=True, **self._params)
+        self.bm25.vocab = vocab
+        self.bm25.token_id_map = None
         self.tokenized_corpus = []  # not retained: the CSR index replaces it (reconstruct lazily if ever needed)
-        self._upload()
         logger.info("BM25 (%s) index on GPU: %d docs, %d terms, %d postings", variant, self.bm25.n_docs,
                     self.bm25.n_terms, len(self.bm25.post_doc))
 
@@ -117,3 +126,28 @@ class BM25Retriever(BaseRetriever):
         """Batched extension: (rows, scores, counts) arrays for many queries in one GPU batch."""
         terms = [self.bm25.term_ids(q.lower().split()) for q in queries]
         return self._engine.bm25_topk(terms, int(top_k))
+
+
+class PyseriniBM25Retriever(BaseRetriever):
+    """Surface of the reference's Lucene-backed retriever (sparse.py:206-276), GPU-backed.
+
+    The reference class needs Pyserini (a JVM) and an on-disk Lucene index; without them its constructor raises
+    ``RuntimeError`` and ``create_retriever_from_env`` falls back to the in-memory ``BM25Retriever`` (factory.py:150-163).
+    Neither exists offline, so parity with Lucene's scorer (its lossy norm encoding, analyzers and idf form) cannot be
+    pinned and is not claimed.  What this class provides is the same constructor contract -- ``index_dir`` must exist,
+    else ``RuntimeError`` -- and, when given the corpus explicitly, the Pyserini DEFAULT PARAMETERS (k1 = 0.9, b = 0.4,
+    ``BM25_K1`` / ``BM25_B`` in the factory) on the GPU Okapi kernel: ``PyseriniBM25Retriever(documents=docs)``.
+    """
+
+    def __init__(self, index_dir: str | None = None, k1: float = 0.9, b: float = 0.4,
+                 documents: list[Document] | None = None, device: int = 0):
+        self.index_dir = index_dir or os.getenv("BM25_INDEX_DIR", "indexes/lucene-index")
+        if documents is None:
+            if not os.path.isdir(self.index_dir):
+                raise RuntimeError(f"Pyserini index directory not found: {self.index_dir}")
+            raise RuntimeError("Pyserini is not installed - Lucene indexes cannot be read by the B200 path; pass "
+                               "documents=... to score them with Pyserini's parameters on the GPU")
+        self._inner = BM25Retriever(documents=documents, variant="okapi", device=device, k1=k1, b=b)
+
+    def retrieve(self, query: str, top_k: int = 10) -> list[Document]:
+        return self._inner.retrieve(query, top_k=top_k)

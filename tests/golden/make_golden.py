@@ -278,10 +278,54 @@ def rerank_flow_cases(ns):
     return cases
 
 
+def selector_cases(ns):
+    """create_document_selector_node (nodes.py:231-372) on random candidate lists: score ties / missing / None scores,
+    repeated ids, empty texts with and without the metadata["content"] fallback, blank texts, token budgets that cut the
+    walk, the user_top_k override, reranked-vs-retrieved precedence."""
+    from src.core.graph.nodes import create_document_selector_node
+    from src.core.graph.state import create_initial_state
+
+    rng = np.random.default_rng(11)
+    cases = []
+    for c in range(40):
+        n = int(rng.integers(0, 14))
+        docs = []
+        for i in range(n):
+            kind = int(rng.integers(0, 10))
+            text = "x" * int(rng.integers(1, 400)) if kind < 8 else ("" if kind < 9 else "   ")
+            meta = {}
+            r = rng.random()
+            if r < 0.7:
+                meta["score"] = float(np.round(rng.random(), 1))  # rounding -> ties: the stable order matters
+            elif r < 0.8:
+                meta["score"] = None
+            if rng.random() < 0.5:
+                meta["content"] = "c" * int(rng.integers(0, 200))
+            did = f"d{int(rng.integers(0, max(2, n - 2)))}" if rng.random() < 0.8 else ""
+            docs.append(dict(id=did, text=text, metadata=meta))
+        top_k = int(rng.integers(1, 8))
+        max_tokens = int(rng.integers(20, 300))
+        use_reranked = bool(rng.random() < 0.6)
+        user_top_k = [None, 2, 5.0, "7"][int(rng.integers(0, 4))]
+        state = create_initial_state("q")
+        mk = lambda d: ns.Document(id=d["id"], text=d["text"], metadata=dict(d["metadata"]))
+        state["retrieved_documents"] = [mk(d) for d in docs]
+        if use_reranked:
+            state["reranked_documents"] = [mk(d) for d in reversed(docs)]
+        if user_top_k is not None:
+            state["metadata"]["user_top_k"] = user_top_k
+        out = create_document_selector_node(top_k=top_k, max_tokens=max_tokens)(state)
+        cases.append(dict(docs=docs, top_k=top_k, max_tokens=max_tokens, use_reranked=use_reranked,
+                          user_top_k=user_top_k,
+                          selected=[[d.id, d.text, d.metadata] for d in out["selected_documents"]],
+                          meta={k: v for k, v in out["metadata"].items() if k != "user_top_k"}))
+    return cases
+
+
 def main():
     ns = refload.load()
     fixtures = dict(fusion=fusion_cases(ns), bm25=bm25_cases(ns), scorers=scorer_cases(ns),
-                    hybrid_e2e=hybrid_e2e_cases(ns), rerank_flow=rerank_flow_cases(ns))
+                    hybrid_e2e=hybrid_e2e_cases(ns), rerank_flow=rerank_flow_cases(ns), selector=selector_cases(ns))
     for name, data in fixtures.items():
         path = os.path.join(HERE, f"{name}.json")
         with open(path, "w") as f:

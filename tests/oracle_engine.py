@@ -54,6 +54,15 @@ class OracleEngine:
         self.fast = FastBM25(data.indptr, data.post_doc, data.post_tf, data.doc_len, data.idf, data.avgdl,
                              data.variant, data.k1, data.b, data.delta)
 
+    def build_bm25_gpu(self, flat_tokens, doc_offsets, variant="okapi", k1=1.5, b=0.75, epsilon=0.25, delta=1.0,
+                       id_base=0, export=False):
+        """Double of B200Engine.build_bm25_gpu: the host builder stands in for the device build."""
+        from sentio_b200.index import build_bm25_from_token_ids
+
+        data = build_bm25_from_token_ids(flat_tokens, doc_offsets, variant, k1, b, epsilon, delta)
+        self.load_bm25(data, id_base)
+        return data
+
     def bm25_scores(self, term_ids):
         return self.fast.get_scores(list(term_ids))
 

@@ -121,3 +121,22 @@ def test_cross_encoder_numpy_oracle_matches_hf():
     assert np.allclose(l_np, l_hf, rtol=1e-4, atol=1e-5)
     assert np.allclose(s_np, s_hf, rtol=1e-5)
     assert w.blob().size == sum(int(np.prod(s)) for _, s in CrossEncoderWeights.tensor_order(cfg))
+
+
+def test_selector_node_matches_reference_golden():
+    """§8f row 3: sentio_b200.selector.create_document_selector_node == the reference node (nodes.py:231-372) on the
+    committed fixture (generated by tests/golden/make_golden.py from the reference's own code)."""
+    from sentio_b200.document import Document
+    from sentio_b200.selector import create_document_selector_node
+
+    for c in load_golden("selector"):
+        mk = lambda d: Document(id=d["id"], text=d["text"], metadata=dict(d["metadata"]))
+        state = dict(query="q", retrieved_documents=[mk(d) for d in c["docs"]], reranked_documents=[],
+                     selected_documents=[], response="", metadata={}, evaluation={})
+        if c["use_reranked"]:
+            state["reranked_documents"] = [mk(d) for d in reversed(c["docs"])]
+        if c["user_top_k"] is not None:
+            state["metadata"]["user_top_k"] = c["user_top_k"]
+        out = create_document_selector_node(top_k=c["top_k"], max_tokens=c["max_tokens"])(state)
+        assert [[d.id, d.text, d.metadata] for d in out["selected_documents"]] == c["selected"]
+        assert {k: v for k, v in out["metadata"].items() if k != "user_top_k"} == c["meta"]
