@@ -246,8 +246,11 @@ def main():
     if args.workload in ("hybrid", "rerank"):
         from sentio_b200.index import build_bm25_from_token_ids
 
-        idx = build_bm25_from_token_ids(wl["flat"], wl["off"])
-        pipe.load_bm25(idx.shard(lo, hi) if sharded else idx, id_base=lo)
+        if sharded:  # corpus-global idf / avgdl: build once on the host, upload this rank's shard
+            idx = build_bm25_from_token_ids(wl["flat"], wl["off"])
+            pipe.load_bm25(idx.shard(lo, hi), id_base=lo)
+        else:        # single shard: the index is built on the device (sb_bm25_build_*), 0.3 s at 1 M docs
+            idx = pipe.engine.build_bm25_gpu(wl["flat"], wl["off"], export=True)
     if rerank:
         from sentio_b200 import synth
         from sentio_b200.cross_encoder import MINILM_L6, CrossEncoderWeights
@@ -325,6 +328,7 @@ def main():
     launches = eng.launch_count() - launches0
     n_scan, scan_ms = eng.profile_read("dense_scan")
     n_ce, ce_ms = eng.profile_read("ce")
+    n_bm, bm_ms = eng.profile_read("bm25_score") if idx is not None else (0, 0.0)
     ce_pairs, ce_rows, ce_sq = eng.ce_stats() if rerank else (0, 0, 0)
     eng.profile(False)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -396,6 +400,25 @@ def main():
         except Exception:
             pass
 
+    if idx is not None and n_bm:
+        # BM25 range kernel (sample + collect launches): algorithmic bytes = the postings of the query terms, 12 B each
+        # (4 B doc + 8 B fp64 ratio); this rank's shard, all queries of the timed steps
+        sidx = idx.shard(lo, hi) if sharded else idx
+        df = np.diff(sidx.indptr)
+        postings = 0
+        for s_ in range(args.steps):
+            for i in batch_slice(args.warmup + s_):
+                t = term_lists[i]
+                postings += int(df[t[t >= 0]].sum())
+        bm_bytes = postings * 12
+        roofline["bm25"] = {"bound": "hbm", "kernel": "bm25_range_kernel (sample + collect)",
+                            "achieved": bm_bytes / (bm_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                            "frac": bm_bytes / (bm_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": bm_bytes,
+                            "postings_per_query": postings / (B * args.steps), "ms_total": bm_ms,
+                            "share_of_step": bm_ms / ms_total,
+                            "note": "posting lists shared by the queries of a batch are served from L2 (ncu: DRAM "
+                                    "traffic ~0.25 GB per 64-query launch vs 1.6 GB algorithmic); the kernel is "
+                                    "issue/latency bound, see profiles/r01_run15_bm25_range_ncu.md"}
     if rerank and n_ce:
         # second roofline: the cross-encoder forward (tensor pipe).  Flops of the work actually done: the packed-token
         # forward computes sum(len) token rows, not P x 128 (library counters); 2.87 GFLOP per pair only at len = 128.

@@ -78,6 +78,22 @@ class HybridPipeline:
         pin.copy_(t)
         return pin.to(self._torch_device, non_blocking=True)
 
+    def _to_host(self, tensors, name: str = "out"):
+        """device tensors -> NumPy arrays through cached pinned buffers: all copies are enqueued, ONE synchronisation."""
+        if self.device is None:
+            return tuple(t.numpy() for t in tensors)
+        outs = []
+        for i, t in enumerate(tensors):
+            key = ("pin_out", name, i, tuple(t.shape), t.dtype)
+            pin = self._bufs.get(key)
+            if pin is None:
+                pin = self.torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                self._bufs[key] = pin
+            pin.copy_(t, non_blocking=True)
+            outs.append(pin)
+        self.torch.cuda.current_stream().synchronize()
+        return tuple(p.numpy().copy() for p in outs)
+
     def _record_layout(self, B: int, k: int, signals: int):
         """Byte layout of one rank's all-gather record: per signal ids[B,k] i64 | scores[B,k] f64 | counts[B] i32."""
         per = B * k * 8 * 2 + ((B * 4 + 7) // 8) * 8
@@ -177,8 +193,7 @@ class HybridPipeline:
             return self.engine.dense_topk(q, k)
         t = self.torch
         q_t = self._to_dev(np.ascontiguousarray(q, dtype=np.float32), "q")
-        ids, sc, cnt = self.dense_dev(q_t, k)
-        return ids.cpu().numpy(), sc.cpu().numpy(), cnt.cpu().numpy()
+        return self._to_host(self.dense_dev(q_t, k), "dense")
 
     def search_hybrid(self, q: np.ndarray, term_lists: Sequence[Sequence[int]], k: int, method: str = "rrf",
                       rrf_k: float = 60, w_dense: float = 0.5, w_sparse: float = 0.5):
@@ -187,9 +202,8 @@ class HybridPipeline:
         q_t = self._to_dev(np.ascontiguousarray(q, dtype=np.float32), "q")
         terms_t = self._to_dev(flat, "terms")
         off_t = self._to_dev(off, "off")
-        ids, sc, src, cnt = self.hybrid_dev(q_t, terms_t, off_t, int(off[-1]), max_len, k, method, rrf_k, w_dense,
-                                            w_sparse)
-        return ids.cpu().numpy(), sc.cpu().numpy(), src.cpu().numpy(), cnt.cpu().numpy()
+        return self._to_host(self.hybrid_dev(q_t, terms_t, off_t, int(off[-1]), max_len, k, method, rrf_k, w_dense,
+                                             w_sparse), "hybrid")
 
     def search_hybrid_rerank(self, q: np.ndarray, term_lists, q_tok: np.ndarray, q_len: np.ndarray, k: int, k_out: int,
                              seq_len: int = 128, method: str = "rrf", rrf_k: float = 60, w_dense: float = 0.5,
@@ -200,6 +214,5 @@ class HybridPipeline:
         terms_t, off_t = self._to_dev(flat, "terms"), self._to_dev(off, "off")
         qt_t = self._to_dev(np.ascontiguousarray(q_tok, dtype=np.int32), "qtok")
         ql_t = self._to_dev(np.ascontiguousarray(q_len, dtype=np.int32), "qlen")
-        ids, sc, cnt = self.hybrid_rerank_dev(q_t, terms_t, off_t, int(off[-1]), max_len, qt_t, ql_t, k, k_out, seq_len,
-                                              method, rrf_k, w_dense, w_sparse)
-        return ids.cpu().numpy(), sc.cpu().numpy(), cnt.cpu().numpy()
+        return self._to_host(self.hybrid_rerank_dev(q_t, terms_t, off_t, int(off[-1]), max_len, qt_t, ql_t, k, k_out,
+                                                    seq_len, method, rrf_k, w_dense, w_sparse), "rerank")
