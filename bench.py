@@ -45,7 +45,8 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="dense", choices=["dense", "hybrid", "rerank"])
     ap.add_argument("--rerank-k", type=int, default=10, help="documents kept after the cross-encoder (config 4: 100 -> 10)")
-    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--batch", type=int, default=None,
+                    help="queries per step PER GPU (default: 256 for dense / hybrid, 64 for rerank = 6400 pairs per step)")
     ap.add_argument("--n-docs", type=int, default=1_000_000)
     ap.add_argument("--dim", type=int, default=1024)
     ap.add_argument("--top-k", type=int, default=100)
@@ -190,6 +191,8 @@ def cpu_reference(args, wl, n_queries):
 # --------------------------------------------------------------------------------------------- main
 def main():
     args = parse_args()
+    if args.batch is None:
+        args.batch = 64 if args.workload == "rerank" else 256
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -1,4 +1,4 @@
-// bm25.cu -- K2: BM25 term-at-a-time scoring over term-major CSR postings + streaming top-k.
+// bm25.cu -- K2: BM25 term-at-a-time scoring over term-major CSR postings + exact top-k.
 //
 // Replaces rank_bm25 0.2.2 BM25Okapi/BM25Plus.get_scores followed by np.argsort / `score > 0`
 // (reference call sites src/core/retrievers/sparse.py:177-198).
@@ -8,11 +8,11 @@
 //   ratio[p]  = (tf[p] * (k1 + 1)) / (tf[p] + dnorm[doc[p]])              (load time, query independent)
 //   Okapi:  score[d] += idf[t] * ratio[p]            for every posting p of query term t, terms in QUERY ORDER
 //   Plus :  score[d] += idf[t] * (delta + ratio or 0.0)   for EVERY doc d (rank_bm25 adds delta to all docs)
-// A doc occurs at most once in a term's posting list, so one launch per query-term position needs no atomics and the
-// per-doc addition order equals NumPy's `score += ...` loop order.
+// A doc occurs at most once in a term's posting list and the terms of a query are applied one after the other (block
+// barrier in between), so no atomics are needed and the per-doc addition order equals NumPy's `score += ...` loop order.
 //
-// Algorithmic bytes per query: sum_t df(t) * (4 B doc + 8 B ratio + 16 B accumulator RMW) + N * 8 B zero fill
-// + N * 8 B top-k read; the accumulators of a sub-batch are sized to stay L2 resident.
+// Algorithmic bytes per query: sum_t df(t) * (4 B doc + 8 B ratio): the accumulators of a doc range live in shared
+// memory (bm25_range_kernel below), nothing of size N is ever written or re-read in HBM / L2.
 #include <algorithm>
 #include <type_traits>
 #include <string.h>

@@ -285,22 +285,60 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-template <int S_MAX>
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// HPC = heads of one pair handled by a CTA, one after the other: while head h is being computed the K/V rows of head
+// h + 1 stream into the second shared-memory buffer with cp.async, so only the first head of a CTA waits for its operands
+// (run 16's profile: a third of all stall samples sat on the K/V staging of one-head CTAs).
+template <int S_MAX, int HPC>
 __global__ void __launch_bounds__(128, 4) ce_attention_mma_kernel(const __half* __restrict__ qkv,
                                                                 const int32_t* __restrict__ lengths,
                                                                 const int32_t* __restrict__ cu, int S, int H,
                                                                 int heads, __half* __restrict__ ctx) {
   constexpr int DH = 32, LDS_ROW = 40;  // halves per padded smem row (80 B)
   constexpr int NT = S_MAX / 8;         // key tiles of 8
-  __shared__ __align__(16) __half Ks[S_MAX * LDS_ROW];
-  __shared__ __align__(16) __half Vs[S_MAX * LDS_ROW];
-  const int pair = blockIdx.x / heads, head = blockIdx.x % heads;
+  constexpr int NBUF = HPC > 1 ? 2 : 1;
+  __shared__ __align__(16) __half Ks_all[NBUF][S_MAX * LDS_ROW];
+  __shared__ __align__(16) __half Vs_all[NBUF][S_MAX * LDS_ROW];
+  const int groups = heads / HPC;
+  const int pair = blockIdx.x / groups, head0 = (blockIdx.x % groups) * HPC;
   const int len = min(min(max(lengths[pair], 1), S), S_MAX);
   const size_t row0 = (size_t)cu[pair];
   const int ld = 3 * H;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  // stage K and V (rows >= len as zeros so that masked products stay finite)
-  // Q fragments (A operand) of both 16-row tiles of this warp, issued BEFORE the K/V staging so the two global round trips
+  const int stage_rows = min(S_MAX, (len + 31) & ~31);  // 32-key groups beyond len are never touched
+  // rows [len, stage_rows) are masked keys: zeros (finite products), written once -- len belongs to the pair, not the head
+  const int zero_slots = (stage_rows - len) * 4;
+  for (int i = tid; i < zero_slots * NBUF; i += 128) {
+    const int bsel = i / zero_slots, r = i % zero_slots;
+    const int j = len + (r >> 2), c = (r & 3) * 8;
+    *reinterpret_cast<uint4*>(&Ks_all[bsel][j * LDS_ROW + c]) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(&Vs_all[bsel][j * LDS_ROW + c]) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  auto stage = [&](int bsel, int head) {
+    for (int i = tid; i < len * 4; i += 128) {
+      const int j = i >> 2, c = (i & 3) * 8;
+      cp_async16(smem_u32(&Ks_all[bsel][j * LDS_ROW + c]), qkv + (row0 + j) * ld + H + head * DH + c);
+      cp_async16(smem_u32(&Vs_all[bsel][j * LDS_ROW + c]), qkv + (row0 + j) * ld + 2 * H + head * DH + c);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage(0, head0);
+  // softmax in base 2: scores are scaled by log2(e) / sqrt(d_head) once, the exponentials are bare ex2
+  const float scale = rsqrtf((float)DH) * 1.4426950408889634f;
+#pragma unroll 1
+  for (int hh = 0; hh < HPC; ++hh) {
+  const int head = head0 + hh;
+  const __half* Ks = Ks_all[hh % NBUF];
+  const __half* Vs = Vs_all[hh % NBUF];
+  // Q fragments (A operand) of both 16-row tiles of this warp, issued before waiting for K/V so the global round trips
   // overlap: rows g / g+8, two k-steps of 16 columns (2t.. and 2t+8..)
   uint32_t qa_all[2][2][4];
 #pragma unroll
@@ -316,19 +354,13 @@ __global__ void __launch_bounds__(128, 4) ce_attention_mma_kernel(const __half* 
       qa_all[mt][ks][3] = *reinterpret_cast<const uint32_t*>(qhi + 8);
     }
   }
-  const int stage_rows = min(S_MAX, (len + 31) & ~31);  // 32-key groups beyond len are never touched
-  for (int i = tid; i < stage_rows * 4; i += 128) {
-    const int j = i >> 2, c = (i & 3) * 8;
-    uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = make_uint4(0u, 0u, 0u, 0u);
-    if (j < len) {
-      kv = *reinterpret_cast<const uint4*>(qkv + (row0 + j) * ld + H + head * DH + c);
-      vv = *reinterpret_cast<const uint4*>(qkv + (row0 + j) * ld + 2 * H + head * DH + c);
-    }
-    *reinterpret_cast<uint4*>(Ks + j * LDS_ROW + c) = kv;
-    *reinterpret_cast<uint4*>(Vs + j * LDS_ROW + c) = vv;
+  if (hh + 1 < HPC) {  // next head's K/V into the other buffer (its last readers passed the barrier that ended hh - 1)
+    stage((hh + 1) % NBUF, head + 1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+  } else {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
-  const float scale = rsqrtf((float)DH);
 #pragma unroll 1
   for (int mt = 0; mt < 2; ++mt) {
     const int r0 = warp * 32 + mt * 16;  // first query row of this 16-row tile
@@ -380,8 +412,8 @@ __global__ void __launch_bounds__(128, 4) ce_attention_mma_kernel(const __half* 
     for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        sc[nt][e] = __expf(sc[nt][e] - mlo);
-        sc[nt][2 + e] = __expf(sc[nt][2 + e] - mhi);
+        sc[nt][e] = ex2_approx(sc[nt][e] - mlo);
+        sc[nt][2 + e] = ex2_approx(sc[nt][2 + e] - mhi);
         llo += sc[nt][e];
         lhi += sc[nt][2 + e];
       }
@@ -416,6 +448,8 @@ __global__ void __launch_bounds__(128, 4) ce_attention_mma_kernel(const __half* 
       if (r0 + g < len) *reinterpret_cast<uint32_t*>(out_lo + n * 8 + 2 * t) = pack_h2(oc[n][0] * ilo, oc[n][1] * ilo);
       if (r0 + g + 8 < len) *reinterpret_cast<uint32_t*>(out_hi + n * 8 + 2 * t) = pack_h2(oc[n][2] * ihi, oc[n][3] * ihi);
     }
+  }
+  __syncthreads();  // every warp is done with this head's buffer before it is refilled
   }
 }
 
@@ -476,6 +510,7 @@ __global__ void __launch_bounds__(128) ce_attention_cls_kernel(const __half* __r
   for (int u = 0; u < KPL; ++u) {
     if (u * 32 >= len) break;  // warp-uniform
     const int nk = min(32, len - u * 32);
+#pragma unroll 8
     for (int jj = 0; jj < nk; ++jj) {
       const float pj = __shfl_sync(0xffffffffu, sc[u], jj);
       acc = fmaf(pj, __half2float(qkv[(row0 + u * 32 + jj) * ld + 2 * H + head * DH + lane]), acc);
@@ -489,7 +524,7 @@ __global__ void __launch_bounds__(128) ce_attention_cls_kernel(const __half* __r
 // One CTA per kHeadPairs pairs: every row of the pooler weight is read once per CTA and dotted with all of its pairs'
 // [CLS] rows (one CTA per pair re-read the 590 KB matrix P times).
 constexpr int kHeadPairs = 8;
-__global__ void __launch_bounds__(256) ce_head_kernel(const float* __restrict__ x32, const int32_t* __restrict__ cu, int P,
+__global__ void __launch_bounds__(512) ce_head_kernel(const float* __restrict__ x32, const int32_t* __restrict__ cu, int P,
                                                       int H, const float* __restrict__ pool_w,
                                                       const float* __restrict__ pool_b, const float* __restrict__ cls_w,
                                                       const float* __restrict__ cls_b, float* __restrict__ logits,
@@ -667,15 +702,19 @@ int ce_forward(sb_ctx* ctx, CeModel* m, const int32_t* ids, const int32_t* tts, 
         SB_CUDA(cudaMemcpyAsync(cls_out, m->xcls32, (size_t)P * H * 4, cudaMemcpyDeviceToDevice, st));
         return SB_OK;
       }
-      ce_head_kernel<<<(P + kHeadPairs - 1) / kHeadPairs, 256, (size_t)kHeadPairs * (H + 8) * sizeof(float), st>>>(
+      ce_head_kernel<<<(P + kHeadPairs - 1) / kHeadPairs, 512, (size_t)kHeadPairs * (H + 32) * sizeof(float), st>>>(
           m->xcls32, nullptr, P, H, m->pool_w, m->pool_b, m->cls_w, m->cls_b, logits, sig);
       SB_CUDA(cudaGetLastError());
       return SB_OK;
     }
-    if (S <= 128)
-      ce_attention_mma_kernel<128><<<P * heads, 128, 0, st>>>(m->qkv16, lens, cu, S, H, heads, m->ctx16);
+    if (S <= 128 && heads % 3 == 0)
+      ce_attention_mma_kernel<128, 3><<<P * (heads / 3), 128, 0, st>>>(m->qkv16, lens, cu, S, H, heads, m->ctx16);
+    else if (S <= 128 && heads % 2 == 0)
+      ce_attention_mma_kernel<128, 2><<<P * (heads / 2), 128, 0, st>>>(m->qkv16, lens, cu, S, H, heads, m->ctx16);
+    else if (S <= 128)
+      ce_attention_mma_kernel<128, 1><<<P * heads, 128, 0, st>>>(m->qkv16, lens, cu, S, H, heads, m->ctx16);
     else if (S <= 256)
-      ce_attention_mma_kernel<256><<<P * heads, 128, 0, st>>>(m->qkv16, lens, cu, S, H, heads, m->ctx16);
+      ce_attention_mma_kernel<256, 1><<<P * heads, 128, 0, st>>>(m->qkv16, lens, cu, S, H, heads, m->ctx16);
     else {
       const size_t att_smem = (size_t)2 * S * 32 * sizeof(float);
       SB_CUDA(cudaFuncSetAttribute(ce_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
@@ -699,7 +738,7 @@ int ce_forward(sb_ctx* ctx, CeModel* m, const int32_t* ids, const int32_t* tts, 
     SB_CUDA(cudaGetLastError());
   }
   SB_REQUIRE(cls_out == nullptr, SB_ERR_UNSUPPORTED, "encoder output needs 32-wide attention heads");
-  ce_head_kernel<<<(P + kHeadPairs - 1) / kHeadPairs, 256, (size_t)kHeadPairs * (H + 8) * sizeof(float), st>>>(
+  ce_head_kernel<<<(P + kHeadPairs - 1) / kHeadPairs, 512, (size_t)kHeadPairs * (H + 32) * sizeof(float), st>>>(
       m->x32, cu, P, H, m->pool_w, m->pool_b, m->cls_w, m->cls_b, logits, sig);
   SB_CUDA(cudaGetLastError());
   return SB_OK;

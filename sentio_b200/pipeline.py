@@ -66,17 +66,21 @@ class HybridPipeline:
         return t
 
     def _to_dev(self, arr: np.ndarray, name: str = "in"):
-        """host array -> device tensor through a cached pinned staging buffer (one per call-site name and shape)."""
+        """host array -> device tensor through a cached (pinned staging, device) buffer pair per call-site name and
+        shape: no allocator activity on the hot path (a fresh torch allocation per call showed 50 ms hiccups)."""
         t = self.torch.from_numpy(arr)
         if self.device is None:
             return t
         key = ("pin", name, tuple(arr.shape), arr.dtype.str)
-        pin = self._bufs.get(key)
-        if pin is None:
-            pin = self.torch.empty(arr.shape, dtype=t.dtype, pin_memory=True)
-            self._bufs[key] = pin
+        pair = self._bufs.get(key)
+        if pair is None:
+            pair = (self.torch.empty(arr.shape, dtype=t.dtype, pin_memory=True),
+                    self.torch.empty(arr.shape, dtype=t.dtype, device=self._torch_device))
+            self._bufs[key] = pair
+        pin, dev = pair
         pin.copy_(t)
-        return pin.to(self._torch_device, non_blocking=True)
+        dev.copy_(pin, non_blocking=True)
+        return dev
 
     def _to_host(self, tensors, name: str = "out"):
         """device tensors -> NumPy arrays through cached pinned buffers: all copies are enqueued, ONE synchronisation."""
@@ -197,13 +201,26 @@ class HybridPipeline:
 
     def search_hybrid(self, q: np.ndarray, term_lists: Sequence[Sequence[int]], k: int, method: str = "rrf",
                       rrf_k: float = 60, w_dense: float = 0.5, w_sparse: float = 0.5):
+        import os
+        import time
+
+        trace = os.environ.get("SENTIO_B200_TRACE") == "1"
+        t0 = time.perf_counter()
         flat, off = B200Engine.pack_queries(term_lists)
         max_len = int(np.diff(off).max()) if len(off) > 1 else 0
+        t1 = time.perf_counter()
         q_t = self._to_dev(np.ascontiguousarray(q, dtype=np.float32), "q")
         terms_t = self._to_dev(flat, "terms")
         off_t = self._to_dev(off, "off")
-        return self._to_host(self.hybrid_dev(q_t, terms_t, off_t, int(off[-1]), max_len, k, method, rrf_k, w_dense,
-                                             w_sparse), "hybrid")
+        t2 = time.perf_counter()
+        dev = self.hybrid_dev(q_t, terms_t, off_t, int(off[-1]), max_len, k, method, rrf_k, w_dense, w_sparse)
+        t3 = time.perf_counter()
+        out = self._to_host(dev, "hybrid")
+        if trace:
+            t4 = time.perf_counter()
+            print(f"[trace] search_hybrid B={len(term_lists)}: pack {1e3 * (t1 - t0):.3f} ms, to_dev {1e3 * (t2 - t1):.3f}, "
+                  f"enqueue {1e3 * (t3 - t2):.3f}, wait+to_host {1e3 * (t4 - t3):.3f}", flush=True)
+        return out
 
     def search_hybrid_rerank(self, q: np.ndarray, term_lists, q_tok: np.ndarray, q_len: np.ndarray, k: int, k_out: int,
                              seq_len: int = 128, method: str = "rrf", rrf_k: float = 60, w_dense: float = 0.5,

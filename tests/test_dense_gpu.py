@@ -32,7 +32,7 @@ def test_dense_topk_matches_oracle_f16_corpus(engine, n, d, k, B):
 
 
 @pytest.mark.parametrize("n,d,k,B", [(9000, 1024, 10, 16), (20000, 256, 100, 40), (30000, 768, 100, 70),
-                                     (200000, 128, 228, 33), (12000, 64, 5, 130)])
+                                     (200000, 128, 228, 33), (12000, 64, 5, 130), (40000, 1024, 100, 260)])
 def test_dense_batched_tcgen05_path_matches_oracle(engine, n, d, k, B):
     """B >= 16 queries take the tcgen05 batched-query scan (dense_mma.cu); results must equal the oracle AND be
     bit-identical to the CUDA-core scan."""
