@@ -5,12 +5,14 @@
                     [--workload dense|hybrid|rerank] [--batch B] [--n-docs N] [--dim D] [--top-k K] [--rerank-k K2]
 
 A "step" = one batch of B synthetic queries through the hot path.  Default workload = BASELINE.json configs[1]:
-1 M docs x 1024-d, dense-only cosine top_k=100 on 1 x B200.  --batch is the number of queries per step PER GPU: a step
-on N GPUs carries N x batch queries.  --shard corpus (default, north_star): the SAME corpus is partitioned N ways
-(contiguous doc ranges), every rank scores all N x batch queries against its shard, ONE NCCL all-gather of the per-shard
-top-k is followed by the merge kernel.  --shard queries: the corpus is replicated, every rank answers its own batch,
-no collective.  Either way per-GPU work per step is constant in N -> "scaling": "weak"; the corpus of the metric
-(1 M docs) never changes.
+1 M docs x 1024-d, dense-only cosine top_k=100 on 1 x B200.  --batch is the number of queries per step PER GPU (default 256;
+64 for the rerank workload, i.e. 6400 pairs per step): a step on N GPUs carries N x batch queries.  Multi-GPU layout =
+C corpus shards x N/C query groups: the C ranks of a group partition the corpus (contiguous doc ranges), score the group's
+C x batch queries against their shards, exchange per-shard top-k in ONE NCCL all-gather and merge; different groups answer
+different queries.  --shard corpus: C = N (north_star's layout for corpora that must be partitioned); --shard queries:
+C = 1 (replicated corpus, no collective); --shard auto (default): the smallest C whose shard fits the per-GPU memory
+budget -- 1 for the 2 GB corpus of the metric.  Per-GPU work per step is constant in N -> "scaling": "weak"; the corpus
+of the metric (1 M docs) never changes.
 
 value   : whole-job queries/sec, inputs already resident in HBM (device entry points, CUDA-event timed, max over ranks)
 e2e     : the same metric through the host-buffer C-ABI entry point (pinned host queries -> H2D -> kernels -> D2H results)
@@ -51,9 +53,15 @@ def parse_args():
     ap.add_argument("--dim", type=int, default=1024)
     ap.add_argument("--top-k", type=int, default=100)
     ap.add_argument("--cpu-sample", type=int, default=24, help="queries in the bounded CPU-baseline sample")
-    ap.add_argument("--shard", default="corpus", choices=["corpus", "queries"],
-                    help="--gpus N > 1: 'corpus' = contiguous doc ranges + ONE NCCL all-gather of per-shard top-k "
-                         "(north_star); 'queries' = corpus replicated on every GPU, queries split, no collective")
+    ap.add_argument("--shard", default="auto", choices=["auto", "corpus", "queries"],
+                    help="--gpus N > 1 layout = C corpus shards x N/C query groups.  'corpus': C = N (contiguous doc ranges "
+                         "+ ONE NCCL all-gather of per-shard top-k, north_star's layout for corpora that must be "
+                         "partitioned); 'queries': C = 1 (corpus replicated, queries split, no collective); 'auto' "
+                         "(default): the smallest C whose shard fits --gpu-mem-budget-gb, i.e. partition only as much "
+                         "as capacity requires")
+    ap.add_argument("--corpus-shards", type=int, default=0, help="explicit C (must divide N); overrides --shard")
+    ap.add_argument("--gpu-mem-budget-gb", type=float, default=64.0,
+                    help="HBM one GPU may spend on index data under --shard auto (B200: 180 GB)")
     return ap.parse_args()
 
 
@@ -200,14 +208,31 @@ def main():
                      + {"dense": "dense-only cosine", "hybrid": "hybrid dense+BM25 rrf",
                         "rerank": "hybrid dense+BM25 rrf + cross-encoder rerank (MiniLM-L6 random-init)"}[args.workload]
                      + f" top_k={args.top_k}" + (f"->{args.rerank_k}" if args.workload == "rerank" else ""))
-    sharded = world > 1 and args.shard == "corpus"
-    replicated = world > 1 and args.shard == "queries"
+    # ---- multi-GPU layout: C corpus shards x (world / C) query groups
+    est_gb = args.n_docs * args.dim * 2 / 1e9 + (args.n_docs * 60 * 12 / 1e9 if args.workload != "dense" else 0.0)
+    if args.corpus_shards:
+        C = args.corpus_shards
+    elif args.shard == "corpus":
+        C = world
+    elif args.shard == "queries":
+        C = 1
+    else:
+        C = next(c for c in range(1, world + 1) if world % c == 0 and (est_gb / c <= args.gpu_mem_budget_gb or c == world))
+    if world % C:
+        raise SystemExit(f"--corpus-shards {C} must divide --gpus {world}")
+    n_groups, my_group, r_in = world // C, rank // C, rank % C
+    sharded = C > 1
+    replicated = n_groups > 1
     B_gpu = args.batch
     B_total = args.batch * world
     config = {"workload": workload_name, "batch_queries_per_step": B_total, "queries_per_gpu_per_step": B_gpu,
-              "store_dtype": "fp16", "shards": world if sharded else 1,
-              "multi_gpu": ("corpus partition + one NCCL all-gather of per-shard top-k" if sharded else
-                            "corpus replicated, queries split, no collective" if replicated else "single GPU"),
+              "store_dtype": "fp16", "shards": C, "query_groups": n_groups, "index_gb_estimate": round(est_gb, 2),
+              "multi_gpu": ("single GPU" if world == 1 else
+                            f"{C} corpus shard(s) x {n_groups} query group(s): "
+                            + ("corpus partition + one NCCL all-gather of per-shard top-k" if sharded else
+                               "corpus replicated, no collective")
+                            + ("; queries split across groups" if replicated else "")
+                            + (f" [--corpus-shards {C}]" if args.corpus_shards else f" [--shard {args.shard}]")),
               "l2_policy": "corpus (2.05 GB) is larger than L2 (126 MB); no flush needed",
               "query_set": "1024 seeded unit vectors, cycled"}
 
@@ -238,11 +263,17 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     n = args.n_docs
     if sharded:
-        lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+        lo, hi = (n * r_in) // C, (n * (r_in + 1)) // C
     else:
         lo, hi = 0, n
     wl = make_workload(args, lo, hi)
-    pipe = HybridPipeline(local_rank, rank=rank if sharded else 0, world=world if sharded else 1)
+    group = None
+    if sharded and n_groups > 1:  # one NCCL communicator per corpus group (every rank creates all of them, in order)
+        for g in range(n_groups):
+            pg = dist.new_group(list(range(g * C, (g + 1) * C)))
+            if g == my_group:
+                group = pg
+    pipe = HybridPipeline(local_rank, rank=r_in if sharded else 0, world=C if sharded else 1, group=group)
     pipe.load_dense(wl["x16"], id_base=lo)
     idx = None
     rerank = args.workload == "rerank"
@@ -265,9 +296,9 @@ def main():
         pipe.load_doc_tokens(doc_tok, doc_len, id_base=0)  # replicated on every rank (240 MB at 1 M docs)
         q_tok_all = vocab_ids[wl["q_tokens"]].astype(np.int32)
     eng = pipe.engine
-    # queries this rank handles per step: all of them when the corpus is partitioned, its own slice when replicated
-    B, k = (B_total if sharded else B_gpu), args.top_k
-    q_shift = rank * B_gpu if replicated else 0
+    # queries this rank handles per step: those of its corpus group (all C ranks of a group score the same queries)
+    B, k = B_gpu * C, args.top_k
+    q_shift = my_group * B
     dev = f"cuda:{local_rank}"
     q_all = torch.from_numpy(wl["q"]).to(dev)
     n_q = q_all.shape[0]
