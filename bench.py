@@ -6,7 +6,7 @@
 
 A "step" = one batch of B synthetic queries through the hot path.  Default workload = BASELINE.json configs[1]:
 1 M docs x 1024-d, dense-only cosine top_k=100 on 1 x B200.  --batch is the number of queries per step PER GPU (default 256;
-64 for the rerank workload, i.e. 6400 pairs per step): a step on N GPUs carries N x batch queries.  Multi-GPU layout =
+128 for hybrid, 64 for the rerank workload, i.e. 6400 pairs per step): a step on N GPUs carries N x batch queries.  Multi-GPU layout =
 C corpus shards x N/C query groups: the C ranks of a group partition the corpus (contiguous doc ranges), score the group's
 C x batch queries against their shards, exchange per-shard top-k in ONE NCCL all-gather and merge; different groups answer
 different queries.  --shard corpus: C = N (north_star's layout for corpora that must be partitioned); --shard queries:
@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--workload", default="dense", choices=["dense", "hybrid", "rerank"])
     ap.add_argument("--rerank-k", type=int, default=10, help="documents kept after the cross-encoder (config 4: 100 -> 10)")
     ap.add_argument("--batch", type=int, default=None,
-                    help="queries per step PER GPU (default: 256 for dense / hybrid, 64 for rerank = 6400 pairs per step)")
+                    help="queries per step PER GPU (default: 256 dense, 128 hybrid, 64 rerank = 6400 pairs per step)")
     ap.add_argument("--n-docs", type=int, default=1_000_000)
     ap.add_argument("--dim", type=int, default=1024)
     ap.add_argument("--top-k", type=int, default=100)
@@ -200,7 +200,7 @@ def cpu_reference(args, wl, n_queries):
 def main():
     args = parse_args()
     if args.batch is None:
-        args.batch = 64 if args.workload == "rerank" else 256
+        args.batch = {"dense": 256, "hybrid": 128, "rerank": 64}[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -210,16 +210,12 @@ def main():
                      + f" top_k={args.top_k}" + (f"->{args.rerank_k}" if args.workload == "rerank" else ""))
     # ---- multi-GPU layout: C corpus shards x (world / C) query groups
     est_gb = args.n_docs * args.dim * 2 / 1e9 + (args.n_docs * 60 * 12 / 1e9 if args.workload != "dense" else 0.0)
-    if args.corpus_shards:
-        C = args.corpus_shards
-    elif args.shard == "corpus":
-        C = world
-    elif args.shard == "queries":
-        C = 1
-    else:
-        C = next(c for c in range(1, world + 1) if world % c == 0 and (est_gb / c <= args.gpu_mem_budget_gb or c == world))
-    if world % C:
-        raise SystemExit(f"--corpus-shards {C} must divide --gpus {world}")
+    from sentio_b200.pipeline import plan_layout
+
+    try:
+        C, _ = plan_layout(world, est_gb, args.shard, args.corpus_shards, args.gpu_mem_budget_gb)
+    except ValueError as exc:
+        raise SystemExit(str(exc))
     n_groups, my_group, r_in = world // C, rank // C, rank % C
     sharded = C > 1
     replicated = n_groups > 1

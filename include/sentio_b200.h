@@ -178,6 +178,16 @@ int sb_fuse_dev(sb_ctx* ctx, int32_t method, double rrf_k, double w_dense, doubl
                 const double* extra, int32_t n_extra, int32_t e_stride, int32_t k,
                 int64_t* out_ids, double* out_scores, int32_t* out_src, int32_t* out_counts, void* stream);
 
+/*
+ * sb_hybrid_topk: the whole retrieve -> fuse path of HybridRetriever.retrieve (reference src/core/retrievers/hybrid.py:131-300)
+ * for B queries from HOST buffers, single shard: q [B x dim of dense slot 0] fp32, query term ids q_terms / q_off[B+1] as
+ * for sb_bm25_topk, fusion parameters as for sb_fuse (no plugin lists).  One H2D of the inputs, K1 + K2 + K3 on the
+ * context's stream, one D2H of out_ids / out_scores / out_src [B*k] and out_counts [B].
+ */
+int sb_hybrid_topk(sb_ctx* ctx, const float* q, const int32_t* q_terms, const int32_t* q_off, int32_t B, int32_t k,
+                   int32_t method, double rrf_k, double w_dense, double w_sparse, int64_t* out_ids, double* out_scores,
+                   int32_t* out_src, int32_t* out_counts);
+
 /* ---------------------------------------------------------------- K4: semantic similarity + MMR ------------- */
 /*
  * Replaces SemanticSimilarityScorer.score and MMRScorer.score (reference src/core/retrievers/scorers.py:152-191,

@@ -83,6 +83,8 @@ void sb_destroy(sb_ctx* ctx) {
   ctx->doc_chars_dev.release();
   ctx->pin_in.release();
   ctx->pin_out.release();
+  ctx->hyb_pin.release();
+  ctx->hyb_dev.release();
   for (auto& r : ctx->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : ctx->prof_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);

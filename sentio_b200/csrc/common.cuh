@@ -138,6 +138,10 @@ struct sb_ctx {
   DevBuf doc_chars_dev;  // K7: characters of every document's usable text (0 = blank), sb_doc_chars_load
   int64_t doc_chars_n = 0, doc_chars_base = 0;
   PinBuf pin_in, pin_out;
+  // sb_hybrid_topk: staging of one whole-path call (its own buffers and lock: the inner entry points take `mu`)
+  std::mutex hyb_mu;
+  PinBuf hyb_pin;
+  DevBuf hyb_dev;
 };
 
 struct DeviceGuard {

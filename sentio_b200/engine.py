@@ -277,6 +277,22 @@ class B200Engine:
                                     _tptr(cnt), self._stream()), "sb_fuse_dev")
         return ids, sc, src, cnt
 
+    def hybrid_topk(self, q: np.ndarray, flat_terms: np.ndarray, off: np.ndarray, k: int, method: str = "rrf",
+                    rrf_k: float = 60, w_dense: float = 0.5, w_sparse: float = 0.5):
+        """Whole retrieve -> fuse path from host buffers (sb_hybrid_topk): (ids, scores, src, counts) NumPy arrays."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        flat = np.ascontiguousarray(flat_terms, dtype=np.int32)
+        off = np.ascontiguousarray(off, dtype=np.int32)
+        B = q.shape[0]
+        ids = np.empty((B, k), dtype=np.int64)
+        sc = np.empty((B, k), dtype=np.float64)
+        src = np.empty((B, k), dtype=np.int32)
+        cnt = np.empty(B, dtype=np.int32)
+        check(self._lib.sb_hybrid_topk(self._h, _ptr(q), _ptr(flat), _ptr(off), B, int(k), FUSION_METHODS[method],
+                                       float(rrf_k), float(w_dense), float(w_sparse), _ptr(ids), _ptr(sc), _ptr(src),
+                                       _ptr(cnt)), "sb_hybrid_topk")
+        return ids, sc, src, cnt
+
     # ------------------------------------------------------------------ K4 scorers
     def semantic_mmr(self, q: np.ndarray, cand: np.ndarray | None = None, cand_ids=None, w_sem: float = 0.7,
                      lambda_: float = 0.7, w_mmr: float = 0.5, want_sem: bool = True, want_mmr: bool = True,

@@ -21,6 +21,29 @@ from .engine import B200Engine
 from .index import Bm25IndexData
 
 
+def plan_layout(world: int, index_gb: float, mode: str = "auto", corpus_shards: int = 0, budget_gb: float = 64.0):
+    """Multi-GPU layout = C corpus shards x world / C query groups -> (C, n_groups).
+
+    ``corpus``: C = world (every rank holds 1/world of the corpus; one all-gather per batch); ``queries``: C = 1
+    (replicated corpus, no collective); ``auto``: the smallest divisor C of ``world`` whose shard (index_gb / C) fits
+    ``budget_gb`` -- partition only as much as capacity requires; an explicit ``corpus_shards`` overrides ``mode``."""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    if corpus_shards:
+        C = int(corpus_shards)
+    elif mode == "corpus":
+        C = world
+    elif mode == "queries":
+        C = 1
+    elif mode == "auto":
+        C = next(c for c in range(1, world + 1) if world % c == 0 and (index_gb / c <= budget_gb or c == world))
+    else:
+        raise ValueError(f"unknown layout mode {mode!r}")
+    if C < 1 or world % C:
+        raise ValueError(f"corpus_shards={C} must divide world={world}")
+    return C, world // C
+
+
 class HybridPipeline:
     def __init__(self, device: int | None = 0, rank: int = 0, world: int = 1, group=None, engine=None):
         """``engine`` may be injected (the CPU/gloo tests pass an oracle-backed double together with device=None);
@@ -207,6 +230,9 @@ class HybridPipeline:
         trace = os.environ.get("SENTIO_B200_TRACE") == "1"
         t0 = time.perf_counter()
         flat, off = B200Engine.pack_queries(term_lists)
+        if self.world == 1 and self.device is not None:
+            # single shard: straight through the C ABI's host entry point (its own pinned staging, no framework on the path)
+            return self.engine.hybrid_topk(q, flat, off, k, method, rrf_k, w_dense, w_sparse)
         max_len = int(np.diff(off).max()) if len(off) > 1 else 0
         t1 = time.perf_counter()
         q_t = self._to_dev(np.ascontiguousarray(q, dtype=np.float32), "q")

@@ -48,7 +48,18 @@ def test_argument_counts_match_header():
         assert n == len(args), f"{name}: header has {n} parameters, ctypes table {len(args)}"
 
 
-@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="a GPU is visible")
+def _gpu_visible() -> bool:
+    if os.path.exists("/dev/nvidia0"):
+        return True
+    try:
+        import torch
+
+        return bool(torch.cuda.is_available())
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_gpu_visible(), reason="a GPU is visible")
 def test_no_cpu_fallback_without_gpu(built_lib):
     """On a box without a GPU the product must fail loudly, not fall back."""
     from sentio_b200._lib import SentioB200Error

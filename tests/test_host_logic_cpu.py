@@ -1,0 +1,118 @@
+"""CPU-only coverage of host logic added around the hot path: Pyserini strategy fallback (factory.py:150-176 of the
+reference), the embedder's tokeniser / BaseEmbedder surface with a fake engine, the selector device-input helper."""
+import asyncio
+
+import numpy as np
+import pytest
+
+from sentio_b200.document import Document
+
+
+class _FakeEmbedder:
+    def embed_sync(self, text):
+        return [1.0, 0.0]
+
+    def embed_many_sync(self, texts):
+        return [[1.0, 0.0] for _ in texts]
+
+
+class _FakeClient:
+    def collection_exists(self, collection_name):
+        return False
+
+    def scroll(self, **kw):
+        return [], None
+
+
+def test_pyserini_strategy_falls_back_like_the_reference(monkeypatch, tmp_path):
+    from sentio_b200.retrievers import factory, get_retriever
+    from sentio_b200.retrievers import sparse as sparse_mod
+
+    built = []
+
+    class _Stub(sparse_mod.BM25Retriever):
+        def __init__(self, documents=None, variant="okapi", **kw):
+            built.append((len(documents or []), variant))
+
+    monkeypatch.setattr(factory, "BM25Retriever", _Stub)
+    monkeypatch.setenv("RETRIEVAL_STRATEGY", "pyserini")
+    monkeypatch.setenv("BM25_INDEX_DIR", str(tmp_path / "missing"))
+    docs = [Document(id="a", text="x y"), Document(id="b", text="y z")]
+    r = factory.create_retriever_from_env(_FakeClient(), _FakeEmbedder(), corpus_docs=docs)
+    assert isinstance(r, _Stub) and built == [(2, "okapi")]  # RuntimeError inside -> in-memory BM25 (factory.py:158-163)
+    with pytest.raises(RuntimeError):                        # get_retriever("pyserini") raises like the reference class
+        get_retriever("pyserini", index_dir=str(tmp_path / "missing"))
+    (tmp_path / "idx").mkdir()
+    with pytest.raises(RuntimeError):                        # an index directory alone is not enough: no JVM / Lucene reader
+        get_retriever("lucene", index_dir=str(tmp_path / "idx"))
+    with pytest.raises(ValueError):
+        get_retriever("nope")
+
+
+def test_embedding_tokeniser_frames_and_truncates():
+    from sentio_b200.embedder import tokenize_for_embedding
+    from sentio_b200.index import CLS_ID, PAD_ID, SEP_ID, _hash_token
+
+    ids, tt, lens = tokenize_for_embedding(["Hello  World", "", "w " * 500], seq_len=16)
+    assert list(ids[0, :4]) == [CLS_ID, _hash_token("hello"), _hash_token("world"), SEP_ID] and lens[0] == 4
+    assert np.all(ids[0, 4:] == PAD_ID) and np.all(tt == 0)
+    assert list(ids[1, :2]) == [CLS_ID, SEP_ID] and lens[1] == 2
+    assert lens[2] == 16 and ids[2, 0] == CLS_ID and ids[2, 15] == SEP_ID
+
+
+def test_embedder_surface_with_fake_engine():
+    from sentio_b200.cross_encoder import CrossEncoderWeights
+    from sentio_b200.embedder import B200Embedder
+
+    calls = []
+
+    class _Eng:
+        def enc_load(self, blob, cfg, pw, pb):
+            self.dim = pw.shape[0] if pw is not None else cfg["hidden"]
+
+        def enc_dim(self):
+            return self.dim
+
+        def enc_embed(self, ids, tt, lens, normalize=True):
+            calls.append(ids.shape[0])
+            v = np.zeros((ids.shape[0], self.dim), np.float32)
+            v[:, 0] = lens
+            return v
+
+    cfg = dict(vocab_size=30522, hidden=128, layers=1, heads=4, intermediate=128, max_pos=64, type_vocab=2, ln_eps=1e-12)
+    emb = B200Embedder(weights=CrossEncoderWeights.random(cfg, seed=1), dimension=256, seq_len=32, engine=_Eng())
+    assert emb.dimension == 256
+    out = emb.embed_many_sync(["a b", "c", "a b"])
+    assert [v[0] for v in out] == [4.0, 3.0, 4.0] and calls == [3]
+    assert emb.embed_sync("a b")[0] == 4.0 and calls == [3]          # served from the cache
+    assert emb.stats["cache_hits"] == 1 and emb.stats["total_requests"] == 4
+    assert asyncio.run(emb.embed_async_many(["zz top"]))[0][0] == 4.0 and calls == [3, 1]
+    assert asyncio.run(emb.warm_up()) is True
+    asyncio.run(emb.close())
+    emb.reset_stats()
+    assert emb.stats["total_requests"] == 0
+
+
+def test_selector_chars_matches_the_text_the_selector_uses():
+    from sentio_b200.selector import selector_chars
+
+    assert selector_chars(Document(id="1", text="abcd")) == 4
+    assert selector_chars(Document(id="2", text="", metadata={"content": "xyz"})) == 3
+    assert selector_chars(Document(id="3", text="   ")) == 0
+    assert selector_chars(Document(id="4", text="", metadata={})) == 0
+
+
+def test_multi_gpu_layout_planner():
+    from sentio_b200.pipeline import plan_layout
+
+    assert plan_layout(1, 2.05) == (1, 1)
+    assert plan_layout(8, 2.05, "auto") == (1, 8)              # the metric's corpus fits one GPU: replicate
+    assert plan_layout(8, 2.05, "corpus") == (8, 1)            # north_star's layout
+    assert plan_layout(8, 2.05, "queries") == (1, 8)
+    assert plan_layout(8, 200.0, "auto", budget_gb=64.0) == (4, 2)   # partition only as much as capacity requires
+    assert plan_layout(8, 2000.0, "auto", budget_gb=64.0) == (8, 1)  # never more shards than GPUs
+    assert plan_layout(4, 2.05, "auto", corpus_shards=2) == (2, 2)
+    with pytest.raises(ValueError):
+        plan_layout(8, 2.05, corpus_shards=3)
+    with pytest.raises(ValueError):
+        plan_layout(8, 2.05, "banana")

@@ -92,12 +92,15 @@ def test_gpu_stack_matches_reference(engine, monkeypatch):
 
 @pytest.mark.gpu
 def test_pipeline_batch_equals_per_query_classes(engine):
-    """HybridPipeline (device-resident batch path) == dense_topk + bm25_topk + fuse composed per query."""
+    """HybridPipeline -- the host entry point (sb_hybrid_topk) AND the device-resident batch path -- == dense_topk +
+    bm25_topk + fuse composed per stage."""
     from sentio_b200 import synth
     from sentio_b200.index import build_bm25_from_token_ids
     from sentio_b200.pipeline import HybridPipeline
 
-    n, d, k, B = 30000, 256, 100, 19
+    import torch
+
+    n, d, k, B = 30000, 256, 100, 70
     x = synth.dense_corpus(n, d)
     flat, off = synth.text_corpus_tokens(n, vocab=4000)
     idx = build_bm25_from_token_ids(flat, off)
@@ -106,8 +109,16 @@ def test_pipeline_batch_equals_per_query_classes(engine):
     pipe.load_bm25(idx)
     q = synth.query_vectors(B, d)
     terms = [idx.term_ids(t) for t in synth.query_tokens(B, vocab=4000)]
+    terms[5] = np.zeros(0, np.int32)          # a query without text
+    terms[6] = np.array([-1, -1], np.int32)   # only unknown tokens
     for method in ("rrf", "comb_sum"):
         ids, sc, src, cnt = pipe.search_hybrid(q, terms, k, method=method, rrf_k=60, w_dense=0.6, w_sparse=0.4)
+        fl, of = pipe.engine.pack_queries(terms)
+        dev = pipe.hybrid_dev(torch.from_numpy(q).cuda(), torch.from_numpy(fl).cuda(), torch.from_numpy(of).cuda(),
+                              int(of[-1]), int(np.diff(of).max()), k, method, 60, 0.6, 0.4)
+        torch.cuda.synchronize()
+        assert np.array_equal(ids, dev[0].cpu().numpy()) and np.array_equal(sc, dev[1].cpu().numpy())
+        assert np.array_equal(src, dev[2].cpu().numpy()) and np.array_equal(cnt, dev[3].cpu().numpy())
         engine.load_dense(x)
         engine.load_bm25(idx)
         dl = engine.dense_topk(q, k)
