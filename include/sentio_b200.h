@@ -187,6 +187,16 @@ int sb_fuse_dev(sb_ctx* ctx, int32_t method, double rrf_k, double w_dense, doubl
 int sb_hybrid_topk(sb_ctx* ctx, const float* q, const int32_t* q_terms, const int32_t* q_off, int32_t B, int32_t k,
                    int32_t method, double rrf_k, double w_dense, double w_sparse, int64_t* out_ids, double* out_scores,
                    int32_t* out_src, int32_t* out_counts);
+/*
+ * sb_hybrid_rerank_topk: the same followed by the cross-encoder rerank of rerank_node (reference
+ * src/core/graph/nodes.py:138-227 / jina_reranker.py:192-295) on the fused top-k: q_tok [B x lq] word pieces and q_len [B]
+ * of the queries (documents come from sb_ce_tokens_load), pairs framed to length S on the device; out_ids / out_scores
+ * (sigmoid relevance) [B x k_out], out_counts [B].  One H2D, one D2H.
+ */
+int sb_hybrid_rerank_topk(sb_ctx* ctx, const float* q, const int32_t* q_terms, const int32_t* q_off, const int32_t* q_tok,
+                          const int32_t* q_len, int32_t lq, int32_t B, int32_t k, int32_t k_out, int32_t S, int32_t method,
+                          double rrf_k, double w_dense, double w_sparse, int64_t* out_ids, float* out_scores,
+                          int32_t* out_counts);
 
 /* ---------------------------------------------------------------- K4: semantic similarity + MMR ------------- */
 /*

@@ -92,6 +92,9 @@ SIGNATURES = {
                                   C.c_int32, C.c_int32, C.c_void_p]),
     "sb_hybrid_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double,
                                  C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sb_hybrid_rerank_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                        C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double,
+                                        C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sb_doc_chars_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]),
     "sb_select_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

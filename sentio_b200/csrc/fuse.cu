@@ -529,54 +529,74 @@ int sb_select_dev(sb_ctx* ctx, const int64_t* cand_ids_dev, const void* cand_sco
   return SB_OK;
 }
 
-/*
- * Host-buffer form of the whole retrieve -> fuse path for one batch (single shard): pinned staging + ONE H2D of the
- * queries / term ids, K1 + K2 + K3 enqueued on the context's stream through the device entry points, ONE D2H of the fused
- * lists.  What HybridRetriever.retrieve does per query (hybrid.py:131-300), for B queries per call, with no framework
- * between the caller's buffers and the kernels.
- */
-int sb_hybrid_topk(sb_ctx* ctx, const float* q, const int32_t* q_terms, const int32_t* q_off, int32_t B, int32_t k,
-                   int32_t method, double rrf_k, double w_dense, double w_sparse, int64_t* out_ids, double* out_scores,
-                   int32_t* out_src, int32_t* out_counts) {
-  SB_REQUIRE(ctx != nullptr, SB_ERR_ARG, "sb_hybrid_topk: ctx is NULL");
-  SB_REQUIRE(B >= 0 && k > 0, SB_ERR_ARG, "sb_hybrid_topk: bad B=%d k=%d", B, k);
+}  // extern "C"
+
+namespace {
+
+// Host-buffer form of the whole path for one batch (single shard): pinned staging + ONE H2D of the queries / term ids
+// (+ query word pieces), K1 + K2 + K3 (+ K5 rerank) enqueued on the context's stream through the device entry points, ONE
+// D2H of the result lists.  What HybridRetriever.retrieve (hybrid.py:131-300) and rerank_node (nodes.py:138-227) do per
+// query, for B queries per call, with no framework between the caller's buffers and the kernels.
+struct RerankArgs {
+  const int32_t* q_tok;   // [B, lq] host
+  const int32_t* q_len;   // [B] host
+  int32_t lq, S, k_out;
+  int64_t* out_ids;       // [B, k_out]
+  float* out_scores;      // [B, k_out]
+  int32_t* out_counts;    // [B]
+};
+
+int hybrid_host_call(sb_ctx* ctx, const char* who, const float* q, const int32_t* q_terms, const int32_t* q_off, int32_t B,
+                     int32_t k, int32_t method, double rrf_k, double w_dense, double w_sparse, int64_t* out_ids,
+                     double* out_scores, int32_t* out_src, int32_t* out_counts, const RerankArgs* rr) {
+  SB_REQUIRE(ctx != nullptr, SB_ERR_ARG, "%s: ctx is NULL", who);
+  SB_REQUIRE(B >= 0 && k > 0, SB_ERR_ARG, "%s: bad B=%d k=%d", who, B, k);
   if (B == 0) return SB_OK;
-  SB_REQUIRE(q && q_off && out_ids && out_scores && out_src && out_counts, SB_ERR_ARG, "sb_hybrid_topk: NULL buffer");
+  SB_REQUIRE(q && q_off, SB_ERR_ARG, "%s: NULL input buffer", who);
   const int n_terms_q = q_off[B];
-  SB_REQUIRE(n_terms_q >= 0 && (n_terms_q == 0 || q_terms), SB_ERR_ARG, "sb_hybrid_topk: bad query term buffers");
+  SB_REQUIRE(n_terms_q >= 0 && (n_terms_q == 0 || q_terms), SB_ERR_ARG, "%s: bad query term buffers", who);
   int max_len = 0;
   for (int b = 0; b < B; ++b) {
-    SB_REQUIRE(q_off[b + 1] >= q_off[b], SB_ERR_ARG, "sb_hybrid_topk: q_off must be non-decreasing");
+    SB_REQUIRE(q_off[b + 1] >= q_off[b], SB_ERR_ARG, "%s: q_off must be non-decreasing", who);
     max_len = std::max(max_len, q_off[b + 1] - q_off[b]);
   }
   std::lock_guard<std::mutex> hl(ctx->hyb_mu);  // serialises whole calls: the staging buffers below belong to one call
   const int d = ctx->dense[0].d;
-  SB_REQUIRE(ctx->dense[0].rows != nullptr && d > 0, SB_ERR_STATE, "sb_hybrid_topk: no dense index loaded in slot 0");
+  SB_REQUIRE(ctx->dense[0].rows != nullptr && d > 0, SB_ERR_STATE, "%s: no dense index loaded in slot 0", who);
   const size_t qb = (size_t)B * d * 4, tb = (size_t)std::max(n_terms_q, 1) * 4, ob = (size_t)(B + 1) * 4;
-  const size_t in_bytes = qb + tb + ob;
+  const size_t rb = rr ? (size_t)B * rr->lq * 4 + (size_t)B * 4 : 0;   // query word pieces + lengths
+  const size_t in_bytes = qb + tb + ob + rb;
   const size_t nid = (size_t)B * k;
-  // device layout: inputs | dense ids sc cnt | sparse ids sc cnt | fused ids sc src cnt   (8-byte aligned pieces first)
+  // device layout: inputs | dense ids sc cnt | sparse ids sc cnt | fused ids sc src cnt | reranked ids sc cnt
   const size_t cnt_b = ((size_t)B * 4 + 7) / 8 * 8;
   const size_t work_bytes = 2 * (nid * 16 + cnt_b);
-  const size_t out_bytes = nid * 16 + nid * 4 + (size_t)B * 4;
+  const size_t fused_bytes = (nid * 16 + nid * 4 + (size_t)B * 4 + 7) / 8 * 8;
+  const size_t nrr = rr ? (size_t)B * rr->k_out : 0;
+  const size_t rr_bytes = rr ? nrr * 12 + (size_t)B * 4 : 0;
   cudaStream_t st = ctx->stream;
   uint8_t *pi, *dv;
   {
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard g(ctx->device);
     int rc;
-    if ((rc = ctx->hyb_pin.reserve(std::max(in_bytes, out_bytes) + 64))) return rc;
-    if ((rc = ctx->hyb_dev.reserve((in_bytes + 7) / 8 * 8 + work_bytes + out_bytes + 64))) return rc;
+    if ((rc = ctx->hyb_pin.reserve(std::max(in_bytes, std::max(fused_bytes, rr_bytes)) + 64))) return rc;
+    if ((rc = ctx->hyb_dev.reserve((in_bytes + 7) / 8 * 8 + work_bytes + fused_bytes + rr_bytes + 64))) return rc;
     pi = ctx->hyb_pin.as<uint8_t>();
     dv = ctx->hyb_dev.as<uint8_t>();
     memcpy(pi, q, qb);
     if (n_terms_q) memcpy(pi + qb, q_terms, (size_t)n_terms_q * 4);
     memcpy(pi + qb + tb, q_off, ob);
+    if (rr) {
+      memcpy(pi + qb + tb + ob, rr->q_tok, (size_t)B * rr->lq * 4);
+      memcpy(pi + qb + tb + ob + (size_t)B * rr->lq * 4, rr->q_len, (size_t)B * 4);
+    }
     SB_CUDA(cudaMemcpyAsync(dv, pi, in_bytes, cudaMemcpyHostToDevice, st));
   }
   const float* q_dev = reinterpret_cast<const float*>(dv);
   const int32_t* t_dev = reinterpret_cast<const int32_t*>(dv + qb);
   const int32_t* o_dev = reinterpret_cast<const int32_t*>(dv + qb + tb);
+  const int32_t* qt_dev = reinterpret_cast<const int32_t*>(dv + qb + tb + ob);
+  const int32_t* ql_dev = rr ? qt_dev + (size_t)B * rr->lq : nullptr;
   uint8_t* w = dv + (in_bytes + 7) / 8 * 8;
   int64_t* d_ids = reinterpret_cast<int64_t*>(w);
   double* d_sc = reinterpret_cast<double*>(w + nid * 8);
@@ -590,23 +610,62 @@ int sb_hybrid_topk(sb_ctx* ctx, const float* q, const int32_t* q_terms, const in
   double* f_sc = reinterpret_cast<double*>(w3 + nid * 8);
   int32_t* f_src = reinterpret_cast<int32_t*>(w3 + nid * 16);
   int32_t* f_cnt = reinterpret_cast<int32_t*>(w3 + nid * 16 + nid * 4);
+  uint8_t* w4 = w3 + fused_bytes;
+  int64_t* r_ids = reinterpret_cast<int64_t*>(w4);
+  float* r_sc = reinterpret_cast<float*>(w4 + nrr * 8);
+  int32_t* r_cnt = reinterpret_cast<int32_t*>(w4 + nrr * 12);
   int rc;
   if ((rc = sb_dense_topk_dev(ctx, 0, q_dev, B, k, d_ids, d_sc, d_cnt, st))) return rc;
   if ((rc = sb_bm25_topk_dev(ctx, t_dev, o_dev, B, n_terms_q, max_len, k, s_ids, s_sc, s_cnt, st))) return rc;
   if ((rc = sb_fuse_dev(ctx, method, rrf_k, w_dense, w_sparse, B, d_ids, d_sc, d_cnt, k, s_ids, s_sc, s_cnt, k, nullptr,
                         nullptr, nullptr, 0, nullptr, 0, 0, k, f_ids, f_sc, f_src, f_cnt, st)))
     return rc;
+  if (rr && (rc = sb_rerank_dev(ctx, qt_dev, ql_dev, rr->lq, f_ids, f_cnt, B, k, rr->S, rr->k_out, r_ids, r_sc, r_cnt, st)))
+    return rc;
   {
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard g(ctx->device);
-    SB_CUDA(cudaMemcpyAsync(pi, w3, out_bytes, cudaMemcpyDeviceToHost, st));
+    if (rr)
+      SB_CUDA(cudaMemcpyAsync(pi, w4, rr_bytes, cudaMemcpyDeviceToHost, st));
+    else
+      SB_CUDA(cudaMemcpyAsync(pi, w3, nid * 16 + nid * 4 + (size_t)B * 4, cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
   }
-  memcpy(out_ids, pi, nid * 8);
-  memcpy(out_scores, pi + nid * 8, nid * 8);
-  memcpy(out_src, pi + nid * 16, nid * 4);
-  memcpy(out_counts, pi + nid * 16 + nid * 4, (size_t)B * 4);
+  if (rr) {
+    memcpy(rr->out_ids, pi, nrr * 8);
+    memcpy(rr->out_scores, pi + nrr * 8, nrr * 4);
+    memcpy(rr->out_counts, pi + nrr * 12, (size_t)B * 4);
+  } else {
+    memcpy(out_ids, pi, nid * 8);
+    memcpy(out_scores, pi + nid * 8, nid * 8);
+    memcpy(out_src, pi + nid * 16, nid * 4);
+    memcpy(out_counts, pi + nid * 16 + nid * 4, (size_t)B * 4);
+  }
   return SB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sb_hybrid_topk(sb_ctx* ctx, const float* q, const int32_t* q_terms, const int32_t* q_off, int32_t B, int32_t k,
+                   int32_t method, double rrf_k, double w_dense, double w_sparse, int64_t* out_ids, double* out_scores,
+                   int32_t* out_src, int32_t* out_counts) {
+  SB_REQUIRE(B == 0 || (out_ids && out_scores && out_src && out_counts), SB_ERR_ARG, "sb_hybrid_topk: NULL output buffer");
+  return hybrid_host_call(ctx, "sb_hybrid_topk", q, q_terms, q_off, B, k, method, rrf_k, w_dense, w_sparse, out_ids,
+                          out_scores, out_src, out_counts, nullptr);
+}
+
+int sb_hybrid_rerank_topk(sb_ctx* ctx, const float* q, const int32_t* q_terms, const int32_t* q_off, const int32_t* q_tok,
+                          const int32_t* q_len, int32_t lq, int32_t B, int32_t k, int32_t k_out, int32_t S, int32_t method,
+                          double rrf_k, double w_dense, double w_sparse, int64_t* out_ids, float* out_scores,
+                          int32_t* out_counts) {
+  SB_REQUIRE(B == 0 || (q_tok && q_len && out_ids && out_scores && out_counts), SB_ERR_ARG,
+             "sb_hybrid_rerank_topk: NULL buffer");
+  SB_REQUIRE(lq > 0 && k_out > 0 && S >= 8, SB_ERR_ARG, "sb_hybrid_rerank_topk: bad lq / k_out / S");
+  RerankArgs rr{q_tok, q_len, lq, S, k_out, out_ids, out_scores, out_counts};
+  return hybrid_host_call(ctx, "sb_hybrid_rerank_topk", q, q_terms, q_off, B, k, method, rrf_k, w_dense, w_sparse, nullptr,
+                          nullptr, nullptr, nullptr, &rr);
 }
 
 }  // extern "C"

@@ -293,6 +293,25 @@ class B200Engine:
                                        _ptr(cnt)), "sb_hybrid_topk")
         return ids, sc, src, cnt
 
+    def hybrid_rerank_topk(self, q: np.ndarray, flat_terms: np.ndarray, off: np.ndarray, q_tok: np.ndarray,
+                           q_len: np.ndarray, k: int, k_out: int, seq_len: int = 128, method: str = "rrf",
+                           rrf_k: float = 60, w_dense: float = 0.5, w_sparse: float = 0.5):
+        """retrieve -> fuse -> rerank from host buffers (sb_hybrid_rerank_topk): (ids, sigmoid scores, counts)."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        flat = np.ascontiguousarray(flat_terms, dtype=np.int32)
+        off = np.ascontiguousarray(off, dtype=np.int32)
+        qt = np.ascontiguousarray(q_tok, dtype=np.int32)
+        ql = np.ascontiguousarray(q_len, dtype=np.int32)
+        B = q.shape[0]
+        ids = np.empty((B, k_out), dtype=np.int64)
+        sc = np.empty((B, k_out), dtype=np.float32)
+        cnt = np.empty(B, dtype=np.int32)
+        check(self._lib.sb_hybrid_rerank_topk(self._h, _ptr(q), _ptr(flat), _ptr(off), _ptr(qt), _ptr(ql), qt.shape[1], B,
+                                              int(k), int(k_out), int(seq_len), FUSION_METHODS[method], float(rrf_k),
+                                              float(w_dense), float(w_sparse), _ptr(ids), _ptr(sc), _ptr(cnt)),
+              "sb_hybrid_rerank_topk")
+        return ids, sc, cnt
+
     # ------------------------------------------------------------------ K4 scorers
     def semantic_mmr(self, q: np.ndarray, cand: np.ndarray | None = None, cand_ids=None, w_sem: float = 0.7,
                      lambda_: float = 0.7, w_mmr: float = 0.5, want_sem: bool = True, want_mmr: bool = True,

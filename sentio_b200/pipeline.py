@@ -252,6 +252,9 @@ class HybridPipeline:
                              seq_len: int = 128, method: str = "rrf", rrf_k: float = 60, w_dense: float = 0.5,
                              w_sparse: float = 0.5):
         flat, off = B200Engine.pack_queries(term_lists)
+        if self.world == 1 and self.device is not None:  # single shard: the C ABI's own host entry point
+            return self.engine.hybrid_rerank_topk(q, flat, off, q_tok, q_len, k, k_out, seq_len, method, rrf_k, w_dense,
+                                                  w_sparse)
         max_len = int(np.diff(off).max()) if len(off) > 1 else 0
         q_t = self._to_dev(np.ascontiguousarray(q, dtype=np.float32), "q")
         terms_t, off_t = self._to_dev(flat, "terms"), self._to_dev(off, "off")
