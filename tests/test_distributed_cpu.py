@@ -79,3 +79,69 @@ def test_two_shards_equal_unsharded(tmp_path):
         assert np.array_equal(r["f_ids"], f_ref[0]) and np.array_equal(r["f_sc"], f_ref[1])
         assert np.array_equal(r["c_ids"], c_ref[0]) and np.array_equal(r["c_sc"], c_ref[1])
         assert np.array_equal(r["f_cnt"], f_ref[3])
+
+
+def _worker_2d(rank, world, port, tmpdir):
+    """C = 2 corpus shards x 2 query groups on 4 ranks: every group runs its own all-gather on its own communicator."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, HERE)
+    import torch.distributed as dist
+
+    from oracle_engine import OracleEngineTorch
+    from sentio_b200 import synth
+    from sentio_b200.index import build_bm25_from_token_ids
+    from sentio_b200.pipeline import HybridPipeline, plan_layout
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    C, n_groups = plan_layout(world, 1.0, corpus_shards=2)
+    my_group, r_in = rank // C, rank % C
+    group = None
+    for g in range(n_groups):  # every rank creates every communicator, in the same order
+        pg = dist.new_group(list(range(g * C, (g + 1) * C)))
+        if g == my_group:
+            group = pg
+    n, d, k, B = 2503, 32, 15, 6
+    x = synth.dense_corpus(n, d)
+    flat, off = synth.text_corpus_tokens(n, vocab=300)
+    idx = build_bm25_from_token_ids(flat, off)
+    q_all = synth.query_vectors(B * n_groups, d)
+    t_all = [idx.term_ids(t) for t in synth.query_tokens(B * n_groups, vocab=300)]
+    q, terms = q_all[my_group * B:(my_group + 1) * B], t_all[my_group * B:(my_group + 1) * B]
+    lo, hi = (n * r_in) // C, (n * (r_in + 1)) // C
+    pipe = HybridPipeline(device=None, rank=r_in, world=C, group=group, engine=OracleEngineTorch())
+    pipe.load_dense(x[lo:hi], id_base=lo)
+    pipe.load_bm25(idx.shard(lo, hi), id_base=lo)
+    f_ids, f_sc, _, f_cnt = pipe.search_hybrid(q, terms, k, method="rrf", rrf_k=60)
+    np.savez(os.path.join(tmpdir, f"rank2d{rank}.npz"), f_ids=f_ids, f_sc=f_sc, f_cnt=f_cnt, group=my_group)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_corpus_shards_times_query_groups_layout(tmp_path):
+    import torch.multiprocessing as mp
+
+    sys.path.insert(0, HERE)
+    from oracle_engine import OracleEngineTorch
+    from sentio_b200 import synth
+    from sentio_b200.index import build_bm25_from_token_ids
+    from sentio_b200.pipeline import HybridPipeline
+
+    port = _free_port()
+    mp.spawn(_worker_2d, args=(4, port, str(tmp_path)), nprocs=4, join=True)
+    n, d, k, B = 2503, 32, 15, 6
+    x = synth.dense_corpus(n, d)
+    flat, off = synth.text_corpus_tokens(n, vocab=300)
+    idx = build_bm25_from_token_ids(flat, off)
+    q_all = synth.query_vectors(B * 2, d)
+    t_all = [idx.term_ids(t) for t in synth.query_tokens(B * 2, vocab=300)]
+    single = HybridPipeline(device=None, engine=OracleEngineTorch())
+    single.load_dense(x)
+    single.load_bm25(idx)
+    ref = single.search_hybrid(q_all, t_all, k, method="rrf", rrf_k=60)
+    for rank in range(4):
+        r = np.load(os.path.join(tmp_path, f"rank2d{rank}.npz"))
+        g = int(r["group"])
+        assert g == rank // 2
+        assert np.array_equal(r["f_ids"], ref[0][g * B:(g + 1) * B]) and np.array_equal(r["f_sc"], ref[1][g * B:(g + 1) * B])
+        assert np.array_equal(r["f_cnt"], ref[3][g * B:(g + 1) * B])
