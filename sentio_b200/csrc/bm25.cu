@@ -581,46 +581,65 @@ __global__ void bm25_fill_empty_kernel(int64_t* ids, double* sc, int32_t* cnt, i
 // Installs a term-major CSR that already lives on the device as the context's BM25 index (sb_bm25_load uploads host
 // arrays first; the GPU builder of bm25_build.cu hands its arrays over directly).  Takes ownership of indptr_dev and
 // post_doc_dev; tf_dev / doc_len_dev are only read (dnorm and the query-independent ratio are derived from them).
-int bm25_install_device_csr(sb_ctx* ctx, int64_t* indptr_dev, int32_t* post_doc_dev, const uint16_t* tf_dev,
-                            const int32_t* doc_len_dev, int64_t n_terms, int64_t nnz, int64_t n_docs, double avgdl,
-                            const double* idf_host, int32_t variant, double k1, double b, double delta, int64_t id_base,
-                            cudaStream_t st) {
-  Bm25Index& ix = ctx->bm25;
-  SB_CUDA(cudaStreamSynchronize(st));
+static void bm25_index_free(Bm25Index& ix) {
   if (ix.indptr) cudaFree(ix.indptr);
   if (ix.post_doc) cudaFree(ix.post_doc);
   if (ix.post_ratio) cudaFree(ix.post_ratio);
   if (ix.dnorm) cudaFree(ix.dnorm);
   if (ix.idf) cudaFree(ix.idf);
   ix = Bm25Index();
-  ix.n_docs = n_docs;
-  ix.n_terms = n_terms;
-  ix.nnz = nnz;
-  ix.id_base = id_base;
-  ix.variant = variant;
-  ix.k1 = k1;
-  ix.b = b;
-  ix.delta = delta;
-  ix.avgdl = avgdl;
-  ix.indptr = indptr_dev;
-  ix.post_doc = post_doc_dev;
-  SB_CUDA(cudaMalloc(&ix.idf, (size_t)std::max<int64_t>(n_terms, 1) * 8));
-  if (n_terms) SB_CUDA(cudaMemcpyAsync(ix.idf, idf_host, (size_t)n_terms * 8, cudaMemcpyHostToDevice, st));
-  SB_CUDA(cudaMalloc(&ix.dnorm, (size_t)std::max<int64_t>(n_docs, 1) * 8));
+}
+
+// The new index is assembled in a local object and swapped in only when every allocation and kernel has succeeded: a failed
+// load leaves the context with its previous index intact (and frees everything it took ownership of).
+static int bm25_install_build(Bm25Index& nx, const uint16_t* tf_dev, const int32_t* doc_len_dev, const double* idf_host,
+                              cudaStream_t st) {
+  SB_CUDA(cudaMalloc(&nx.idf, (size_t)std::max<int64_t>(nx.n_terms, 1) * 8));
+  if (nx.n_terms) SB_CUDA(cudaMemcpyAsync(nx.idf, idf_host, (size_t)nx.n_terms * 8, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMalloc(&nx.dnorm, (size_t)std::max<int64_t>(nx.n_docs, 1) * 8));
   // query-independent fp64 ratio tf*(k1+1)/(tf+dnorm[doc]) (8 B per posting) replaces the 2 B tf + 8 B dnorm gather
-  SB_CUDA(cudaMalloc(&ix.post_ratio, (size_t)std::max<int64_t>(nnz, 1) * 8));
-  if (n_docs) {
-    const double omb = 1.0 - b;  // Python evaluates `1 - self.b` first (left-to-right)
-    bm25_dnorm_kernel<<<(unsigned)((n_docs + 255) / 256), 256, 0, st>>>(doc_len_dev, n_docs, k1, b, omb, avgdl, ix.dnorm);
+  SB_CUDA(cudaMalloc(&nx.post_ratio, (size_t)std::max<int64_t>(nx.nnz, 1) * 8));
+  if (nx.n_docs) {
+    const double omb = 1.0 - nx.b;  // Python evaluates `1 - self.b` first (left-to-right)
+    bm25_dnorm_kernel<<<(unsigned)((nx.n_docs + 255) / 256), 256, 0, st>>>(doc_len_dev, nx.n_docs, nx.k1, nx.b, omb,
+                                                                          nx.avgdl, nx.dnorm);
     SB_CUDA(cudaGetLastError());
   }
-  if (nnz) {
-    const double k1p1 = k1 + 1.0;
-    bm25_ratio_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(ix.post_doc, tf_dev, nnz, ix.dnorm, k1p1,
-                                                                     ix.post_ratio);
+  if (nx.nnz) {
+    const double k1p1 = nx.k1 + 1.0;
+    bm25_ratio_kernel<<<(unsigned)((nx.nnz + 255) / 256), 256, 0, st>>>(nx.post_doc, tf_dev, nx.nnz, nx.dnorm, k1p1,
+                                                                       nx.post_ratio);
     SB_CUDA(cudaGetLastError());
   }
   SB_CUDA(cudaStreamSynchronize(st));
+  return SB_OK;
+}
+
+int bm25_install_device_csr(sb_ctx* ctx, int64_t* indptr_dev, int32_t* post_doc_dev, const uint16_t* tf_dev,
+                            const int32_t* doc_len_dev, int64_t n_terms, int64_t nnz, int64_t n_docs, double avgdl,
+                            const double* idf_host, int32_t variant, double k1, double b, double delta, int64_t id_base,
+                            cudaStream_t st) {
+  Bm25Index nx;
+  nx.n_docs = n_docs;
+  nx.n_terms = n_terms;
+  nx.nnz = nnz;
+  nx.id_base = id_base;
+  nx.variant = variant;
+  nx.k1 = k1;
+  nx.b = b;
+  nx.delta = delta;
+  nx.avgdl = avgdl;
+  nx.indptr = indptr_dev;      // ownership taken here, whatever happens next
+  nx.post_doc = post_doc_dev;
+  const int rc = bm25_install_build(nx, tf_dev, doc_len_dev, idf_host, st);
+  if (rc != SB_OK) {
+    cudaStreamSynchronize(st);
+    bm25_index_free(nx);
+    return rc;
+  }
+  cudaStreamSynchronize(st);   // nothing queued may still read the index that is about to be released
+  bm25_index_free(ctx->bm25);
+  ctx->bm25 = nx;
   return SB_OK;
 }
 
@@ -642,16 +661,25 @@ int sb_bm25_load(sb_ctx* ctx, const int64_t* indptr, const int32_t* post_doc, co
   SB_CUDA(cudaStreamSynchronize(st));
   int64_t* indptr_dev = nullptr;
   int32_t* post_doc_dev = nullptr;
-  SB_CUDA(cudaMalloc(&indptr_dev, (size_t)(n_terms + 1) * 8));
-  SB_CUDA(cudaMemcpyAsync(indptr_dev, indptr, (size_t)(n_terms + 1) * 8, cudaMemcpyHostToDevice, st));
-  SB_CUDA(cudaMalloc(&post_doc_dev, (size_t)std::max<int64_t>(nnz, 1) * 4));
-  int rc;
-  if ((rc = ctx->misc_dev.reserve((size_t)std::max<int64_t>(n_docs, 1) * 4))) return rc;
-  if ((rc = ctx->misc2_dev.reserve((size_t)std::max<int64_t>(nnz, 1) * 2))) return rc;
-  if (n_docs) SB_CUDA(cudaMemcpyAsync(ctx->misc_dev.p, doc_len, (size_t)n_docs * 4, cudaMemcpyHostToDevice, st));
-  if (nnz) {
-    SB_CUDA(cudaMemcpyAsync(post_doc_dev, post_doc, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
-    SB_CUDA(cudaMemcpyAsync(ctx->misc2_dev.p, post_tf, (size_t)nnz * 2, cudaMemcpyHostToDevice, st));
+  auto stage = [&]() -> int {
+    SB_CUDA(cudaMalloc(&indptr_dev, (size_t)(n_terms + 1) * 8));
+    SB_CUDA(cudaMemcpyAsync(indptr_dev, indptr, (size_t)(n_terms + 1) * 8, cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMalloc(&post_doc_dev, (size_t)std::max<int64_t>(nnz, 1) * 4));
+    int rc;
+    if ((rc = ctx->misc_dev.reserve((size_t)std::max<int64_t>(n_docs, 1) * 4))) return rc;
+    if ((rc = ctx->misc2_dev.reserve((size_t)std::max<int64_t>(nnz, 1) * 2))) return rc;
+    if (n_docs) SB_CUDA(cudaMemcpyAsync(ctx->misc_dev.p, doc_len, (size_t)n_docs * 4, cudaMemcpyHostToDevice, st));
+    if (nnz) {
+      SB_CUDA(cudaMemcpyAsync(post_doc_dev, post_doc, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+      SB_CUDA(cudaMemcpyAsync(ctx->misc2_dev.p, post_tf, (size_t)nnz * 2, cudaMemcpyHostToDevice, st));
+    }
+    return SB_OK;
+  };
+  if (int rc = stage()) {  // nothing has taken ownership yet
+    cudaStreamSynchronize(st);
+    if (indptr_dev) cudaFree(indptr_dev);
+    if (post_doc_dev) cudaFree(post_doc_dev);
+    return rc;
   }
   return bm25_install_device_csr(ctx, indptr_dev, post_doc_dev, ctx->misc2_dev.as<uint16_t>(), ctx->misc_dev.as<int32_t>(),
                                  n_terms, nnz, n_docs, avgdl, idf, variant, k1, b, delta, id_base, st);

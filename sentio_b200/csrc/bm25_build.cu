@@ -336,14 +336,15 @@ int sb_bm25_build_finish(sb_ctx* ctx, const double* idf, double avgdl, int32_t v
   DeviceGuard g(ctx->device);
   Bm25Build* B = ctx->bm25_build;
   SB_REQUIRE(B != nullptr, SB_ERR_STATE, "sb_bm25_build_finish: no build in progress (sb_bm25_build_tokens)");
-  int rc = bm25_install_device_csr(ctx, B->indptr, B->post_doc, B->tf, B->doc_len, B->V, B->nnz, B->n_docs, avgdl, idf,
-                                   variant, k1, b, delta, id_base, ctx->stream);
-  if (rc) return rc;
-  B->indptr = nullptr;    // ownership moved into ctx->bm25
+  int64_t* indptr = B->indptr;
+  int32_t* post_doc = B->post_doc;
+  B->indptr = nullptr;    // ownership of the CSR passes to bm25_install_device_csr unconditionally (it frees on failure)
   B->post_doc = nullptr;
-  bm25_build_free(B);
+  const int rc = bm25_install_device_csr(ctx, indptr, post_doc, B->tf, B->doc_len, B->V, B->nnz, B->n_docs, avgdl, idf,
+                                         variant, k1, b, delta, id_base, ctx->stream);
+  bm25_build_free(B);     // the build is consumed either way
   ctx->bm25_build = nullptr;
-  return SB_OK;
+  return rc;
 }
 
 }  // extern "C"
