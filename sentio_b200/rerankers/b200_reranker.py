@@ -64,6 +64,48 @@ class B200Reranker(Reranker):
             logger.error("B200 reranker failed, falling back to original order: %s", exc)
             return self._default_ranking(docs, top_k)
 
+    def rerank_batch(self, queries, docs_per_query, top_k: int = 5, **kwargs: Any) -> list[list[Document]]:
+        """All (query, document) pairs of all jobs in ONE cross-encoder forward; per job the same semantics as ``rerank``
+        (blank queries / empty lists / failures degrade per job, never raise)."""
+        if len(queries) != len(docs_per_query):
+            raise ValueError("queries and docs_per_query must have the same length")
+        out: list[list[Document] | None] = [None] * len(queries)
+        jobs = []
+        for i, (q, docs) in enumerate(zip(queries, docs_per_query)):
+            if not docs:
+                out[i] = []
+            elif not q or q.strip() == "":
+                out[i] = self._default_ranking(docs, top_k)
+            else:
+                jobs.append(i)
+        if jobs:
+            try:
+                parts = []
+                for i in jobs:
+                    texts = [d.text if d.text or not (d.metadata and "content" in d.metadata) else d.metadata["content"]
+                             for d in docs_per_query[i]]
+                    parts.append(self._tokenize(queries[i], texts, self.seq_len))
+                ids = np.concatenate([p[0] for p in parts])
+                tt = np.concatenate([p[1] for p in parts])
+                lens = np.concatenate([p[2] for p in parts])
+                _, sig = self._engine.ce_score(ids, tt, lens)
+                at = 0
+                for i in jobs:
+                    docs = docs_per_query[i]
+                    for doc, score in zip(docs, sig[at:at + len(docs)]):
+                        if not doc.text and doc.metadata and "content" in doc.metadata:
+                            doc.text = doc.metadata["content"]
+                        doc.metadata["rerank_score"] = float(score)
+                        doc.metadata["score"] = float(score)
+                    at += len(docs)
+                    out[i] = sorted(docs, key=lambda d: d.metadata.get("rerank_score", 0.0), reverse=True)[:top_k]
+            except Exception as exc:
+                logger.error("B200 reranker batch failed, falling back to original order: %s", exc)
+                for i in jobs:
+                    if out[i] is None:
+                        out[i] = self._default_ranking(docs_per_query[i], top_k)
+        return out  # type: ignore[return-value]
+
     def _default_ranking(self, docs: list[Document], top_k: int) -> list[Document]:
         result = docs[:top_k]
         for idx, doc in enumerate(result):

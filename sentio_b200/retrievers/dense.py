@@ -52,6 +52,11 @@ class DenseRetriever(BaseRetriever):
             kwargs.pop("vector_name", None)
             points = self._client.search(**kwargs)
 
+        docs = self._documents(points)
+        logger.debug("DenseRetriever: %d documents for top_k=%d", len(docs), top_k)
+        return docs
+
+    def _documents(self, points) -> list[Document]:
         docs = []
         for point in points:
             payload = point.payload or {}
@@ -60,5 +65,18 @@ class DenseRetriever(BaseRetriever):
             if text and "content" not in metadata:
                 metadata["content"] = text
             docs.append(self._document_cls(id=str(point.id), text=text, metadata=metadata))
-        logger.debug("DenseRetriever: %d documents for top_k=%d", len(docs), top_k)
         return docs
+
+    def retrieve_batch(self, queries, top_k: int = 10) -> list[list[Document]]:
+        """Many queries, one embedding call and ONE device scan when the store offers ``search_batch`` (B200VectorStore);
+        any other client falls back to the per-query loop of the base class."""
+        queries = list(queries)
+        if not queries:
+            return []
+        search_batch = getattr(self._client, "search_batch", None)
+        embed_many = getattr(self._embedder, "embed_many_sync", None)
+        if search_batch is None or embed_many is None:
+            return super().retrieve_batch(queries, top_k=top_k)
+        vectors = embed_many(queries)
+        hits = search_batch(collection_name=self._collection, query_vectors=vectors, limit=top_k, with_payload=True)
+        return [self._documents(points) for points in hits]

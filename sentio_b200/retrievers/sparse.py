@@ -122,6 +122,32 @@ class BM25Retriever(BaseRetriever):
             logger.error("BM25 retrieval error: %s", exc)
             return []
 
+    def retrieve_batch(self, queries, top_k: int = 10) -> list[list[Document]]:
+        """Many queries in ONE device batch; per query the same documents, scores and side effects as ``retrieve``."""
+        queries = list(queries)
+        if not self.bm25 or self._engine is None:
+            logger.warning("BM25 index not initialized")
+            return [[] for _ in queries]
+        if not queries:
+            return []
+        try:
+            ids, scores, counts = self.retrieve_batch_arrays(queries, top_k)
+            out = []
+            for b in range(len(queries)):
+                results = []
+                for j in range(int(counts[b])):
+                    doc_id = self.doc_ids[int(ids[b, j])]
+                    doc = self.doc_map.get(doc_id)
+                    if doc is None:
+                        doc = Document(id=doc_id, text="")
+                    doc.metadata["bm25_score"] = float(scores[b, j])
+                    results.append(doc)
+                out.append(results)
+            return out
+        except Exception as exc:
+            logger.error("BM25 batch retrieval error: %s", exc)
+            return [[] for _ in queries]
+
     def retrieve_batch_arrays(self, queries: list[str], top_k: int):
         """Batched extension: (rows, scores, counts) arrays for many queries in one GPU batch."""
         terms = [self.bm25.term_ids(q.lower().split()) for q in queries]

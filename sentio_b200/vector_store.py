@@ -107,6 +107,22 @@ class B200VectorStore:
                                    payload=col.payloads[row] if with_payload else None))
         return out
 
+    def search_batch(self, collection_name: str, query_vectors, limit: int = 10, with_payload: bool = True,
+                     **_ignored) -> list[list[ScoredPoint]]:
+        """``search`` for many query vectors in ONE device batch (the tcgen05 scan serves 64 queries per HBM pass)."""
+        col = self._collections.get(collection_name)
+        if col is None:
+            raise ValueError(f"Collection {collection_name} not found")
+        q = np.asarray(query_vectors, dtype=np.float32)
+        if q.ndim != 2:
+            raise ValueError("query_vectors must be [B, d]")
+        if q.shape[0] == 0:
+            return []
+        ids, scores, counts = col.engine.dense_topk(q, int(limit))
+        return [[ScoredPoint(id=col.ids[int(ids[b, j])], score=float(scores[b, j]),
+                             payload=col.payloads[int(ids[b, j])] if with_payload else None)
+                 for j in range(int(counts[b]))] for b in range(q.shape[0])]
+
     def search_batch_arrays(self, collection_name: str, query_vectors: np.ndarray, limit: int):
         """Batched extension: (rows [B,k] int64, scores [B,k] float64, counts [B]) without Python objects."""
         col = self._collections[collection_name]

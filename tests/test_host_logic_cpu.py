@@ -116,3 +116,34 @@ def test_multi_gpu_layout_planner():
         plan_layout(8, 2.05, corpus_shards=3)
     with pytest.raises(ValueError):
         plan_layout(8, 2.05, "banana")
+
+
+def test_reranker_batch_equals_per_query_with_fake_engine():
+    """B200Reranker.rerank_batch (one forward over all pairs) == rerank per job; blank / empty jobs degrade per job."""
+    from sentio_b200.cross_encoder import CrossEncoderWeights
+    from sentio_b200.rerankers.b200_reranker import B200Reranker
+    from sentio_b200.rerankers.base import RerankingResult
+
+    class _Eng:
+        device = 0
+
+        def ce_load(self, blob, cfg):
+            pass
+
+        def ce_score(self, ids, tt, lens):  # deterministic pseudo relevance from the token ids
+            s = (ids.astype(np.int64).sum(axis=1) % 97) / 97.0
+            return s, s.astype(np.float32)
+
+    cfg = dict(vocab_size=30522, hidden=128, layers=1, heads=4, intermediate=128, max_pos=64, type_vocab=2, ln_eps=1e-12)
+    mk = lambda: [[Document(id=f"a{i}", text=f"w{i} w{i + 3}") for i in range(7)],
+                  [Document(id="b0", text="", metadata={"content": "w5 w6"}), Document(id="b1", text="w9")], [],
+                  [Document(id=f"c{i}", text=f"w{2 * i}", metadata={"score": 0.5}) for i in range(4)]]
+    qs = ["w1 w2", "w5", "w7", "   "]
+    rr = B200Reranker(weights=CrossEncoderWeights.random(cfg, seed=1), engine=_Eng(), seq_len=32)
+    a = rr.rerank_batch(qs, mk(), top_k=3)
+    b = [rr.rerank(q, d, top_k=3) for q, d in zip(qs, mk())]
+    assert [[(d.id, d.metadata.get("rerank_score"), d.text) for d in x] for x in a] == \
+           [[(d.id, d.metadata.get("rerank_score"), d.text) for d in x] for x in b]
+    assert a[2] == [] and [d.metadata["rerank_score"] for d in a[3]] == [1.0, 0.9, 0.8]
+    res = RerankingResult(a[0], None, None)
+    assert len(res) == 3 and res.top_document is a[0][0] and list(res) == a[0] and res.metadata == {}

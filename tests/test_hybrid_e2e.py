@@ -125,3 +125,31 @@ def test_pipeline_batch_equals_per_query_classes(engine):
         sl = engine.bm25_topk(terms, k)
         f = engine.fuse(method, 60, 0.6, 0.4, k, dense=dl, sparse=sl)
         assert np.array_equal(ids, f[0]) and np.array_equal(sc, f[1]) and np.array_equal(cnt, f[3])
+
+
+def test_batch_retrieval_equals_per_query_with_oracle_engine(monkeypatch):
+    """retrieve_batch of the dense / BM25 retrievers == retrieve per query (host logic; oracle-backed engine double)."""
+    from helpers import HashEmbedder
+    from oracle_engine import OracleEngine
+    from sentio_b200 import vector_store as vs_mod
+    from sentio_b200.retrievers import sparse as sparse_mod
+    from sentio_b200.retrievers.dense import DenseRetriever
+
+    monkeypatch.delenv("BM25_VARIANT", raising=False)
+    monkeypatch.setattr(sparse_mod, "B200Engine", lambda device=0: OracleEngine())
+    monkeypatch.setattr(vs_mod, "B200Engine", lambda device=0: OracleEngine())
+    texts = [f"w{i % 7} w{i % 11} w{i % 13} topic{i % 5}" for i in range(60)]
+    docs = [Document(id=f"d{i}", text=t) for i, t in enumerate(texts)]
+    emb = HashEmbedder(32)
+    store = vs_mod.B200VectorStore(device=0)
+    store.create_collection("c", np.asarray(emb.embed_many_sync(texts), np.float32).astype(np.float16),
+                            ids=[d.id for d in docs], payloads=[{"content": t} for t in texts])
+    dense = DenseRetriever(client=store, embedder=emb, collection_name="c")
+    bm25 = sparse_mod.BM25Retriever(documents=docs)
+    queries = ["w1 w2 topic3", "w5", "nothing-known", "w6 w6 w10"]
+    for r in (dense, bm25):
+        batch = r.retrieve_batch(queries, top_k=7)
+        single = [r.retrieve(q, top_k=7) for q in queries]
+        key = "score" if r is dense else "bm25_score"
+        assert [[(d.id, d.metadata[key]) for d in x] for x in batch] == [[(d.id, d.metadata[key]) for d in x] for x in single]
+    assert dense.retrieve_batch([], top_k=3) == [] and bm25.retrieve_batch([], top_k=3) == []
