@@ -123,7 +123,11 @@ class BM25Retriever(BaseRetriever):
             return []
 
     def retrieve_batch(self, queries, top_k: int = 10) -> list[list[Document]]:
-        """Many queries in ONE device batch; per query the same documents, scores and side effects as ``retrieve``."""
+        """Many queries in ONE device batch; per query the same ids, order and ``bm25_score`` as ``retrieve``.
+
+        ``retrieve`` hands out the shared corpus objects and overwrites their ``bm25_score`` (sparse.py:189-197); a batch
+        cannot do that -- the same document may be a hit of several queries -- so every hit here is a COPY of the corpus
+        document carrying its own score."""
         queries = list(queries)
         if not self.bm25 or self._engine is None:
             logger.warning("BM25 index not initialized")
@@ -137,11 +141,10 @@ class BM25Retriever(BaseRetriever):
                 results = []
                 for j in range(int(counts[b])):
                     doc_id = self.doc_ids[int(ids[b, j])]
-                    doc = self.doc_map.get(doc_id)
-                    if doc is None:
-                        doc = Document(id=doc_id, text="")
-                    doc.metadata["bm25_score"] = float(scores[b, j])
-                    results.append(doc)
+                    src = self.doc_map.get(doc_id)
+                    meta = dict(src.metadata) if src is not None and src.metadata else {}
+                    meta["bm25_score"] = float(scores[b, j])
+                    results.append(Document(id=doc_id, text=src.text if src is not None else "", metadata=meta))
                 out.append(results)
             return out
         except Exception as exc:

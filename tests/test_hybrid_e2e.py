@@ -148,8 +148,12 @@ def test_batch_retrieval_equals_per_query_with_oracle_engine(monkeypatch):
     bm25 = sparse_mod.BM25Retriever(documents=docs)
     queries = ["w1 w2 topic3", "w5", "nothing-known", "w6 w6 w10"]
     for r in (dense, bm25):
-        batch = r.retrieve_batch(queries, top_k=7)
-        single = [r.retrieve(q, top_k=7) for q in queries]
         key = "score" if r is dense else "bm25_score"
-        assert [[(d.id, d.metadata[key]) for d in x] for x in batch] == [[(d.id, d.metadata[key]) for d in x] for x in single]
+        batch = [[(d.id, d.metadata[key], d.text) for d in x] for x in r.retrieve_batch(queries, top_k=7)]
+        for q, got in zip(queries, batch):  # compare query by query: ``retrieve`` mutates the shared corpus objects
+            assert got == [(d.id, d.metadata[key], d.text) for d in r.retrieve(q, top_k=7)]
+    # batch hits are copies: a document that is a hit of two queries keeps both scores
+    hits = bm25.retrieve_batch(["w1", "w1 w2"], top_k=60)
+    shared = {d.id for d in hits[0]} & {d.id for d in hits[1]}
+    assert shared and all(a is not b for a in hits[0] for b in hits[1] if a.id == b.id)
     assert dense.retrieve_batch([], top_k=3) == [] and bm25.retrieve_batch([], top_k=3) == []
