@@ -8,7 +8,9 @@ Public surface (names match the reference's ``src/core/retrievers`` / ``src/core
     from sentio_b200.retrievers.scorers import KeywordMatchScorer, RecencyScorer, SemanticSimilarityScorer, MMRScorer
     from sentio_b200.rerankers.b200_reranker import B200Reranker
     from sentio_b200.vector_store import B200VectorStore          # QdrantClient-shaped store in HBM
-    from sentio_b200.pipeline import HybridPipeline                # batched / sharded arrays-in arrays-out path
+    from sentio_b200.embedder import B200Embedder                  # BaseEmbedder surface, encoder forward on the GPU
+    from sentio_b200.selector import create_document_selector_node # the node that follows the reranker
+    from sentio_b200.pipeline import HybridPipeline, plan_layout   # batched / sharded arrays-in arrays-out path
 
 All arithmetic runs in libsentio_b200.so (hand-written sm_100a CUDA, C ABI in include/sentio_b200.h).  Importing this
 package does not touch the GPU; creating an engine without the built library or without a B200 raises.

@@ -147,3 +147,18 @@ def test_reranker_batch_equals_per_query_with_fake_engine():
     assert a[2] == [] and [d.metadata["rerank_score"] for d in a[3]] == [1.0, 0.9, 0.8]
     res = RerankingResult(a[0], None, None)
     assert len(res) == 3 and res.top_document is a[0][0] and list(res) == a[0] and res.metadata == {}
+
+
+def test_every_module_imports_without_a_gpu():
+    """Importing the package (all modules) must not touch CUDA or need the built library."""
+    import importlib
+    import pkgutil
+
+    import sentio_b200
+
+    names = [m.name for m in pkgutil.walk_packages(sentio_b200.__path__, "sentio_b200.")]
+    assert {"sentio_b200.embedder", "sentio_b200.selector", "sentio_b200.pipeline"} <= set(names)
+    for name in names:
+        if name.endswith(".build"):
+            continue
+        importlib.import_module(name)
