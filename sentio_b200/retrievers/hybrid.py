@@ -91,11 +91,28 @@ class HybridRetriever(BaseRetriever):
     # ------------------------------------------------------------------ public API
     def retrieve(self, query: str, top_k: int = 10) -> list[Document]:
         dense_hits = self._dense.retrieve(query, top_k=top_k)  # failures propagate, like the reference
-        all_dense = self._cache_hits(query, top_k) + dense_hits
-
         sparse_docs: list[Document] = []
         if self._sparse_retriever:
             sparse_docs = self._sparse_retriever.retrieve(query, top_k=top_k)
+        return self._fuse(query, dense_hits, sparse_docs, top_k)
+
+    def retrieve_batch(self, queries, top_k: int = 10) -> list[list[Document]]:
+        """Many queries: the two retrieval stages run as ONE device batch each (``retrieve_batch`` of the dense and the
+        sparse retriever -- the sparse one hands out per-query copies, see ``BM25Retriever.retrieve_batch``), the fusion
+        of every query is the same code as ``retrieve``."""
+        queries = list(queries)
+        if not queries:
+            return []
+        dense_lists = self._dense.retrieve_batch(queries, top_k=top_k)
+        if self._sparse_retriever:
+            sparse_lists = self._sparse_retriever.retrieve_batch(queries, top_k=top_k)
+        else:
+            sparse_lists = [[] for _ in queries]
+        return [self._fuse(q, d, s, top_k) for q, d, s in zip(queries, dense_lists, sparse_lists)]
+
+    def _fuse(self, query: str, dense_hits: list[Document], sparse_docs: list[Document], top_k: int) -> list[Document]:
+        """Everything of ``HybridRetriever.retrieve`` after the two retrieval calls (hybrid.py:146-300)."""
+        all_dense = self._cache_hits(query, top_k) + dense_hits
 
         plugin_hits: list[tuple[str, float]] = []
         for plugin in self._retriever_plugins:

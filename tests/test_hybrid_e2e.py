@@ -157,3 +157,11 @@ def test_batch_retrieval_equals_per_query_with_oracle_engine(monkeypatch):
     shared = {d.id for d in hits[0]} & {d.id for d in hits[1]}
     assert shared and all(a is not b for a in hits[0] for b in hits[1] if a.id == b.id)
     assert dense.retrieve_batch([], top_k=3) == [] and bm25.retrieve_batch([], top_k=3) == []
+    # HybridRetriever: batched retrieval stages + the same fusion code as the single-query path
+    for method in ("rrf", "weighted_rrf", "comb_sum"):
+        hr = HybridRetriever(dense_retriever=dense, sparse_retriever=bm25, rrf_k=60, fusion_method=method,
+                             dense_weight=0.6, sparse_weight=0.4, scorer_plugins=[], engine=OracleEngine())
+        got = [[(d.id, d.metadata["hybrid_score"]) for d in x] for x in hr.retrieve_batch(queries, top_k=9)]
+        for q, g in zip(queries, got):
+            assert g == [(d.id, d.metadata["hybrid_score"]) for d in hr.retrieve(q, top_k=9)], (method, q)
+        assert hr.retrieve_batch([], top_k=9) == []
