@@ -56,6 +56,26 @@ def dense_topk(rows16: np.ndarray, q: np.ndarray, k: int, chunk: int = 131072):
     return best_i, best_s
 
 
+def dense_topk_multi(rows16: np.ndarray, Q: np.ndarray, k: int, chunk: int = 131072):
+    """Exact top-k for several queries at once (each corpus chunk is widened to fp64 once): list of (indices, scores)."""
+    Q64 = np.asarray(Q, dtype=np.float32).astype(np.float64)
+    qn = np.sqrt((Q64 * Q64).sum(axis=1))
+    best = [(np.zeros(0, np.int64), np.zeros(0)) for _ in range(len(Q64))]
+    for lo in range(0, len(rows16), chunk):
+        x = rows16[lo:lo + chunk].astype(np.float64)
+        xn = np.sqrt((x * x).sum(axis=1))
+        for b in range(len(Q64)):
+            den = xn * qn[b]
+            s = np.zeros(len(x))
+            np.divide(x @ Q64[b], den, out=s, where=den > 0)
+            i, v = topk(s, k)
+            bi = np.concatenate([best[b][0], i + lo])
+            bs = np.concatenate([best[b][1], v])
+            o = np.lexsort((bi, -bs))[:k]
+            best[b] = (bi[o], bs[o])
+    return best
+
+
 def fast_topk_f32(x32: np.ndarray, q: np.ndarray, k: int):
     """The reference-CPU-arm implementation timed by bench.py: fp32 `X @ q` (BLAS, all cores) on pre-normalised rows,
     then the best-first top-k the way the reference code base does it (full ``np.argsort``, cf. sparse.py:180)."""

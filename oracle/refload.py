@@ -13,7 +13,19 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("SENTIO_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _pick_root() -> str:
+    """/root/reference in the build container; on the GPU box the git-ignored (but shipped) snapshot baseline/_ref that
+    ``__graft_entry__.build()`` takes from it -- never committed, never product."""
+    for cand in (os.environ.get("SENTIO_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "src", "core", "retrievers")):
+            return cand
+    return os.environ.get("SENTIO_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def available() -> bool:

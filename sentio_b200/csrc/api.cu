@@ -1,5 +1,6 @@
 // api.cu -- context lifetime + error plumbing of libsentio_b200.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -43,6 +44,9 @@ int sb_create(int device, sb_ctx** out) {
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  // tuning knobs for experiments (bench / profiling); the defaults are the measured best
+  if (const char* v = getenv("SB_DENSE_PAIR")) ctx->dense_pair = atoi(v) != 0;
+  if (const char* v = getenv("SB_DENSE_SAMPLE")) ctx->dense_sample_per_cta = atoi(v) > 0 ? atoi(v) : 2;
   cudaError_t se = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (se != cudaSuccess) {
     sb_set_error("sb_create: cudaStreamCreate failed: %s", cudaGetErrorString(se));
@@ -80,6 +84,8 @@ void sb_destroy(sb_ctx* ctx) {
   ctx->misc2_dev.release();
   ctx->misc3_dev.release();
   ctx->acc_dev.release();
+  ctx->qn_dev.release();
+  ctx->qaux_dev.release();
   ctx->doc_chars_dev.release();
   ctx->pin_in.release();
   ctx->pin_out.release();

@@ -127,6 +127,9 @@ struct sb_ctx {
   CeDocTokens* ce_tokens = nullptr;
   Bm25Build* bm25_build = nullptr;  // GPU index build in progress (sb_bm25_build_tokens .. sb_bm25_build_finish)
   int dense_mode = 0;  // 0 = auto, 1 = CUDA-core scan only, 2 = tcgen05 batched scan whenever eligible
+  int dense_pair = 1;  // 1 = groups of > 64 queries use the cta_group::2 pair kernel (env SB_DENSE_PAIR=0 disables)
+  int dense_sample_per_cta = 2;  // tiles per CTA of the sampling pass (env SB_DENSE_SAMPLE)
+  int max_clusters2 = 0;  // co-resident 2-CTA clusters of the pair kernel (0 = not queried yet)
   // bookkeeping: kernels launched by this library, optional per-kernel CUDA-event timing (bench.py roofline leg)
   uint64_t launches = 0;
   bool prof_on = false;
@@ -135,6 +138,8 @@ struct sb_ctx {
   std::vector<cudaEvent_t> prof_pool;
   // scratch
   DevBuf q_dev, cand_dev, out_ids_dev, out_sc_dev, out_cnt_dev, misc_dev, misc2_dev, misc3_dev, acc_dev;
+  DevBuf qn_dev;     // dense: normalised fp32 queries [B][d_pad] fed to the scans
+  DevBuf qaux_dev;   // dense: per-query eps [B] fp32 | fallback flags [B] i32
   DevBuf doc_chars_dev;  // K7: characters of every document's usable text (0 = blank), sb_doc_chars_load
   int64_t doc_chars_n = 0, doc_chars_base = 0;
   PinBuf pin_in, pin_out;

@@ -9,8 +9,10 @@
 //                       and push candidates that beat the CTA's running K'-th best into a smem candidate buffer that
 //                       is compacted by an in-smem bitonic sort.  Output: one sorted top-K' list per CTA per query
 //                       (K' = k + slack, power of two).
-//   dense_merge_kernel  one CTA per query: truncating bitonic merge tree over the per-CTA lists, exact fp64 re-score
-//                       of the K' survivors against the STORED fp16 rows, final sort by (score desc, id asc), write k.
+//   dense_merge_kernel  one CTA per query: the k-th best approximate key over the per-CTA lists, then EVERY row inside
+//                       the error window below it (dense_common.cuh) is re-scored in fp64 against the STORED fp16 rows,
+//                       final sort by (score desc, id asc), write k.  Queries whose window cannot be served from the
+//                       lists raise a flag and are answered by dense_exact_fallback_kernel (brute force, fp64).
 //
 // Algorithmic HBM bytes per pass = n_pad * d_pad * 2 (+ n_pad * 4 for the inverse norms); see DESIGN.md.
 #include <math.h>
@@ -440,16 +442,18 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
 }
 
 // ------------------------------------------------------------------------------------------------ merge kernel
-constexpr int kSelCap = 2048;  // shared-memory capacity of the threshold-selected candidate set
+constexpr int kSelCap = 2048;  // shared-memory capacity of the window (winner) set
 
 struct MergeParams {
-  unsigned long long* cand;  // [nq][G][kprime] sorted descending lists (clobbered only on the slow path)
+  const unsigned long long* cand;  // [nq][G][kprime] sorted descending lists
   int32_t G;
   int32_t kprime;
   int32_t heads_per_list;    // R = ceil(kprime / G)
   int32_t heads_pow2;        // power of two >= G * R  (<= kSelCap)
   const __half* rows;
-  const float* q;            // [nq][d_pad]
+  const float* q;            // [nq][d_pad] the caller's fp32 queries (exact stage)
+  const float* eps;          // [nq] error bound of the approximate scores (0 for an all-zero query)
+  int32_t* fallback;         // [nq] raised when the lists cannot serve the window
   int32_t d_pad;
   int32_t ch;
   int64_t id_base;
@@ -478,61 +482,34 @@ __device__ __forceinline__ void block_sort_desc_u64(unsigned long long* a, int l
   }
 }
 
-// Slow path (adversarial score distributions only): truncating bitonic merge tree over the G lists, in place.
-__device__ void merge_tree_inplace(unsigned long long* L, int G, int K, int tid, int nt) {
-  for (int step = 1; step < G; step <<= 1) {
-    const int pairs = (G - step + 2 * step - 1) / (2 * step);
-    for (int t = tid; t < pairs * K; t += nt) {
-      const int pi = t / K, i = t - pi * K;
-      const int a = pi * 2 * step, b = a + step;
-      if (b < G) {
-        const unsigned long long x = L[(size_t)a * K + i], y = L[(size_t)b * K + (K - 1 - i)];
-        if (y > x) L[(size_t)a * K + i] = y;
-      }
-    }
-    __syncthreads();
-    for (int j = K >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < pairs * (K >> 1); t += nt) {
-        const int pi = t / (K >> 1), h = t - pi * (K >> 1);
-        const int a = pi * 2 * step;
-        if (a + step < G) {
-          const int i = ((h / j) * 2 * j) + (h % j);
-          unsigned long long* A = L + (size_t)a * K;
-          const unsigned long long x = A[i], y = A[i + j];
-          if (x < y) {
-            A[i] = y;
-            A[i + j] = x;
-          }
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
-// One CTA per query.  (1) a lower bound of the global K'-th best key = the K'-th largest among the first
-// R = ceil(K'/G) entries of every list; (2) every list contributes its (short) prefix >= bound to a shared-memory set;
-// (3) that set is sorted -> global top-K'; (4) exact fp64 re-score against the stored fp16 rows; (5) final order.
+// One CTA per query.  (1) a lower bound of the global k-th best approximate key = the k-th largest among the first
+// R = ceil(K'/G) entries of every list (G*R >= K' >= k real keys); (2) every list contributes its prefix inside the
+// error window below that key; a FULL list whose last entry is still inside the window may have dropped members ->
+// fallback; (3) exact fp64 re-score of the whole window; (4) final order, emit k.
 __global__ void __launch_bounds__(kMergeThreads, 1) dense_merge_kernel(const MergeParams p) {
   extern __shared__ __align__(16) uint8_t msmem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
   const int qi = blockIdx.x;
   const int G = p.G, K = p.kprime;
   unsigned long long* sel = reinterpret_cast<unsigned long long*>(msmem);   // [kSelCap]
-  unsigned long long* ek = sel + kSelCap;                                   // [K] exact score keys
-  uint32_t* ei = reinterpret_cast<uint32_t*>(ek + K);                       // [K] row index
+  unsigned long long* ek = sel + kSelCap;                                   // [kSelCap] exact score keys
+  uint32_t* ei = reinterpret_cast<uint32_t*>(ek + kSelCap);                 // [kSelCap] row index
   __shared__ double qq_s;
-  __shared__ int s_nsel;
+  __shared__ int s_nsel, s_trunc;
   __shared__ unsigned long long s_bound;
-  unsigned long long* L = p.cand + (size_t)qi * G * K;
+  const unsigned long long* L = p.cand + (size_t)qi * G * K;
 
   // (1) bound from the list heads
   const int R = p.heads_per_list, nh = G * R, HP = p.heads_pow2;
   for (int t = tid; t < HP; t += nt) sel[t] = t < nh ? L[(size_t)(t / R) * K + (t % R)] : 0ull;
-  if (tid == 0) s_nsel = 0;
+  if (tid == 0) {
+    s_nsel = 0;
+    s_trunc = 0;
+  }
   __syncthreads();
   block_sort_desc_u64(sel, HP, tid, nt);
-  if (tid == 0) s_bound = nh >= K ? sel[K - 1] : 0ull;
+  // fewer than k rows in the whole corpus -> sel[k-1] is an empty slot (0): everything is a member
+  if (tid == 0) s_bound = sel[p.k - 1] != 0ull ? window_lo_key(sel[p.k - 1], p.eps[qi]) : 0ull;
   __syncthreads();
   const unsigned long long bound = s_bound;
   __syncthreads();  // sel is reused below
@@ -553,23 +530,18 @@ __global__ void __launch_bounds__(kMergeThreads, 1) dense_merge_kernel(const Mer
         if (at < kSelCap) sel[at] = key;
       }
       if (m != 0xffffffffu) break;
+      if (base + 32 >= K && lane == 0) s_trunc = 1;  // the whole (full) list is inside the window
     }
   }
   __syncthreads();
   const int nsel = s_nsel;
-  if (nsel <= kSelCap) {
-    int P = 32;
-    while (P < nsel || P < K) P <<= 1;
-    for (int t = nsel + tid; t < P; t += nt) sel[t] = 0ull;
-    __syncthreads();
-    block_sort_desc_u64(sel, P, tid, nt);
-  } else {
-    merge_tree_inplace(L, G, K, tid, nt);
-    for (int t = tid; t < K; t += nt) sel[t] = L[t];
-    __syncthreads();
+  if (nsel > kSelCap || s_trunc) {
+    if (tid == 0) p.fallback[qi] = 1;
+    return;
   }
+  int P = 32;
+  while (P < nsel) P <<= 1;
 
-  // (4)+(5) exact fp64 re-score, final order, emit
   RescoreArgs ra;
   ra.rows = p.rows;
   ra.q = p.q + (size_t)qi * p.d_pad;
@@ -580,10 +552,147 @@ __global__ void __launch_bounds__(kMergeThreads, 1) dense_merge_kernel(const Mer
   ra.out_ids = p.out_ids + (size_t)qi * p.k;
   ra.out_scores = p.out_scores + (size_t)qi * p.k;
   ra.out_count = p.out_counts + qi;
-  rescore_and_emit(sel, K, ek, ei, &qq_s, ra);
+  rescore_and_emit(sel, nsel, P, ek, ei, &qq_s, ra);
+}
+
+// ------------------------------------------------------------------------------------------------ query preparation
+// One CTA per operand row r (rows >= nq are padding): qn[r] = q[r] / ||q[r]|| in fp32 (the scans rank by cosine, so the
+// caller's scale must not reach the fp32 / fp16 arithmetic), optionally q16[r] = fp16(qn[r]) for the tcgen05 scan, and
+// eps[r] = the bound on |approximate - exact cosine| the hand-off window uses (0 for an all-zero query).
+__global__ void __launch_bounds__(256) dense_prep_queries_kernel(const float* __restrict__ q_pad, int nq, int d_pad,
+                                                                 float* __restrict__ qn, __half* __restrict__ q16,
+                                                                 float* __restrict__ eps, int mma) {
+  __shared__ double s_red[8];
+  __shared__ double s_tot;
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool real = r < nq;
+  const float* src = q_pad + (size_t)r * d_pad;
+  double ss = 0.0;
+  if (real)
+    for (int i = tid; i < d_pad; i += blockDim.x) {
+      const double v = (double)src[i];
+      ss += v * v;
+    }
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0) s_red[warp] = ss;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
+    s_tot = t;
+  }
+  __syncthreads();
+  const double nrm = sqrt(s_tot);
+  const bool zero = !(nrm > 0.0) || !real;
+  double dd = 0.0;  // ||fp16(qn) - qn||^2
+  for (int i = tid; i < d_pad; i += blockDim.x) {
+    const float v = zero ? 0.f : (float)((double)src[i] / nrm);
+    if (qn) qn[(size_t)r * d_pad + i] = v;
+    if (q16) {
+      const __half h = __float2half_rn(v);
+      q16[(size_t)r * d_pad + i] = h;
+      const double e = (double)__half2float(h) - (double)v;
+      dd += e * e;
+    }
+  }
+  if (eps == nullptr || !real) return;
+  for (int o = 16; o; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
+  __syncthreads();
+  if (lane == 0) s_red[warp] = dd;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
+    float e = 0.f;
+    if (!zero) e = mma ? (float)(sqrt(t) * 1.0001) + dense_eps_mma_acc(d_pad) : dense_eps_fp32(d_pad);
+    eps[r] = e;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ exact fallback
+// One CTA per FLAGGED query (the others exit at once): brute force over every stored row in fp64 -- 1024 rows per round
+// are scored by the CTA's 32 warps and folded into the running best list by a 2048-pair bitonic sort (skipped when no
+// new row beats the current k-th best).  Slow (tens of ms at 1 M rows) and exact for any score distribution.
+constexpr int kFbThreads = 1024;
+constexpr int kFbBest = 1024;  // >= the largest supported k
+
+struct FallbackParams {
+  const int32_t* flag;   // [nq]
+  const __half* rows;
+  const float* q;        // [nq][d_pad]
+  int64_t n;
+  int32_t d_pad, ch;
+  int64_t id_base;
+  int32_t k;
+  int64_t* out_ids;
+  double* out_scores;
+  int32_t* out_counts;
+};
+
+__global__ void __launch_bounds__(kFbThreads, 1) dense_exact_fallback_kernel(const FallbackParams p) {
+  const int qi = blockIdx.x;
+  if (p.flag[qi] == 0) return;
+  __shared__ unsigned long long ek[2 * kFbBest];
+  __shared__ uint32_t ei[2 * kFbBest];
+  __shared__ double qq_s;
+  __shared__ int s_beats;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
+  const float* q = p.q + (size_t)qi * p.d_pad;
+  const double qn = query_norm_cta(q, p.d_pad, &qq_s);
+  if (!(qn > 0.0)) {
+    // all-zero query: every cosine is exactly 0 -> the first k rows in index order, no scan needed
+    const int m = (int)min((int64_t)p.k, p.n);
+    for (int i = tid; i < p.k; i += nt) {
+      p.out_ids[(size_t)qi * p.k + i] = i < m ? p.id_base + i : -1;
+      p.out_scores[(size_t)qi * p.k + i] = 0.0;
+    }
+    if (tid == 0) p.out_counts[qi] = m;
+    return;
+  }
+  for (int i = tid; i < 2 * kFbBest; i += nt) {
+    ek[i] = 0ull;
+    ei[i] = 0xffffffffu;
+  }
+  __syncthreads();
+  for (int64_t r0 = 0; r0 < p.n; r0 += kFbBest) {
+    if (tid == 0) s_beats = 0;
+    __syncthreads();
+    const unsigned long long kth = ek[p.k - 1];  // 0 while fewer than k rows have been seen
+    bool beat = false;
+    for (int c = warp; c < kFbBest; c += nw) {
+      const int64_t row = r0 + c;
+      unsigned long long okey = 0ull;
+      if (row < p.n) {
+        okey = f64_orderable(exact_cosine_warp(p.rows, (uint32_t)row, q, p.d_pad, p.ch, qn, lane));
+        if (okey == 0ull) okey = 1ull;
+      }
+      if (lane == 0) {
+        ek[kFbBest + c] = okey;
+        ei[kFbBest + c] = row < p.n ? (uint32_t)row : 0xffffffffu;
+        beat |= okey > kth;   // equal keys: the earlier row is already in the list and wins the tie
+      }
+    }
+    if (beat) s_beats = 1;
+    __syncthreads();
+    if (s_beats) sort_exact_pairs(ek, ei, 2 * kFbBest, tid, nt);
+    __syncthreads();
+  }
+  RescoreArgs ra;
+  ra.rows = p.rows;
+  ra.q = q;
+  ra.d_pad = p.d_pad;
+  ra.ch = p.ch;
+  ra.id_base = p.id_base;
+  ra.k = p.k;
+  ra.out_ids = p.out_ids + (size_t)qi * p.k;
+  ra.out_scores = p.out_scores + (size_t)qi * p.k;
+  ra.out_count = p.out_counts + qi;
+  emit_exact_pairs(ek, ei, kFbBest, ra);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+constexpr int kDenseMaxK = 1024;  // per-call top_k limit of both scans (per-CTA lists / winner buffers)
+
 int next_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;
@@ -611,10 +720,12 @@ int make_plan(sb_ctx* ctx, const DenseIndex& ix, int k, ScanPlan* pl) {
   SB_REQUIRE(pl->nchunk > 0, SB_ERR_UNSUPPORTED, "dense: dimension %d too large (max 4096)", ix.d);
   pl->rw = pl->nchunk <= 4 ? 4 : (pl->nchunk <= 8 ? 2 : 1);
   pl->qb_max = pl->nchunk <= 4 ? 4 : (pl->nchunk <= 8 ? 2 : 1);
-  const int slack = 28;
-  pl->kprime = next_pow2(k + slack);
+  // per-CTA list length: >= k (the k-th best approximate key must be in the lists); the spare entries above k are what
+  // usually lets a list serve the error window without a fallback
+  pl->kprime = next_pow2(k + 28);
   if (pl->kprime < 128) pl->kprime = 128;
-  SB_REQUIRE(pl->kprime <= 1024, SB_ERR_UNSUPPORTED, "dense: top_k %d too large (max %d)", k, 1024 - slack);
+  if (pl->kprime > kDenseMaxK) pl->kprime = kDenseMaxK;
+  SB_REQUIRE(k <= kDenseMaxK, SB_ERR_UNSUPPORTED, "dense: top_k %d too large (max %d per call)", k, kDenseMaxK);
   const int R = kConsumerWarps * pl->rw;
   // compaction sorts best[K'] + one batch in registers across one warp: 512 / 1024 / 1024 / 2048 keys
   pl->bcap = pl->kprime <= 256 ? 3 * pl->kprime : pl->kprime;
@@ -639,7 +750,7 @@ int make_plan(sb_ctx* ctx, const DenseIndex& ix, int k, ScanPlan* pl) {
   pl->heads_per_list = (pl->kprime + pl->grid - 1) / pl->grid;
   pl->heads_pow2 = next_pow2(pl->grid * pl->heads_per_list);
   SB_REQUIRE(pl->heads_pow2 <= kSelCap, SB_ERR_UNSUPPORTED, "dense: internal merge capacity exceeded");
-  pl->merge_smem = (size_t)kSelCap * 8 + (size_t)pl->kprime * 12 + 64;
+  pl->merge_smem = (size_t)kSelCap * 20 + 64;
   return SB_OK;
 }
 
@@ -693,13 +804,17 @@ int dense_topk_enqueue(sb_ctx* ctx, DenseIndex& ix, const float* q_pad, int B, i
   ScanPlan pl;
   int rc = make_plan(ctx, ix, k, &pl);
   if (rc) return rc;
-  // batches of >= 16 queries ride the tensor cores: one HBM pass per 64 queries instead of one per 4
+  // batches of >= 16 queries ride the tensor cores: one HBM pass per 64 / 128 queries instead of one per 4
   if (ctx->dense_mode != 1 && dense_mma_eligible(ctx, ix, B))
-    return dense_mma_topk_enqueue(ctx, ix, q_pad, B, k, pl.kprime, out_ids, out_scores, out_counts, st);
+    return dense_mma_topk_enqueue(ctx, ix, q_pad, B, k, out_ids, out_scores, out_counts, st);
   const int chunk = B < kMergeChunk ? B : kMergeChunk;
   const size_t per_q = (size_t)pl.grid * pl.kprime;
   rc = ctx->cand_dev.reserve((size_t)chunk * per_q * 8);
   if (rc) return rc;
+  // normalised queries for the scan, eps + fallback flags for the hand-off
+  float *qn = nullptr, *eps = nullptr;
+  int32_t* fb = nullptr;
+  if ((rc = dense_prep_queries(ctx, ix, q_pad, B, B, /*mma=*/false, &qn, nullptr, &eps, &fb, st))) return rc;
   SB_CUDA(cudaFuncSetAttribute(dense_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.merge_smem));
   for (int c0 = 0; c0 < B; c0 += chunk) {
     const int nq = std::min(chunk, B - c0);
@@ -710,7 +825,7 @@ int dense_topk_enqueue(sb_ctx* ctx, DenseIndex& ix, const float* q_pad, int B, i
       ScanParams sp;
       sp.rows = ix.rows;
       sp.inv_norm = ix.inv_norm;
-      sp.q = q_pad + (size_t)(c0 + b0) * ix.d_pad;
+      sp.q = qn + (size_t)(c0 + b0) * ix.d_pad;
       sp.cand = ctx->cand_dev.as<unsigned long long>() + (size_t)b0 * per_q;
       sp.n = ix.n;
       sp.d_pad = ix.d_pad;
@@ -735,6 +850,8 @@ int dense_topk_enqueue(sb_ctx* ctx, DenseIndex& ix, const float* q_pad, int B, i
     mp.heads_pow2 = pl.heads_pow2;
     mp.rows = ix.rows;
     mp.q = q_pad + (size_t)c0 * ix.d_pad;
+    mp.eps = eps + c0;
+    mp.fallback = fb + c0;
     mp.d_pad = ix.d_pad;
     mp.ch = ix.d_pad / 8;
     mp.id_base = ix.id_base;
@@ -748,7 +865,7 @@ int dense_topk_enqueue(sb_ctx* ctx, DenseIndex& ix, const float* q_pad, int B, i
     }
     SB_CUDA(cudaGetLastError());
   }
-  return SB_OK;
+  return dense_fallback_enqueue(ctx, ix, q_pad, B, k, fb, out_ids, out_scores, out_counts, st);
 }
 
 __global__ void fill_empty_topk_kernel(int64_t* ids, double* sc, int32_t* cnt, int B, int k) {
@@ -770,6 +887,49 @@ __global__ void dense_fetch_kernel(const __half* rows, int d, int d_pad, int64_t
 }
 
 }  // namespace
+
+// Shared with dense_mma.cu: query preparation (normalised fp32 copy, optional fp16 operand rows, eps, cleared fallback
+// flags) and the brute-force fallback launch.  `rows` >= B operand rows are prepared (rows >= B are zero padding).
+int dense_prep_queries(sb_ctx* ctx, const DenseIndex& ix, const float* q_pad, int B, int rows, bool mma, float** qn_out,
+                       __half* q16, float** eps_out, int32_t** fb_out, cudaStream_t st) {
+  int rc;
+  if ((rc = ctx->qaux_dev.reserve((size_t)rows * 8 + 64))) return rc;
+  float* eps = ctx->qaux_dev.as<float>();
+  int32_t* fb = reinterpret_cast<int32_t*>(eps + rows);
+  float* qn = nullptr;
+  if (qn_out) {
+    if ((rc = ctx->qn_dev.reserve((size_t)rows * ix.d_pad * sizeof(float)))) return rc;
+    qn = ctx->qn_dev.as<float>();
+    *qn_out = qn;
+  }
+  SB_CUDA(cudaMemsetAsync(fb, 0, (size_t)rows * 4, st));
+  ctx->launches += 1;
+  dense_prep_queries_kernel<<<rows, 256, 0, st>>>(q_pad, B, ix.d_pad, qn, q16, eps, mma ? 1 : 0);
+  SB_CUDA(cudaGetLastError());
+  *eps_out = eps;
+  *fb_out = fb;
+  return SB_OK;
+}
+
+int dense_fallback_enqueue(sb_ctx* ctx, const DenseIndex& ix, const float* q_pad, int B, int k, const int32_t* fb,
+                           int64_t* out_ids, double* out_scores, int32_t* out_counts, cudaStream_t st) {
+  FallbackParams fp;
+  fp.flag = fb;
+  fp.rows = ix.rows;
+  fp.q = q_pad;
+  fp.n = ix.n;
+  fp.d_pad = ix.d_pad;
+  fp.ch = ix.d_pad / 8;
+  fp.id_base = ix.id_base;
+  fp.k = k;
+  fp.out_ids = out_ids;
+  fp.out_scores = out_scores;
+  fp.out_counts = out_counts;
+  ctx->launches += 1;
+  dense_exact_fallback_kernel<<<B, kFbThreads, 0, st>>>(fp);
+  SB_CUDA(cudaGetLastError());
+  return SB_OK;
+}
 
 // Shared with other translation units (hybrid batch path, scorers).
 int sb_dense_pad_queries(sb_ctx* ctx, const DenseIndex& ix, const float* q, int B, bool q_on_device, float** q_pad_out,

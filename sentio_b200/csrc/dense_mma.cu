@@ -1,21 +1,29 @@
 // dense_mma.cu -- K1b: batched-query dense scan on the 5th-gen tensor cores (tcgen05 / TMEM / TMA).
 //
-// One HBM pass over the fp16 corpus serves QBN = 16 / 32 / 64 queries at once: the scores of a 128-row corpus tile against
-// all QBN queries are one UMMA accumulator  D[128, QBN] = A[128, D] * Q[QBN, D]^T  (A = corpus tile, K-major fp16,
-// streamed by TMA in 64-column SWIZZLE_128B boxes; B = the query block, K-major fp16, resident in shared memory for the
-// whole kernel; D in tensor memory, double buffered).  The pass stays HBM bound: per 16 KB of corpus the tensor pipe
-// needs 4 MMAs of 128 x QBN x 16, a few percent of its capacity.
+// One HBM pass over the fp16 corpus serves a whole GROUP of queries: the scores of a 128-row corpus tile against all
+// queries of the group are one UMMA accumulator  D[128, N] = A[128, D] * Q[N, D]^T  (A = corpus tile, K-major fp16,
+// streamed by TMA in 64-column SWIZZLE_128B boxes; B = the normalised fp16 query block, K-major, resident in shared
+// memory for the whole kernel; D in tensor memory, double buffered).
+//   * dense_scan_mma_kernel<QBN>   one CTA per SM, N = QBN = 16 / 32 / 64 queries (cta_group::1).
+//   * dense_scan_mma2_kernel<128>  a CTA PAIR (2-CTA cluster, cta_group::2): one UMMA of M = 256 (128 corpus rows per
+//     CTA) x N = 128 queries whose B operand is split across the pair -- each CTA keeps 64 query rows (128 KB at
+//     d = 1024, the shared-memory limit of one SM), streams its own A tiles, and receives D[128 rows, 128 queries] in its
+//     own tensor memory: 128 queries per HBM pass with no extra L2 traffic.
+// The pass stays HBM bound: per 16 KB of corpus the tensor pipe needs 4 MMAs, a third of its capacity at N = 128.
 //
-// Exactness is kept by construction, not by luck:
-//   * every query gets a SAFE initial threshold from a sampling pass (the K'-th best approximate score over a sample of
-//     corpus tiles is <= the global K'-th best), so only ~1 % of the rows survive the epilogue compare;
-//   * survivors are appended to a per-(CTA, query) global buffer that is sized for the worst case (every row of the
-//     CTA's share) -- nothing is ever dropped, an adversarial corpus order only costs time in the select kernel;
-//   * dense_select_kernel reduces each query's survivors to the K' best approximate keys (chunked bitonic sort) and the
-//     shared exact stage (dense_common.cuh) re-scores them in fp64 against the stored rows and the fp32 query.
+// Exactness (dense_common.cuh, DESIGN.md "K1: exactness"):
+//   * queries are L2-normalised before the fp16 rounding (cosine is scale invariant; the caller's scale never reaches
+//     the fp16 range) and eps[q] = ||fp16(qn) - qn|| + accumulation bound is computed per query;
+//   * a sampling pass gives every query a SAFE threshold: (k-th best approximate score of a corpus sample) - 2 eps is
+//     <= (global k-th best) - 2 eps, the lower edge of the hand-off window, so every window member survives the epilogue;
+//   * survivors are appended to per-(CTA, query) lists; a list that overflows its capacity raises the query's fallback
+//     flag instead of dropping anything silently;
+//   * dense_select_kernel finds the k-th best approximate key (radix select), gathers EVERY survivor inside the window
+//     below it and re-scores them all in fp64 against the stored rows and the caller's fp32 query; a window larger than
+//     the winner buffer raises the fallback flag (dense_exact_fallback_kernel, dense.cu).
 //
 // Warp roles (192 threads, 1 CTA / SM, persistent): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (tcgen05.ld 32x32b, one corpus row per thread, QBN scores in registers).
+// warps 2..5 = epilogue (tcgen05.ld 32x32b, one corpus row per thread).
 #include <cuda.h>
 
 #include <algorithm>
@@ -30,9 +38,9 @@ constexpr int kTileRows = 128;
 constexpr int kBK = 64;                       // fp16 elements per 128-byte swizzle row
 constexpr uint32_t kATileBytes = kTileRows * kBK * 2;   // 16 KB
 constexpr int kMmaThreads = 192;
-constexpr int kSelectThreads = 1024;
-constexpr int kSelStage = 20480;              // survivors staged in shared memory by dense_select_kernel (160 KB)
-constexpr int kSelTop = 2048;                 // winner buffer: < K' keys above the selected bucket + the bucket
+constexpr int kSelectThreads = 512;
+constexpr int kSelStage = 8192;               // survivors staged in shared memory by dense_select_kernel (64 KB)
+constexpr int kSelTop = 2048;                 // window (winner) buffer; larger windows go to the exact fallback
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile(
@@ -63,6 +71,50 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// ---- cta_group::2 forms (the pair kernel); PTX as in cute/arch/{copy_sm100_tma,mma_sm100_umma}.hpp, cutlass/arch/barrier.h
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of `smem_addr` (a shared::cta address of this CTA) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  __syncwarp();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are signalled on an mbarrier of the LEADER CTA (bar_cluster = mapa(bar, 0))
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar_cluster)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrive (once all MMAs issued so far have completed) on the barrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+
 template <int N>
 struct TmemLd;
 template <>
@@ -82,6 +134,7 @@ struct MmaScanParams {
   const float* thr_init;        // [QBN] safe initial thresholds (NULL = -inf: sampling pass)
   unsigned long long* cand;     // [QBN][grid][capg]
   int32_t* counts;              // [QBN][grid]
+  int32_t* fallback;            // [QBN] raised when a (CTA, query) list overflows capg (NULL: cannot overflow)
   int64_t n;                    // valid rows
   int32_t kb_count;             // d_pad / 64
   int32_t num_tiles;            // tiles visited by this launch
@@ -222,9 +275,173 @@ dense_scan_mma_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  for (int i = threadIdx.x; i < QBN; i += blockDim.x) p.counts[(size_t)i * grid + cta] = min(cnt[i], p.capg);
+  for (int i = threadIdx.x; i < QBN; i += blockDim.x) {
+    p.counts[(size_t)i * grid + cta] = min(cnt[i], p.capg);
+    if (cnt[i] > p.capg && p.fallback) p.fallback[i] = 1;   // nothing is dropped silently: brute force answers this query
+  }
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * QBN) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pair kernel
+// cta_group::2: CTA rank 0 (the leader) issues every MMA for the pair; both CTAs stream their own A tiles and load
+// their own half of the query block, with TMA completion bytes landing on the LEADER's full barriers; tcgen05.commit
+// multicasts the "stage free" / "accumulator ready" arrivals to both CTAs; the epilogue warps of both CTAs arrive on the
+// leader's "accumulator drained" barrier through the cluster address space.
+template <int NQ>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMmaThreads, 1)
+dense_scan_mma2_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_q,
+                       const MmaScanParams p) {
+  constexpr int HQ = NQ / 2;                            // operand rows held by each CTA
+  extern __shared__ uint8_t msm_raw[];
+  const uint32_t raw = smem_u32(msm_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = msm_raw + (base - raw);
+  constexpr uint32_t kQBlockBytes = HQ * kBK * 2;
+  const uint32_t q_bytes = (uint32_t)p.kb_count * kQBlockBytes;
+  const uint32_t a0 = base + q_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + q_bytes + (size_t)p.stages * kATileBytes);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + p.stages);
+  const uint32_t bar_q = smem_u32(bars + 2 * p.stages);
+  const uint32_t bar_acc_full = smem_u32(bars + 2 * p.stages + 1), bar_acc_empty = smem_u32(bars + 2 * p.stages + 3);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 5);
+  volatile float* thr = reinterpret_cast<volatile float*>(tmem_slot + 2);   // [NQ]
+  int* cnt = reinterpret_cast<int*>(const_cast<float*>(thr) + NQ);         // [NQ]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int grid = gridDim.x, cta = blockIdx.x;
+  const int pair = cta >> 1, npairs = grid >> 1;
+  const int n_tp = (p.num_tiles + 1) >> 1;              // tile pairs of this launch
+  const int my_tiles = pair < n_tp ? (n_tp - 1 - pair) / npairs + 1 : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);    // used in the leader only: its own expect_tx arrival + the bytes of both CTAs
+      mbar_init(bar_empty + 8 * s, 1);   // one multicast commit per use
+    }
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_acc_full + 8 * s, 1);
+      mbar_init(bar_acc_empty + 8 * s, 8);  // leader only: 4 epilogue warps x 2 CTAs
+    }
+    mbar_fence_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_rows) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_q) : "memory");
+  }
+  for (int i = threadIdx.x; i < NQ; i += blockDim.x) {
+    thr[i] = p.thr_init ? p.thr_init[i] : -INFINITY;
+    cnt[i] = 0;
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(2 * NQ)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();   // the peer's barriers are initialised before anything is signalled across the pair
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer (both CTAs)
+    if (lane == 0) {
+      const uint32_t lead_q = mapa_u32(bar_q, 0);
+      if (rank == 0) mbar_expect_tx(bar_q, 2u * q_bytes);
+      for (int kb = 0; kb < p.kb_count; ++kb)
+        tma_load_2d_pair(base + (uint32_t)kb * kQBlockBytes, &tm_q, kb * kBK, (int)rank * HQ, lead_q);
+      int it = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int li = 2 * (pair + t * npairs) + (int)rank;
+        // the odd tile of the last pair may not exist: load tile 0 again (served by L2), the epilogue ignores it
+        const int tile = li < p.num_tiles ? p.tile_first + li * p.tile_step : p.tile_first;
+        for (int kb = 0; kb < p.kb_count; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t use = (uint32_t)(it / p.stages);
+          if (it >= p.stages) mbar_wait(bar_empty + 8 * s, (use & 1u) ^ 1u);
+          if (rank == 0) mbar_expect_tx(bar_full + 8 * s, 2u * kATileBytes);
+          tma_load_2d_pair(a0 + (uint32_t)s * kATileBytes, &tm_rows, kb * kBK, tile * kTileRows,
+                           mapa_u32(bar_full + 8 * s, 0));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
+      // kind::f16: D = f32, A = B = f16 K-major, N >> 3 at [17,23), M >> 4 at [24,29); M = 256 across the pair
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(NQ >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      mbar_wait(bar_q, 0);
+      int it = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int as = t & 1;
+        if (t >= 2) mbar_wait(bar_acc_empty + 8 * as, (((uint32_t)t >> 1) & 1u) ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * NQ);
+        for (int kb = 0; kb < p.kb_count; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t use = (uint32_t)(it / p.stages);
+          mbar_wait(bar_full + 8 * s, use & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = make_smem_desc_sw128(a0 + (uint32_t)s * kATileBytes);
+          const uint64_t db = make_smem_desc_sw128(base + (uint32_t)kb * kQBlockBytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_f16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          umma_commit_pair(bar_empty + 8 * s);
+        }
+        umma_commit_pair(bar_acc_full + 8 * as);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue warps 2..5 (both CTAs): one row per thread
+    const int quad = warp & 3;
+    unsigned long long* my_cand = p.cand + (size_t)cta * p.capg;
+    const size_t q_stride = (size_t)grid * p.capg;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int as = t & 1;
+      const int li = 2 * (pair + t * npairs) + (int)rank;
+      const int tile = p.tile_first + li * p.tile_step;
+      const int64_t row = (int64_t)tile * kTileRows + quad * 32 + lane;
+      const bool live = li < p.num_tiles && row < p.n;
+      const float invn = live ? __ldg(p.inv_norm + row) : 0.f;
+      mbar_wait(bar_acc_full + 8 * as, ((uint32_t)t >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // 32 columns per round (two x16 loads in flight, one wait); not unrolled: 128 live accumulator registers spill
+#pragma unroll 1
+      for (int c0 = 0; c0 < NQ; c0 += 32) {
+        uint32_t v[16], w[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * NQ + c0);
+        TmemLd<16>::ld(taddr, v);
+        TmemLd<16>::ld(taddr + 16u, w);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float score = __uint_as_float(j < 16 ? v[j] : w[j - 16]) * invn;
+            if (score >= thr[c0 + j]) {
+              const int pos = atomicAdd(&cnt[c0 + j], 1);
+              if (pos < p.capg) my_cand[(size_t)(c0 + j) * q_stride + pos] = make_key32(score, (uint32_t)row);
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(bar_acc_empty + 8 * as, 0));
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  for (int i = threadIdx.x; i < NQ; i += blockDim.x) {
+    p.counts[(size_t)i * grid + cta] = min(cnt[i], p.capg);
+    if (cnt[i] > p.capg && p.fallback) p.fallback[i] = 1;
+  }
+  cluster_sync_all();   // no CTA leaves (or frees tensor memory) while its peer can still signal it
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * NQ) : "memory");
   }
 }
 
@@ -232,12 +449,14 @@ dense_scan_mma_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_
 struct SelectParams {
   const unsigned long long* cand;   // [nq][grid][capg]
   const int32_t* counts;            // [nq][grid]
-  int32_t grid, capg, kprime;
+  int32_t grid, capg;
   int32_t nq;                       // real queries in this block (padded operand rows get a +inf threshold)
-  int32_t mode;                     // 0 = write the K'-th best approximate score (threshold pass), 1 = exact stage + emit
-  float* thr_out;                   // [nq]  (mode 0)
+  int32_t mode;                     // 0 = write the safe threshold (sampling pass), 1 = window + exact stage + emit
+  float* thr_out;                   // [rows] (mode 0)
+  const float* eps;                 // [nq] error bound of the approximate scores (0 = all-zero query)
+  int32_t* fallback;                // [nq] (mode 1)
   const __half* rows;               // mode 1
-  const float* q;                   // [nq][d_pad]
+  const float* q;                   // [nq][d_pad] the caller's fp32 queries
   int32_t d_pad, ch;
   int64_t id_base;
   int32_t k;
@@ -246,45 +465,34 @@ struct SelectParams {
   int32_t* out_counts;
 };
 
-__device__ __forceinline__ void select_sort_desc(unsigned long long* a, int len, int tid, int nt) {
-  for (int k = 2; k <= len; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < len; i += nt) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const unsigned long long x = a[i], y = a[ixj];
-          const bool desc = (i & k) == 0;
-          if (desc ? (x < y) : (x > y)) {
-            a[i] = y;
-            a[ixj] = x;
-          }
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
-// One CTA per query: the K' best approximate keys among the survivors of all CTAs by an MSB-first RADIX SELECT
-// (8-bit digits, shared-memory histogram; the pass loop stops as soon as the bucket holding the K'-th key is small),
-// then a small sort of {keys above the bucket} U {bucket}.  Survivors are staged in shared memory when they fit
-// (the normal case: ~1.5 % of the corpus); otherwise every pass streams them from HBM/L2 -- slower, still exact.
-__global__ void __launch_bounds__(kSelectThreads, 1) dense_select_kernel(const SelectParams p) {
+// One CTA per query.  A lower bound of the k-th best approximate key among the survivors of all CTAs by an MSB-first
+// RADIX SELECT (8-bit digits, shared-memory histogram; the pass loop stops as soon as the bucket holding the k-th key
+// is small -- the undecided low bits are taken as zero, which only widens the window).
+//   mode 0 (sampling pass): threshold = that score - 2 eps.
+//   mode 1: gather every survivor inside the window below it, exact fp64 re-score of all of them, emit k.
+// Survivors are staged in shared memory when they fit (the normal case: ~0.3 % of the corpus); otherwise every pass
+// streams them from HBM/L2 -- slower, still exact.
+__global__ void __launch_bounds__(kSelectThreads, 2) dense_select_kernel(const SelectParams p) {
   extern __shared__ __align__(16) uint8_t ssm[];
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(ssm);  // [kSelStage] staged survivors
-  unsigned long long* top = keys + kSelStage;                             // [kSelTop]   gathered winners
-  unsigned long long* ek = top + kSelTop;                                 // [K]
-  uint32_t* ei = reinterpret_cast<uint32_t*>(ek + p.kprime);              // [K]
+  unsigned long long* top = keys + kSelStage;                             // [kSelTop]   window members
+  unsigned long long* ek = top + kSelTop;                                 // [kSelTop]   exact keys      (mode 1)
+  uint32_t* ei = reinterpret_cast<uint32_t*>(ek + kSelTop);               // [kSelTop]   rows            (mode 1)
   __shared__ double qq_s;
-  __shared__ int s_prefix[1024 + 1];
+  __shared__ int s_prefix[kSelectThreads + 1];
   __shared__ int s_hist[256];
   __shared__ int s_scal[4];
   __shared__ int s_ntop;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5, qi = blockIdx.x;
-  const int K = p.kprime, G = p.grid;
+  const int K = p.k, G = p.grid;
+  if (p.mode == 0 && qi >= p.nq) {   // padded operand row: nothing may survive
+    if (tid == 0) p.thr_out[qi] = INFINITY;
+    return;
+  }
+  if (p.mode == 1 && p.fallback[qi] != 0) return;   // a list overflowed: the brute-force kernel answers this query
   const int32_t* counts = p.counts + (size_t)qi * G;
   const unsigned long long* cand = p.cand + (size_t)qi * G * p.capg;
-  // exclusive prefix of the per-CTA survivor counts (G <= 1024): one element per thread, warp scans + a scan of the sums
+  // exclusive prefix of the per-CTA survivor counts (G <= blockDim): one element per thread
   {
     const int v = tid < G ? counts[tid] : 0;
     int x = v;
@@ -359,30 +567,30 @@ __global__ void __launch_bounds__(kSelectThreads, 1) dense_select_kernel(const S
       need = s_scal[1];
       const int bucket = s_scal[2];
       __syncthreads();
-      // mode 1: {above} (< K keys) + a small bucket: finish by sorting.  mode 0 only needs a LOWER BOUND of the K-th
-      // best key, so it narrows the bucket a little further and takes the bucket's lower edge -- no gather, no sort.
-      if (p.mode == 0 ? bucket <= 16 : (bucket <= 256 && bucket <= kSelTop - K)) break;
+      if (bucket <= 16) break;
     }
   }
+  // `prefix` (undecided low bits zero) <= the k-th best key; total <= k: every survivor is a member (prefix = 0)
+  const float eps = p.eps[qi];
+  const unsigned long long lo_key = total > K ? window_lo_key(prefix, eps) : 0ull;
   if (p.mode == 0) {
-    // undecided low bits of `prefix` are zero: a key <= the K-th best; its score field (possibly with cleared low bits)
-    // is a safe threshold.  Fewer than K survivors: no threshold.
-    if (tid == 0) p.thr_out[qi] = qi >= p.nq ? INFINITY : (total > K ? key32_score(prefix) : -INFINITY);
+    // fewer than k sampled rows: no threshold.  The score field of lo_key is (k-th best of the sample) - 2 eps.
+    if (tid == 0) p.thr_out[qi] = total > K ? key32_score(lo_key) : -INFINITY;
     return;
   }
-  // winners: every key whose decided digits are >= the selected bucket's (at most K - 1 + bucket <= kSelTop keys)
-  SB_FOR_EACH_KEY(if ((key & mask) >= prefix) {
+  SB_FOR_EACH_KEY(if (key >= lo_key) {
     const int at = atomicAdd(&s_ntop, 1);
     if (at < kSelTop) top[at] = key;
   })
 #undef SB_FOR_EACH_KEY
   __syncthreads();
-  const int ntop = min(s_ntop, kSelTop);
+  const int ntop = s_ntop;
+  if (ntop > kSelTop) {
+    if (tid == 0) p.fallback[qi] = 1;
+    return;
+  }
   int P = 32;
-  while (P < ntop || P < K) P <<= 1;
-  for (int i = ntop + tid; i < P; i += nt) top[i] = 0ull;
-  __syncthreads();
-  select_sort_desc(top, P, tid, nt);
+  while (P < ntop) P <<= 1;
   RescoreArgs ra;
   ra.rows = p.rows;
   ra.q = p.q + (size_t)qi * p.d_pad;
@@ -393,15 +601,7 @@ __global__ void __launch_bounds__(kSelectThreads, 1) dense_select_kernel(const S
   ra.out_ids = p.out_ids + (size_t)qi * p.k;
   ra.out_scores = p.out_scores + (size_t)qi * p.k;
   ra.out_count = p.out_counts + qi;
-  rescore_and_emit(top, K, ek, ei, &qq_s, ra);
-}
-
-// fp32 padded queries -> fp16 operand block [QBN][d_pad] (rows beyond nq are zero)
-__global__ void queries_to_f16_kernel(const float* __restrict__ q_pad, int nq, int qbn, int d_pad, __half* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)qbn * d_pad) return;
-  const int r = (int)(i / d_pad);
-  out[i] = r < nq ? __float2half_rn(q_pad[i]) : __float2half_rn(0.f);
+  rescore_and_emit(top, ntop, P, ek, ei, &qq_s, ra);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -450,6 +650,41 @@ int dispatch_mma(int qbn, const CUtensorMap& tm_rows, const CUtensorMap& tm_q, c
   return SB_ERR_UNSUPPORTED;
 }
 
+// the pair kernel: 2-CTA clusters, grid = 2 x (co-resident clusters)
+int launch_mma_pair(const CUtensorMap& tm_rows, const CUtensorMap& tm_q, const MmaScanParams& mp, int grid, size_t smem,
+                    cudaStream_t st) {
+  auto kern = dense_scan_mma2_kernel<128>;
+  SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kMmaThreads, smem, st>>>(tm_rows, tm_q, mp);
+  SB_CUDA(cudaGetLastError());
+  return SB_OK;
+}
+
+// co-resident 2-CTA clusters of the pair kernel at its largest shared-memory footprint (queried once per context)
+int pair_clusters(sb_ctx* ctx, size_t smem) {
+  if (ctx->max_clusters2 > 0) return ctx->max_clusters2;
+  auto kern = dense_scan_mma2_kernel<128>;
+  int n = 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(ctx->num_sms & ~1), 1, 1);
+    cfg.blockDim = dim3(kMmaThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) n = 0;
+  }
+  (void)cudaGetLastError();
+  if (n <= 0 || n > ctx->num_sms / 2) n = ctx->num_sms / 2;
+  ctx->max_clusters2 = n;
+  return n;
+}
+
 }  // namespace
 
 bool dense_mma_eligible(const sb_ctx* ctx, const DenseIndex& ix, int B) {
@@ -460,66 +695,94 @@ bool dense_mma_eligible(const sb_ctx* ctx, const DenseIndex& ix, int B) {
   return need <= ctx->smem_optin;
 }
 
-int dense_mma_topk_enqueue(sb_ctx* ctx, DenseIndex& ix, const float* q_pad, int B, int k, int kprime, int64_t* out_ids,
+int dense_mma_topk_enqueue(sb_ctx* ctx, DenseIndex& ix, const float* q_pad, int B, int k, int64_t* out_ids,
                            double* out_scores, int32_t* out_counts, cudaStream_t st) {
   const int kb_count = ix.d_pad / kBK;
   const int total_tiles = (int)(ix.n_pad / kTileRows);
-  // largest query block whose resident operand leaves >= 3 pipeline stages
+  // largest single-CTA query block whose resident operand leaves >= 3 pipeline stages
   int qbn_max = 64;
   while (qbn_max > 16 && (size_t)qbn_max * ix.d_pad * 2 + 3 * (size_t)kATileBytes + 4096 > ctx->smem_optin) qbn_max >>= 1;
-  const int grid = std::min(ctx->num_sms, total_tiles);
-  const int capg = ((total_tiles + grid - 1) / grid) * kTileRows;  // worst case: every row of the CTA's share survives
+  // the pair kernel holds 64 operand rows per CTA: usable whenever the 64-row block fits
+  const bool pair_ok = ctx->dense_pair != 0 && qbn_max == 64 && total_tiles >= 2;
+  const int gsz = pair_ok ? 128 : qbn_max;          // operand rows per group
+  const int grid1 = std::min(ctx->num_sms, total_tiles);
+  int grid2 = 0, stages2 = 0;
+  size_t smem2 = 0;
+  if (pair_ok) {
+    const size_t q_bytes = (size_t)64 * ix.d_pad * 2;
+    stages2 = std::max(3, std::min((int)((ctx->smem_optin - q_bytes - 4096) / kATileBytes), 8));
+    smem2 = q_bytes + (size_t)stages2 * kATileBytes + 2048 + 1024;
+    grid2 = 2 * std::min(pair_clusters(ctx, smem2), (total_tiles + 1) / 2);
+  }
+  const int grid = std::max(grid1, grid2);          // list slots per query: both kernels index [row][grid][capg]
+  const int grid_min = grid2 > 0 ? std::min(grid1, grid2) : grid1;
+  // sampling pass geometry: a few tiles per CTA spread evenly over the corpus
+  const int sample_tiles = std::min(ctx->dense_sample_per_cta * grid, total_tiles);
+  const int sample_step = total_tiles / sample_tiles;
+  const int sgrid1 = std::min(grid1, sample_tiles);
+  const int sgrid2 = pair_ok ? std::min(grid2, (sample_tiles + 1) & ~1) : 0;
+  const int sgrid = std::max(sgrid1, sgrid2);
+  const int sgrid_min = sgrid2 > 0 ? std::min(sgrid1, sgrid2) : sgrid1;
+  // per-(CTA, query) list capacity.  The sampling pass appends every sampled row of the CTA; the full pass about
+  // rows_per_cta * k / sampled_rows (threshold = k-th best of the sample): 16x that plus slack.  An overflowing list
+  // raises the query's fallback flag, so the capacity only trades memory against the odds of a brute-force answer.
+  const int64_t worst = (int64_t)((total_tiles + grid_min - 1) / grid_min + 1) * kTileRows;
+  const int64_t samp_rows = (int64_t)((sample_tiles + sgrid_min - 1) / sgrid_min + 1) * kTileRows;
+  const int64_t expect = worst * (int64_t)k / std::max<int64_t>(1, (int64_t)sample_tiles * kTileRows);
+  const int capg = (int)std::min<int64_t>(worst, std::max<int64_t>(16 * expect + 256, samp_rows));
   int rc;
-  // Query groups of qbn_max (the last one may use a smaller operand block).  Several groups are kept in flight so that
-  // the two select launches (one CTA per query) cover ALL their queries at once instead of qbn at a time: with small
-  // shards the selects, not the scans, would otherwise dominate.  In-flight groups are bounded by the survivor scratch.
-  const int n_groups = (B + qbn_max - 1) / qbn_max;
-  const size_t cand_per_group = (size_t)qbn_max * grid * capg * 8;
-  int gmax = (int)std::max<size_t>(1, (size_t)(2048ull << 20) / cand_per_group);
+  SB_REQUIRE(grid <= kSelectThreads, SB_ERR_UNSUPPORTED, "dense_mma: %d CTAs exceed the select kernel's prefix width", grid);
+  const int n_groups = (B + gsz - 1) / gsz;
+  const size_t cand_per_group = (size_t)gsz * grid * capg * 8;
+  int gmax = (int)std::max<size_t>(1, (size_t)(1024ull << 20) / cand_per_group);
   gmax = std::min(gmax, n_groups);
-  // scratch: fp16 query blocks | thresholds | counts | survivors
-  const size_t q16_group = (size_t)qbn_max * ix.d_pad * 2;
-  if ((rc = ctx->misc2_dev.reserve(q16_group * gmax + 256))) return rc;
-  if ((rc = ctx->misc3_dev.reserve(((size_t)qbn_max * 4 + (size_t)qbn_max * grid * 4) * gmax + 256))) return rc;
+  // scratch: fp16 operand rows | thresholds + counts | survivors
+  if ((rc = ctx->misc2_dev.reserve((size_t)n_groups * gsz * ix.d_pad * 2 + 256))) return rc;
+  if ((rc = ctx->misc3_dev.reserve(((size_t)gsz * 4 + (size_t)gsz * grid * 4) * gmax + 256))) return rc;
   if ((rc = ctx->cand_dev.reserve(cand_per_group * gmax))) return rc;
   __half* q16 = ctx->misc2_dev.as<__half>();
   float* thr = ctx->misc3_dev.as<float>();
-  int32_t* counts = reinterpret_cast<int32_t*>(thr + (size_t)qbn_max * gmax);
+  int32_t* counts = reinterpret_cast<int32_t*>(thr + (size_t)gsz * gmax);
   unsigned long long* cand = ctx->cand_dev.as<unsigned long long>();
   if (ix.tm_rows_ptr != ix.rows) {  // (re)build the corpus tensor map once per loaded index
     if ((rc = encode_map(reinterpret_cast<CUtensorMap*>(ix.tm_rows), ix.rows, ix.n_pad, ix.d_pad, kTileRows))) return rc;
     ix.tm_rows_ptr = ix.rows;
   }
   const CUtensorMap& tm_rows = *reinterpret_cast<const CUtensorMap*>(ix.tm_rows);
-  const size_t sel_smem = (size_t)(kSelStage + kSelTop) * 8 + (size_t)kprime * 12 + 64;
+  const size_t sel_smem = (size_t)kSelStage * 8 + (size_t)kSelTop * 20 + 64;
   SB_CUDA(cudaFuncSetAttribute(dense_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
-  // sampling pass geometry: ~64 tiles spread evenly over the corpus
-  const int sample_tiles = std::min(64, total_tiles);
-  const int sample_step = total_tiles / sample_tiles;
-  const int sgrid = std::min(grid, sample_tiles);
-  for (int c0 = 0; c0 < B; c0 += gmax * qbn_max) {
-    const int nq_chunk = std::min(B - c0, gmax * qbn_max);   // real queries of this chunk of groups
-    const int ng = (nq_chunk + qbn_max - 1) / qbn_max;
-    struct Group { int qbn, nq; CUtensorMap tm_q; size_t smem; int stages; };
+  // normalised fp16 operand rows of the whole batch (rows beyond B are zero), eps, cleared fallback flags
+  float* eps = nullptr;
+  int32_t* fb = nullptr;
+  if ((rc = dense_prep_queries(ctx, ix, q_pad, B, n_groups * gsz, /*mma=*/true, nullptr, q16, &eps, &fb, st))) return rc;
+
+  for (int c0 = 0; c0 < B; c0 += gmax * gsz) {
+    const int nq_chunk = std::min(B - c0, gmax * gsz);   // real queries of this chunk of groups
+    const int ng = (nq_chunk + gsz - 1) / gsz;
+    struct Group { int qbn, nq; bool pair; CUtensorMap tm_q; size_t smem; int stages; };
     std::vector<Group> gs((size_t)ng);
     int rows_total = 0;  // operand rows of the chunk (padding only at the very end)
     for (int g = 0; g < ng; ++g) {
       Group& G = gs[(size_t)g];
-      const int left = nq_chunk - g * qbn_max;
-      G.qbn = qbn_max;
-      while (G.qbn > 16 && G.qbn / 2 >= left) G.qbn >>= 1;
-      G.nq = std::min(G.qbn, left);
-      __half* q16g = q16 + (size_t)g * qbn_max * ix.d_pad;
-      if ((rc = encode_map(&G.tm_q, q16g, G.qbn, ix.d_pad, G.qbn))) return rc;
-      const int64_t nconv = (int64_t)G.qbn * ix.d_pad;
-      ctx->launches += 1;
-      queries_to_f16_kernel<<<(unsigned)((nconv + 255) / 256), 256, 0, st>>>(
-          q_pad + (size_t)(c0 + g * qbn_max) * ix.d_pad, G.nq, G.qbn, ix.d_pad, q16g);
-      SB_CUDA(cudaGetLastError());
-      const size_t q_bytes = (size_t)G.qbn * ix.d_pad * 2;
-      G.stages = std::max(3, std::min((int)((ctx->smem_optin - q_bytes - 4096) / kATileBytes), 8));
-      G.smem = q_bytes + (size_t)G.stages * kATileBytes + 2048 + 1024;
-      rows_total = g * qbn_max + G.qbn;
+      const int left = nq_chunk - g * gsz;
+      __half* q16g = q16 + (size_t)(c0 + g * gsz) * ix.d_pad;
+      G.pair = pair_ok && left > 64;
+      if (G.pair) {
+        G.qbn = 128;
+        G.nq = std::min(128, left);
+        if ((rc = encode_map(&G.tm_q, q16g, 128, ix.d_pad, 64))) return rc;   // box = one CTA's 64 operand rows
+        G.stages = stages2;
+        G.smem = smem2;
+      } else {
+        G.qbn = qbn_max;
+        while (G.qbn > 16 && G.qbn / 2 >= left) G.qbn >>= 1;
+        G.nq = std::min(G.qbn, left);
+        if ((rc = encode_map(&G.tm_q, q16g, G.qbn, ix.d_pad, G.qbn))) return rc;
+        const size_t q_bytes = (size_t)G.qbn * ix.d_pad * 2;
+        G.stages = std::max(3, std::min((int)((ctx->smem_optin - q_bytes - 4096) / kATileBytes), 8));
+        G.smem = q_bytes + (size_t)G.stages * kATileBytes + 2048 + 1024;
+      }
+      rows_total = g * gsz + G.qbn;
     }
     MmaScanParams mp;
     mp.inv_norm = ix.inv_norm;
@@ -530,9 +793,10 @@ int dense_mma_topk_enqueue(sb_ctx* ctx, DenseIndex& ix, const float* q_pad, int 
     sp.cand = cand;
     sp.counts = counts;
     sp.capg = capg;
-    sp.kprime = kprime;
     sp.nq = nq_chunk;
     sp.thr_out = thr;
+    sp.eps = eps + c0;
+    sp.fallback = fb + c0;
     sp.rows = ix.rows;
     sp.q = q_pad + (size_t)c0 * ix.d_pad;
     sp.d_pad = ix.d_pad;
@@ -542,18 +806,23 @@ int dense_mma_topk_enqueue(sb_ctx* ctx, DenseIndex& ix, const float* q_pad, int 
     sp.out_ids = out_ids + (size_t)c0 * k;
     sp.out_scores = out_scores + (size_t)c0 * k;
     sp.out_counts = out_counts + c0;
-    // (1) sampling passes -> safe thresholds for every query of the chunk (one select launch)
+    // (1) sampling passes -> safe thresholds for every query of the chunk (one select launch).  Both kernels write
+    // list slot `cta` of [row][launch grid][capg], so every group is launched with exactly sgrid CTAs (idle ones
+    // report empty lists).
     mp.thr_init = nullptr;
+    mp.fallback = nullptr;   // capg >= the sampled rows of a CTA: the sampling pass cannot overflow
     mp.num_tiles = sample_tiles;
     mp.tile_first = 0;
     mp.tile_step = sample_step;
     for (int g = 0; g < ng; ++g) {
       const Group& G = gs[(size_t)g];
-      mp.cand = cand + (size_t)g * qbn_max * sgrid * capg;
-      mp.counts = counts + (size_t)g * qbn_max * sgrid;
+      mp.cand = cand + (size_t)g * gsz * sgrid * capg;
+      mp.counts = counts + (size_t)g * gsz * sgrid;
       mp.stages = G.stages;
       ctx->launches += 1;
-      if ((rc = dispatch_mma(G.qbn, tm_rows, G.tm_q, mp, sgrid, G.smem, st))) return rc;
+      if (G.pair) rc = launch_mma_pair(tm_rows, G.tm_q, mp, sgrid, G.smem, st);
+      else rc = dispatch_mma(G.qbn, tm_rows, G.tm_q, mp, sgrid, G.smem, st);
+      if (rc) return rc;
     }
     sp.grid = sgrid;
     sp.mode = 0;
@@ -566,12 +835,15 @@ int dense_mma_topk_enqueue(sb_ctx* ctx, DenseIndex& ix, const float* q_pad, int 
     mp.tile_step = 1;
     for (int g = 0; g < ng; ++g) {
       const Group& G = gs[(size_t)g];
-      mp.thr_init = thr + (size_t)g * qbn_max;
-      mp.cand = cand + (size_t)g * qbn_max * grid * capg;
-      mp.counts = counts + (size_t)g * qbn_max * grid;
+      mp.thr_init = thr + (size_t)g * gsz;
+      mp.fallback = fb + c0 + (size_t)g * gsz;
+      mp.cand = cand + (size_t)g * gsz * grid * capg;
+      mp.counts = counts + (size_t)g * gsz * grid;
       mp.stages = G.stages;
       ProfScope ps(ctx, SB_PROF_DENSE_SCAN, st);
-      if ((rc = dispatch_mma(G.qbn, tm_rows, G.tm_q, mp, grid, G.smem, st))) return rc;
+      if (G.pair) rc = launch_mma_pair(tm_rows, G.tm_q, mp, grid, G.smem, st);
+      else rc = dispatch_mma(G.qbn, tm_rows, G.tm_q, mp, grid, G.smem, st);
+      if (rc) return rc;
     }
     sp.grid = grid;
     sp.mode = 1;
@@ -581,5 +853,5 @@ int dense_mma_topk_enqueue(sb_ctx* ctx, DenseIndex& ix, const float* q_pad, int 
     }
     SB_CUDA(cudaGetLastError());
   }
-  return SB_OK;
+  return dense_fallback_enqueue(ctx, ix, q_pad, B, k, fb, out_ids, out_scores, out_counts, st);
 }

@@ -23,6 +23,9 @@ from .base import BaseRetriever
 
 logger = logging.getLogger(__name__)
 
+_SAVE_FORMAT = "sentio_b200.bm25retriever.v1"
+_KERNEL_MAX_K = 1024  # top-k limit of one sb_bm25_topk call (shared-memory winner buffer, bm25.cu)
+
 
 class BM25Retriever(BaseRetriever):
     def __init__(self, documents: list[Document] | None = None, variant: str = "okapi", cache_dir: str | None = None,
@@ -76,7 +79,7 @@ class BM25Retriever(BaseRetriever):
             filepath = os.path.join(self.cache_dir, "bm25_index.pkl")
         try:
             with open(filepath, "wb") as f:
-                pickle.dump({"format": "sentio_b200.bm25retriever.v1", "bm25": self.bm25, "doc_ids": self.doc_ids,
+                pickle.dump({"format": _SAVE_FORMAT, "bm25": self.bm25, "doc_ids": self.doc_ids,
                              "doc_map": self.doc_map, "variant": self.variant}, f, protocol=pickle.HIGHEST_PROTOCOL)
         except Exception as exc:  # same contract as the reference: log, do not raise
             logger.error("Failed to save BM25 index: %s", exc)
@@ -90,11 +93,19 @@ class BM25Retriever(BaseRetriever):
                 return False
             with open(filepath, "rb") as f:
                 data = pickle.load(f)
-            self.bm25 = data["bm25"]
-            self.doc_ids = data["doc_ids"]
+            # validate into locals first: a foreign pickle (e.g. the reference's rank_bm25 cache) or a failed upload
+            # must leave the retriever exactly as it was
+            if not isinstance(data, dict) or data.get("format") != _SAVE_FORMAT:
+                raise ValueError(f"{filepath} is not a {_SAVE_FORMAT} file")
+            bm25, doc_ids = data["bm25"], list(data["doc_ids"])
+            if not isinstance(bm25, Bm25IndexData) or len(doc_ids) != int(bm25.n_docs):
+                raise ValueError("BM25 index payload is inconsistent")
+            if self._engine is None:
+                self._engine = B200Engine(self._device)
+            self._engine.load_bm25(bm25, id_base=0)
+            self.bm25, self.doc_ids = bm25, doc_ids
             self.doc_map = data.get("doc_map", {})
             self.variant = data.get("variant", "okapi")
-            self._upload()
             return True
         except Exception as exc:
             logger.error("Failed to load BM25 index: %s", exc)
@@ -106,8 +117,7 @@ class BM25Retriever(BaseRetriever):
             logger.warning("BM25 index not initialized")
             return []
         try:
-            terms = self.bm25.term_ids(query.lower().split())
-            ids, scores, counts = self._engine.bm25_topk([terms], int(top_k))
+            ids, scores, counts = self.retrieve_batch_arrays([query], int(top_k))
             results = []
             for j in range(int(counts[0])):
                 row = int(ids[0, j])
@@ -154,7 +164,24 @@ class BM25Retriever(BaseRetriever):
     def retrieve_batch_arrays(self, queries: list[str], top_k: int):
         """Batched extension: (rows, scores, counts) arrays for many queries in one GPU batch."""
         terms = [self.bm25.term_ids(q.lower().split()) for q in queries]
-        return self._engine.bm25_topk(terms, int(top_k))
+        k = int(top_k)
+        if k <= 0:
+            B = len(queries)
+            return np.zeros((B, 0), np.int64), np.zeros((B, 0)), np.zeros(B, np.int32)
+        k = min(k, int(self.bm25.n_docs))   # the reference's argsort[:top_k] never returns more than the corpus
+        if k <= _KERNEL_MAX_K:
+            return self._engine.bm25_topk(terms, k)
+        # top_k beyond one kernel call (the reference supports any top_k): the device scores every document
+        # (sb_bm25_scores, the same bit-exact fp64 kernel), the cut is the reference's own expression (sparse.py:180-184)
+        ids = np.full((len(terms), k), -1, np.int64)
+        sc = np.zeros((len(terms), k))
+        cnt = np.zeros(len(terms), np.int32)
+        for b, t in enumerate(terms):
+            scores = self._engine.bm25_scores(t)
+            order = np.argsort(-scores, kind="stable")[:k]
+            order = order[scores[order] > 0]
+            ids[b, :len(order)], sc[b, :len(order)], cnt[b] = order, scores[order], len(order)
+        return ids, sc, cnt
 
 
 class PyseriniBM25Retriever(BaseRetriever):

@@ -248,6 +248,57 @@ def hybrid_e2e_cases(ns):
     return out
 
 
+def hybrid_cache_cases(ns):
+    """The reference stack with a POPULATED ``web_cache`` second collection (hybrid.py:146-182,208): cache hits are
+    prepended to the dense hits, an id present in both lists accumulates twice (rrf) / keeps the last raw score
+    (comb_sum dict semantics)."""
+    import src.core.retrievers.sparse as ref_sparse
+
+    ref_sparse.np = _StableArgsortNumpy()
+    rng = np.random.default_rng(33)
+    dim = 48
+    emb = HashEmbedder(dim)
+    words = [f"w{j}" for j in range(200)]
+    p = np.arange(1, 201) ** -1.07
+    p /= p.sum()
+    texts = [" ".join(rng.choice(words, size=int(rng.integers(8, 30)), p=p)) for _ in range(300)]
+    ids = [f"doc-{i}" for i in range(len(texts))]
+    # the cache: 40 corpus documents under their corpus ids (duplicates across the two collections), 25 of them with an
+    # edited text (different vector, same id), plus 30 web-only pages
+    cache_texts, cache_ids = [], []
+    for j, i in enumerate(rng.choice(len(texts), size=40, replace=False)):
+        cache_ids.append(ids[int(i)])
+        cache_texts.append(texts[int(i)] + (" cached copy" if j < 25 else ""))
+    for j in range(30):
+        cache_ids.append(f"web-{j}")
+        cache_texts.append(" ".join(rng.choice(words, size=int(rng.integers(8, 30)), p=p)))
+    client = ns.NumpyQdrantClient()
+    client.add_collection("Sentio_docs", dense_oracle.stored_rows(np.asarray([emb.embed_sync(t) for t in texts], np.float32)),
+                          ids, [{"content": t, "metadata": {"source": f"s{i % 5}"}} for i, t in enumerate(texts)])
+    client.add_collection("web_cache", dense_oracle.stored_rows(np.asarray([emb.embed_sync(t) for t in cache_texts], np.float32)),
+                          cache_ids, [{"content": t, "metadata": {"source": "web"}} for t in cache_texts])
+    queries = [" ".join(rng.choice(words, size=5, p=p)) for _ in range(8)] + [cache_texts[3], texts[17], "w0"]
+    out = dict(dim=dim, texts=texts, ids=ids, cache_texts=cache_texts, cache_ids=cache_ids, queries=queries, runs=[])
+    os.environ["CACHE_COLLECTION_NAME"] = "web_cache"
+    for method, with_plugins in (("rrf", False), ("weighted_rrf", False), ("comb_sum", False), ("rrf", True)):
+        corpus_docs = [ns.Document(id=i, text=t, metadata={"source": "corpus"}) for i, t in zip(ids, texts)]
+        dense = ns.DenseRetriever(client=client, embedder=emb, collection_name="Sentio_docs")
+        sparse = ns.BM25Retriever(documents=corpus_docs)
+        plugins = None
+        if with_plugins:
+            plugins = [ns.SemanticSimilarityScorer(embedder=emb, weight=0.8), ns.KeywordMatchScorer(weight=0.2),
+                       ns.MMRScorer(embedder=emb, lambda_=0.5, weight=0.5)]
+        hr = ns.HybridRetriever(dense_retriever=dense, sparse_retriever=sparse, rrf_k=60, scorer_plugins=plugins,
+                                fusion_method=method, dense_weight=0.6, sparse_weight=0.4)
+        assert hr._has_cache_collection
+        res = []
+        for q in queries:
+            docs = hr.retrieve(q, top_k=12)
+            res.append([[d.id, d.metadata["score"], d.text] for d in docs])
+        out["runs"].append(dict(method=method, plugins=with_plugins, results=res))
+    return out
+
+
 def rerank_flow_cases(ns):
     """JinaReranker ordering / fallback behaviour with the HTTP call replaced by canned relevance scores."""
     from src.core.rerankers.jina_reranker import JinaReranker
@@ -325,7 +376,8 @@ def selector_cases(ns):
 def main():
     ns = refload.load()
     fixtures = dict(fusion=fusion_cases(ns), bm25=bm25_cases(ns), scorers=scorer_cases(ns),
-                    hybrid_e2e=hybrid_e2e_cases(ns), rerank_flow=rerank_flow_cases(ns), selector=selector_cases(ns))
+                    hybrid_e2e=hybrid_e2e_cases(ns), hybrid_cache=hybrid_cache_cases(ns),
+                    rerank_flow=rerank_flow_cases(ns), selector=selector_cases(ns))
     for name, data in fixtures.items():
         path = os.path.join(HERE, f"{name}.json")
         with open(path, "w") as f:

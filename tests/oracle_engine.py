@@ -118,6 +118,25 @@ class OracleEngine:
         return sem, mmr
 
 
+    # K5 (NumPy restatement of the forward pass, pinned to HuggingFace BERT in tests/test_oracle_golden.py)
+    def ce_load(self, blob, cfg):
+        from sentio_b200.cross_encoder import CrossEncoderWeights
+
+        w = CrossEncoderWeights(dict(cfg), {})
+        at = 0
+        for name, shape in CrossEncoderWeights.tensor_order(cfg):
+            n = int(np.prod(shape))
+            w.tensors[name] = np.asarray(blob[at:at + n], dtype=np.float32).reshape(shape)
+            at += n
+        self.ce_weights = w
+
+    def ce_score(self, ids, tt, lens):
+        from oracle import cross_encoder as ce_oracle
+
+        logits, sig = ce_oracle.numpy_forward(self.ce_weights, ids, tt, lens, dtype=np.float64)
+        return logits.astype(np.float32), sig.astype(np.float32)
+
+
 class OracleEngineTorch(OracleEngine):
     """Adds the `*_dev` methods on CPU torch tensors so HybridPipeline's sharded control flow (record packing, the single
     all-gather, shard merge, fusion) can run under gloo with world_size 2 on a box without GPUs."""

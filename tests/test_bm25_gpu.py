@@ -132,3 +132,90 @@ def test_full_size_1m_docs_properties(engine):
         assert np.all(s > 0) and np.all(np.diff(s) <= 0)
         tie = np.diff(s) == 0
         assert np.all(np.diff(ids[b, :c])[tie] > 0)  # ties ordered by ascending doc index
+
+
+def test_pyserini_parameters_k1_09_b_04_bit_exact(engine, monkeypatch):
+    """SURVEY 8(f)4 / reference sparse.py:219, factory.py:150-157: Pyserini's defaults (k1 = 0.9, b = 0.4) on the GPU
+    Okapi kernel, bit-exact against BOTH the faithful rank_bm25 port and the CSR port with the same parameters."""
+    monkeypatch.delenv("BM25_VARIANT", raising=False)
+    from sentio_b200.retrievers.sparse import PyseriniBM25Retriever
+
+    flat, off = synth.text_corpus_tokens(20000, vocab=3000)
+    idx = build_bm25_from_token_ids(flat, off, k1=0.9, b=0.4)
+    fast = FastBM25(idx.indptr, idx.post_doc, idx.post_tf, idx.doc_len, idx.idf, idx.avgdl, "okapi", k1=0.9, b=0.4)
+    engine.load_bm25(idx)
+    term_lists = [idx.term_ids(q) for q in synth.query_tokens(20, vocab=3000)]
+    ids, sc, cnt = engine.bm25_topk(term_lists, 30)
+    for b, terms in enumerate(term_lists):
+        want = fast.get_scores(list(terms))
+        assert np.array_equal(engine.bm25_scores(terms), want)
+        order = np.argsort(-want, kind="stable")[:30]
+        order = order[want[order] > 0]
+        assert np.array_equal(ids[b, :cnt[b]], order) and np.array_equal(sc[b, :cnt[b]], want[order])
+    # the retriever class with the corpus given explicitly, against the faithful (dict-based) port
+    rng = np.random.default_rng(8)
+    texts = [" ".join(f"t{rng.integers(0, 60)}" for _ in range(rng.integers(3, 30))) for _ in range(300)]
+    ref = BM25Okapi([t.lower().split() for t in texts], k1=0.9, b=0.4)
+    r = PyseriniBM25Retriever(documents=[Document(id=f"d{i}", text=t) for i, t in enumerate(texts)])
+    for q in ["t1 t2 t3", "t59 t59 t0", "t7"]:
+        want = ref.get_scores(q.split())
+        order = np.argsort(-want, kind="stable")[:12]
+        order = order[want[order] > 0]
+        got = r.retrieve(q, top_k=12)
+        assert [d.id for d in got] == [f"d{i}" for i in order]
+        assert [d.metadata["bm25_score"] for d in got] == [float(want[i]) for i in order]
+    with pytest.raises(RuntimeError):   # constructor contract of the reference class: no index directory -> RuntimeError
+        PyseriniBM25Retriever(index_dir="/nonexistent/lucene-index")
+
+
+def test_save_load_round_trip_into_a_fresh_retriever(tmp_path, monkeypatch):
+    """Reference sparse.py:102-157: save() -> a FRESH object .load() -> identical retrieve output; a foreign pickle or a
+    missing file returns False and leaves the retriever untouched."""
+    import pickle
+
+    monkeypatch.delenv("BM25_VARIANT", raising=False)
+    rng = np.random.default_rng(3)
+    texts = [" ".join(f"w{rng.integers(0, 80)}" for _ in range(rng.integers(4, 40))) for _ in range(500)]
+    docs = [Document(id=f"doc-{i}", text=t, metadata={"source": f"s{i % 3}"}) for i, t in enumerate(texts)]
+    queries = ["w1 w2 w3", "w79 w0 w0", "unknown-token w5", "w10"]
+    for variant in ("okapi", "plus"):
+        a = BM25Retriever(documents=docs, variant=variant, cache_dir=str(tmp_path / variant))
+        want = [[(d.id, d.metadata["bm25_score"], d.text) for d in a.retrieve(q, top_k=25)] for q in queries]
+        a.save()                                                    # default path: <cache_dir>/bm25_index.pkl
+        b = BM25Retriever(cache_dir=str(tmp_path / variant))
+        assert b.retrieve("w1", top_k=5) == []                      # nothing indexed yet
+        assert b.load() is True and b.variant == variant
+        got = [[(d.id, d.metadata["bm25_score"], d.text) for d in b.retrieve(q, top_k=25)] for q in queries]
+        assert got == want
+        assert all(d.metadata["source"] in ("s0", "s1", "s2") for d in b.retrieve(queries[0], top_k=25))  # doc_map restored
+        # explicit file path + failure modes
+        path = str(tmp_path / f"{variant}.pkl")
+        a.save(path)
+        c = BM25Retriever()
+        assert c.load(str(tmp_path / "missing.pkl")) is False
+        foreign = str(tmp_path / "foreign.pkl")
+        with open(foreign, "wb") as f:
+            pickle.dump({"bm25": object(), "doc_ids": ["x"], "doc_map": {}, "variant": "okapi"}, f)  # reference-style cache
+        assert c.load(path) is True
+        before = [(d.id, d.metadata["bm25_score"]) for d in c.retrieve(queries[1], top_k=9)]
+        assert c.load(foreign) is False
+        assert [(d.id, d.metadata["bm25_score"]) for d in c.retrieve(queries[1], top_k=9)] == before == \
+               [(i, s) for i, s, _ in want[1][:9]]
+
+
+def test_top_k_beyond_one_kernel_call(engine, monkeypatch):
+    """the reference's argsort[:top_k] supports any top_k; beyond the kernel's 1024 the device still scores
+    (sb_bm25_scores) and the retriever applies the reference's cut -- never an empty list."""
+    monkeypatch.delenv("BM25_VARIANT", raising=False)
+    rng = np.random.default_rng(5)
+    texts = [" ".join(f"w{rng.integers(0, 30)}" for _ in range(rng.integers(5, 25))) for _ in range(3000)]
+    r = BM25Retriever(documents=[Document(id=f"d{i}", text=t) for i, t in enumerate(texts)])
+    ref = BM25Okapi([t.split() for t in texts])
+    want = ref.get_scores(["w3", "w4"])
+    order = np.argsort(-want, kind="stable")[:2000]
+    order = order[want[order] > 0]
+    got = r.retrieve("w3 w4", top_k=2000)
+    assert len(got) == len(order) > 1024
+    assert [d.id for d in got] == [f"d{i}" for i in order]
+    assert [d.metadata["bm25_score"] for d in got] == [float(want[i]) for i in order]
+    assert len(r.retrieve("w3 w4", top_k=10**6)) == int((want > 0).sum())

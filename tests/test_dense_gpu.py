@@ -52,6 +52,80 @@ def test_dense_batched_tcgen05_path_matches_oracle(engine, n, d, k, B):
     assert np.array_equal(ids, ids1) and np.array_equal(sc, sc1) and np.array_equal(cnt, cnt1)
 
 
+def _near_tie_corpus(rng, n, d, cluster, ulps=1):
+    """Random unit corpus whose rows [200, 200+cluster) are 1-ulp (fp16) perturbations of one base row: their cosines
+    with any query differ by ~1e-6 .. 1e-5, far below the fp16-query rounding error of the tcgen05 scan."""
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    x16 = x.astype(np.float16)
+    base = x16[7].copy()
+    for j in range(cluster):
+        row = base.copy()
+        for c in rng.choice(d, size=1 + (j % 3), replace=False):
+            row[c] = np.nextafter(row[c], np.float16(np.inf if (j + c) % 2 else -np.inf)) if ulps else row[c]
+        x16[200 + j] = row
+    return x16, base.astype(np.float32)
+
+
+@pytest.mark.parametrize("n,d,k,B,cluster", [(20000, 256, 100, 16, 200), (40960, 1024, 100, 24, 200),
+                                             (30000, 512, 10, 70, 64), (9000, 128, 50, 3, 120)])
+def test_dense_near_tie_cluster_straddling_rank_k(engine, n, d, k, B, cluster):
+    """a cluster of rows whose cosines differ by less than the approximate scores' error straddles rank k.
+    The error-bounded hand-off window must re-score all of them: ids == oracle, for both scans."""
+    rng = np.random.default_rng(n + cluster)
+    x16, base = _near_tie_corpus(rng, n, d, cluster)
+    q = rng.standard_normal((B, d)).astype(np.float32)
+    q[0] = base                                      # the cluster is the top of the list, rank k falls inside it
+    q[1] = base + 0.05 * rng.standard_normal(d).astype(np.float32)
+    q[2] = 3.0 * base + 0.3 * rng.standard_normal(d).astype(np.float32)
+    for mode in (0, 1):
+        engine.dense_set_mode(mode)
+        try:
+            _check(engine, x16, q, k)
+        finally:
+            engine.dense_set_mode(0)
+
+
+@pytest.mark.parametrize("B", [2, 20])
+def test_dense_window_larger_than_the_winner_buffer_uses_the_exact_fallback(engine, B):
+    """3000 near-identical rows on top: the window (> 2048 rows) cannot be re-scored in shared memory; the brute-force
+    fp64 kernel must answer -- same ids as the oracle.  5000 EXACT duplicates exercise the tie order (lowest row first)."""
+    rng = np.random.default_rng(77)
+    x16, base = _near_tie_corpus(rng, 24000, 256, 3000)
+    x16[8000:13000] = x16[9]                          # 5000 exact duplicates
+    q = rng.standard_normal((B, 256)).astype(np.float32)
+    q[0] = base
+    q[1] = x16[9].astype(np.float32)
+    ids, sc, cnt = _check(engine, x16, q, 10)
+    assert list(ids[1]) == [9] + list(range(8000, 8009))
+
+
+def test_dense_query_scale_does_not_change_the_result(engine):
+    """cosine is scale invariant -- queries scaled by 1e6 / 1e-6 / 1e-30 / 1e30 must give the same ids on
+    the CUDA-core scan (B = 1) and on the tcgen05 scan (B = 64), whose fp16 operand would otherwise overflow / vanish."""
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((20000, 256)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    engine.load_dense(x.astype(np.float16))
+    q = rng.standard_normal((64, 256)).astype(np.float32)
+    want, _, _ = engine.dense_topk(q, 50)
+    for scale in (1e6, 1e-6, 1e30, 1e-30):
+        qs = (q.astype(np.float64) * scale).astype(np.float32)
+        got, sc, _ = engine.dense_topk(qs, 50)
+        assert np.array_equal(got, want), f"batched, scale {scale}"
+        one, sc1, _ = engine.dense_topk(qs[:1], 50)
+        assert np.array_equal(one[0], want[0]), f"single, scale {scale}"
+        assert np.all(np.isfinite(sc)) and np.all(np.abs(sc) <= 1.0 + 1e-9)
+
+
+def test_dense_top_k_up_to_1024(engine):
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((30000, 128)).astype(np.float16)
+    q = rng.standard_normal((18, 128)).astype(np.float32)
+    _check(engine, x, q[:2], 1024)
+    _check(engine, x, q, 1000)
+
+
 def test_dense_f32_input_is_normalised_then_rounded(engine):
     rng = np.random.default_rng(5)
     x = (rng.standard_normal((3000, 200)) * rng.uniform(0.1, 50, size=(3000, 1))).astype(np.float32)
@@ -127,12 +201,16 @@ def test_dense_full_size_1m_x_1024(engine):
     for b in range(2):
         wi, ws = dense_oracle.dense_topk(x16, q[b], k)
         assert_topk_matches(ids[b], sc[b], cnt[b], wi, ws, what=f"1M b={b}")
-    # (e) a 64-query batch takes the tcgen05 batched scan: identical to the CUDA-core scan, bit for bit
-    q64 = np.concatenate([synth.query_vectors(61, d, seed=99), x16[probe].astype(np.float32)])
+    # (e) the bench configuration: a 256-query batch (two 128-query groups on the cta_group::2 pair kernel), compared
+    #     with the oracle on 8 sampled queries and bit for bit with the CUDA-core scan on the first 64
+    q256 = np.concatenate([synth.query_vectors(253, d, seed=99), x16[probe].astype(np.float32)])
     engine.dense_set_mode(0)
-    a = engine.dense_topk(q64, k)
+    a = engine.dense_topk(q256, k)
+    picks = [0, 63, 64, 127, 128, 200, 252, 255]
+    for b, (wi, ws) in zip(picks, dense_oracle.dense_topk_multi(x16, q256[picks], k)):
+        assert_topk_matches(a[0][b], a[1][b], a[2][b], wi, ws, what=f"1M batch-256 b={b}")
     engine.dense_set_mode(1)
-    b_ = engine.dense_topk(q64, k)
+    b_ = engine.dense_topk(q256[:64], k)
     engine.dense_set_mode(0)
-    assert np.array_equal(a[0], b_[0]) and np.array_equal(a[1], b_[1]) and np.array_equal(a[2], b_[2])
-    assert list(a[0][61:, 0]) == list(probe)
+    assert np.array_equal(a[0][:64], b_[0]) and np.array_equal(a[1][:64], b_[1]) and np.array_equal(a[2][:64], b_[2])
+    assert list(a[0][253:, 0]) == list(probe)

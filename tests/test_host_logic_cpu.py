@@ -162,3 +162,62 @@ def test_every_module_imports_without_a_gpu():
         if name.endswith(".build") or "libsentio_b200" in name:  # the C-ABI library is not a Python extension module
             continue
         importlib.import_module(name)
+
+
+def test_bm25_persistence_large_top_k_and_scroll_corpus_host_logic(tmp_path, monkeypatch):
+    """Host logic of sparse.py:102-157 (save / load into a fresh object), of top_k beyond one kernel call and of the
+    factory's Qdrant-payload scroll (factory.py:83-133), on the oracle-backed engine double."""
+    import pickle
+
+    import numpy as np
+
+    from oracle_engine import OracleEngine
+    from sentio_b200.retrievers import factory as factory_mod
+    from sentio_b200.retrievers import sparse as sparse_mod
+
+    monkeypatch.delenv("BM25_VARIANT", raising=False)
+    monkeypatch.setattr(sparse_mod, "B200Engine", lambda device=0: OracleEngine())
+    rng = np.random.default_rng(3)
+    texts = [" ".join(f"w{rng.integers(0, 40)}" for _ in range(rng.integers(4, 30))) for _ in range(1500)]
+    docs = [Document(id=f"doc-{i}", text=t, metadata={"source": f"s{i % 3}"}) for i, t in enumerate(texts)]
+    a = sparse_mod.BM25Retriever(documents=docs, cache_dir=str(tmp_path))
+    want = [(d.id, d.metadata["bm25_score"]) for d in a.retrieve("w1 w2 w2", top_k=20)]
+    a.save()
+    b = sparse_mod.BM25Retriever(cache_dir=str(tmp_path))
+    assert b.load() is True
+    assert [(d.id, d.metadata["bm25_score"]) for d in b.retrieve("w1 w2 w2", top_k=20)] == want
+    foreign = str(tmp_path / "foreign.pkl")
+    with open(foreign, "wb") as f:
+        pickle.dump({"bm25": object(), "doc_ids": ["x"]}, f)
+    assert b.load(foreign) is False and b.load(str(tmp_path / "none.pkl")) is False
+    assert [(d.id, d.metadata["bm25_score"]) for d in b.retrieve("w1 w2 w2", top_k=20)] == want
+    big = a.retrieve("w1 w2 w3 w4 w5 w6 w7 w8", top_k=1400)   # > 1024: device score dump + the reference's own cut
+    assert 1024 < len(big) <= 1400 and [d.metadata["bm25_score"] for d in big] == sorted(
+        (d.metadata["bm25_score"] for d in big), reverse=True)
+    assert [d.id for d in big[:20]] == [d.id for d in a.retrieve("w1 w2 w3 w4 w5 w6 w7 w8", top_k=20)]
+    assert a.retrieve("w1", top_k=0) == []
+
+    # ---- _scroll_corpus: Qdrant payload schema {content, metadata} + string point ids, paged by 100
+    class Point:
+        def __init__(self, i, payload):
+            self.id, self.payload = i, payload
+
+    class Client:
+        def __init__(self):
+            self.calls = 0
+            self.points = [Point(f"p{i}", {"content": f"text {i}", "metadata": {"page": i}}) for i in range(230)]
+            self.points[7] = Point("p7", {"text": "from text key", "content": "ignored"})
+            self.points[8] = Point("p8", None)                       # no payload: skipped (factory.py:110)
+            self.points[9] = Point(9, {"page_content": "pc"})        # integer id -> str
+
+        def scroll(self, collection_name, with_payload, with_vectors, limit, offset):
+            self.calls += 1
+            start = int(offset or 0)
+            stop = min(len(self.points), start + limit)
+            return self.points[start:stop], (stop if stop < len(self.points) else None)
+
+    client = Client()
+    got = factory_mod._scroll_corpus(client, "Sentio_docs")
+    assert client.calls == 3 and len(got) == 229
+    assert got[0].id == "p0" and got[0].text == "text 0" and got[0].metadata == {"page": 0}
+    assert got[7].text == "from text key" and got[8].id == "9" and got[8].text == "pc" and got[8].metadata == {}

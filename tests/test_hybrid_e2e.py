@@ -47,21 +47,63 @@ def _run(gold, make_store, make_sparse, fusion_engine, scorer_engine):
 class _OracleStore:
     """QdrantClient-shaped store on the oracle engine double (CPU host-logic test only)."""
 
-    def __init__(self, vecs, ids, payloads):
-        from oracle_engine import OracleEngine
+    def __init__(self, vecs=None, ids=None, payloads=None):
         from sentio_b200.vector_store import ScoredPoint
 
-        self.eng = OracleEngine()
-        self.eng.load_dense(vecs)
-        self.ids, self.payloads, self.SP = ids, payloads, ScoredPoint
+        self.cols, self.SP = {}, ScoredPoint
+        if vecs is not None:
+            self.create_collection("Sentio_docs", vecs, ids=ids, payloads=payloads)
+
+    def create_collection(self, name, vecs, ids=None, payloads=None):
+        from oracle_engine import OracleEngine
+
+        eng = OracleEngine()
+        eng.load_dense(vecs)
+        self.cols[name] = (eng, ids, payloads)
 
     def collection_exists(self, collection_name):
-        return collection_name == "Sentio_docs"
+        return collection_name in self.cols
 
     def search(self, collection_name, query_vector, limit=10, with_payload=True, with_vectors=False):
-        i, s, c = self.eng.dense_topk(np.asarray(query_vector, np.float32)[None], limit)
-        return [self.SP(id=self.ids[int(i[0, j])], score=float(s[0, j]), payload=self.payloads[int(i[0, j])])
+        eng, ids, payloads = self.cols[collection_name]
+        i, s, c = eng.dense_topk(np.asarray(query_vector, np.float32)[None], limit)
+        return [self.SP(id=ids[int(i[0, j])], score=float(s[0, j]), payload=payloads[int(i[0, j])])
                 for j in range(int(c[0]))]
+
+
+def _run_cache(gold, make_store, make_sparse, fusion_engine, scorer_engine):
+    """golden hybrid_cache.json: the reference stack with a populated ``web_cache`` collection (hybrid.py:146-182,208)."""
+    emb = HashEmbedder(gold["dim"])
+    store = make_store()
+    store.create_collection("Sentio_docs", np.asarray(emb.embed_many_sync(gold["texts"]), np.float32), ids=gold["ids"],
+                            payloads=[{"content": t, "metadata": {"source": f"s{i % 5}"}} for i, t in enumerate(gold["texts"])])
+    store.create_collection("web_cache", np.asarray(emb.embed_many_sync(gold["cache_texts"]), np.float32),
+                            ids=gold["cache_ids"],
+                            payloads=[{"content": t, "metadata": {"source": "web"}} for t in gold["cache_texts"]])
+    seen_web = seen_both = 0
+    for run in gold["runs"]:
+        corpus = [Document(id=i, text=t, metadata={"source": "corpus"}) for i, t in zip(gold["ids"], gold["texts"])]
+        dense = DenseRetriever(client=store, embedder=emb, collection_name="Sentio_docs")
+        plugins = None
+        if run["plugins"]:
+            plugins = [SemanticSimilarityScorer(embedder=emb, weight=0.8, engine=scorer_engine),
+                       KeywordMatchScorer(weight=0.2),
+                       MMRScorer(embedder=emb, lambda_=0.5, weight=0.5, engine=scorer_engine)]
+        hr = HybridRetriever(dense_retriever=dense, sparse_retriever=make_sparse(corpus), rrf_k=60, scorer_plugins=plugins,
+                             fusion_method=run["method"], dense_weight=0.6, sparse_weight=0.4, engine=fusion_engine)
+        assert hr._has_cache_collection
+        for q, want in zip(gold["queries"], run["results"]):
+            got = hr.retrieve(q, top_k=12)
+            assert [d.id for d in got] == [w[0] for w in want], (run["method"], run["plugins"], q)
+            assert [d.text for d in got] == [w[2] for w in want]       # the cached (edited) text wins, like the reference
+            gs, ws = np.asarray([d.metadata["score"] for d in got]), np.asarray([w[1] for w in want])
+            if run["plugins"] or run["method"] == "comb_sum":
+                assert np.allclose(gs, ws, rtol=1e-9, atol=1e-12)
+            else:
+                assert np.array_equal(gs, ws), (run["method"], q)
+            seen_web += sum(d.id.startswith("web-") for d in got)
+            seen_both += sum(d.id in set(gold["cache_ids"]) and d.id.startswith("doc-") for d in got)
+    assert seen_web > 0 and seen_both > 0   # the fixture really exercises cache-only and doubly-listed ids
 
 
 def test_host_logic_with_oracle_engine(monkeypatch):
@@ -73,6 +115,28 @@ def test_host_logic_with_oracle_engine(monkeypatch):
     monkeypatch.setattr(sparse_mod, "B200Engine", lambda device=0: OracleEngine())
     eng = OracleEngine()
     _run(load_golden("hybrid_e2e"), _OracleStore, lambda corpus: sparse_mod.BM25Retriever(documents=corpus), eng, eng)
+
+
+def test_web_cache_collection_host_logic_with_oracle_engine(monkeypatch):
+    from oracle_engine import OracleEngine
+    from sentio_b200.retrievers import sparse as sparse_mod
+
+    monkeypatch.delenv("BM25_VARIANT", raising=False)
+    monkeypatch.setenv("CACHE_COLLECTION_NAME", "web_cache")
+    monkeypatch.setattr(sparse_mod, "B200Engine", lambda device=0: OracleEngine())
+    eng = OracleEngine()
+    _run_cache(load_golden("hybrid_cache"), _OracleStore, lambda corpus: sparse_mod.BM25Retriever(documents=corpus), eng, eng)
+
+
+@pytest.mark.gpu
+def test_gpu_stack_with_web_cache_collection_matches_reference(engine, monkeypatch):
+    from sentio_b200.retrievers.sparse import BM25Retriever
+    from sentio_b200.vector_store import B200VectorStore
+
+    monkeypatch.delenv("BM25_VARIANT", raising=False)
+    monkeypatch.setenv("CACHE_COLLECTION_NAME", "web_cache")
+    _run_cache(load_golden("hybrid_cache"), lambda: B200VectorStore(0), lambda corpus: BM25Retriever(documents=corpus),
+               engine, engine)
 
 
 @pytest.mark.gpu
