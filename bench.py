@@ -2,23 +2,31 @@
 """bench.py -- retrieval queries/sec on BASELINE.json's configurations.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--workload dense|hybrid|rerank] [--batch B] [--n-docs N] [--dim D] [--top-k K] [--rerank-k K2]
+                    [--workload dense|hybrid|rerank|bm25] [--batch B] [--inner R] [--n-docs N] [--dim D] [--top-k K]
+                    [--rerank-k K2] [--shard auto|corpus|queries] [--no-extras]
 
-A "step" = one batch of B synthetic queries through the hot path.  Default workload = BASELINE.json configs[1]:
-1 M docs x 1024-d, dense-only cosine top_k=100 on 1 x B200.  --batch is the number of queries per step PER GPU (default 256;
-128 for hybrid, 64 for the rerank workload, i.e. 6400 pairs per step): a step on N GPUs carries N x batch queries.  Multi-GPU layout =
-C corpus shards x N/C query groups: the C ranks of a group partition the corpus (contiguous doc ranges), score the group's
-C x batch queries against their shards, exchange per-shard top-k in ONE NCCL all-gather and merge; different groups answer
-different queries.  --shard corpus: C = N (north_star's layout for corpora that must be partitioned); --shard queries:
-C = 1 (replicated corpus, no collective); --shard auto (default): the smallest C whose shard fits the per-GPU memory
-budget -- 1 for the 2 GB corpus of the metric.  Per-GPU work per step is constant in N -> "scaling": "weak"; the corpus
-of the metric (1 M docs) never changes.
+Headline (`value`, `e2e`, `roofline`, `cpu_baseline`) = BASELINE.json configs[1]: 1 M docs x 1024-d, dense-only cosine
+top_k=100 on 1 x B200.  A STEP = `--inner` R batches of `--batch` B queries per GPU through the hot path (defaults 64 x 256
+dense, 32 x 128 hybrid, 2 x 64 rerank): R is chosen so that the K timed steps hold >= 1 s of device work, and is stated in
+`config`.  The same JSON line carries, after the headline leg (unless --no-extras):
+
+  workloads.hybrid      configs[2]  hybrid dense+BM25 rrf                       value / e2e / roofline.bm25 / cpu_baseline
+  workloads.rerank      configs[3]  hybrid + cross-encoder rerank 100 -> 10     value / e2e / roofline.cross_encoder / cpu_baseline
+  workloads.bm25_10k    configs[0]  10 k docs, BM25-only top_k=10: the reference CPU path (1024 queries) beside the GPU class
+  latency_b1            HybridRetriever.retrieve(query, top_k=100) through the Document surface, one query at a time
+  partitioned (N > 1)   the SAME 1 M corpus partitioned C = N ways (north_star's layout: corpus partition + ONE NCCL
+                        all-gather of per-shard top-k): value, e2e and per-stage microseconds
+
+Multi-GPU layout of the headline = C corpus shards x N/C query groups (--shard auto: the smallest C whose shard fits the
+memory budget, 1 for the 2 GB corpus of the metric -> replicas, no collective).  Per-GPU work per step is constant in N
+-> "scaling": "weak".
 
 value   : whole-job queries/sec, inputs already resident in HBM (device entry points, CUDA-event timed, max over ranks)
-e2e     : the same metric through the host-buffer C-ABI entry point (pinned host queries -> H2D -> kernels -> D2H results)
-roofline: dominant kernel (dense_scan_kernel) algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json hbm_gbs
-cpu_baseline / --impl reference: the reference's CPU path (exact cosine in NumPy: fp32 `X @ q` with BLAS on all host
-          cores + full np.argsort, oracle/dense.py:fast_topk_f32; BM25 via the rank_bm25 restatement) on a bounded sample.
+e2e     : the same metric through the host-buffer C-ABI entry point (host queries -> H2D -> kernels -> D2H results)
+roofline: dominant kernel (the dense scan) algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json hbm_gbs
+cpu_baseline / --impl reference: the reference's CPU path (exact cosine in NumPy: fp32 `X @ q` with BLAS on a stated
+          number of host threads + the best-first cut, both as the code base writes it -- full np.argsort,
+          sparse.py:180 -- and with np.argpartition; BM25 via the rank_bm25 restatement) on a bounded sample.
 """
 from __future__ import annotations
 
@@ -30,13 +38,24 @@ import sys
 import threading
 import time
 
-import numpy as np
+_CORES = os.cpu_count() or 1
+_BLAS_THREADS = min(_CORES, 64)
+if "reference" in sys.argv or int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    # the CPU arms state their BLAS thread count instead of inheriting it (torchrun exports OMP_NUM_THREADS=1)
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(_BLAS_THREADS)
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "retrieval queries/sec @1M docs,1024-d,top_k=100"  # BASELINE.json metric (the workload actually run is in config)
 UNIT = "queries/s"
+DEFAULT_BATCH = {"dense": 256, "hybrid": 128, "rerank": 64, "bm25": 256}
+DEFAULT_INNER = {"dense": 64, "hybrid": 32, "rerank": 2, "bm25": 64}
+NAMES = {"dense": "dense-only cosine", "hybrid": "hybrid dense+BM25 rrf", "bm25": "BM25-only",
+         "rerank": "hybrid dense+BM25 rrf + cross-encoder rerank (MiniLM-L6 random-init)"}
 
 
 def parse_args():
@@ -45,20 +64,24 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="dense", choices=["dense", "hybrid", "rerank"])
+    ap.add_argument("--workload", default="dense", choices=["dense", "hybrid", "rerank", "bm25"])
     ap.add_argument("--rerank-k", type=int, default=10, help="documents kept after the cross-encoder (config 4: 100 -> 10)")
-    ap.add_argument("--batch", type=int, default=None,
-                    help="queries per step PER GPU (default: 256 dense, 128 hybrid, 64 rerank = 6400 pairs per step)")
+    ap.add_argument("--batch", type=int, default=None, help="queries per batch PER GPU (256 dense, 128 hybrid, 64 rerank)")
+    ap.add_argument("--inner", type=int, default=None,
+                    help="batches per step (64 dense, 32 hybrid, 2 rerank): sized for >= 1 s of timed device work")
     ap.add_argument("--n-docs", type=int, default=1_000_000)
     ap.add_argument("--dim", type=int, default=1024)
     ap.add_argument("--top-k", type=int, default=100)
-    ap.add_argument("--cpu-sample", type=int, default=24, help="queries in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=24, help="queries in the bounded CPU-baseline sample (0 = skip)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="headline leg only (skip workloads.* / latency_b1 / partitioned)")
+    ap.add_argument("--extras", default="hybrid,rerank,bm25_10k,latency_b1,partitioned",
+                    help="comma list of the extra legs run after a default dense headline")
     ap.add_argument("--shard", default="auto", choices=["auto", "corpus", "queries"],
                     help="--gpus N > 1 layout = C corpus shards x N/C query groups.  'corpus': C = N (contiguous doc ranges "
                          "+ ONE NCCL all-gather of per-shard top-k, north_star's layout for corpora that must be "
                          "partitioned); 'queries': C = 1 (corpus replicated, queries split, no collective); 'auto' "
-                         "(default): the smallest C whose shard fits --gpu-mem-budget-gb, i.e. partition only as much "
-                         "as capacity requires")
+                         "(default): the smallest C whose shard fits --gpu-mem-budget-gb")
     ap.add_argument("--corpus-shards", type=int, default=0, help="explicit C (must divide N); overrides --shard")
     ap.add_argument("--gpu-mem-budget-gb", type=float, default=64.0,
                     help="HBM one GPU may spend on index data under --shard auto (B200: 180 GB)")
@@ -70,8 +93,8 @@ def peaks():
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        return float(p["hbm_gbs"]), float(p.get("bf16_tflops_sustained", 1429.5)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md: 6.65 TB/s, 1.4 PF sustained bf16)"
 
 
 class ClockSampler:
@@ -103,7 +126,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
@@ -111,105 +134,444 @@ class ClockSampler:
             try:
                 sm.append(float(f[1]))
                 mx.append(float(f[2]))
+                pw.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_name(n_docs, dim, kind, top_k, rerank_k):
+    return (f"{n_docs}-doc synthetic, {dim}-d, {NAMES[kind]} top_k={top_k}" + (f"->{rerank_k}" if kind == "rerank" else ""))
 
 
 # --------------------------------------------------------------------------------------------- synthetic workload
-def make_workload(args, lo=None, hi=None):
-    """Synthetic corpus / queries.  Corpora above 2 M docs are generated shard-locally from
-    independently seeded chunks (synth.dense_corpus_range), so a rank only ever materialises its own rows."""
-    from sentio_b200 import synth
+class Workload:
+    """Synthetic corpus / queries, generated lazily: the text side only when a leg needs it.
+    Corpora above 2 M docs are generated shard-locally from independently seeded chunks (synth.dense_corpus_range), so
+    a rank only ever materialises its own rows."""
 
-    t0 = time.time()
-    if args.n_docs > 2_000_000 and lo is not None:
-        x16 = synth.dense_corpus_range(lo, hi, args.dim)
-    else:
-        x16 = synth.dense_corpus(args.n_docs, args.dim)
-        if lo is not None:
-            x16 = x16[lo:hi]
-    queries = synth.query_vectors(1024, args.dim)
-    wl = {"x16": x16, "q": queries, "gen_s": None}
-    if args.workload in ("hybrid", "rerank"):
-        flat, off = synth.text_corpus_tokens(args.n_docs)
-        wl["flat"], wl["off"] = flat, off
-        wl["q_tokens"] = synth.query_tokens(1024)
-    wl["gen_s"] = round(time.time() - t0, 1)
-    return wl
+    def __init__(self, n_docs, dim):
+        self.n_docs, self.dim = n_docs, dim
+        self.gen_s = 0.0
+        self._x16 = {}
+        self._text = None
+        from sentio_b200 import synth
+
+        self.synth = synth
+        self.q = synth.query_vectors(1024, dim)
+        self.q_tokens = synth.query_tokens(1024)
+
+    def rows(self, lo, hi):
+        key = (lo, hi)
+        if key not in self._x16:
+            t0 = time.time()
+            if self.n_docs > 2_000_000:
+                x = self.synth.dense_corpus_range(lo, hi, self.dim)
+            else:
+                full = self._x16.get((0, self.n_docs))
+                if full is None:
+                    full = self.synth.dense_corpus(self.n_docs, self.dim)
+                    self._x16[(0, self.n_docs)] = full
+                x = full[lo:hi]
+            self._x16[key] = x
+            self.gen_s += time.time() - t0
+        return self._x16[key]
+
+    def text(self):
+        if self._text is None:
+            t0 = time.time()
+            self._text = self.synth.text_corpus_tokens(self.n_docs)
+            self.gen_s += time.time() - t0
+        return self._text
 
 
 # --------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference(args, wl, n_queries):
+def cpu_reference(kind, wl: Workload, n_queries, top_k, rerank_k):
     """Times the reference's CPU path on this box's host cores on a bounded sample of the same workload."""
     from oracle import dense as dense_oracle
 
-    cores = os.cpu_count() or 1
-    x16 = wl["x16"]
+    x16 = wl.rows(0, wl.n_docs)
     x32 = x16.astype(np.float32)
     x32 /= np.linalg.norm(x32, axis=1, keepdims=True)  # Qdrant normalises at upsert; the scan is then a plain dot
-    q = wl["q"]
-    fast = None
-    ce_model = None
-    if args.workload in ("hybrid", "rerank"):
+    q = wl.q
+    fast = ce_model = None
+    if kind in ("hybrid", "rerank"):
         from oracle import fusion as fusion_oracle
         from oracle.rank_bm25_port import FastBM25
         from sentio_b200.index import build_bm25_from_token_ids
 
-        idx = build_bm25_from_token_ids(wl["flat"], wl["off"])
+        flat, off = wl.text()
+        idx = build_bm25_from_token_ids(flat, off)
         fast = FastBM25(idx.indptr, idx.post_doc, idx.post_tf, idx.doc_len, idx.idf, idx.avgdl)
-        terms = [idx.term_ids(t) for t in wl["q_tokens"]]
-    if args.workload == "rerank":
+        terms = [idx.term_ids(t) for t in wl.q_tokens]
+    if kind == "rerank":
         from oracle import cross_encoder as ce_oracle
         from sentio_b200.cross_encoder import MINILM_L6
         from sentio_b200.index import hash_tokenize_pairs
-        from sentio_b200 import synth
 
         ce_model = ce_oracle.hf_model(MINILM_L6, seed=0)
     for i in range(2):  # warm-up
-        dense_oracle.fast_topk_f32(x32, q[i], args.top_k)
+        dense_oracle.fast_topk_f32(x32, q[i], top_k)
     t0 = time.perf_counter()
     for i in range(n_queries):
-        di, ds = dense_oracle.fast_topk_f32(x32, q[i % len(q)], args.top_k)
+        di, ds = dense_oracle.fast_topk_f32(x32, q[i % len(q)], top_k)
         if fast is not None:
             s = fast.get_scores(list(terms[i % len(terms)]))
-            order = np.argsort(-s)[: args.top_k]
+            order = np.argsort(-s)[:top_k]
             sp = [(int(j), float(s[j])) for j in order if s[j] > 0]
-            fused = fusion_oracle.fuse("rrf", 60, 0.5, 0.5, [(int(a), float(b)) for a, b in zip(di, ds)], sp, [],
-                                       args.top_k)
+            fused = fusion_oracle.fuse("rrf", 60, 0.5, 0.5, [(int(a), float(b)) for a, b in zip(di, ds)], sp, [], top_k)
             if ce_model is not None:
-                qtext = synth.token_text(wl["q_tokens"][i % len(terms)])
-                texts = [synth.token_text(wl["flat"][wl["off"][d]:wl["off"][d + 1]]) for d, _, _ in fused]
+                flat, off = wl.text()
+                qtext = wl.synth.token_text(wl.q_tokens[i % len(terms)])
+                texts = [wl.synth.token_text(flat[off[d]:off[d + 1]]) for d, _, _ in fused]
                 ids, tt, lens = hash_tokenize_pairs(qtext, texts, 128)
                 _, sig = ce_oracle.hf_scores(ce_model, ids, tt, lens, batch=len(texts))
-                sorted(range(len(sig)), key=lambda j: -sig[j])[: args.rerank_k]
+                sorted(range(len(sig)), key=lambda j: -sig[j])[:rerank_k]
     dt = time.perf_counter() - t0
-    kind = "port"
-    sample = (f"{n_queries} queries of the same workload; dense = fp32 X@q (NumPy/BLAS, {cores} threads) + np.argsort"
-              + ("; BM25 = CSR restatement of rank_bm25 get_scores + np.argsort; rrf fusion in Python" if fast else "")
-              + ("; rerank = HuggingFace BertForSequenceClassification (MiniLM-L6 shape) fp32 on CPU, 100 pairs/query"
-                 if ce_model is not None else ""))
-    return {"value": n_queries / dt, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}, dt / n_queries
+    out = {"value": n_queries / dt, "unit": UNIT, "cores": _BLAS_THREADS, "host_cpus": _CORES, "kind": "port",
+           "sample": (f"{n_queries} queries of the same workload; dense = fp32 X@q (NumPy/BLAS, {_BLAS_THREADS} threads "
+                      f"set explicitly) + np.argsort[:k] (the cut as the reference writes it, sparse.py:180)"
+                      + ("; BM25 = CSR restatement of rank_bm25 get_scores + np.argsort; rrf fusion in Python" if fast else "")
+                      + ("; rerank = HuggingFace BertForSequenceClassification (MiniLM-L6 shape) fp32 on CPU, 100 pairs/query"
+                         if ce_model is not None else ""))}
+    if kind == "dense":   # the same scan with a partial sort: what a tuned NumPy implementation would do
+        t0 = time.perf_counter()
+        for i in range(n_queries):
+            s = x32 @ q[i % len(q)]
+            part = np.argpartition(-s, top_k)[:top_k]
+            part[np.argsort(-s[part])]
+        out["value_argpartition"] = n_queries / (time.perf_counter() - t0)
+    return out, dt / n_queries
+
+
+def bm25_10k_leg(device, top_k=10, n_queries=1024):
+    """BASELINE configs[0]: 10 k docs, BM25-only top_k = 10.  The reference CPU path (rank_bm25's dict-based get_scores
+    as restated in oracle/, np.argsort, score > 0 filter -- sparse.py:159-203) over all 1024 queries, beside the GPU
+    BM25Retriever arrays path on the same corpus and queries, ids compared."""
+    from oracle.rank_bm25_port import BM25Okapi
+    from sentio_b200 import synth
+    from sentio_b200.document import Document
+    from sentio_b200.retrievers.sparse import BM25Retriever
+
+    n = 10_000
+    flat, off = synth.text_corpus_tokens(n)
+    texts = [synth.token_text(flat[off[i]:off[i + 1]]) for i in range(n)]
+    queries = [synth.token_text(t) for t in synth.query_tokens(n_queries)]
+    ref = BM25Okapi([t.lower().split() for t in texts])
+    t0 = time.perf_counter()
+    want = []
+    for qtext in queries:
+        s = ref.get_scores(qtext.lower().split())
+        order = np.argsort(-s, kind="stable")[:top_k]
+        want.append([int(i) for i in order if s[i] > 0])
+    cpu_s = time.perf_counter() - t0
+    os.environ.pop("BM25_VARIANT", None)
+    r = BM25Retriever(documents=[Document(id=str(i), text=t) for i, t in enumerate(texts)], device=device)
+    r.retrieve_batch_arrays(queries[:64], top_k)
+    t0 = time.perf_counter()
+    ids, sc, cnt = r.retrieve_batch_arrays(queries, top_k)
+    gpu_s = time.perf_counter() - t0
+    same = all([int(x) for x in ids[b, :cnt[b]]] == want[b] for b in range(n_queries))
+    t0 = time.perf_counter()
+    for qtext in queries[:128]:
+        r.retrieve(qtext, top_k=top_k)
+    one_s = (time.perf_counter() - t0) / 128
+    return {"workload": f"{n}-doc synthetic, 768-d (unused: BM25-only), top_k={top_k}, {n_queries} queries",
+            "cpu_reference_qps": n_queries / cpu_s, "cpu_kind": "port (rank_bm25 0.2.2 restatement, 1 thread: pure Python)",
+            "gpu_batch_qps": n_queries / gpu_s, "gpu_retrieve_one_by_one_qps": 1.0 / one_s,
+            "ids_identical_to_reference_path": bool(same), "unit": UNIT}
+
+
+# --------------------------------------------------------------------------------------------- one timed leg
+class Leg:
+    """One workload on one pipeline: the device-resident timed region and the host-buffer (e2e) timed region."""
+
+    def __init__(self, kind, pipe, wl: Workload, args, world, rank, local_rank, C, my_group, lo, hi, idx, rerank_state):
+        import torch
+
+        self.torch = torch
+        self.kind, self.pipe, self.wl, self.args = kind, pipe, wl, args
+        self.world, self.rank, self.local_rank, self.C, self.my_group = world, rank, local_rank, C, my_group
+        self.lo, self.hi, self.idx = lo, hi, idx
+        self.eng = pipe.engine
+        self.dev = f"cuda:{local_rank}"
+        self.k = args.top_k
+        self.B_gpu = args.batch if kind == args.workload and args.batch else DEFAULT_BATCH[kind]
+        self.inner = args.inner if kind == args.workload and args.inner else DEFAULT_INNER[kind]
+        self.B = self.B_gpu * C                     # queries this rank scores per batch (all C ranks of a group: the same)
+        self.B_total = self.B_gpu * world           # queries per batch over the whole job
+        self.q_shift = my_group * self.B
+        self.q_all = torch.from_numpy(wl.q).to(self.dev)
+        self.n_q = self.q_all.shape[0]
+        self.term_lists = [idx.term_ids(t) for t in wl.q_tokens] if idx is not None else None
+        self.q_tok_all = rerank_state["q_tok_all"] if rerank_state else None
+        self.ring = max(1, min(8, self.n_q // max(1, self.B_total)))   # distinct batches (1024 seeded queries, cycled)
+
+    # ---- inputs
+    def batch_ids(self, j):
+        s = (j * self.B_total + self.q_shift) % self.n_q
+        return [(s + i) % self.n_q for i in range(self.B)]
+
+    def dev_inputs(self, j):
+        torch, ids = self.torch, self.batch_ids(j)
+        qt = self.q_all[ids].contiguous()
+        if self.kind == "dense":
+            return (qt,)
+        flat, off = self.eng.pack_queries([self.term_lists[i] for i in ids])
+        base = (qt, torch.from_numpy(flat).to(self.dev), torch.from_numpy(off).to(self.dev), int(off[-1]),
+                int(np.diff(off).max()))
+        if self.kind != "rerank":
+            return base
+        qtok = torch.from_numpy(self.q_tok_all[ids]).to(self.dev)
+        qlen = torch.full((self.B,), self.q_tok_all.shape[1], dtype=torch.int32, device=self.dev)
+        return base + (qtok, qlen)
+
+    def run_dev(self, inp):
+        p, k, a = self.pipe, self.k, self.args
+        if self.kind == "dense":
+            return p.dense_dev(inp[0], k)
+        if self.kind == "bm25":
+            return p.engine.bm25_topk_dev(inp[1], inp[2], self.B, inp[3], inp[4], k)
+        if self.kind == "rerank":
+            return p.hybrid_rerank_dev(inp[0], inp[1], inp[2], inp[3], inp[4], inp[5], inp[6], k, a.rerank_k, 128, "rrf",
+                                       60, 0.5, 0.5)
+        return p.hybrid_dev(inp[0], inp[1], inp[2], inp[3], inp[4], k, "rrf", 60, 0.5, 0.5)
+
+    def run_host(self, j):
+        p, k, a = self.pipe, self.k, self.args
+        ids = self.batch_ids(j)
+        q = self.host_q[j % self.ring]
+        if self.kind == "dense":
+            return p.search_dense(q, k)
+        terms = self.host_terms[j % self.ring]
+        if self.kind == "bm25":
+            return p.engine.bm25_topk(terms, k)
+        if self.kind == "rerank":
+            return p.search_hybrid_rerank(q, terms, self.q_tok_all[ids], np.full(self.B, self.q_tok_all.shape[1], np.int32),
+                                          k, a.rerank_k, 128, "rrf", 60, 0.5, 0.5)
+        return p.search_hybrid(q, terms, k, "rrf", 60, 0.5, 0.5)
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def _max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- the two timed regions
+    def run(self, steps, warmup, sample_clocks=True):
+        torch, eng = self.torch, self.eng
+        inputs = [self.dev_inputs(j) for j in range(self.ring)]
+        for s in range(warmup):
+            for r in range(self.inner):
+                self.run_dev(inputs[(s * self.inner + r) % self.ring])
+        self.barrier()
+        eng.profile(True)
+        if self.kind == "rerank":
+            eng.ce_stats(reset=True)
+        launches0 = eng.launch_count()
+        sampler = ClockSampler(self.local_rank)
+        if self.rank == 0 and sample_clocks:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        ev0.record()
+        for s in range(steps):
+            for r in range(self.inner):
+                self.run_dev(inputs[(s * self.inner + r) % self.ring])
+        ev1.record()
+        self.barrier()
+        ms_total = ev0.elapsed_time(ev1)
+        clocks = sampler.stop() if (self.rank == 0 and sample_clocks) else None
+        launches = eng.launch_count() - launches0
+        prof = {name: eng.profile_read(name) for name in ("dense_scan", "dense_merge", "dense_sample", "bm25_score",
+                                                          "bm25_select", "fuse", "ce")}
+        ce_stats = eng.ce_stats() if self.kind == "rerank" else (0, 0, 0)
+        eng.profile(False)
+        ms_total = self._max_over_ranks(ms_total)
+        n_batches = steps * self.inner
+        value = self.B_total * n_batches / (ms_total / 1e3)
+
+        # e2e: host buffers in, host results out, every batch
+        self.host_q = [self.wl.q[self.batch_ids(j)] for j in range(self.ring)]
+        self.host_terms = None
+        if self.term_lists is not None:
+            self.host_terms = [[self.term_lists[i] for i in self.batch_ids(j)] for j in range(self.ring)]
+        for s in range(min(warmup, 2) * self.inner):
+            self.run_host(s)
+        self.barrier()
+        t0 = time.perf_counter()
+        for s in range(n_batches):
+            self.run_host(s)
+        self.barrier()
+        e2e_s = self._max_over_ranks(time.perf_counter() - t0)
+        B, k, a = self.B, self.k, self.args
+        h2d = B * a.dim * 4 if self.kind != "bm25" else 0
+        d2h = B * k * 16 + B * 4
+        if self.term_lists is not None:
+            h2d += sum(len(x) for x in self.host_terms[0]) * 4 + (B + 1) * 4
+            d2h += B * k * 4 if self.kind != "bm25" else 0
+        if self.kind == "rerank":
+            h2d += B * self.q_tok_all.shape[1] * 4 + B * 4
+            d2h = self.B_gpu * a.rerank_k * 12 + self.B_gpu * 4  # every rank returns the rows of the queries it reranked
+        e2e = {"value": self.B_total * n_batches / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d * self.world * self.inner,
+               "d2h_bytes_per_step": d2h * self.world * self.inner,
+               "timer": "host wall clock around the public host-buffer calls of the step (H2D, kernels, D2H, one sync "
+                        "per call); bytes are summed over ranks and over the step's batches"}
+        return {"value": value, "ms_total": ms_total, "ms_per_step": ms_total / steps, "steps": steps, "n_batches": n_batches,
+                "clocks": clocks, "launches": int(launches), "prof": prof, "ce_stats": ce_stats, "e2e": e2e,
+                "timed_region_s": ms_total / 1e3}
+
+    # ---- rooflines
+    def roofline_dense(self, res):
+        hbm, _, src = peaks()
+        rows = self.hi - self.lo
+        n_pad = (rows + 127) // 128 * 128
+        d_pad = (self.args.dim + 7) // 8 * 8
+        alg = n_pad * d_pad * 2 + n_pad * 4
+        n_scan, scan_ms = res["prof"]["dense_scan"]
+        avg = scan_ms / max(n_scan, 1)
+        ach = alg / (avg * 1e-3) / 1e9 if n_scan else 0.0
+        qpl = (self.B * res["n_batches"]) / max(n_scan, 1)
+        kern = ("dense_scan_mma2_kernel (tcgen05 cta_group::2 pair, 128 queries per pass)" if qpl > 64 else
+                "dense_scan_mma_kernel (tcgen05, <= 64 queries per pass)" if self.B >= 16 else "dense_scan_kernel (FFMA2)")
+        out = {"bound": "hbm", "kernel": kern, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+               "traffic": None, "traffic_source": None, "peak_source": src, "algorithmic_bytes_per_launch": alg,
+               "avg_launch_ms": avg, "launches_timed": n_scan, "queries_per_launch": qpl,
+               "share_of_step": scan_ms / res["ms_total"],
+               "other_dense_stages_ms_per_batch": {
+                   "sampling_passes+threshold_select": res["prof"]["dense_sample"][1] / max(res["n_batches"], 1),
+                   "window_select+fp64_rescore": res["prof"]["dense_merge"][1] / max(res["n_batches"], 1)}}
+        prof = os.path.join(ROOT, "profiles", "r02_dense_scan_ncu.json")
+        if os.path.exists(prof) and self.C == 1:
+            try:
+                out["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+                out["traffic_source"] = "profiles/r02_dense_scan_ncu.json (ncu --set full of the same kernel, static)"
+            except Exception:
+                pass
+        return out
+
+    def roofline_bm25(self, res):
+        hbm, _, _ = peaks()
+        n_bm, bm_ms = res["prof"]["bm25_score"]
+        if not n_bm or self.idx is None:
+            return None
+        sidx = self.idx.shard(self.lo, self.hi) if self.C > 1 else self.idx
+        df = np.diff(sidx.indptr)
+        postings = 0
+        for j in range(self.ring):
+            for i in self.batch_ids(j):
+                t = self.term_lists[i]
+                postings += int(df[t[t >= 0]].sum())
+        postings = postings * res["n_batches"] / self.ring
+        return {"bound": "issue", "kernel": "bm25_range_kernel (sample + collect)",
+                "postings_per_s": postings / (bm_ms * 1e-3), "postings_per_query": postings / (self.B * res["n_batches"]),
+                "algorithmic_bytes": postings * 12, "posting_GBps": postings * 12 / (bm_ms * 1e-3) / 1e9,
+                "frac_of_hbm_peak_if_every_posting_came_from_dram": postings * 12 / (bm_ms * 1e-3) / 1e9 / hbm,
+                "ms_total": bm_ms, "share_of_step": bm_ms / res["ms_total"],
+                "note": "the posting lists shared by a batch are served by L2 (ncu: DRAM traffic << posting bytes); the "
+                        "kernel is instruction-issue bound, so postings/s is the figure of merit, not GB/s"}
+
+    def roofline_ce(self, res):
+        _, tpeak, _ = peaks()
+        n_ce, ce_ms = res["prof"]["ce"]
+        if not n_ce:
+            return None
+        ce_pairs, ce_rows, ce_sq = res["ce_stats"]
+        flops = 6 * (24 * 384 * 384 * ce_rows + 4 * 384 * ce_sq)
+        tf = flops / (ce_ms * 1e-3) / 1e12
+        return {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak, "ms_total": ce_ms,
+                "forward_calls": n_ce, "pairs": ce_pairs, "mean_pair_len": ce_rows / max(ce_pairs, 1),
+                "flops_counted": "L*(24*H^2*sum(len) + 4*H*sum(len^2)), padding excluded",
+                "share_of_step": ce_ms / res["ms_total"]}
+
+
+def latency_b1(pipe, wl: Workload, idx, n_queries=200, top_k=100):
+    """The call the graph makes: HybridRetriever.retrieve(query, top_k=100), one query at a time, through the Document
+    surface (DenseRetriever over a vector-store facade on the loaded index + BM25Retriever on the loaded postings)."""
+    from sentio_b200.document import Document
+    from sentio_b200.retrievers.dense import DenseRetriever
+    from sentio_b200.retrievers.hybrid import HybridRetriever
+    from sentio_b200.retrievers.sparse import BM25Retriever
+    from sentio_b200.vector_store import ScoredPoint
+
+    flat, off = wl.text()
+    synth, eng = wl.synth, pipe.engine
+
+    class Store:   # QdrantClient-shaped facade over the ALREADY loaded dense index (no second 2 GB copy)
+        def collection_exists(self, collection_name):
+            return collection_name == "Sentio_docs"
+
+        def search(self, collection_name, query_vector, limit=10, with_payload=True, with_vectors=False, **kw):
+            ids, sc, cnt = eng.dense_topk(np.asarray(query_vector, np.float32).reshape(1, -1), int(limit))
+            return [ScoredPoint(id=str(int(ids[0, j])), score=float(sc[0, j]),
+                                payload={"content": synth.token_text(flat[off[int(ids[0, j])]:off[int(ids[0, j]) + 1]]),
+                                         "metadata": {"source": "synthetic"}}) for j in range(int(cnt[0]))]
+
+    class Embedder:  # the query embedding forward is a separate row (SURVEY 8f-1); here a table of seeded unit vectors
+        def __init__(self):
+            self.at = {}
+
+        def embed_sync(self, text):
+            return self.at[text]
+
+    class DocMap:    # materialises a corpus Document on demand (1 M Python objects up front would measure the allocator)
+        def get(self, doc_id, default=None):
+            i = int(doc_id)
+            return Document(id=doc_id, text=synth.token_text(flat[off[i]:off[i + 1]]), metadata={"source": "synthetic"})
+
+    class DocIds:
+        def __getitem__(self, row):
+            return str(row)
+
+    emb = Embedder()
+    sparse = BM25Retriever(device=pipe.device)
+    sparse.bm25, sparse.doc_ids, sparse.doc_map, sparse._engine = idx, DocIds(), DocMap(), eng
+    dense = DenseRetriever(client=Store(), embedder=emb, collection_name="Sentio_docs")
+    hr = HybridRetriever(dense_retriever=dense, sparse_retriever=sparse, rrf_k=60, scorer_plugins=[], fusion_method="rrf",
+                         engine=eng)
+    texts = [synth.token_text(t) for t in wl.q_tokens[:n_queries + 8]]
+    for i, t in enumerate(texts):
+        emb.at[t] = wl.q[i]
+    out = {}
+    for name, fn in (("hybrid", lambda t: hr.retrieve(t, top_k=top_k)), ("dense", lambda t: dense.retrieve(t, top_k=top_k))):
+        for t in texts[:8]:
+            fn(t)
+        lat = []
+        for t in texts[8:]:
+            t0 = time.perf_counter()
+            docs = fn(t)
+            lat.append(time.perf_counter() - t0)
+        lat = np.asarray(lat) * 1e3
+        out[name] = {"p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
+                     "mean_ms": float(lat.mean()), "queries": len(lat), "docs_returned": len(docs)}
+    out["call"] = f"HybridRetriever.retrieve(query, top_k={top_k}) / DenseRetriever.retrieve, B = 1, Document objects out"
+    return out
 
 
 # --------------------------------------------------------------------------------------------- main
 def main():
     args = parse_args()
-    if args.batch is None:
-        args.batch = {"dense": 256, "hybrid": 128, "rerank": 64}[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload_name = (f"{args.n_docs}-doc synthetic, {args.dim}-d, "
-                     + {"dense": "dense-only cosine", "hybrid": "hybrid dense+BM25 rrf",
-                        "rerank": "hybrid dense+BM25 rrf + cross-encoder rerank (MiniLM-L6 random-init)"}[args.workload]
-                     + f" top_k={args.top_k}" + (f"->{args.rerank_k}" if args.workload == "rerank" else ""))
-    # ---- multi-GPU layout: C corpus shards x (world / C) query groups
-    est_gb = args.n_docs * args.dim * 2 / 1e9 + (args.n_docs * 60 * 12 / 1e9 if args.workload != "dense" else 0.0)
+    kind = args.workload
+    B_gpu = args.batch or DEFAULT_BATCH[kind]
+    inner = args.inner or DEFAULT_INNER[kind]
+    name = workload_name(args.n_docs, args.dim, kind, args.top_k, args.rerank_k)
+    est_gb = args.n_docs * args.dim * 2 / 1e9 + (args.n_docs * 60 * 12 / 1e9 if kind != "dense" else 0.0)
     from sentio_b200.pipeline import plan_layout
 
     try:
@@ -217,17 +579,14 @@ def main():
     except ValueError as exc:
         raise SystemExit(str(exc))
     n_groups, my_group, r_in = world // C, rank // C, rank % C
-    sharded = C > 1
-    replicated = n_groups > 1
-    B_gpu = args.batch
-    B_total = args.batch * world
-    config = {"workload": workload_name, "batch_queries_per_step": B_total, "queries_per_gpu_per_step": B_gpu,
-              "store_dtype": "fp16", "shards": C, "query_groups": n_groups, "index_gb_estimate": round(est_gb, 2),
+    config = {"workload": name, "queries_per_batch_per_gpu": B_gpu, "batches_per_step": inner,
+              "batch_queries_per_step": B_gpu * world * inner, "store_dtype": "fp16", "shards": C, "query_groups": n_groups,
+              "index_gb_estimate": round(est_gb, 2),
               "multi_gpu": ("single GPU" if world == 1 else
                             f"{C} corpus shard(s) x {n_groups} query group(s): "
-                            + ("corpus partition + one NCCL all-gather of per-shard top-k" if sharded else
+                            + ("corpus partition + one NCCL all-gather of per-shard top-k" if C > 1 else
                                "corpus replicated, no collective")
-                            + ("; queries split across groups" if replicated else "")
+                            + ("; queries split across groups" if n_groups > 1 else "")
                             + (f" [--corpus-shards {C}]" if args.corpus_shards else f" [--shard {args.shard}]")),
               "l2_policy": "corpus (2.05 GB) is larger than L2 (126 MB); no flush needed",
               "query_set": "1024 seeded unit vectors, cycled"}
@@ -235,14 +594,15 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        wl = make_workload(args)
-        per_step = max(1, min(args.batch, 4))
+        wl = Workload(args.n_docs, args.dim)
+        per_step = max(1, min(B_gpu, 4))
         total = per_step * (args.steps + args.warmup)
-        base, per_q = cpu_reference(args, wl, total)
+        base, per_q = cpu_reference(kind if kind != "bm25" else "dense", wl, total, args.top_k, args.rerank_k)
         line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_q * per_step * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": {**config, "batch_queries_per_step": per_step},
+                "data": "synthetic", "config": {**config, "batch_queries_per_step": per_step, "batches_per_step": 1,
+                                                "queries_per_batch_per_gpu": per_step},
                 "cpu_baseline": {**base, "sample": f"{per_step} queries per step; " + base["sample"]},
                 "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -258,220 +618,142 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     n = args.n_docs
-    if sharded:
-        lo, hi = (n * r_in) // C, (n * (r_in + 1)) // C
-    else:
-        lo, hi = 0, n
-    wl = make_workload(args, lo, hi)
-    group = None
-    if sharded and n_groups > 1:  # one NCCL communicator per corpus group (every rank creates all of them, in order)
-        for g in range(n_groups):
-            pg = dist.new_group(list(range(g * C, (g + 1) * C)))
-            if g == my_group:
-                group = pg
-    pipe = HybridPipeline(local_rank, rank=r_in if sharded else 0, world=C if sharded else 1, group=group)
-    pipe.load_dense(wl["x16"], id_base=lo)
-    idx = None
-    rerank = args.workload == "rerank"
-    if args.workload in ("hybrid", "rerank"):
+    lo, hi = ((n * r_in) // C, (n * (r_in + 1)) // C) if C > 1 else (0, n)
+    wl = Workload(n, args.dim)
+    groups = {}
+
+    def group_for(c):   # one NCCL communicator per corpus group (every rank creates all of them, in order)
+        if c == 1 or c in groups:
+            return groups.get(c)
+        mine = None
+        if c == world:
+            mine = dist.group.WORLD
+        else:
+            for g in range(world // c):
+                pg = dist.new_group(list(range(g * c, (g + 1) * c)))
+                if g == rank // c:
+                    mine = pg
+        groups[c] = mine
+        return mine
+
+    pipe = HybridPipeline(local_rank, rank=r_in if C > 1 else 0, world=C if C > 1 else 1, group=group_for(C))
+    pipe.load_dense(wl.rows(lo, hi), id_base=lo)
+    state = {"idx": None, "rerank": None}
+
+    def need_bm25(p, c, lo_, hi_):
         from sentio_b200.index import build_bm25_from_token_ids
 
-        if sharded:  # corpus-global idf / avgdl: build once on the host, upload this rank's shard
-            idx = build_bm25_from_token_ids(wl["flat"], wl["off"])
-            pipe.load_bm25(idx.shard(lo, hi), id_base=lo)
-        else:        # single shard: the index is built on the device (sb_bm25_build_*), 0.3 s at 1 M docs
-            idx = pipe.engine.build_bm25_gpu(wl["flat"], wl["off"], export=True)
-    if rerank:
-        from sentio_b200 import synth
+        flat, off = wl.text()
+        if c > 1:   # corpus-global idf / avgdl: build once on the host, upload this rank's shard
+            if state["idx"] is None:
+                state["idx"] = build_bm25_from_token_ids(flat, off)
+            p.load_bm25(state["idx"].shard(lo_, hi_), id_base=lo_)
+        else:       # single shard: the index is built on the device (sb_bm25_build_*), 0.3 s at 1 M docs
+            state["idx"] = p.engine.build_bm25_gpu(flat, off, export=True)
+        return state["idx"]
+
+    def need_rerank(p):
         from sentio_b200.cross_encoder import MINILM_L6, CrossEncoderWeights
         from sentio_b200.index import doc_token_matrix, hash_vocab_ids
 
-        vocab_ids = hash_vocab_ids(synth.VOCAB)
-        doc_tok, doc_len = doc_token_matrix(wl["flat"], wl["off"], vocab_ids, ld=120)
-        pipe.load_cross_encoder(CrossEncoderWeights.random(MINILM_L6, seed=0))
-        pipe.load_doc_tokens(doc_tok, doc_len, id_base=0)  # replicated on every rank (240 MB at 1 M docs)
-        q_tok_all = vocab_ids[wl["q_tokens"]].astype(np.int32)
-    eng = pipe.engine
-    # queries this rank handles per step: those of its corpus group (all C ranks of a group score the same queries)
-    B, k = B_gpu * C, args.top_k
-    q_shift = my_group * B
-    dev = f"cuda:{local_rank}"
-    q_all = torch.from_numpy(wl["q"]).to(dev)
-    n_q = q_all.shape[0]
-    terms_dev = None
-    if idx is not None:
-        term_lists = [idx.term_ids(t) for t in wl["q_tokens"]]
+        flat, off = wl.text()
+        vocab_ids = hash_vocab_ids(wl.synth.VOCAB)
+        doc_tok, doc_len = doc_token_matrix(flat, off, vocab_ids, ld=120)
+        p.load_cross_encoder(CrossEncoderWeights.random(MINILM_L6, seed=0))
+        p.load_doc_tokens(doc_tok, doc_len, id_base=0)  # replicated on every rank (240 MB at 1 M docs)
+        state["rerank"] = {"q_tok_all": vocab_ids[wl.q_tokens].astype(np.int32)}
+        return state["rerank"]
 
-    def batch_slice(step):
-        s = (step * B_total + q_shift) % n_q
-        idxs = [(s + i) % n_q for i in range(B)]
-        return idxs
+    idx = need_bm25(pipe, C, lo, hi) if kind in ("hybrid", "rerank", "bm25") else None
+    rr = need_rerank(pipe) if kind == "rerank" else None
+    leg = Leg(kind, pipe, wl, args, world, rank, local_rank, C, my_group, lo, hi, idx, rr)
+    res = leg.run(args.steps, args.warmup)
+    roofline = leg.roofline_dense(res) if kind != "bm25" else {}
+    if kind in ("hybrid", "rerank", "bm25"):
+        roofline["bm25"] = leg.roofline_bm25(res)
+    if kind == "rerank":
+        roofline["cross_encoder"] = leg.roofline_ce(res)
 
-    def dev_inputs(step):
-        ids = batch_slice(step)
-        qt = q_all[ids].contiguous()
-        if idx is None:
-            return (qt,)
-        flat, off = eng.pack_queries([term_lists[i] for i in ids])
-        base = (qt, torch.from_numpy(flat).to(dev), torch.from_numpy(off).to(dev), int(off[-1]),
-                int(np.diff(off).max()))
-        if not rerank:
-            return base
-        qtok = torch.from_numpy(q_tok_all[ids]).to(dev)
-        qlen = torch.full((B,), q_tok_all.shape[1], dtype=torch.int32, device=dev)
-        return base + (qtok, qlen)
+    extras = set() if (args.no_extras or kind != "dense" or args.n_docs > 2_000_000) else set(args.extras.split(","))
+    workloads, lat, part = {}, None, None
+    sub_steps, sub_warm = max(3, min(args.steps, 8)), max(3, min(args.warmup, 3))
 
-    def run_dev(inp):
-        if idx is None:
-            return pipe.dense_dev(inp[0], k)
-        if rerank:
-            return pipe.hybrid_rerank_dev(inp[0], inp[1], inp[2], inp[3], inp[4], inp[5], inp[6], k, args.rerank_k, 128,
-                                          "rrf", 60, 0.5, 0.5)
-        return pipe.hybrid_dev(inp[0], inp[1], inp[2], inp[3], inp[4], k, "rrf", 60, 0.5, 0.5)
+    def sub_leg(k2, p, c, lo_, hi_, my_group_, idx_, rr_):
+        lg = Leg(k2, p, wl, args, world, rank, local_rank, c, my_group_, lo_, hi_, idx_, rr_)
+        r = lg.run(sub_steps, sub_warm, sample_clocks=True)
+        o = {"workload": workload_name(n, args.dim, k2, args.top_k, args.rerank_k), "value": r["value"], "unit": UNIT,
+             "ms_per_step": r["ms_per_step"], "steps": sub_steps, "warmup": sub_warm, "queries_per_batch_per_gpu": lg.B_gpu,
+             "batches_per_step": lg.inner, "timed_region_s": r["timed_region_s"], "e2e": r["e2e"],
+             "gpu_launches": r["launches"], "clocks": r["clocks"], "roofline": {"dense_scan": lg.roofline_dense(r)}}
+        if k2 in ("hybrid", "rerank"):
+            o["roofline"]["bm25"] = lg.roofline_bm25(r)
+        if k2 == "rerank":
+            o["roofline"]["cross_encoder"] = lg.roofline_ce(r)
+        return o, r
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    if C == 1 and ("hybrid" in extras or "rerank" in extras or "latency_b1" in extras):
+        idx = need_bm25(pipe, 1, 0, n)
+    if C == 1 and "hybrid" in extras:
+        workloads["hybrid"], _ = sub_leg("hybrid", pipe, 1, 0, n, my_group, idx, None)
+    if C == 1 and "latency_b1" in extras and world == 1:
+        lat = latency_b1(pipe, wl, idx)
+    if C == 1 and "rerank" in extras:
+        rr = need_rerank(pipe)
+        workloads["rerank"], _ = sub_leg("rerank", pipe, 1, 0, n, my_group, idx, rr)
 
-    # ---------------- resident leg: inputs already in HBM, device entry points, CUDA events on torch's current stream
-    inputs = [dev_inputs(s) for s in range(args.warmup + args.steps)]
-    for s in range(args.warmup):
-        run_dev(inputs[s])
-    barrier()
-    eng.profile(True)
-    if rerank:
-        eng.ce_stats(reset=True)
-    launches0 = eng.launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for s in range(args.steps):
-        run_dev(inputs[args.warmup + s])
-    ev1.record()
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
-    launches = eng.launch_count() - launches0
-    n_scan, scan_ms = eng.profile_read("dense_scan")
-    n_ce, ce_ms = eng.profile_read("ce")
-    n_bm, bm_ms = eng.profile_read("bm25_score") if idx is not None else (0, 0.0)
-    ce_pairs, ce_rows, ce_sq = eng.ce_stats() if rerank else (0, 0, 0)
-    eng.profile(False)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    value = B_total * args.steps / (ms_total / 1e3)
-
-    # ---------------- e2e leg: host (pinned by the library) buffers in, host results out, every step
-    host_batches = [wl["q"][batch_slice(s)] for s in range(args.warmup + args.steps)]
-    host_terms = None
-    if idx is not None:
-        host_terms = [[term_lists[i] for i in batch_slice(s)] for s in range(args.warmup + args.steps)]
-
-    def run_host(s):
-        if idx is None:
-            return pipe.search_dense(host_batches[s], k)
-        if rerank:
-            sl = batch_slice(s)
-            return pipe.search_hybrid_rerank(host_batches[s], host_terms[s], q_tok_all[sl],
-                                             np.full(B, q_tok_all.shape[1], np.int32), k, args.rerank_k, 128, "rrf", 60,
-                                             0.5, 0.5)
-        return pipe.search_hybrid(host_batches[s], host_terms[s], k, "rrf", 60, 0.5, 0.5)
-
-    for s in range(args.warmup):
-        run_host(s)
-    barrier()
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        out = run_host(args.warmup + s)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
-    h2d = B * args.dim * 4 + (0 if idx is None else sum(len(x) for x in host_terms[0]) * 4 + (B + 1) * 4)
-    d2h = B * k * 16 + B * 4 + (B * k * 4 if idx is not None else 0)
-    if rerank:
-        h2d += B * q_tok_all.shape[1] * 4 + B * 4
-        d2h = B_gpu * args.rerank_k * 12 + B_gpu * 4  # every rank returns the rows of the queries it reranked
-    e2e = {"value": B_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
-           "d2h_bytes_per_step": d2h * world,
-           "timer": "host wall clock around the public host-buffer call (includes H2D, kernels, D2H, sync); "
-                    "bytes are summed over ranks"}
+    # ---- north_star's multi-GPU layout on the SAME corpus: C = world corpus shards + one all-gather per batch
+    if world > 1 and C == 1 and "partitioned" in extras:
+        plo, phi = (n * rank) // world, (n * (rank + 1)) // world
+        ppipe = HybridPipeline(local_rank, rank=rank, world=world, group=group_for(world))
+        ppipe.load_dense(wl.rows(plo, phi), id_base=plo)
+        ppipe.stage_timing = True
+        pd, pr = sub_leg("dense", ppipe, world, plo, phi, 0, None, None)
+        nb = pr["n_batches"]
+        stage = {"sampling_passes+threshold_select_us": pr["prof"]["dense_sample"][1] / nb * 1e3,
+                 "scan_us": pr["prof"]["dense_scan"][1] / nb * 1e3,
+                 "window_select+fp64_rescore_us": pr["prof"]["dense_merge"][1] / nb * 1e3}
+        stage.update({k_: v / max(ppipe.stage_counts.get(k_, 1), 1) * 1e3 for k_, v in ppipe.stage_ms().items()})
+        part = {"layout": f"{world} corpus shards (contiguous doc ranges of the same {n}-doc corpus) x 1 query group; every "
+                          f"rank scores the step's {world} x {pd['queries_per_batch_per_gpu']} queries against its shard, "
+                          "ONE all_gather_into_tensor of the per-shard top-k records, merge_shards on global ranks",
+                "dense": pd, "per_batch_stage_us_rank0": stage}
+        if "hybrid" in extras:
+            pidx = need_bm25(ppipe, world, plo, phi)
+            ph, _ = sub_leg("hybrid", ppipe, world, plo, phi, 0, pidx, None)
+            part["hybrid"] = ph
+        ppipe.engine.close()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ---------------- roofline of the dominant kernel (dense_scan_kernel), this rank's shard
-    peak, peak_src = peaks()
-    rows = hi - lo
-    n_pad = (rows + 31) // 32 * 32
-    d_pad = (args.dim + 7) // 8 * 8
-    alg_bytes = n_pad * d_pad * 2 + n_pad * 4
-    avg_ms = scan_ms / max(n_scan, 1)
-    achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if n_scan else 0.0
-    scan_kernel = "dense_scan_mma_kernel (tcgen05, batched queries)" if B >= 16 else "dense_scan_kernel (FFMA2)"
-    roofline = {"bound": "hbm", "kernel": scan_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms, "launches_timed": n_scan,
-                "queries_per_launch": (B * args.steps) / max(n_scan, 1), "share_of_step": scan_ms / ms_total}
-    prof = os.path.join(ROOT, "profiles", "r01_dense_scan_ncu.json")
-    if os.path.exists(prof) and world == 1:
-        try:
-            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
-        except Exception:
-            pass
-
-    if idx is not None and n_bm:
-        # BM25 range kernel (sample + collect launches): algorithmic bytes = the postings of the query terms, 12 B each
-        # (4 B doc + 8 B fp64 ratio); this rank's shard, all queries of the timed steps
-        sidx = idx.shard(lo, hi) if sharded else idx
-        df = np.diff(sidx.indptr)
-        postings = 0
-        for s_ in range(args.steps):
-            for i in batch_slice(args.warmup + s_):
-                t = term_lists[i]
-                postings += int(df[t[t >= 0]].sum())
-        bm_bytes = postings * 12
-        roofline["bm25"] = {"bound": "hbm", "kernel": "bm25_range_kernel (sample + collect)",
-                            "achieved": bm_bytes / (bm_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                            "frac": bm_bytes / (bm_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": bm_bytes,
-                            "postings_per_query": postings / (B * args.steps), "ms_total": bm_ms,
-                            "share_of_step": bm_ms / ms_total,
-                            "note": "posting lists shared by the queries of a batch are served from L2 (ncu: DRAM "
-                                    "traffic ~0.25 GB per 64-query launch vs 1.6 GB algorithmic); the kernel is "
-                                    "issue/latency bound, see profiles/r01_run15_bm25_range_ncu.md"}
-    if rerank and n_ce:
-        # second roofline: the cross-encoder forward (tensor pipe).  Flops of the work actually done: the packed-token
-        # forward computes sum(len) token rows, not P x 128 (library counters); 2.87 GFLOP per pair only at len = 128.
-        flops = 6 * (24 * 384 * 384 * ce_rows + 4 * 384 * ce_sq)
-        tf = flops / (ce_ms * 1e-3) / 1e12
-        tpeak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1429.5) \
-            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1400.0
-        roofline["cross_encoder"] = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s",
-                                     "frac": tf / tpeak, "ms_total": ce_ms, "forward_calls": n_ce,
-                                     "pairs": ce_pairs, "mean_pair_len": ce_rows / max(ce_pairs, 1),
-                                     "flops_counted": "L*(24*H^2*sum(len) + 4*H*sum(len^2)), padding excluded",
-                                     "share_of_step": ce_ms / ms_total}
-
-    # ---------------- bounded CPU baseline on this box's host cores (rank 0, N=1 only)
+    # ---------------- bounded CPU baselines on this box's host cores (rank 0, N=1 only)
     cpu = None
     if world == 1 and args.cpu_sample > 0 and args.n_docs <= 2_000_000:
-        cpu, _ = cpu_reference(args, wl, args.cpu_sample)
+        cpu, _ = cpu_reference(kind if kind != "bm25" else "dense", wl, args.cpu_sample, args.top_k, args.rerank_k)
+        if "hybrid" in workloads:
+            workloads["hybrid"]["cpu_baseline"], _ = cpu_reference("hybrid", wl, 8, args.top_k, args.rerank_k)
+        if "rerank" in workloads:
+            workloads["rerank"]["cpu_baseline"], _ = cpu_reference("rerank", wl, 2, args.top_k, args.rerank_k)
+    if world == 1 and "bm25_10k" in extras:
+        try:
+            workloads["bm25_10k"] = bm25_10k_leg(local_rank)
+        except Exception as exc:  # a broken extra leg must not cost the headline line
+            workloads["bm25_10k"] = {"error": str(exc)}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+    line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16 store / f32 scan / f64 exact re-score",
-            "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "corpus_gen_s": wl["gen_s"]}
+            "data": "synthetic", "config": config, "clocks": res["clocks"], "e2e": res["e2e"],
+            "gpu_launches": res["launches"], "timed_region_s": res["timed_region_s"], "roofline": roofline,
+            "cpu_baseline": cpu, "corpus_gen_s": round(wl.gen_s, 1)}
+    if workloads:
+        line["workloads"] = workloads
+    if lat:
+        line["latency_b1"] = lat
+    if part:
+        line["partitioned"] = part
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -65,7 +65,8 @@ int64_t sb_launch_count(sb_ctx* ctx);
 /*
  * Optional per-kernel timing for the roofline leg of bench.py: when enabled every launch of the kernels below is
  * bracketed by a CUDA event pair on the launching stream; sb_profile_read drains the finished pairs of one kernel id
- * (0 dense_scan, 1 dense_merge, 2 bm25_score, 3 bm25_select+final, 4 fuse, 5 cross-encoder forward) and returns the
+ * (0 dense_scan, 1 dense_merge, 2 bm25_score, 3 bm25_select+final, 4 fuse, 5 cross-encoder forward, 6 dense sampling
+ * passes + threshold select) and returns the
  * launch count and the summed device time in milliseconds.
  */
 int sb_profile(sb_ctx* ctx, int enable);

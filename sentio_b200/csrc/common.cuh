@@ -164,7 +164,7 @@ struct DeviceGuard {
 
 // kernel ids for sb_profile_read
 enum { SB_PROF_DENSE_SCAN = 0, SB_PROF_DENSE_MERGE = 1, SB_PROF_BM25_SCORE = 2, SB_PROF_BM25_SELECT = 3,
-       SB_PROF_FUSE = 4, SB_PROF_CE = 5, SB_PROF_COUNT = 6 };
+       SB_PROF_FUSE = 4, SB_PROF_CE = 5, SB_PROF_DENSE_SAMPLE = 6, SB_PROF_COUNT = 7 };
 
 static inline cudaEvent_t prof_event(sb_ctx* ctx) {
   if (!ctx->prof_pool.empty()) {

@@ -814,20 +814,21 @@ int dense_mma_topk_enqueue(sb_ctx* ctx, DenseIndex& ix, const float* q_pad, int 
     mp.num_tiles = sample_tiles;
     mp.tile_first = 0;
     mp.tile_step = sample_step;
-    for (int g = 0; g < ng; ++g) {
-      const Group& G = gs[(size_t)g];
-      mp.cand = cand + (size_t)g * gsz * sgrid * capg;
-      mp.counts = counts + (size_t)g * gsz * sgrid;
-      mp.stages = G.stages;
-      ctx->launches += 1;
-      if (G.pair) rc = launch_mma_pair(tm_rows, G.tm_q, mp, sgrid, G.smem, st);
-      else rc = dispatch_mma(G.qbn, tm_rows, G.tm_q, mp, sgrid, G.smem, st);
-      if (rc) return rc;
+    {
+      ProfScope ps(ctx, SB_PROF_DENSE_SAMPLE, st, ng + 1);   // the sampling passes + their threshold select, as one span
+      for (int g = 0; g < ng; ++g) {
+        const Group& G = gs[(size_t)g];
+        mp.cand = cand + (size_t)g * gsz * sgrid * capg;
+        mp.counts = counts + (size_t)g * gsz * sgrid;
+        mp.stages = G.stages;
+        if (G.pair) rc = launch_mma_pair(tm_rows, G.tm_q, mp, sgrid, G.smem, st);
+        else rc = dispatch_mma(G.qbn, tm_rows, G.tm_q, mp, sgrid, G.smem, st);
+        if (rc) return rc;
+      }
+      sp.grid = sgrid;
+      sp.mode = 0;
+      dense_select_kernel<<<rows_total, kSelectThreads, sel_smem, st>>>(sp);
     }
-    sp.grid = sgrid;
-    sp.mode = 0;
-    ctx->launches += 1;
-    dense_select_kernel<<<rows_total, kSelectThreads, sel_smem, st>>>(sp);
     SB_CUDA(cudaGetLastError());
     // (2) the full passes, then one select + exact re-score launch for the chunk
     mp.num_tiles = total_tiles;

@@ -14,6 +14,8 @@ weights (tests/test_embedder_gpu.py).
 """
 from __future__ import annotations
 
+import logging
+
 import asyncio
 import time
 from typing import Any
@@ -38,11 +40,16 @@ def tokenize_for_embedding(texts, seq_len: int = 128):
     return ids, tt, lens
 
 
+logger = logging.getLogger(__name__)
+
+
 class B200Embedder:
     def __init__(self, model_name: str = "b200-minilm-l6-random", weights: CrossEncoderWeights | None = None,
                  proj_w: np.ndarray | None = None, proj_b: np.ndarray | None = None, dimension: int = 1024,
                  seq_len: int = 128, device: int = 0, engine=None, cache_enabled: bool = True, cache_size: int = 10_000,
-                 seed: int = 0, **kwargs: Any) -> None:
+                 seed: int = 0, allow_random_init: bool = False, **kwargs: Any) -> None:
+        """``weights`` are required (no checkpoint ships offline): ``allow_random_init=True`` builds the random-init
+        MiniLM-L6 encoder the tests and benchmarks use -- its embeddings are well formed and meaningless."""
         self.model_name = model_name
         self.seq_len = int(seq_len)
         self._cache_enabled = cache_enabled
@@ -50,6 +57,10 @@ class B200Embedder:
         self._cache_size = int(cache_size)
         self._stats = {"total_requests": 0, "cache_hits": 0, "errors": 0, "total_time": 0.0}
         if weights is None:
+            if not allow_random_init:
+                raise ValueError("B200Embedder needs weights=CrossEncoderWeights(...); pass allow_random_init=True only "
+                                 "for tests / benchmarks")
+            logger.warning("B200Embedder: RANDOM-INIT encoder weights (seed %d) -- embeddings are meaningless", seed)
             weights = CrossEncoderWeights.random(MINILM_L6, seed=seed)
         hidden = int(weights.config["hidden"])
         if proj_w is None and dimension != hidden:

@@ -63,7 +63,7 @@ class B200Engine:
     def launch_count(self) -> int:
         return int(self._lib.sb_launch_count(self._h))
 
-    PROF_IDS = {"dense_scan": 0, "dense_merge": 1, "bm25_score": 2, "bm25_select": 3, "fuse": 4, "ce": 5}
+    PROF_IDS = {"dense_scan": 0, "dense_merge": 1, "bm25_score": 2, "bm25_select": 3, "fuse": 4, "ce": 5, "dense_sample": 6}
 
     def profile(self, enable: bool) -> None:
         check(self._lib.sb_profile(self._h, 1 if enable else 0), "sb_profile")

@@ -62,6 +62,10 @@ class HybridPipeline:
         self._torch_device = "cpu" if device is None else f"cuda:{device}"
         self.id_base = 0
         self._bufs = {}
+        # optional per-stage CUDA-event timing of the sharded path (bench.py's `partitioned` leg)
+        self.stage_timing = False
+        self._stage_events: list = []
+        self.stage_counts: dict = {}
 
     # ------------------------------------------------------------------ loading
     def load_dense(self, vecs: np.ndarray, id_base: int = 0) -> None:
@@ -140,7 +144,40 @@ class HybridPipeline:
         import torch.distributed as dist
 
         out = self._buf("gathered", (self.world, rec.numel()), self.torch.uint8)
-        dist.all_gather_into_tensor(out.view(-1), rec, group=self.group)
+        with self._stage("all_gather_us"):
+            dist.all_gather_into_tensor(out.view(-1), rec, group=self.group)
+        return out
+
+    # ------------------------------------------------------------------ optional stage timing
+    class _Span:
+        def __init__(self, pipe, name):
+            self.pipe, self.name = pipe, name
+
+        def __enter__(self):
+            if self.pipe.stage_timing and self.pipe.device is not None:
+                t = self.pipe.torch
+                self.a, self.b = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+                self.a.record()
+            return self
+
+        def __exit__(self, *exc):
+            if self.pipe.stage_timing and self.pipe.device is not None:
+                self.b.record()
+                self.pipe._stage_events.append((self.name, self.a, self.b))
+            return False
+
+    def _stage(self, name: str):
+        return HybridPipeline._Span(self, name)
+
+    def stage_ms(self) -> dict:
+        """Drains the recorded stage spans: name -> summed milliseconds (and ``stage_counts[name]`` spans)."""
+        self.torch.cuda.synchronize()
+        out: dict = {}
+        self.stage_counts = {}
+        for name, a, b in self._stage_events:
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+            self.stage_counts[name] = self.stage_counts.get(name, 0) + 1
+        self._stage_events = []
         return out
 
     # ------------------------------------------------------------------ device-resident path
@@ -154,12 +191,14 @@ class HybridPipeline:
             return self.engine.dense_topk_dev(q_t, k, out=out)
         _, nbytes = self._record_layout(B, k, 1)
         rec = self._buf("rec1", (nbytes,), t.uint8)
-        self.engine.dense_topk_dev(q_t, k, out=self._views(rec, B, k, 0))
+        with self._stage("local_dense_topk_us"):
+            self.engine.dense_topk_dev(q_t, k, out=self._views(rec, B, k, 0))
         g = self._gather(rec)
         ids0, sc0, cnt0 = self._views(g[0], B, k, 0)
         out = (self._buf("d_ids", (B, k), t.int64), self._buf("d_sc", (B, k), t.float64),
                self._buf("d_cnt", (B,), t.int32))
-        return self.engine.merge_shards_dev(ids0, sc0, cnt0, nbytes, self.world, out=out)
+        with self._stage("merge_shards_us"):
+            return self.engine.merge_shards_dev(ids0, sc0, cnt0, nbytes, self.world, out=out)
 
     def hybrid_dev(self, q_t, terms_t, off_t, n_terms: int, max_len: int, k: int, method: str = "rrf",
                    rrf_k: float = 60, w_dense: float = 0.5, w_sparse: float = 0.5):

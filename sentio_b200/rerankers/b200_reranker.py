@@ -26,12 +26,22 @@ logger = logging.getLogger(__name__)
 class B200Reranker(Reranker):
     def __init__(self, weights: CrossEncoderWeights | None = None, engine: B200Engine | None = None, device: int = 0,
                  seq_len: int = 128, tokenizer: Callable | None = None, model_name: str = "b200-minilm-l6",
-                 seed: int = 0):
+                 seed: int = 0, allow_random_init: bool = False):
+        """``weights`` (and normally ``tokenizer``) are required: a reranker without trained weights reorders documents at
+        random.  ``allow_random_init=True`` is for tests and benchmarks (BASELINE.json config 4 is a random-init model)."""
         self.model_name = model_name
         self.seq_len = int(seq_len)
+        if weights is None:
+            if not allow_random_init:
+                raise ValueError("B200Reranker needs weights=CrossEncoderWeights(...) (e.g. from_hf_state_dict); pass "
+                                 "allow_random_init=True only for tests / benchmarks")
+            logger.warning("B200Reranker: RANDOM-INIT MiniLM-L6 weights (seed %d) -- scores are meaningless", seed)
+            weights = CrossEncoderWeights.random_minilm_l6(seed=seed)
+        if tokenizer is None:
+            logger.warning("B200Reranker: no tokenizer given, using the crc32 hashing tokeniser (benchmark / test only)")
         self._tokenize = tokenizer or hash_tokenize_pairs
         self._engine = engine or B200Engine(device)
-        self.weights = weights or CrossEncoderWeights.random_minilm_l6(seed=seed)
+        self.weights = weights
         self._engine.ce_load(self.weights.blob(), self.weights.config)
 
     # ------------------------------------------------------------------ scoring
