@@ -188,6 +188,18 @@ class Workload:
             self.gen_s += time.time() - t0
         return self._text
 
+    def text_range(self, lo, hi):
+        """(flat, off) of docs [lo, hi), shard-local offsets: a slice of the corpus up to 2 M docs, generated shard-locally
+        (independently seeded chunks) above."""
+        t0 = time.time()
+        if self.n_docs > 2_000_000:
+            out = self.synth.text_corpus_tokens_range(lo, hi)
+        else:
+            flat, off = self.text()
+            out = (flat[off[lo]:off[hi]], off[lo:hi + 1] - off[lo])
+        self.gen_s += time.time() - t0
+        return out
+
 
 # --------------------------------------------------------------------------------------------- CPU reference arm
 def cpu_reference(kind, wl: Workload, n_queries, top_k, rerank_k):
@@ -346,7 +358,7 @@ class Leg:
         ids = self.batch_ids(j)
         q = self.host_q[j % self.ring]
         if self.kind == "dense":
-            return p.search_dense(q, k)
+            return p.search_dense(q, k, out=self.host_out[j % len(self.host_out)] if self.host_out else None)
         terms = self.host_terms[j % self.ring]
         if self.kind == "bm25":
             return p.engine.bm25_topk(terms, k)
@@ -405,7 +417,19 @@ class Leg:
         value = self.B_total * n_batches / (ms_total / 1e3)
 
         # e2e: host buffers in, host results out, every batch
-        self.host_q = [self.wl.q[self.batch_ids(j)] for j in range(self.ring)]
+        # the caller's request / response buffers: page-locked and reused (a serving loop's I/O rings), so the library
+        # copies straight between them and the device
+        self.host_q, self.host_out = [], []
+        for j in range(self.ring):
+            src = self.wl.q[self.batch_ids(j)]
+            if self.world == 1 and self.kind == "dense" and hasattr(eng, "pinned_empty"):
+                buf = eng.pinned_empty(src.shape, np.float32)
+                buf[...] = src
+                self.host_q.append(buf)
+                self.host_out.append((eng.pinned_empty((self.B, self.k), np.int64),
+                                      eng.pinned_empty((self.B, self.k), np.float64), eng.pinned_empty((self.B,), np.int32)))
+            else:
+                self.host_q.append(src)
         self.host_terms = None
         if self.term_lists is not None:
             self.host_terms = [[self.term_lists[i] for i in self.batch_ids(j)] for j in range(self.ring)]
@@ -429,7 +453,9 @@ class Leg:
         e2e = {"value": self.B_total * n_batches / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d * self.world * self.inner,
                "d2h_bytes_per_step": d2h * self.world * self.inner,
                "timer": "host wall clock around the public host-buffer calls of the step (H2D, kernels, D2H, one sync "
-                        "per call); bytes are summed over ranks and over the step's batches"}
+                        "per call); bytes are summed over ranks and over the step's batches",
+               "host_buffers": "page-locked request / response arrays reused across calls (engine.pinned_empty)"
+                               if self.host_out else "pageable NumPy arrays (staged through the library's pinned buffers)"}
         return {"value": value, "ms_total": ms_total, "ms_per_step": ms_total / steps, "steps": steps, "n_batches": n_batches,
                 "clocks": clocks, "launches": int(launches), "prof": prof, "ce_stats": ce_stats, "e2e": e2e,
                 "timed_region_s": ms_total / 1e3}
@@ -468,7 +494,7 @@ class Leg:
         n_bm, bm_ms = res["prof"]["bm25_score"]
         if not n_bm or self.idx is None:
             return None
-        sidx = self.idx.shard(self.lo, self.hi) if self.C > 1 else self.idx
+        sidx = self.idx   # C > 1: a shard-local index (pipeline.build_bm25_sharded), its df are the shard's
         df = np.diff(sidx.indptr)
         postings = 0
         for j in range(self.ring):
@@ -507,8 +533,14 @@ def latency_b1(pipe, wl: Workload, idx, n_queries=200, top_k=100):
     from sentio_b200.retrievers.sparse import BM25Retriever
     from sentio_b200.vector_store import ScoredPoint
 
-    flat, off = wl.text()
+    import dataclasses
+
     synth, eng = wl.synth, pipe.engine
+    # text queries need a token-string vocabulary (the device-built index of the integer corpus only maps raw token ids)
+    idx = dataclasses.replace(idx, vocab={f"w{raw}": int(t) for raw, t in enumerate(idx.token_id_map) if t >= 0})
+
+    def text_of(i):   # placeholder document text: the synthetic corpus has token ids, not strings, and rendering 80 tokens
+        return f"synthetic document {i}"   # per hit would time str.join, not the retrieval surface
 
     class Store:   # QdrantClient-shaped facade over the ALREADY loaded dense index (no second 2 GB copy)
         def collection_exists(self, collection_name):
@@ -517,8 +549,8 @@ def latency_b1(pipe, wl: Workload, idx, n_queries=200, top_k=100):
         def search(self, collection_name, query_vector, limit=10, with_payload=True, with_vectors=False, **kw):
             ids, sc, cnt = eng.dense_topk(np.asarray(query_vector, np.float32).reshape(1, -1), int(limit))
             return [ScoredPoint(id=str(int(ids[0, j])), score=float(sc[0, j]),
-                                payload={"content": synth.token_text(flat[off[int(ids[0, j])]:off[int(ids[0, j]) + 1]]),
-                                         "metadata": {"source": "synthetic"}}) for j in range(int(cnt[0]))]
+                                payload={"content": text_of(int(ids[0, j])), "metadata": {"source": "synthetic"}})
+                    for j in range(int(cnt[0]))]
 
     class Embedder:  # the query embedding forward is a separate row; here a table of seeded unit vectors
         def __init__(self):
@@ -529,8 +561,7 @@ def latency_b1(pipe, wl: Workload, idx, n_queries=200, top_k=100):
 
     class DocMap:    # materialises a corpus Document on demand (1 M Python objects up front would measure the allocator)
         def get(self, doc_id, default=None):
-            i = int(doc_id)
-            return Document(id=doc_id, text=synth.token_text(flat[off[i]:off[i + 1]]), metadata={"source": "synthetic"})
+            return Document(id=doc_id, text=text_of(int(doc_id)), metadata={"source": "synthetic"})
 
     class DocIds:
         def __getitem__(self, row):
@@ -557,7 +588,8 @@ def latency_b1(pipe, wl: Workload, idx, n_queries=200, top_k=100):
         lat = np.asarray(lat) * 1e3
         out[name] = {"p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
                      "mean_ms": float(lat.mean()), "queries": len(lat), "docs_returned": len(docs)}
-    out["call"] = f"HybridRetriever.retrieve(query, top_k={top_k}) / DenseRetriever.retrieve, B = 1, Document objects out"
+    out["call"] = (f"HybridRetriever.retrieve(query, top_k={top_k}) / DenseRetriever.retrieve, B = 1, Document objects out "
+                   "(placeholder document texts; query embedding = table lookup)")
     return out
 
 
@@ -643,29 +675,46 @@ def main():
     def need_bm25(p, c, lo_, hi_):
         from sentio_b200.index import build_bm25_from_token_ids
 
-        flat, off = wl.text()
-        if c > 1:   # corpus-global idf / avgdl: build once on the host, upload this rank's shard
-            if state["idx"] is None:
-                state["idx"] = build_bm25_from_token_ids(flat, off)
-            p.load_bm25(state["idx"].shard(lo_, hi_), id_base=lo_)
-        else:       # single shard: the index is built on the device (sb_bm25_build_*), 0.3 s at 1 M docs
-            state["idx"] = p.engine.build_bm25_gpu(flat, off, export=True)
+        if c > 1:   # every rank builds ITS doc range on its GPU; only (term, df) statistics are exchanged (all-gather)
+            flat_l, off_l = wl.text_range(lo_, hi_)
+            return p.build_bm25_sharded(flat_l, off_l, id_base=lo_, export=True)
+        flat, off = wl.text()   # single shard: the index is built on the device (sb_bm25_build_*), 0.3 s at 1 M docs
+        state["idx"] = p.engine.build_bm25_gpu(flat, off, export=True)
         return state["idx"]
 
-    def need_rerank(p):
+    def need_rerank(p, c=1, lo_=0, hi_=None):
         from sentio_b200.cross_encoder import MINILM_L6, CrossEncoderWeights
         from sentio_b200.index import doc_token_matrix, hash_vocab_ids
 
-        flat, off = wl.text()
         vocab_ids = hash_vocab_ids(wl.synth.VOCAB)
-        doc_tok, doc_len = doc_token_matrix(flat, off, vocab_ids, ld=120)
+        if c > 1 and n > 2_000_000:
+            # every rank tokenises its own doc range; the (small) uint16 token matrices are all-gathered over NCCL so any
+            # global candidate can be framed locally (replicated: 240 B per doc)
+            flat_l, off_l = wl.text_range(lo_, hi_)
+            tok_l, len_l = doc_token_matrix(flat_l, off_l, vocab_ids, ld=120)
+            per = (n + c - 1) // c
+            tk = torch.zeros((per, tok_l.shape[1]), dtype=torch.int16, device=f"cuda:{local_rank}")
+            ln = torch.zeros((per,), dtype=torch.int32, device=f"cuda:{local_rank}")
+            tk[:len(tok_l)] = torch.from_numpy(tok_l.view(np.int16)).to(tk.device)
+            ln[:len(len_l)] = torch.from_numpy(len_l.astype(np.int32)).to(ln.device)
+            tk_all = torch.empty((c * per, tok_l.shape[1]), dtype=torch.int16, device=tk.device)
+            ln_all = torch.empty((c * per,), dtype=torch.int32, device=tk.device)
+            dist.all_gather_into_tensor(tk_all, tk, group=group_for(c))
+            dist.all_gather_into_tensor(ln_all, ln, group=group_for(c))
+            bounds = [((n * r) // c, (n * (r + 1)) // c) for r in range(c)]
+            doc_tok = np.concatenate([tk_all[r * per:r * per + (b_ - a_)].cpu().numpy().view(np.uint16)
+                                      for r, (a_, b_) in enumerate(bounds)])
+            doc_len = np.concatenate([ln_all[r * per:r * per + (b_ - a_)].cpu().numpy() for r, (a_, b_) in enumerate(bounds)])
+        else:
+            flat, off = wl.text()
+            doc_tok, doc_len = doc_token_matrix(flat, off, vocab_ids, ld=120)
         p.load_cross_encoder(CrossEncoderWeights.random(MINILM_L6, seed=0))
         p.load_doc_tokens(doc_tok, doc_len, id_base=0)  # replicated on every rank (240 MB at 1 M docs)
         state["rerank"] = {"q_tok_all": vocab_ids[wl.q_tokens].astype(np.int32)}
         return state["rerank"]
 
     idx = need_bm25(pipe, C, lo, hi) if kind in ("hybrid", "rerank", "bm25") else None
-    rr = need_rerank(pipe) if kind == "rerank" else None
+    rr = need_rerank(pipe, C, lo, hi) if kind == "rerank" else None
     leg = Leg(kind, pipe, wl, args, world, rank, local_rank, C, my_group, lo, hi, idx, rr)
     res = leg.run(args.steps, args.warmup)
     roofline = leg.roofline_dense(res) if kind != "bm25" else {}

@@ -21,6 +21,7 @@
 #ifndef SENTIO_B200_H
 #define SENTIO_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -60,6 +61,13 @@ int sb_num_sms(sb_ctx* ctx);
 int sb_sync(sb_ctx* ctx);
 /* the context's cudaStream_t (as void*), so torch can order its own work against it */
 void* sb_stream(sb_ctx* ctx);
+/*
+ * Page-locked host buffers for callers that reuse their I/O arrays (a server's request / response rings): the host
+ * entry points below detect page-locked pointers (cudaPointerGetAttributes) and then copy straight between the
+ * caller's buffer and the device -- no staging memcpy on either side.  Pageable pointers work as before (staged).
+ */
+void* sb_host_alloc(size_t bytes);
+void sb_host_free(void* p);
 /* number of kernels this library has launched on behalf of the context (bench.py's gpu_launches) */
 int64_t sb_launch_count(sb_ctx* ctx);
 /*

@@ -32,6 +32,8 @@ SIGNATURES = {
     "sb_version": (C.c_int, []),
     "sb_num_sms": (C.c_int, [C.c_void_p]),
     "sb_sync": (C.c_int, [C.c_void_p]),
+    "sb_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "sb_host_free": (None, [C.c_void_p]),
     "sb_stream": (C.c_void_p, [C.c_void_p]),
     "sb_launch_count": (C.c_int64, [C.c_void_p]),
     "sb_profile": (C.c_int, [C.c_void_p, C.c_int]),

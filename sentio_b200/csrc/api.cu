@@ -47,6 +47,8 @@ int sb_create(int device, sb_ctx** out) {
   // tuning knobs for experiments (bench / profiling); the defaults are the measured best
   if (const char* v = getenv("SB_DENSE_PAIR")) ctx->dense_pair = atoi(v) != 0;
   if (const char* v = getenv("SB_DENSE_SAMPLE")) ctx->dense_sample_per_cta = atoi(v) > 0 ? atoi(v) : 2;
+  if (const char* v = getenv("SB_DENSE_PREFETCH")) ctx->dense_prefetch = atoi(v) > 0 ? atoi(v) : 0;
+  if (const char* v = getenv("SB_DENSE_STAGES")) ctx->dense_max_stages = atoi(v) >= 3 ? atoi(v) : 8;
   cudaError_t se = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (se != cudaSuccess) {
     sb_set_error("sb_create: cudaStreamCreate failed: %s", cudaGetErrorString(se));
@@ -95,6 +97,21 @@ void sb_destroy(sb_ctx* ctx) {
   for (auto e : ctx->prof_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
+}
+
+void* sb_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 16;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+    (void)cudaGetLastError();
+    sb_set_error("sb_host_alloc: cudaMallocHost(%zu) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+
+void sb_host_free(void* p) {
+  if (p) cudaFreeHost(p);
 }
 
 int sb_num_sms(sb_ctx* ctx) { return ctx ? ctx->num_sms : 0; }

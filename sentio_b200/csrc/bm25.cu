@@ -44,25 +44,31 @@ __global__ void bm25_ratio_kernel(const int32_t* __restrict__ post_doc, const ui
 }
 
 // ------------------------------------------------------------------------------------------------ range scoring
-// One CTA scores ONE query over a run of consecutive doc ranges of kRange docs.  The fp64 accumulators of the range live
-// in shared memory (64 KB), so the only HBM traffic of scoring is the postings themselves (4 B doc + 8 B ratio each):
-// no N x 8 B zero fill, no accumulator read-modify-write through L2, no N x 8 B re-read for the top-k.
+// One CTA scores ONE query over a run of consecutive doc ranges of kRange docs.  The fp64 accumulators live in shared
+// memory (64 KB per CTA), so the only memory traffic of scoring is the postings themselves (4 B doc + 8 B ratio each, most
+// of them L2 hits: the head terms' lists are shared by the queries of a batch): no N x 8 B zero fill, no accumulator
+// read-modify-write through L2, no N x 8 B re-read for the top-k.
 //
-//  * postings of a term are sorted by doc, so the slice of a posting list that falls into [r0, r1) is contiguous; its
-//    start is found once per (CTA, term) with a warp-cooperative 32-ary search and then carried from range to range
-//    (the end of range i is the start of range i + 1);
-//  * terms are processed strictly in QUERY ORDER with a block barrier between them, and a doc occurs at most once per
-//    posting list, so the per-doc addition order equals NumPy's `score += ...` loop order without any atomics
-//    => bit-identical fp64;
-//  * what happens to the finished range depends on MODE:
-//      kModeSample : (S ranges spread over the corpus) ceil(k/S)-th best positive score of the range, min over the S
-//                    ranges -> thr[q], a lower bound of the global k-th best score
+// WARP-PRIVATE STRIPS (round 2; round 1 walked every (range, term) with the whole CTA and two block barriers per step --
+// 69 thread instructions per posting, issue bound):
+//  * the CTA's doc span is cut into 16 contiguous strips, one per warp; a warp walks its strip in sub-ranges of kSub = 512
+//    docs whose accumulators are its private 4 KB slice of shared memory -- no block barrier after the set-up;
+//  * postings of a term are sorted by doc, so a strip's slice of a posting list is contiguous: its start is found once
+//    per (warp, term) with a warp-cooperative 32-ary search and then carried from sub-range to sub-range;
+//  * inside a sub-range the terms are applied strictly in QUERY ORDER by the same warp (a doc occurs at most once per
+//    posting list), so the per-doc addition order equals NumPy's `score += ...` loop order without any atomics
+//    => bit-identical fp64 (every operation is an explicit __dmul_rn / __dadd_rn);
+//  * a finished sub-range is consumed by its warp according to MODE:
+//      kModeSample : (S ranges spread over the corpus, one per CTA) ceil(k/S)-th best positive score of the range, min
+//                    over the S ranges -> thr[q], a lower bound of the global k-th best score
 //      kModeCollect: every doc with score > 0 and >= thr[q] is appended to the query's candidate list
 //      kModeDump   : the accumulators are written to out[q][doc] (sb_bm25_scores, the bit-exactness hook)
-constexpr int kRange = 8192;            // docs per range
+constexpr int kRange = 8192;            // docs per range (= 16 warps x kSub)
 constexpr unsigned long long kPosZero = 0x8000000000000000ull;  // f64_orderable(+0.0)
 constexpr int kRsThreads = 512;
-constexpr int kRsPost = 4;              // postings per thread per chunk
+constexpr int kRsWarps = kRsThreads / 32;
+constexpr int kSub = kRange / kRsWarps; // docs per warp sub-range
+constexpr int kRsPost = 4;              // 32-posting chunks a warp keeps in flight for the long lists
 enum { kModeSample = 0, kModeCollect = 1, kModeDump = 2 };
 
 struct RangeParams {
@@ -117,13 +123,13 @@ __device__ unsigned long long block_kth_largest(const unsigned long long* keys, 
 template <int MODE, bool PLUS>
 __global__ void __launch_bounds__(kRsThreads, 3) bm25_range_kernel(const RangeParams p) {
   extern __shared__ __align__(16) uint8_t rsm[];
-  double* acc = reinterpret_cast<double*>(rsm);                               // [kRange]
+  double* acc = reinterpret_cast<double*>(rsm);                               // [kRange]: warp w owns [w*kSub, (w+1)*kSub)
   int64_t* s_lo = reinterpret_cast<int64_t*>(acc + kRange);                   // [max_len] first posting of the term's list
   double* s_idf = reinterpret_cast<double*>(s_lo + p.max_len);                // [max_len] 0.0 = term contributes nothing
-  int32_t* s_cur = reinterpret_cast<int32_t*>(s_idf + p.max_len);             // [2][max_len] cursor, relative to s_lo
-  int32_t* s_n = s_cur + 2 * (size_t)p.max_len;                               // [max_len] postings in the list (df < 2^31)
-  int32_t* s_wid = s_n + p.max_len;                                           // [max_len] postings per thread per chunk
-  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_wid + p.max_len);          // [kRange / 32] PLUS: doc had a posting
+  int32_t* s_n = reinterpret_cast<int32_t*>(s_idf + p.max_len);               // [max_len] postings in the list (df < 2^31)
+  int32_t* s_wid = s_n + p.max_len;                                           // [max_len] chunks in flight for this term
+  int32_t* s_cur = s_wid + p.max_len;                                         // [kRsWarps][max_len] cursor, relative to s_lo
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_cur + (size_t)kRsWarps * p.max_len);  // [kRange / 32] PLUS: doc had a posting
   __shared__ int hist[256];
   __shared__ int scal[4];
   __shared__ int npos;
@@ -136,123 +142,130 @@ __global__ void __launch_bounds__(kRsThreads, 3) bm25_range_kernel(const RangePa
   const int64_t last = MODE == kModeSample ? first + 1 : min(first + (int64_t)p.ranges_per_cta, n_ranges);  // exclusive
   const int q0 = p.q_off[qi];
   const int len = min(p.q_off[qi + 1] - q0, p.max_len);
-  // per-term state: posting cursor at the first range's lower doc bound
-  for (int j = warp; j < len; j += kRsThreads / 32) {
+  // per-term state shared by the CTA
+  for (int j = tid; j < len; j += kRsThreads) {
     const int t = p.q_terms[q0 + j];
     double w = 0.0;
-    int64_t lo = 0, pos = 0, hi = 0;
+    int64_t lo = 0, hi = 0;
     if (t >= 0 && t < p.n_terms) {
       w = p.idf[t];
       if (w != 0.0) {
         lo = p.indptr[t];
         hi = p.indptr[t + 1];
-        pos = first == 0 ? lo : warp_lower_bound(p.post_doc, lo, hi, (int32_t)(first * kRange), lane);
       }
     }
-    if (lane == 0) {
-      s_lo[j] = lo;
-      s_cur[j] = (int32_t)(pos - lo);
-      s_n[j] = (int32_t)(hi - lo);
-      s_idf[j] = w;
-      // expected postings of the term inside one range -> chunk width (rare terms must not over-read)
-      const int64_t per_range = ((hi - lo) * kRange) / max(p.n_docs, (int64_t)1);
-      s_wid[j] = per_range < kRsThreads / 2 ? 1 : kRsPost;
-    }
+    s_lo[j] = lo;
+    s_n[j] = (int32_t)(hi - lo);
+    s_idf[j] = w;
+    // expected postings of the term inside one sub-range -> chunks kept in flight (rare terms must not over-read)
+    const int64_t per_sub = ((hi - lo) * kSub) / max(p.n_docs, (int64_t)1);
+    s_wid[j] = per_sub < 48 ? 1 : kRsPost;
   }
-  for (int i = tid; i < kRange; i += kRsThreads) acc[i] = 0.0;
-  if (PLUS)
-    for (int i = tid; i < kRange / 32; i += kRsThreads) s_bits[i] = 0u;
+  double* a = acc + warp * kSub;
+  for (int i = lane; i < kSub; i += 32) a[i] = 0.0;
+  uint32_t* bits = s_bits + warp * (kSub / 32);
+  if (PLUS && lane < kSub / 32) bits[lane] = 0u;
   __syncthreads();
 
-  for (int64_t r = first; r < last; ++r) {
-    const int32_t r0 = (int32_t)(r * kRange);
-    const int32_t r1 = (int32_t)min((int64_t)r0 + kRange, p.n_docs);
-    const int nd = r1 - r0;
-    const int par = (int)((r - first) & 1);
-    const int32_t* cur_in = s_cur + (size_t)par * p.max_len;
-    int32_t* cur_out = s_cur + (size_t)(par ^ 1) * p.max_len;
+  // this warp's strip: kSub * (ranges of the CTA) consecutive docs
+  const int64_t strip_len = (last - first) * kSub;
+  const int64_t strip0 = first * kRange + (int64_t)warp * strip_len;
+  int32_t* my_cur = s_cur + (size_t)warp * p.max_len;
+  for (int j = 0; j < len; ++j) {
+    int64_t pos = 0;
+    if (s_idf[j] != 0.0 && strip0 > 0 && strip0 < p.n_docs)
+      pos = warp_lower_bound(p.post_doc + s_lo[j], 0, s_n[j], (int32_t)strip0, lane);
+    if (lane == 0) my_cur[j] = (int32_t)pos;
+  }
+  __syncwarp();
 
+  const unsigned long long thr_key = MODE == kModeCollect ? p.thr[qi] : 0ull;
+  const double td = orderable_f64(thr_key);
+  for (int64_t s0l = strip0; s0l < strip0 + strip_len && s0l < p.n_docs; s0l += kSub) {
+    const int32_t s0 = (int32_t)s0l;
+    const int32_t s1 = (int32_t)min(s0l + kSub, p.n_docs);
+    const int nd = s1 - s0;
     for (int j = 0; j < len; ++j) {
       const double w = s_idf[j];
-      if (w == 0.0) continue;  // block-uniform
-      const int32_t pos0 = cur_in[j], n = s_n[j];
-      const int wid = s_wid[j];   // postings a thread fetches per chunk: 1 for rare terms (no over-read), else kRsPost
+      if (w == 0.0) continue;  // warp-uniform
+      const int32_t n = s_n[j];
       const int32_t* __restrict__ pd = p.post_doc + s_lo[j];
       const double* __restrict__ pr = p.ratio + s_lo[j];
-      // one posting (index i of the list, doc d, ratio rt): accumulate when d is inside the range; otherwise it lies beyond
-      // the range and, if it is the FIRST such posting -- doc(i) >= r1 (doc(n) = +inf) and (i == pos0 or doc(i-1) < r1) --
-      // its index is the term's cursor for the next range.  Returns true for "beyond".
-      auto apply = [&](int32_t i, int32_t d, double rt) -> bool {
-        if (d < r1) {
-          const int x = d - r0;
-          if (PLUS) {
-            acc[x] = __dadd_rn(acc[x], __dmul_rn(w, __dadd_rn(p.delta, rt)));
-            atomicOr(&s_bits[x >> 5], 1u << (x & 31));
-          } else {
-            acc[x] = __dadd_rn(acc[x], __dmul_rn(w, rt));
-          }
-          return false;
-        }
-        if (i <= n && (i == pos0 || __ldg(pd + i - 1) < r1)) cur_out[j] = i;
-        return true;
-      };
-      // chunk loop, specialised on the chunk width (block-uniform) so the unrolled body carries no per-slot predicates
+      int32_t cur = my_cur[j];
+      // chunk loop, specialised on the number of 32-posting chunks in flight (warp-uniform).  The postings of the list are
+      // sorted by doc, so the ones inside [s0, s1) are a prefix of what is fetched: their count advances the cursor.
       auto walk = [&](auto width) {
         constexpr int W = decltype(width)::value;
-        const int32_t* __restrict__ qd = pd + tid;
-        const double* __restrict__ qr = pr + tid;
-        int32_t pos = pos0;
         for (;;) {
           int32_t doc[W];
           double rat[W];
 #pragma unroll
           for (int u = 0; u < W; ++u) {
-            const int32_t i = pos + u * kRsThreads + tid;
+            const int32_t i = cur + u * 32 + lane;
             doc[u] = 0x7fffffff;
             rat[u] = 0.0;
             if (i < n) {
-              doc[u] = __ldg(qd + pos + u * kRsThreads);
-              rat[u] = __ldg(qr + pos + u * kRsThreads);
+              doc[u] = __ldg(pd + i);
+              rat[u] = __ldg(pr + i);
             }
           }
-          bool any_out = false;
+          int inside = 0;
 #pragma unroll
-          for (int u = 0; u < W; ++u) any_out |= apply(pos + u * kRsThreads + tid, doc[u], rat[u]);
-          if (__syncthreads_or(any_out)) break;
-          pos += W * kRsThreads;
+          for (int u = 0; u < W; ++u) {
+            const bool in = doc[u] < s1;
+            if (in) {
+              const int x = doc[u] - s0;
+              if (PLUS) {
+                a[x] = __dadd_rn(a[x], __dmul_rn(w, __dadd_rn(p.delta, rat[u])));
+                atomicOr(&bits[x >> 5], 1u << (x & 31));
+              } else {
+                a[x] = __dadd_rn(a[x], __dmul_rn(w, rat[u]));
+              }
+            }
+            inside += __popc(__ballot_sync(0xffffffffu, in));
+          }
+          cur += inside;
+          if (inside < 32 * W) break;
         }
       };
-      if (wid == 1)
-        walk(std::integral_constant<int, 1>());
-      else
-        walk(std::integral_constant<int, kRsPost>());
+      if (cur < n) {   // warp-uniform: the list still has postings at or beyond this sub-range
+        if (s_wid[j] == 1)
+          walk(std::integral_constant<int, 1>());
+        else
+          walk(std::integral_constant<int, kRsPost>());
+        if (lane == 0) my_cur[j] = cur;
+      }
+      __syncwarp();   // the next term's lanes may touch accumulators this term's other lanes just wrote
       if (PLUS) {
-        // every doc of the range WITHOUT a posting of this term gets idf * (delta + 0.0); a warp owns one bit word
+        // every doc of the sub-range WITHOUT a posting of this term gets idf * (delta + 0.0)
         const double wd = __dmul_rn(w, __dadd_rn(p.delta, 0.0));
-        for (int i = tid; i < kRange; i += kRsThreads) {
-          const uint32_t word = s_bits[i >> 5];
-          if (i < nd && !((word >> (i & 31)) & 1u)) acc[i] = __dadd_rn(acc[i], wd);
-          __syncwarp();
-          if (lane == 0 && word) s_bits[i >> 5] = 0u;
+#pragma unroll 4
+        for (int c = 0; c < kSub / 32; ++c) {
+          const uint32_t word = bits[c];
+          const int i = c * 32 + lane;
+          if (i < nd && !((word >> lane) & 1u)) a[i] = __dadd_rn(a[i], wd);
         }
-        __syncthreads();
+        __syncwarp();
+        if (lane < kSub / 32) bits[lane] = 0u;
+        __syncwarp();
       }
     }
-    // the barrier that ended the last term's loop (or the initial one) ordered all accumulator updates before this point
+    // the sub-range is complete: consume it
     if (MODE == kModeDump) {
-      double* out = p.dump + (size_t)qi * p.n_docs + r0;
-      for (int i = tid; i < nd; i += kRsThreads) out[i] = acc[i];
-      for (int i = tid; i < kRange; i += kRsThreads) acc[i] = 0.0;
+      double* out = p.dump + (size_t)qi * p.n_docs + s0;
+      for (int i = lane; i < kSub; i += 32) {
+        if (i < nd) out[i] = a[i];
+        a[i] = 0.0;
+      }
     } else if (MODE == kModeCollect) {
       // thr is the orderable image of a positive double (or of "every positive score"): for positive scores the key order
       // is the numeric order, so the filter compares doubles and only survivors are converted
-      const unsigned long long t = p.thr[qi];
-      const double td = orderable_f64(t);
       unsigned long long* ok = p.ckey + (size_t)qi * p.n_docs;
       uint32_t* oi = p.cidx + (size_t)qi * p.n_docs;
-      for (int i = tid; i < kRange; i += kRsThreads) {
-        const double sv = acc[i];
-        acc[i] = 0.0;
+#pragma unroll 4
+      for (int i = lane; i < kSub; i += 32) {
+        const double sv = a[i];
+        a[i] = 0.0;
         const bool pass = i < nd && sv > 0.0 && sv >= td && sv <= 1.7976931348623157e308;  // finite positive (NaN fails)
         const unsigned m = __ballot_sync(0xffffffffu, pass);
         if (m) {
@@ -262,33 +275,37 @@ __global__ void __launch_bounds__(kRsThreads, 3) bm25_range_kernel(const RangePa
           if (pass) {
             at += __popc(m & ((1u << lane) - 1u));
             ok[at] = f64_orderable(sv);
-            oi[at] = (uint32_t)(r0 + i);
+            oi[at] = (uint32_t)(s0 + i);
           }
         }
       }
-    } else {  // kModeSample: the accumulators become sort keys in place
-      unsigned long long* keys = reinterpret_cast<unsigned long long*>(acc);
-      if (tid == 0) npos = 0;
-      __syncthreads();
-      int local = 0;
-      for (int i = tid; i < kRange; i += kRsThreads) {
-        const double s = acc[i];
-        const unsigned long long key = (i < nd && s > 0.0) ? f64_orderable(s) : 0ull;
-        keys[i] = key;
-        local += key != 0ull;
-      }
-      local = __reduce_add_sync(0xffffffffu, local);
-      if (lane == 0 && local) atomicAdd(&npos, local);
-      __syncthreads();
-      // S sample ranges each report their ceil(k / S)-th best positive score; at least k docs score >= the MINIMUM of
-      // those, so it is a lower bound of the global k-th best (a range with too few positives degrades the bound to
-      // "every positive score", never below).  thr[] was preset to all-ones by the host.
-      unsigned long long t = kPosZero + 1ull;
-      if (npos >= p.k) t = block_kth_largest(keys, kRange, p.k, hist, scal, 3);  // sign + exponent + 12 mantissa bits
-      if (tid == 0) atomicMin(p.thr + qi, t);
-      return;
     }
+    __syncwarp();
+  }
+  if (MODE == kModeSample) {
+    // the CTA's single range is scored (one sub-range per warp): its accumulators become sort keys in place
     __syncthreads();
+    const int32_t r0 = (int32_t)(first * kRange);
+    const int nd = (int)min((int64_t)kRange, p.n_docs - r0);
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(acc);
+    if (tid == 0) npos = 0;
+    __syncthreads();
+    int local = 0;
+    for (int i = tid; i < kRange; i += kRsThreads) {
+      const double sc = acc[i];
+      const unsigned long long key = (i < nd && sc > 0.0) ? f64_orderable(sc) : 0ull;
+      keys[i] = key;
+      local += key != 0ull;
+    }
+    local = __reduce_add_sync(0xffffffffu, local);
+    if (lane == 0 && local) atomicAdd(&npos, local);
+    __syncthreads();
+    // S sample ranges each report their ceil(k / S)-th best positive score; at least k docs score >= the MINIMUM of
+    // those, so it is a lower bound of the global k-th best (a range with too few positives degrades the bound to
+    // "every positive score", never below).  thr[] was preset to all-ones by the host.
+    unsigned long long t = kPosZero + 1ull;
+    if (npos >= p.k) t = block_kth_largest(keys, kRange, p.k, hist, scal, 3);  // sign + exponent + 12 mantissa bits
+    if (tid == 0) atomicMin(p.thr + qi, t);
   }
 }
 
@@ -471,7 +488,7 @@ int pow2_at_least(int v) {
 }
 
 size_t range_smem_bytes(int max_len) {
-  return (size_t)kRange * 8 + (size_t)std::max(max_len, 1) * (8 + 8 + 8 + 4 + 4) + (kRange / 32) * 4 + 16;
+  return (size_t)kRange * 8 + (size_t)std::max(max_len, 1) * (8 + 8 + 4 + 4 + 4 * kRsWarps) + (kRange / 32) * 4 + 16;
 }
 
 template <int MODE, bool PLUS>
@@ -512,9 +529,9 @@ RangeParams range_params(sb_ctx* ctx, const int32_t* q_terms_dev, const int32_t*
 // consecutive ranges per CTA: long runs amortise the per-term posting-list search, short runs fill the machine
 int ranges_per_cta(sb_ctx* ctx, int nq, int64_t n_ranges) {
   const int64_t resident = (int64_t)ctx->num_sms * 3;  // 3 CTAs of bm25_range_kernel per SM
-  int64_t r = ((int64_t)nq * n_ranges) / (resident * 4);
+  int64_t r = ((int64_t)nq * n_ranges) / (resident * 2);   // about two waves of CTAs: long strips, balanced tail
   if (r < 1) r = 1;
-  if (r > 8) r = 8;
+  if (r > 32) r = 32;
   return (int)r;
 }
 

@@ -9,6 +9,8 @@
 // Epilogues:  BIAS_F16        out16 = acc + bias                      (QKV projection)
 //             BIAS_GELU_F16   out16 = gelu_erf(acc + bias)            (FFN up-projection)
 //             BIAS_RES_F32    out32 = acc + bias + residual32         (attention output / FFN down-projection, pre-LN)
+//             BIAS_RES16_F16  out16 = fp16(acc + bias + residual16)   (the same two GEMMs on the fp16 residual stream:
+//                             half the epilogue bytes; the pre-LN sum is rounded to fp16 once)
 //
 // Bound: tensor pipe (2*M*N*K flops); see DESIGN.md for the per-pair flop count.
 #include <cuda.h>
@@ -255,7 +257,25 @@ template <int EPI>
 __device__ __forceinline__ void epilogue_store_32(const uint32_t (&v)[32], int row, int col, int N,
                                                   const float* __restrict__ bias, const float* __restrict__ residual,
                                                   __half* __restrict__ out16, float* __restrict__ out32) {
-  if (EPI == CE_EPI_BIAS_RES_F32) {
+  if (EPI == CE_EPI_BIAS_RES16_F16) {
+    __half* o = out16 + (size_t)row * N + col;
+    const __half* r = reinterpret_cast<const __half*>(residual) + (size_t)row * N + col;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const uint4 rraw = *reinterpret_cast<const uint4*>(r + j);
+      const __half2* rh = reinterpret_cast<const __half2*>(&rraw);
+      uint4 pk;
+      uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 rf = __half22float2(rh[e]);
+        const __half2 h = __floats2half2_rn(__uint_as_float(v[j + 2 * e]) + __ldg(bias + col + j + 2 * e) + rf.x,
+                                            __uint_as_float(v[j + 2 * e + 1]) + __ldg(bias + col + j + 2 * e + 1) + rf.y);
+        pw[e] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      *reinterpret_cast<uint4*>(o + j) = pk;
+    }
+  } else if (EPI == CE_EPI_BIAS_RES_F32) {
     float* o = out32 + (size_t)row * N + col;
     const float* r = residual + (size_t)row * N + col;
 #pragma unroll
@@ -444,7 +464,44 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       for (int j = 0; j < 32; ++j) {
         f[j] = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bias_lane, j);
       }
-      if (EPI == CE_EPI_BIAS_RES_F32) {
+      if (EPI == CE_EPI_BIAS_RES16_F16) {
+        const __half* res16 = reinterpret_cast<const __half*>(residual);
+#pragma unroll 1
+        for (int p2 = 0; p2 < 2; ++p2) {  // the fp32 sums are staged (no double rounding), the residual joins on the way out
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 w;
+            w.x = p2 ? f[16 + j + 0] : f[j + 0];
+            w.y = p2 ? f[16 + j + 1] : f[j + 1];
+            w.z = p2 ? f[16 + j + 2] : f[j + 2];
+            w.w = p2 ? f[16 + j + 3] : f[j + 3];
+            *reinterpret_cast<float4*>(st + (size_t)lane * kStageRow + (size_t)j * 4) = w;
+          }
+          __syncwarp();
+          // drain: lane = (row parity `sub`, column pair c8 of 8) x 2 row groups -> 4 rows per instruction, every global
+          // access a full 32-byte sector (16 fp16 columns of one row)
+          const int c8 = lane & 7, rsel = lane >> 3;            // rsel in [0, 4)
+          const int col = col0 + 16 * p2 + 2 * c8;
+#pragma unroll 1
+          for (int r0 = 0; r0 < 32; r0 += 16) {
+            uint32_t res[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int row = row0 + r0 + 4 * u + rsel;
+              res[u] = row < M ? __ldg(reinterpret_cast<const uint32_t*>(res16 + (size_t)row * N + col)) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int rr = r0 + 4 * u + rsel, row = row0 + rr;
+              const float2 x = *reinterpret_cast<const float2*>(st + (size_t)rr * kStageRow + (size_t)c8 * 8);
+              const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(&res[u]));
+              const __half2 h = __floats2half2_rn(x.x + rf.x, x.y + rf.y);
+              if (row < M) *reinterpret_cast<uint32_t*>(out16 + (size_t)row * N + col) = *reinterpret_cast<const uint32_t*>(&h);
+            }
+          }
+          __syncwarp();
+        }
+      } else if (EPI == CE_EPI_BIAS_RES_F32) {
 #pragma unroll 1
         for (int p2 = 0; p2 < 2; ++p2) {  // two passes of 16 fp32 columns (64 bytes per staged row)
 #pragma unroll
@@ -575,6 +632,8 @@ int ce_gemm_launch(int epi, const CUtensorMap& map_a, const CUtensorMap& map_w, 
           return launch_ws<CE_EPI_BIAS_GELU_F16, true>(map_a, map_w, M, N, K, bias, residual, out16, out32, st, m_dev);
         case CE_EPI_BIAS_RES_F32:
           return launch_ws<CE_EPI_BIAS_RES_F32, true>(map_a, map_w, M, N, K, bias, residual, out16, out32, st, m_dev);
+        case CE_EPI_BIAS_RES16_F16:
+          return launch_ws<CE_EPI_BIAS_RES16_F16, true>(map_a, map_w, M, N, K, bias, residual, out16, out32, st, m_dev);
       }
     } else {
       switch (epi) {
@@ -584,6 +643,8 @@ int ce_gemm_launch(int epi, const CUtensorMap& map_a, const CUtensorMap& map_w, 
           return launch_ws<CE_EPI_BIAS_GELU_F16, false>(map_a, map_w, M, N, K, bias, residual, out16, out32, st, m_dev);
         case CE_EPI_BIAS_RES_F32:
           return launch_ws<CE_EPI_BIAS_RES_F32, false>(map_a, map_w, M, N, K, bias, residual, out16, out32, st, m_dev);
+        case CE_EPI_BIAS_RES16_F16:
+          return launch_ws<CE_EPI_BIAS_RES16_F16, false>(map_a, map_w, M, N, K, bias, residual, out16, out32, st, m_dev);
       }
     }
   }
@@ -619,6 +680,17 @@ int ce_gemm_launch(int epi, const CUtensorMap& map_a, const CUtensorMap& map_w, 
       }
       ce_gemm_kernel<CE_EPI_BIAS_RES_F32><<<grid, kGemmThreads, kGemmSmem, st>>>(map_a, map_w, M, N, K, bias, residual,
                                                                                  out16, out32, m_dev);
+      break;
+    }
+    case CE_EPI_BIAS_RES16_F16: {
+      static bool once = false;
+      if (!once) {
+        SB_CUDA(cudaFuncSetAttribute(ce_gemm_kernel<CE_EPI_BIAS_RES16_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)kGemmSmem));
+        once = true;
+      }
+      ce_gemm_kernel<CE_EPI_BIAS_RES16_F16><<<grid, kGemmThreads, kGemmSmem, st>>>(map_a, map_w, M, N, K, bias, residual,
+                                                                                   out16, out32, m_dev);
       break;
     }
     default:

@@ -4,7 +4,9 @@
 
 #include "common.cuh"
 
-enum { CE_EPI_BIAS_F16 = 0, CE_EPI_BIAS_GELU_F16 = 1, CE_EPI_BIAS_RES_F32 = 2 };
+// CE_EPI_BIAS_RES16_F16: out16 = fp16(acc + bias + residual16) -- the all-fp16 residual stream of the reranker; `residual`
+// then points at fp16 data (reinterpreted inside the kernels)
+enum { CE_EPI_BIAS_F16 = 0, CE_EPI_BIAS_GELU_F16 = 1, CE_EPI_BIAS_RES_F32 = 2, CE_EPI_BIAS_RES16_F16 = 3 };
 
 // 2-D tensor map over a row-major fp16 matrix [rows][cols] (cols contiguous), box 64 x 128, SWIZZLE_128B
 int ce_make_tensor_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols);

@@ -130,6 +130,8 @@ struct sb_ctx {
   int dense_pair = 1;  // 1 = groups of > 64 queries use the cta_group::2 pair kernel (env SB_DENSE_PAIR=0 disables)
   int dense_sample_per_cta = 2;  // tiles per CTA of the sampling pass (env SB_DENSE_SAMPLE)
   int max_clusters2 = 0;  // co-resident 2-CTA clusters of the pair kernel (0 = not queried yet)
+  int dense_prefetch = 0;      // boxes prefetched into L2 beyond the ring (env SB_DENSE_PREFETCH; 0 = off)
+  int dense_max_stages = 8;    // cap on the TMA ring depth (env SB_DENSE_STAGES)
   // bookkeeping: kernels launched by this library, optional per-kernel CUDA-event timing (bench.py roofline leg)
   uint64_t launches = 0;
   bool prof_on = false;
@@ -194,6 +196,16 @@ struct ProfScope {
     if (b) cudaEventRecord(b, st);
   }
 };
+
+// true when [p, p + bytes) is page-locked host memory the copy engines can reach directly (cudaMallocHost / registered)
+static inline bool host_ptr_is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
 
 static inline cudaStream_t pick_stream(sb_ctx* ctx, void* stream) {
   return stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream;

@@ -38,6 +38,12 @@ struct CeModel {
   // activation workspace (grow-only), sized for m_cap rows
   int64_t m_cap = 0;
   float *x32 = nullptr, *pre32 = nullptr;          // residual stream, pre-LayerNorm sums  [M,H]
+  __half* pre16 = nullptr;                         // pre-LayerNorm sums of the fp16 residual stream  [M,H]
+  // fp16 residual stream (the reranker): x16 is BOTH the GEMM operand and the residual, the pre-LN sum is stored in fp16;
+  // half the bytes of the two N = 384 GEMM epilogues and of the LayerNorms.  CPU study (oracle forward with the LayerNorm
+  // inputs and outputs rounded to fp16): sigmoid scores move by 1.6e-4 relative (tolerance 1e-3).  The embedder keeps the
+  // fp32 stream: its output is the hidden state itself, compared element-wise.
+  bool fp16_stream = false;
   __half *x16 = nullptr, *qkv16 = nullptr, *ctx16 = nullptr, *ffn16 = nullptr;  // [M,H] [M,3H] [M,H] [M,I]
   CUtensorMap m_x16, m_ctx16, m_ffn16;
   std::vector<void*> act_allocs;
@@ -173,14 +179,18 @@ __global__ void ce_embed_ln_kernel(const int32_t* __restrict__ ids, const int32_
   for (int i = 0; i < PER; ++i) {
     const int c = lane + 32 * i;
     const float y = (v[i] - mean) * rstd * g[c] + b[c];
-    x32[(size_t)row * H + c] = y;
+    if (x32) x32[(size_t)row * H + c] = y;
     x16[(size_t)row * H + c] = __float2half_rn(y);
   }
 }
 
-// One warp per row: LayerNorm of the pre-LN sum -> fp32 residual + fp16 GEMM copy.
-template <int H>
-__global__ void ce_ln_kernel(const float* __restrict__ pre, int M_host, const int32_t* __restrict__ m_dev,
+__device__ __forceinline__ float ln_load(const float* p) { return *p; }
+__device__ __forceinline__ float ln_load(const __half* p) { return __half2float(*p); }
+
+// One warp per row: LayerNorm of the pre-LN sum (fp32, or fp16 on the fp16 residual stream) -> fp16 GEMM copy
+// (+ the fp32 residual when x32 != NULL).
+template <int H, typename TIn>
+__global__ void ce_ln_kernel(const TIn* __restrict__ pre, int M_host, const int32_t* __restrict__ m_dev,
                              const float* __restrict__ g, const float* __restrict__ b, float eps,
                              float* __restrict__ x32, __half* __restrict__ x16) {
   constexpr int PER = H / 32;
@@ -190,7 +200,7 @@ __global__ void ce_ln_kernel(const float* __restrict__ pre, int M_host, const in
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
-    v[i] = pre[(size_t)row * H + lane + 32 * i];
+    v[i] = ln_load(pre + (size_t)row * H + lane + 32 * i);
     sum += v[i];
   }
   for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
@@ -207,7 +217,7 @@ __global__ void ce_ln_kernel(const float* __restrict__ pre, int M_host, const in
   for (int i = 0; i < PER; ++i) {
     const int c = lane + 32 * i;
     const float y = (v[i] - mean) * rstd * g[c] + b[c];
-    x32[(size_t)row * H + c] = y;
+    if (x32) x32[(size_t)row * H + c] = y;
     x16[(size_t)row * H + c] = __float2half_rn(y);
   }
 }
@@ -461,6 +471,7 @@ __global__ void __launch_bounds__(128) ce_attention_cls_kernel(const __half* __r
                                                                 const int32_t* __restrict__ lengths,
                                                                 const int32_t* __restrict__ cu, int P, int S, int H,
                                                                 int heads, const float* __restrict__ x32,
+                                                                const __half* __restrict__ x16,
                                                                 __half* __restrict__ ctx_cls, float* __restrict__ xcls32) {
   constexpr int DH = 32, KPL = 16;  // keys per lane: S <= 512
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -517,7 +528,9 @@ __global__ void __launch_bounds__(128) ce_attention_cls_kernel(const __half* __r
     }
   }
   ctx_cls[(size_t)pair * H + head * DH + lane] = __float2half_rn(acc / l);
-  xcls32[(size_t)pair * H + head * DH + lane] = x32[row0 * H + head * DH + lane];
+  // the [CLS] row of the residual stream (fp32 stream, or the fp16 stream widened: the P-row tail of the last layer is fp32)
+  xcls32[(size_t)pair * H + head * DH + lane] =
+      x32 ? x32[row0 * H + head * DH + lane] : __half2float(x16[row0 * H + head * DH + lane]);
 }
 
 // pooled = tanh(Wp x_cls + bp); logit = w . pooled + b; relevance = sigmoid(logit).  fp32 throughout.
@@ -637,6 +650,7 @@ int ensure_workspace(CeModel* m, int64_t P, int64_t M, cudaStream_t st) {
   int rc;
   if ((rc = dev_alloc(m->act_allocs, (void**)&m->x32, (size_t)Mp * H * 4))) return rc;
   if ((rc = dev_alloc(m->act_allocs, (void**)&m->pre32, (size_t)Mp * H * 4))) return rc;
+  if ((rc = dev_alloc(m->act_allocs, (void**)&m->pre16, (size_t)Mp * H * 2))) return rc;
   if ((rc = dev_alloc(m->act_allocs, (void**)&m->x16, (size_t)Mp * H * 2))) return rc;
   if ((rc = dev_alloc(m->act_allocs, (void**)&m->qkv16, (size_t)Mp * 3 * H * 2))) return rc;
   if ((rc = dev_alloc(m->act_allocs, (void**)&m->ctx16, (size_t)Mp * H * 2))) return rc;
@@ -664,11 +678,13 @@ int ce_forward(sb_ctx* ctx, CeModel* m, const int32_t* ids, const int32_t* tts, 
   ProfScope ps(ctx, SB_PROF_CE, st, 3 + (int)m->layers.size() * 7);
   int32_t* cu = m->cu;
   const int32_t* m_dev = cu + P;  // packed row count of this pass (device side only)
+  const bool cls_tail = H % 32 == 0 && H / heads == 32;   // last layer on the P [CLS] rows only
+  const bool h16 = m->fp16_stream && cls_tail;            // fp16 residual stream (see CeModel::fp16_stream)
   ce_cu_kernel<<<1, 1024, 0, st>>>(lens, P, S, cu, m->stats);
   SB_CUDA(cudaGetLastError());
   ce_embed_ln_kernel<H><<<ln_blocks, rows_per_block * 32, 0, st>>>(ids, tts, lens, cu, M, S, c.vocab_size, c.type_vocab,
                                                                    m->word_emb, m->pos_emb, m->type_emb, m->emb_ln_g,
-                                                                   m->emb_ln_b, c.ln_eps, m->x32, m->x16);
+                                                                   m->emb_ln_b, c.ln_eps, h16 ? nullptr : m->x32, m->x16);
   SB_CUDA(cudaGetLastError());
   int rc;
   const int Pp = (P + 127) / 128 * 128;
@@ -678,16 +694,17 @@ int ce_forward(sb_ctx* ctx, CeModel* m, const int32_t* ids, const int32_t* tts, 
     if ((rc = ce_gemm_launch(CE_EPI_BIAS_F16, m->m_x16, L.m_wqkv, Mp, 3 * H, H, L.bqkv, nullptr, m->qkv16, nullptr, st,
                              m_dev)))
       return rc;
-    if (li + 1 == m->layers.size() && H % 32 == 0 && H / heads == 32) {
+    if (li + 1 == m->layers.size() && cls_tail) {
       // last layer: K/V of every token, everything else for the P [CLS] rows only
-      ce_attention_cls_kernel<<<(unsigned)((P * heads + 3) / 4), 128, 0, st>>>(m->qkv16, lens, cu, P, S, H, heads, m->x32,
-                                                                              m->ctxcls16, m->xcls32);
+      ce_attention_cls_kernel<<<(unsigned)((P * heads + 3) / 4), 128, 0, st>>>(m->qkv16, lens, cu, P, S, H, heads,
+                                                                              h16 ? nullptr : m->x32, m->x16, m->ctxcls16,
+                                                                              m->xcls32);
       SB_CUDA(cudaGetLastError());
       if ((rc = ce_gemm_launch(CE_EPI_BIAS_RES_F32, m->m_ctxcls16, L.m_wo, Pp, H, H, L.bo, m->xcls32, nullptr,
                                m->precls32, st)))
         return rc;
-      ce_ln_kernel<H><<<cls_ln_blocks, rows_per_block * 32, 0, st>>>(m->precls32, P, nullptr, L.ln1_g, L.ln1_b, c.ln_eps,
-                                                                     m->xcls32, m->xcls16);
+      ce_ln_kernel<H, float><<<cls_ln_blocks, rows_per_block * 32, 0, st>>>(m->precls32, P, nullptr, L.ln1_g, L.ln1_b,
+                                                                            c.ln_eps, m->xcls32, m->xcls16);
       SB_CUDA(cudaGetLastError());
       if ((rc = ce_gemm_launch(CE_EPI_BIAS_GELU_F16, m->m_xcls16, L.m_w1, Pp, I, H, L.b1, nullptr, m->ffncls16, nullptr,
                                st)))
@@ -695,8 +712,8 @@ int ce_forward(sb_ctx* ctx, CeModel* m, const int32_t* ids, const int32_t* tts, 
       if ((rc = ce_gemm_launch(CE_EPI_BIAS_RES_F32, m->m_ffncls16, L.m_w2, Pp, H, I, L.b2, m->xcls32, nullptr,
                                m->precls32, st)))
         return rc;
-      ce_ln_kernel<H><<<cls_ln_blocks, rows_per_block * 32, 0, st>>>(m->precls32, P, nullptr, L.ln2_g, L.ln2_b, c.ln_eps,
-                                                                     m->xcls32, m->xcls16);
+      ce_ln_kernel<H, float><<<cls_ln_blocks, rows_per_block * 32, 0, st>>>(m->precls32, P, nullptr, L.ln2_g, L.ln2_b,
+                                                                            c.ln_eps, m->xcls32, m->xcls16);
       SB_CUDA(cudaGetLastError());
       if (cls_out) {  // embedder: hand the final [CLS] states over instead of running the classifier head
         SB_CUDA(cudaMemcpyAsync(cls_out, m->xcls32, (size_t)P * H * 4, cudaMemcpyDeviceToDevice, st));
@@ -721,11 +738,30 @@ int ce_forward(sb_ctx* ctx, CeModel* m, const int32_t* ids, const int32_t* tts, 
       ce_attention_kernel<32><<<P * heads, 128, att_smem, st>>>(m->qkv16, lens, cu, S, H, heads, m->ctx16);
     }
     SB_CUDA(cudaGetLastError());
+    if (h16) {
+      // fp16 residual stream: pre16 = fp16(ctx Wo^T + bo + x16), x16 = LN(pre16); the same for the FFN
+      if ((rc = ce_gemm_launch(CE_EPI_BIAS_RES16_F16, m->m_ctx16, L.m_wo, Mp, H, H, L.bo,
+                               reinterpret_cast<const float*>(m->x16), m->pre16, nullptr, st, m_dev)))
+        return rc;
+      ce_ln_kernel<H, __half><<<ln_blocks, rows_per_block * 32, 0, st>>>(m->pre16, M, m_dev, L.ln1_g, L.ln1_b, c.ln_eps,
+                                                                         nullptr, m->x16);
+      SB_CUDA(cudaGetLastError());
+      if ((rc = ce_gemm_launch(CE_EPI_BIAS_GELU_F16, m->m_x16, L.m_w1, Mp, I, H, L.b1, nullptr, m->ffn16, nullptr, st,
+                               m_dev)))
+        return rc;
+      if ((rc = ce_gemm_launch(CE_EPI_BIAS_RES16_F16, m->m_ffn16, L.m_w2, Mp, H, I, L.b2,
+                               reinterpret_cast<const float*>(m->x16), m->pre16, nullptr, st, m_dev)))
+        return rc;
+      ce_ln_kernel<H, __half><<<ln_blocks, rows_per_block * 32, 0, st>>>(m->pre16, M, m_dev, L.ln2_g, L.ln2_b, c.ln_eps,
+                                                                         nullptr, m->x16);
+      SB_CUDA(cudaGetLastError());
+      continue;
+    }
     if ((rc = ce_gemm_launch(CE_EPI_BIAS_RES_F32, m->m_ctx16, L.m_wo, Mp, H, H, L.bo, m->x32, nullptr, m->pre32, st,
                              m_dev)))
       return rc;
-    ce_ln_kernel<H><<<ln_blocks, rows_per_block * 32, 0, st>>>(m->pre32, M, m_dev, L.ln1_g, L.ln1_b, c.ln_eps, m->x32,
-                                                               m->x16);
+    ce_ln_kernel<H, float><<<ln_blocks, rows_per_block * 32, 0, st>>>(m->pre32, M, m_dev, L.ln1_g, L.ln1_b, c.ln_eps,
+                                                                      m->x32, m->x16);
     SB_CUDA(cudaGetLastError());
     if ((rc = ce_gemm_launch(CE_EPI_BIAS_GELU_F16, m->m_x16, L.m_w1, Mp, I, H, L.b1, nullptr, m->ffn16, nullptr, st,
                              m_dev)))
@@ -733,8 +769,8 @@ int ce_forward(sb_ctx* ctx, CeModel* m, const int32_t* ids, const int32_t* tts, 
     if ((rc = ce_gemm_launch(CE_EPI_BIAS_RES_F32, m->m_ffn16, L.m_w2, Mp, H, I, L.b2, m->x32, nullptr, m->pre32, st,
                              m_dev)))
       return rc;
-    ce_ln_kernel<H><<<ln_blocks, rows_per_block * 32, 0, st>>>(m->pre32, M, m_dev, L.ln2_g, L.ln2_b, c.ln_eps, m->x32,
-                                                               m->x16);
+    ce_ln_kernel<H, float><<<ln_blocks, rows_per_block * 32, 0, st>>>(m->pre32, M, m_dev, L.ln2_g, L.ln2_b, c.ln_eps,
+                                                                      m->x32, m->x16);
     SB_CUDA(cudaGetLastError());
   }
   SB_REQUIRE(cls_out == nullptr, SB_ERR_UNSUPPORTED, "encoder output needs 32-wide attention heads");
@@ -1023,6 +1059,9 @@ int sb_ce_load(sb_ctx* ctx, const float* weights, int64_t n_floats, const sb_ce_
   int rc = ce_load_model(ctx, weights, n_floats, cfg, &m);
   if (rc) return rc;
   if (ctx->ce) ce_model_free(ctx->ce);
+  // the reranker runs on the fp16 residual stream (env SB_CE_FP32_STREAM=1 keeps the fp32 stream for A/B measurements)
+  const char* keep32 = getenv("SB_CE_FP32_STREAM");
+  m->fp16_stream = !(keep32 && atoi(keep32) != 0);
   ctx->ce = m;
   return SB_OK;
 }

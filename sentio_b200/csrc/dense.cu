@@ -1053,17 +1053,31 @@ int sb_dense_topk(sb_ctx* ctx, int slot, const float* q, int32_t B, int32_t k, i
   }
   int rc;
   const size_t qbytes = (size_t)B * ix.d * sizeof(float);
-  if ((rc = ctx->pin_in.reserve(qbytes))) return rc;
-  memcpy(ctx->pin_in.p, q, qbytes);
-  float* q_pad = nullptr;
-  if ((rc = sb_dense_pad_queries(ctx, ix, ctx->pin_in.as<float>(), B, false, &q_pad, st))) return rc;
   const size_t nid = (size_t)B * k;
+  // page-locked caller buffers are used in place; pageable ones go through the context's pinned staging
+  const bool in_pinned = host_ptr_is_pinned(q);
+  const bool out_pinned = host_ptr_is_pinned(out_ids) && host_ptr_is_pinned(out_scores) && host_ptr_is_pinned(out_counts);
+  const float* q_src = q;
+  if (!in_pinned) {
+    if ((rc = ctx->pin_in.reserve(qbytes))) return rc;
+    memcpy(ctx->pin_in.p, q, qbytes);
+    q_src = ctx->pin_in.as<float>();
+  }
+  float* q_pad = nullptr;
+  if ((rc = sb_dense_pad_queries(ctx, ix, q_src, B, false, &q_pad, st))) return rc;
   if ((rc = ctx->out_ids_dev.reserve(nid * 8))) return rc;
   if ((rc = ctx->out_sc_dev.reserve(nid * 8))) return rc;
   if ((rc = ctx->out_cnt_dev.reserve((size_t)B * 4))) return rc;
   if ((rc = dense_topk_enqueue(ctx, ix, q_pad, B, k, ctx->out_ids_dev.as<int64_t>(), ctx->out_sc_dev.as<double>(),
                                ctx->out_cnt_dev.as<int32_t>(), st)))
     return rc;
+  if (out_pinned) {
+    SB_CUDA(cudaMemcpyAsync(out_ids, ctx->out_ids_dev.p, nid * 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(out_scores, ctx->out_sc_dev.p, nid * 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(out_counts, ctx->out_cnt_dev.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    return SB_OK;
+  }
   if ((rc = ctx->pin_out.reserve(nid * 16 + (size_t)B * 4))) return rc;
   uint8_t* po = ctx->pin_out.as<uint8_t>();
   SB_CUDA(cudaMemcpyAsync(po, ctx->out_ids_dev.p, nid * 8, cudaMemcpyDeviceToHost, st));

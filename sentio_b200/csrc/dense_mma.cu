@@ -26,6 +26,8 @@
 // warps 2..5 = epilogue (tcgen05.ld 32x32b, one corpus row per thread).
 #include <cuda.h>
 
+#include <math.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -48,6 +50,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+// L2 prefetch of a tensor-map box (no shared-memory destination): keeps more HBM requests in flight than the ring holds
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+
 __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
@@ -129,6 +136,20 @@ struct TmemLd<16> {
   }
 };
 
+// Sampling-pass epilogue.  The threshold only needs a LOWER bound of the k-th best score, and the k-th largest of ANY
+// set of distinct rows' scores is one: each warp contributes the best score among its 32 rows (one REDUX per query
+// column, no atomics, one 8-byte store per (warp, query) at slot `slot` of the CTA's list) instead of all 32.
+template <int NV>
+__device__ __forceinline__ void sample_emit(const uint32_t (&v)[NV], bool live, float invn, unsigned long long* my_cand,
+                                            size_t q_stride, int c0, int slot, int lane) {
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const float score = live ? __uint_as_float(v[j]) * invn : -INFINITY;
+    const uint32_t best = __reduce_max_sync(0xffffffffu, f32_orderable(score));
+    if (lane == (j & 31)) my_cand[(size_t)(c0 + j) * q_stride + slot] = ((unsigned long long)best << 32) | 0xffffffffull;
+  }
+}
+
 struct MmaScanParams {
   const float* inv_norm;
   const float* thr_init;        // [QBN] safe initial thresholds (NULL = -inf: sampling pass)
@@ -141,6 +162,7 @@ struct MmaScanParams {
   int32_t tile_first, tile_step; // global tile index = tile_first + t * tile_step,  t in [0, num_tiles)
   int32_t capg;
   int32_t stages;
+  int32_t prefetch;             // boxes (16 KB) prefetched into L2 beyond the shared-memory ring (0 = off)
 };
 
 template <int QBN>
@@ -201,11 +223,17 @@ dense_scan_mma_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_
       mbar_expect_tx(bar_q, q_bytes);
       for (int kb = 0; kb < p.kb_count; ++kb) tma_load_2d(base + (uint32_t)kb * kQBlockBytes, &tm_q, kb * kBK, 0, bar_q);
       int it = 0;
+      const int total_it = my_tiles * p.kb_count;
       for (int t = 0; t < my_tiles; ++t) {
         const int tile = p.tile_first + (cta + t * grid) * p.tile_step;
         for (int kb = 0; kb < p.kb_count; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t use = (uint32_t)(it / p.stages);
+          const int pf = it + p.stages + p.prefetch;   // a box the ring will only reach later: pull it into L2 now
+          if (p.prefetch > 0 && pf < total_it) {
+            const int pt = pf / p.kb_count, pkb = pf - pt * p.kb_count;
+            tma_prefetch_l2_2d(&tm_rows, pkb * kBK, (p.tile_first + (cta + pt * grid) * p.tile_step) * kTileRows);
+          }
           if (it >= p.stages) mbar_wait(bar_empty + 8 * s, (use & 1u) ^ 1u);
           mbar_expect_tx(bar_full + 8 * s, kATileBytes);
           tma_load_2d(a0 + (uint32_t)s * kATileBytes, &tm_rows, kb * kBK, tile * kTileRows, bar_full + 8 * s);
@@ -256,6 +284,11 @@ dense_scan_mma_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_
         uint32_t v[16];
         TmemLd<16>::ld(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * QBN + c0), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (p.thr_init == nullptr) {
+          // sampling pass: one key per (warp, query) = the best score among the warp's 32 rows (see sample_emit)
+          sample_emit<16>(v, row < p.n, invn, my_cand, q_stride, c0, t * 4 + quad, lane);
+          continue;
+        }
         if (row < p.n) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -276,8 +309,9 @@ dense_scan_mma_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   for (int i = threadIdx.x; i < QBN; i += blockDim.x) {
-    p.counts[(size_t)i * grid + cta] = min(cnt[i], p.capg);
-    if (cnt[i] > p.capg && p.fallback) p.fallback[i] = 1;   // nothing is dropped silently: brute force answers this query
+    const int c = p.thr_init == nullptr ? my_tiles * 4 : cnt[i];   // sampling pass: 4 warp maxima per tile
+    p.counts[(size_t)i * grid + cta] = min(c, p.capg);
+    if (c > p.capg && p.fallback) p.fallback[i] = 1;   // nothing is dropped silently: brute force answers this query
   }
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * QBN) : "memory");
@@ -354,6 +388,7 @@ dense_scan_mma2_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid
       for (int kb = 0; kb < p.kb_count; ++kb)
         tma_load_2d_pair(base + (uint32_t)kb * kQBlockBytes, &tm_q, kb * kBK, (int)rank * HQ, lead_q);
       int it = 0;
+      const int total_it = my_tiles * p.kb_count;
       for (int t = 0; t < my_tiles; ++t) {
         const int li = 2 * (pair + t * npairs) + (int)rank;
         // the odd tile of the last pair may not exist: load tile 0 again (served by L2), the epilogue ignores it
@@ -361,6 +396,12 @@ dense_scan_mma2_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid
         for (int kb = 0; kb < p.kb_count; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t use = (uint32_t)(it / p.stages);
+          const int pf = it + p.stages + p.prefetch;   // a box the ring will only reach later: pull it into L2 now
+          if (p.prefetch > 0 && pf < total_it) {
+            const int pt = pf / p.kb_count, pkb = pf - pt * p.kb_count;
+            const int pli = 2 * (pair + pt * npairs) + (int)rank;
+            if (pli < p.num_tiles) tma_prefetch_l2_2d(&tm_rows, pkb * kBK, (p.tile_first + pli * p.tile_step) * kTileRows);
+          }
           if (it >= p.stages) mbar_wait(bar_empty + 8 * s, (use & 1u) ^ 1u);
           if (rank == 0) mbar_expect_tx(bar_full + 8 * s, 2u * kATileBytes);
           tma_load_2d_pair(a0 + (uint32_t)s * kATileBytes, &tm_rows, kb * kBK, tile * kTileRows,
@@ -417,6 +458,11 @@ dense_scan_mma2_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid
         TmemLd<16>::ld(taddr, v);
         TmemLd<16>::ld(taddr + 16u, w);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (p.thr_init == nullptr) {   // sampling pass: one key per (warp, query)
+          sample_emit<16>(v, live, invn, my_cand, q_stride, c0, t * 4 + quad, lane);
+          sample_emit<16>(w, live, invn, my_cand, q_stride, c0 + 16, t * 4 + quad, lane);
+          continue;
+        }
         if (live) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -436,8 +482,9 @@ dense_scan_mma2_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   for (int i = threadIdx.x; i < NQ; i += blockDim.x) {
-    p.counts[(size_t)i * grid + cta] = min(cnt[i], p.capg);
-    if (cnt[i] > p.capg && p.fallback) p.fallback[i] = 1;
+    const int c = p.thr_init == nullptr ? my_tiles * 4 : cnt[i];
+    p.counts[(size_t)i * grid + cta] = min(c, p.capg);
+    if (c > p.capg && p.fallback) p.fallback[i] = 1;
   }
   cluster_sync_all();   // no CTA leaves (or frees tensor memory) while its peer can still signal it
   if (warp == 1) {
@@ -710,26 +757,31 @@ int dense_mma_topk_enqueue(sb_ctx* ctx, DenseIndex& ix, const float* q_pad, int 
   size_t smem2 = 0;
   if (pair_ok) {
     const size_t q_bytes = (size_t)64 * ix.d_pad * 2;
-    stages2 = std::max(3, std::min((int)((ctx->smem_optin - q_bytes - 4096) / kATileBytes), 8));
+    stages2 = std::max(3, std::min((int)((ctx->smem_optin - q_bytes - 3072) / kATileBytes), ctx->dense_max_stages));
     smem2 = q_bytes + (size_t)stages2 * kATileBytes + 2048 + 1024;
     grid2 = 2 * std::min(pair_clusters(ctx, smem2), (total_tiles + 1) / 2);
   }
   const int grid = std::max(grid1, grid2);          // list slots per query: both kernels index [row][grid][capg]
   const int grid_min = grid2 > 0 ? std::min(grid1, grid2) : grid1;
-  // sampling pass geometry: a few tiles per CTA spread evenly over the corpus
-  const int sample_tiles = std::min(ctx->dense_sample_per_cta * grid, total_tiles);
+  // sampling pass geometry: a few tiles per CTA spread evenly over the corpus; every warp of a sampled tile reports the
+  // best of its 32 rows, so a query gets n_s = 4 * sample_tiles keys -- aim for n_s >= 4 k
+  const int per_cta = std::max(ctx->dense_sample_per_cta, std::min(8, (k + grid - 1) / grid));
+  const int sample_tiles = std::min(per_cta * grid, total_tiles);
   const int sample_step = total_tiles / sample_tiles;
   const int sgrid1 = std::min(grid1, sample_tiles);
   const int sgrid2 = pair_ok ? std::min(grid2, (sample_tiles + 1) & ~1) : 0;
   const int sgrid = std::max(sgrid1, sgrid2);
   const int sgrid_min = sgrid2 > 0 ? std::min(sgrid1, sgrid2) : sgrid1;
-  // per-(CTA, query) list capacity.  The sampling pass appends every sampled row of the CTA; the full pass about
-  // rows_per_cta * k / sampled_rows (threshold = k-th best of the sample): 16x that plus slack.  An overflowing list
-  // raises the query's fallback flag, so the capacity only trades memory against the odds of a brute-force answer.
+  // per-(CTA, query) list capacity.  Sampling pass: 4 keys per sampled tile of the CTA.  Full pass: the threshold is the
+  // k-th best of n_s maxima of 32 rows, passed by a fraction p of the rows with (1 - p)^32 = 1 - k / n_s; 8x the expected
+  // rows_per_cta * p plus slack.  An overflowing list raises the query's fallback flag, so the capacity only trades
+  // memory against the odds of a brute-force answer; no threshold at all (k >= n_s) means every row survives.
   const int64_t worst = (int64_t)((total_tiles + grid_min - 1) / grid_min + 1) * kTileRows;
-  const int64_t samp_rows = (int64_t)((sample_tiles + sgrid_min - 1) / sgrid_min + 1) * kTileRows;
-  const int64_t expect = worst * (int64_t)k / std::max<int64_t>(1, (int64_t)sample_tiles * kTileRows);
-  const int capg = (int)std::min<int64_t>(worst, std::max<int64_t>(16 * expect + 256, samp_rows));
+  const int64_t samp_keys = (int64_t)((sample_tiles + sgrid_min - 1) / sgrid_min + 1) * 4;
+  const double f = (double)k / (4.0 * sample_tiles);
+  const double pass = f >= 0.95 ? 1.0 : -log(1.0 - f) / 32.0;
+  const int64_t expect = (int64_t)((double)worst * pass) + 1;
+  const int capg = (int)std::min<int64_t>(worst, std::max<int64_t>(8 * expect + 256, samp_keys));
   int rc;
   SB_REQUIRE(grid <= kSelectThreads, SB_ERR_UNSUPPORTED, "dense_mma: %d CTAs exceed the select kernel's prefix width", grid);
   const int n_groups = (B + gsz - 1) / gsz;
@@ -779,7 +831,7 @@ int dense_mma_topk_enqueue(sb_ctx* ctx, DenseIndex& ix, const float* q_pad, int 
         G.nq = std::min(G.qbn, left);
         if ((rc = encode_map(&G.tm_q, q16g, G.qbn, ix.d_pad, G.qbn))) return rc;
         const size_t q_bytes = (size_t)G.qbn * ix.d_pad * 2;
-        G.stages = std::max(3, std::min((int)((ctx->smem_optin - q_bytes - 4096) / kATileBytes), 8));
+        G.stages = std::max(3, std::min((int)((ctx->smem_optin - q_bytes - 3072) / kATileBytes), ctx->dense_max_stages));
         G.smem = q_bytes + (size_t)G.stages * kATileBytes + 2048 + 1024;
       }
       rows_total = g * gsz + G.qbn;
@@ -789,6 +841,7 @@ int dense_mma_topk_enqueue(sb_ctx* ctx, DenseIndex& ix, const float* q_pad, int 
     mp.n = ix.n;
     mp.kb_count = kb_count;
     mp.capg = capg;
+    mp.prefetch = ctx->dense_prefetch;
     SelectParams sp;
     sp.cand = cand;
     sp.counts = counts;

@@ -40,12 +40,16 @@ class B200Engine:
         self.bm25: Bm25IndexData | None = None
         self.bm25_id_base = 0
         self.ce_config = None
+        self._pinned: list = []
 
     # ------------------------------------------------------------------ lifetime
     def close(self) -> None:
         if getattr(self, "_h", None):
             self._lib.sb_destroy(self._h)
             self._h = None
+            for p in getattr(self, "_pinned", []):
+                self._lib.sb_host_free(C.c_void_p(p))
+            self._pinned = []
 
     def __del__(self):  # pragma: no cover
         try:
@@ -100,16 +104,34 @@ class B200Engine:
         """0 = auto, 1 = CUDA-core scan only, 2 = tcgen05 batched scan whenever eligible."""
         check(self._lib.sb_dense_set_mode(self._h, int(mode)), "sb_dense_set_mode")
 
-    def dense_topk(self, q: np.ndarray, k: int, slot: int = 0):
+    def pinned_empty(self, shape, dtype) -> np.ndarray:
+        """A page-locked NumPy array (``sb_host_alloc``): host entry points copy straight from / into such arrays, with
+        no staging memcpy.  For callers that reuse their request / response buffers; freed with the engine."""
+        shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        dt = np.dtype(dtype)
+        nbytes = max(1, int(np.prod(shape)) * dt.itemsize)
+        p = self._lib.sb_host_alloc(nbytes)
+        if not p:
+            raise SentioB200Error("sb_host_alloc failed")
+        self._pinned.append(p)
+        buf = (C.c_uint8 * nbytes).from_address(p)
+        return np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+
+    def dense_topk(self, q: np.ndarray, k: int, slot: int = 0, out=None):
+        """``out`` = (ids [B,k] int64, scores [B,k] float64, counts [B] int32) to be filled in place (e.g. page-locked
+        arrays from ``pinned_empty``); fresh arrays otherwise."""
         q = np.ascontiguousarray(np.atleast_2d(q), dtype=np.float32)
         B, d = q.shape
         if slot not in self.dense_dim:
             raise SentioB200Error(f"dense slot {slot} has no index loaded")
         if d != self.dense_dim[slot]:
             raise ValueError(f"query dimension {d} != index dimension {self.dense_dim[slot]}")
-        ids = np.empty((B, k), dtype=np.int64)
-        sc = np.empty((B, k), dtype=np.float64)
-        cnt = np.empty(B, dtype=np.int32)
+        if out is None:
+            out = (np.empty((B, k), dtype=np.int64), np.empty((B, k), dtype=np.float64), np.empty(B, dtype=np.int32))
+        ids, sc, cnt = out
+        if ids.shape != (B, k) or sc.shape != (B, k) or cnt.shape != (B,) or ids.dtype != np.int64 \
+                or sc.dtype != np.float64 or cnt.dtype != np.int32 or not (ids.flags.c_contiguous and sc.flags.c_contiguous):
+            raise ValueError("dense_topk: out must be (int64 [B,k], float64 [B,k], int32 [B]) C-contiguous arrays")
         check(self._lib.sb_dense_topk(self._h, slot, _ptr(q), B, k, _ptr(ids), _ptr(sc), _ptr(cnt)), "sb_dense_topk")
         return ids, sc, cnt
 
@@ -149,11 +171,15 @@ class B200Engine:
 
     def build_bm25_gpu(self, flat_tokens: np.ndarray, doc_offsets: np.ndarray, variant: str = "okapi", k1: float = 1.5,
                        b: float = 0.75, epsilon: float = 0.25, delta: float = 1.0, id_base: int = 0,
-                       export: bool = False) -> Bm25IndexData:
+                       export: bool = False, stats_hook=None) -> Bm25IndexData:
         """Index build on the device (sb_bm25_build_*): sort-based CSR construction from an integer token stream, idf on
         the host from the device-computed df, index installed without the postings ever visiting the host
         (``export=True`` additionally copies the CSR back, for ``save`` / ``shard``).  Same index as
-        ``index.build_bm25_from_token_ids`` + ``load_bm25`` (tests/test_bm25_build_gpu.py)."""
+        ``index.build_bm25_from_token_ids`` + ``load_bm25`` (tests/test_bm25_build_gpu.py).
+
+        ``stats_hook(term_token, df, n_docs, n_tokens) -> (idf_of_token, average_idf, avgdl)`` turns the build into one
+        SHARD of a partitioned corpus: the hook exchanges the per-shard statistics (HybridPipeline.build_bm25_sharded
+        all-gathers them) and returns the corpus-global idf / avgdl that this shard's postings are scored with."""
         from .index import finish_gpu_built_index
 
         variant = variant.lower()
@@ -173,7 +199,8 @@ class B200Engine:
         if export:
             csr = (np.empty(V + 1, np.int64), np.empty(nnz, np.int32), np.empty(nnz, np.uint16), np.empty(n_docs, np.int32))
             check(self._lib.sb_bm25_build_export(self._h, *[_ptr(a) for a in csr]), "sb_bm25_build_export")
-        data = finish_gpu_built_index(df, term_token, n_docs, len(flat), variant, k1, b, epsilon, delta, csr)
+        gstats = stats_hook(term_token, df, n_docs, len(flat)) if stats_hook is not None else None
+        data = finish_gpu_built_index(df, term_token, n_docs, len(flat), variant, k1, b, epsilon, delta, csr, gstats)
         idf = np.ascontiguousarray(data.idf, dtype=np.float64)
         check(self._lib.sb_bm25_build_finish(self._h, _ptr(idf), float(data.avgdl), 1 if variant == "plus" else 0,
                                              float(k1), float(b), float(delta), int(id_base)), "sb_bm25_build_finish")

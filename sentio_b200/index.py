@@ -104,18 +104,45 @@ def _idf_table(df: np.ndarray, n_docs: int, variant: str, epsilon: float) -> tup
     return idf, average_idf
 
 
-def finish_gpu_built_index(df: np.ndarray, term_token: np.ndarray, n_docs: int, n_tokens: int, variant: str, k1: float,
-                           b: float, epsilon: float, delta: float, csr=None) -> Bm25IndexData:
-    """Host half of the GPU index build (engine.build_bm25_gpu): idf table from the device-computed df (math.log, bit for
-    bit like rank_bm25) + raw token -> term id map.  ``csr`` = (indptr, post_doc, post_tf, doc_len) when exported."""
+def global_bm25_stats(shard_term_tokens, shard_dfs, shard_n_docs, shard_n_tokens, variant: str, epsilon: float):
+    """Corpus-global BM25 statistics from per-shard GPU builds (contiguous doc ranges, shards in corpus order).
+
+    ``shard_term_tokens[r]`` = raw token of every local term of shard r in LOCAL first-occurrence order, ``shard_dfs[r]`` the
+    matching document frequencies.  The global vocabulary order (which fixes the summation order of rank_bm25's average
+    idf) is the corpus' first-occurrence order = shard 0's terms, then the terms first seen in shard 1, ...  Returns
+    (idf_of_token: dict raw token -> idf, average_idf, n_docs, avgdl): bit-identical to ``_idf_table`` on the whole corpus."""
+    order, df_of = [], {}
+    for toks, dfs in zip(shard_term_tokens, shard_dfs):
+        for t, f in zip(np.asarray(toks).tolist(), np.asarray(dfs).tolist()):
+            if t in df_of:
+                df_of[t] += f
+            else:
+                df_of[t] = f
+                order.append(t)
+    n_docs = int(sum(shard_n_docs))
+    df = np.fromiter((df_of[t] for t in order), dtype=np.int64, count=len(order))
     idf, average_idf = _idf_table(df, n_docs, variant, epsilon)
+    return dict(zip(order, idf.tolist())), average_idf, n_docs, float(sum(shard_n_tokens)) / n_docs
+
+
+def finish_gpu_built_index(df: np.ndarray, term_token: np.ndarray, n_docs: int, n_tokens: int, variant: str, k1: float,
+                           b: float, epsilon: float, delta: float, csr=None, global_stats=None) -> Bm25IndexData:
+    """Host half of the GPU index build (engine.build_bm25_gpu): idf table from the device-computed df (math.log, bit for
+    bit like rank_bm25) + raw token -> term id map.  ``csr`` = (indptr, post_doc, post_tf, doc_len) when exported.
+    ``global_stats`` = (idf_of_token, average_idf, avgdl) for a corpus SHARD: idf / avgdl stay corpus-global."""
+    if global_stats is not None:
+        idf_of_token, average_idf, avgdl = global_stats
+        idf = np.fromiter((idf_of_token[int(t)] for t in term_token), dtype=np.float64, count=len(term_token))
+    else:
+        idf, average_idf = _idf_table(df, n_docs, variant, epsilon)
+        avgdl = n_tokens / n_docs
     size = int(term_token.max()) + 1 if len(term_token) else 0
     token_id_map = np.full(size, -1, dtype=np.int32)
     token_id_map[term_token] = np.arange(len(term_token), dtype=np.int32)
     empty = (np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros(0, np.uint16), np.zeros(0, np.int32))
     indptr, post_doc, post_tf, doc_len = csr if csr is not None else empty
     return Bm25IndexData(variant=variant, k1=float(k1), b=float(b), epsilon=float(epsilon), delta=float(delta),
-                         n_docs=int(n_docs), avgdl=n_tokens / n_docs, indptr=indptr, post_doc=post_doc, post_tf=post_tf,
+                         n_docs=int(n_docs), avgdl=avgdl, indptr=indptr, post_doc=post_doc, post_tf=post_tf,
                          doc_len=doc_len, idf=idf, vocab=None, token_id_map=token_id_map, average_idf=average_idf,
                          extras={"built_on": "gpu", "postings_on_host": csr is not None})
 

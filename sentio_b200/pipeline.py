@@ -75,6 +75,33 @@ class HybridPipeline:
     def load_bm25(self, data: Bm25IndexData, id_base: int = 0) -> None:
         self.engine.load_bm25(data, id_base=id_base)
 
+    def build_bm25_sharded(self, flat_tokens: np.ndarray, doc_offsets: np.ndarray, id_base: int = 0, variant: str = "okapi",
+                           k1: float = 1.5, b: float = 0.75, epsilon: float = 0.25, delta: float = 1.0,
+                           export: bool = False) -> Bm25IndexData:
+        """Index build of a PARTITIONED corpus without a host-side global index: every rank builds the postings of its own
+        doc range on its GPU (sb_bm25_build_*), the per-shard (term, df, doc / token counts) are all-gathered -- a few
+        hundred KB -- and every rank derives the same corpus-global idf / avgdl (index.global_bm25_stats: bit-identical to
+        the single-index build), which its shard is then scored with.  Replaces building the whole index on every host."""
+        import torch.distributed as dist
+
+        from .index import global_bm25_stats
+
+        def hook(term_token, df, n_docs, n_tokens):
+            if self.world == 1:
+                parts = [(term_token, df, n_docs, n_tokens)]
+            else:
+                parts = [None] * self.world
+                dist.all_gather_object(parts, (np.asarray(term_token), np.asarray(df), int(n_docs), int(n_tokens)),
+                                       group=self.group)
+            idf_of, avg_idf, _, avgdl = global_bm25_stats([p[0] for p in parts], [p[1] for p in parts],
+                                                          [p[2] for p in parts], [p[3] for p in parts], variant, epsilon)
+            return idf_of, avg_idf, avgdl
+
+        data = self.engine.build_bm25_gpu(flat_tokens, doc_offsets, variant=variant, k1=k1, b=b, epsilon=epsilon,
+                                          delta=delta, id_base=id_base, export=export, stats_hook=hook)
+        data.extras["shard_local"] = True   # postings / doc_len cover THIS rank's doc range only
+        return data
+
     def load_cross_encoder(self, weights) -> None:
         """weights: sentio_b200.cross_encoder.CrossEncoderWeights"""
         self.engine.ce_load(weights.blob(), weights.config)
@@ -112,7 +139,7 @@ class HybridPipeline:
     def _to_host(self, tensors, name: str = "out"):
         """device tensors -> NumPy arrays through cached pinned buffers: all copies are enqueued, ONE synchronisation."""
         if self.device is None:
-            return tuple(t.numpy() for t in tensors)
+            return tuple(t.numpy().copy() for t in tensors)   # copies: the tensors are cached buffers reused by the next call
         outs = []
         for i, t in enumerate(tensors):
             key = ("pin_out", name, i, tuple(t.shape), t.dtype)
@@ -253,10 +280,11 @@ class HybridPipeline:
         return min(B, self.rank * per), min(B, (self.rank + 1) * per)
 
     # ------------------------------------------------------------------ host (e2e) path
-    def search_dense(self, q: np.ndarray, k: int):
-        """Host in / host out.  world == 1: straight through the C-ABI host entry point."""
+    def search_dense(self, q: np.ndarray, k: int, out=None):
+        """Host in / host out.  world == 1: straight through the C-ABI host entry point (``out``: arrays to fill in
+        place -- page-locked ones from ``engine.pinned_empty`` skip the staging copies)."""
         if self.world == 1:
-            return self.engine.dense_topk(q, k)
+            return self.engine.dense_topk(q, k, out=out) if out is not None else self.engine.dense_topk(q, k)
         t = self.torch
         q_t = self._to_dev(np.ascontiguousarray(q, dtype=np.float32), "q")
         return self._to_host(self.dense_dev(q_t, k), "dense")

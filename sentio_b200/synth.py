@@ -68,6 +68,31 @@ def text_corpus_tokens(n: int, seed: int = 1235, vocab: int = VOCAB, mean_len: i
     return flat, off
 
 
+def text_corpus_tokens_range(lo: int, hi: int, seed: int = 1235, vocab: int = VOCAB, mean_len: int = 80, min_len: int = 8,
+                             chunk: int = 65536):
+    """Docs [lo, hi) of a text corpus whose 65536-doc chunks are seeded independently (SeedSequence([seed, chunk_index])),
+    so a rank only ever generates its own shard: -> (flat_tokens int32, doc_offsets int64 [hi - lo + 1], shard-local).
+    (A different corpus than ``text_corpus_tokens``, same distribution; used for corpora above 2 M docs.)"""
+    cdf = _zipf_cdf(vocab)
+    flats, lens_all = [], []
+    c = lo // chunk
+    while c * chunk < hi:
+        rng = np.random.default_rng(np.random.SeedSequence([seed, c]))
+        lens = np.maximum(min_len, rng.poisson(mean_len, size=chunk)).astype(np.int64)
+        off = np.zeros(chunk + 1, dtype=np.int64)
+        np.cumsum(lens, out=off[1:])
+        flat = np.searchsorted(cdf, rng.random(int(off[-1])), side="right").astype(np.int32)
+        np.minimum(flat, vocab - 1, out=flat)
+        a, b = max(lo, c * chunk) - c * chunk, min(hi, (c + 1) * chunk) - c * chunk
+        flats.append(flat[off[a]:off[b]])
+        lens_all.append(lens[a:b])
+        c += 1
+    lens = np.concatenate(lens_all) if lens_all else np.zeros(0, np.int64)
+    out_off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=out_off[1:])
+    return (np.concatenate(flats) if flats else np.zeros(0, np.int32)), out_off
+
+
 def query_tokens(b: int, seed: int = 4322, vocab: int = VOCAB, length: int = 6) -> np.ndarray:
     rng = np.random.default_rng(seed)
     cdf = _zipf_cdf(vocab)

@@ -55,11 +55,19 @@ class OracleEngine:
                              data.variant, data.k1, data.b, data.delta)
 
     def build_bm25_gpu(self, flat_tokens, doc_offsets, variant="okapi", k1=1.5, b=0.75, epsilon=0.25, delta=1.0,
-                       id_base=0, export=False):
-        """Double of B200Engine.build_bm25_gpu: the host builder stands in for the device build."""
+                       id_base=0, export=False, stats_hook=None):
+        """Double of B200Engine.build_bm25_gpu: the host builder stands in for the device build (``stats_hook``: the
+        shard's idf / avgdl are replaced by the corpus-global ones, like the product does)."""
         from sentio_b200.index import build_bm25_from_token_ids
 
         data = build_bm25_from_token_ids(flat_tokens, doc_offsets, variant, k1, b, epsilon, delta)
+        if stats_hook is not None:
+            term_token = np.full(data.n_terms, -1, np.int64)
+            known = np.nonzero(data.token_id_map >= 0)[0]
+            term_token[data.token_id_map[known]] = known
+            idf_of, avg_idf, avgdl = stats_hook(term_token, np.diff(data.indptr), data.n_docs, int(data.doc_len.sum()))
+            data.idf = np.asarray([idf_of[int(t)] for t in term_token], dtype=np.float64)
+            data.average_idf, data.avgdl = avg_idf, avgdl
         self.load_bm25(data, id_base)
         return data
 

@@ -44,8 +44,17 @@ def _worker(rank, world, port, tmpdir):
     d_ids, d_sc, d_cnt = pipe.search_dense(q, k)
     f_ids, f_sc, f_src, f_cnt = pipe.search_hybrid(q, terms, k, method="rrf", rrf_k=60)
     c_ids, c_sc, _, c_cnt = pipe.search_hybrid(q, terms, k, method="comb_sum", rrf_k=60, w_dense=0.7, w_sparse=0.3)
+    # the same shard built WITHOUT a global host index: local postings + all-gathered statistics (build_bm25_sharded)
+    pipe2 = HybridPipeline(device=None, rank=rank, world=world, engine=OracleEngineTorch())
+    pipe2.load_dense(x[lo:hi], id_base=lo)
+    sidx = pipe2.build_bm25_sharded(flat[off[lo]:off[hi]], off[lo:hi + 1] - off[lo], id_base=lo)
+    assert sidx.avgdl == idx.avgdl and sidx.average_idf == idx.average_idf
+    raw = np.nonzero(sidx.token_id_map >= 0)[0]
+    assert np.array_equal(sidx.idf[sidx.token_id_map[raw]], idx.idf[idx.token_id_map[raw]])   # bit-identical global idf
+    terms2 = [sidx.term_ids(t) for t in synth.query_tokens(B, vocab=300)]
+    g_ids, g_sc, _, g_cnt = pipe2.search_hybrid(q, terms2, k, method="rrf", rrf_k=60)
     np.savez(os.path.join(tmpdir, f"rank{rank}.npz"), d_ids=d_ids, d_sc=d_sc, d_cnt=d_cnt, f_ids=f_ids, f_sc=f_sc,
-             f_cnt=f_cnt, c_ids=c_ids, c_sc=c_sc, c_cnt=c_cnt)
+             f_cnt=f_cnt, c_ids=c_ids, c_sc=c_sc, c_cnt=c_cnt, g_ids=g_ids, g_sc=g_sc, g_cnt=g_cnt)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -79,6 +88,8 @@ def test_two_shards_equal_unsharded(tmp_path):
         assert np.array_equal(r["f_ids"], f_ref[0]) and np.array_equal(r["f_sc"], f_ref[1])
         assert np.array_equal(r["c_ids"], c_ref[0]) and np.array_equal(r["c_sc"], c_ref[1])
         assert np.array_equal(r["f_cnt"], f_ref[3])
+        assert np.array_equal(r["g_ids"], f_ref[0]) and np.array_equal(r["g_sc"], f_ref[1])   # sharded build == global build
+        assert np.array_equal(r["g_cnt"], f_ref[3])
 
 
 def _worker_2d(rank, world, port, tmpdir):

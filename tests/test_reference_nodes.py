@@ -25,7 +25,7 @@ DIM = 48
 TEXTS = [f"topic{i % 9} w{i % 13} w{(i * 7) % 31} alpha{i % 5} chunk number {i}" for i in range(240)]
 IDS = [f"doc-{i}" for i in range(len(TEXTS))]
 QUERIES = ["topic3 w4 alpha2", "w7 chunk", "nothing-in-the-vocabulary", "topic8 topic8 w30"]
-CE_CFG = dict(vocab_size=30522, hidden=64, layers=2, heads=4, intermediate=128, max_pos=64, type_vocab=2, ln_eps=1e-12)
+CE_CFG = dict(vocab_size=30522, hidden=128, layers=2, heads=4, intermediate=256, max_pos=64, type_vocab=2, ln_eps=1e-12)
 
 
 def _build(make_store, make_sparse, engine):
