@@ -50,6 +50,18 @@ def main():
             same = bool(np.array_equal(rs[0], results[method][0]) and np.array_equal(rs[1], results[method][1]))
             print(f"hybrid {method} sharded == single:", same, flush=True)
             ok &= same
+    # the shard built ON THE DEVICE from the local tokens + all-gathered statistics (no global host index) == the shard cut
+    # from the global host-built index
+    pipe_b = HybridPipeline(local, rank=rank, world=world)
+    pipe_b.load_dense(x[lo:hi], id_base=lo)
+    sidx = pipe_b.build_bm25_sharded(flat[off[lo]:off[hi]], off[lo:hi + 1] - off[lo], id_base=lo)
+    terms_b = [sidx.term_ids(t) for t in synth.query_tokens(B, vocab=20000)]
+    rb = pipe_b.search_hybrid(q, terms_b, k, method="rrf", rrf_k=60, w_dense=0.6, w_sparse=0.4)
+    same = bool(np.array_equal(rb[0], results["rrf"][0]) and np.array_equal(rb[1], results["rrf"][1]))
+    same &= sidx.avgdl == idx.avgdl and sidx.average_idf == idx.average_idf
+    print(f"[rank {rank}] device-built shard (all-gathered statistics) == host-built shard:", same, flush=True)
+    ok &= same
+    pipe_b.engine.close()
     # rerank: every rank holds the merged candidates of all queries and reranks ITS slice of the queries
     from sentio_b200.cross_encoder import CrossEncoderWeights
     from sentio_b200.index import doc_token_matrix, hash_vocab_ids

@@ -213,6 +213,24 @@ ce_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             w.w = __uint_as_float(v[j + 3]) + bb.w + rb.w;
             *reinterpret_cast<float4*>(o + j) = w;
           }
+        } else if (EPI == CE_EPI_BIAS_RES16_F16) {
+          __half* o = out16 + (size_t)row * N + col;
+          const __half* r = reinterpret_cast<const __half*>(residual) + (size_t)row * N + col;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const uint4 rraw = *reinterpret_cast<const uint4*>(r + j);
+            const __half2* rh = reinterpret_cast<const __half2*>(&rraw);
+            uint4 pk;
+            uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 rf = __half22float2(rh[e]);
+              const __half2 h = __floats2half2_rn(__uint_as_float(v[j + 2 * e]) + __ldg(bias + col + j + 2 * e) + rf.x,
+                                                  __uint_as_float(v[j + 2 * e + 1]) + __ldg(bias + col + j + 2 * e + 1) + rf.y);
+              pw[e] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(o + j) = pk;
+          }
         } else {
           __half* o = out16 + (size_t)row * N + col;
 #pragma unroll

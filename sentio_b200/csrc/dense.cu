@@ -494,6 +494,7 @@ __global__ void __launch_bounds__(kMergeThreads, 1) dense_merge_kernel(const Mer
   unsigned long long* sel = reinterpret_cast<unsigned long long*>(msmem);   // [kSelCap]
   unsigned long long* ek = sel + kSelCap;                                   // [kSelCap] exact score keys
   uint32_t* ei = reinterpret_cast<uint32_t*>(ek + kSelCap);                 // [kSelCap] row index
+  float* q_s = reinterpret_cast<float*>(ei + kSelCap);                      // [d_pad]   the query, staged once
   __shared__ double qq_s;
   __shared__ int s_nsel, s_trunc;
   __shared__ unsigned long long s_bound;
@@ -552,7 +553,7 @@ __global__ void __launch_bounds__(kMergeThreads, 1) dense_merge_kernel(const Mer
   ra.out_ids = p.out_ids + (size_t)qi * p.k;
   ra.out_scores = p.out_scores + (size_t)qi * p.k;
   ra.out_count = p.out_counts + qi;
-  rescore_and_emit(sel, nsel, P, ek, ei, &qq_s, ra);
+  rescore_and_emit(sel, nsel, P, ek, ei, &qq_s, q_s, ra);
 }
 
 // ------------------------------------------------------------------------------------------------ query preparation
@@ -750,7 +751,7 @@ int make_plan(sb_ctx* ctx, const DenseIndex& ix, int k, ScanPlan* pl) {
   pl->heads_per_list = (pl->kprime + pl->grid - 1) / pl->grid;
   pl->heads_pow2 = next_pow2(pl->grid * pl->heads_per_list);
   SB_REQUIRE(pl->heads_pow2 <= kSelCap, SB_ERR_UNSUPPORTED, "dense: internal merge capacity exceeded");
-  pl->merge_smem = (size_t)kSelCap * 20 + 64;
+  pl->merge_smem = (size_t)kSelCap * 20 + (size_t)ix.d_pad * 4 + 64;
   return SB_OK;
 }
 

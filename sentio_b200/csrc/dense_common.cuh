@@ -52,10 +52,10 @@ __device__ __forceinline__ double exact_cosine_warp(const __half* rows, uint32_t
     for (int e = 0; e < 4; ++e) {
       const float2 xf = __half22float2(h2[e]);
       const double x0 = (double)xf.x, x1 = (double)xf.y;
-      dot += x0 * (double)qv[2 * e];
-      dot += x1 * (double)qv[2 * e + 1];
-      xx += x0 * x0;
-      xx += x1 * x1;
+      dot = __fma_rn(x0, (double)qv[2 * e], dot);       // explicit FMAs: the one- and two-row variants must agree bit for bit
+      dot = __fma_rn(x1, (double)qv[2 * e + 1], dot);
+      xx = __fma_rn(x0, x0, xx);
+      xx = __fma_rn(x1, x1, xx);
     }
   }
   for (int o = 16; o; o >>= 1) {
@@ -123,25 +123,83 @@ __device__ __forceinline__ void emit_exact_pairs(const unsigned long long* ek, c
   }
 }
 
+// Two rows at once (twice the loads in flight per warp): same arithmetic and order as exact_cosine_warp, per row.
+__device__ __forceinline__ void exact_cosine_warp2(const __half* rows, uint32_t idx0, uint32_t idx1, const float* q, int d_pad,
+                                                   int nch, double qn, int lane, double* out0, double* out1) {
+  const uint4* r0 = reinterpret_cast<const uint4*>(rows + (size_t)idx0 * d_pad);
+  const uint4* r1 = reinterpret_cast<const uint4*>(rows + (size_t)idx1 * d_pad);
+  double dot0 = 0.0, xx0 = 0.0, dot1 = 0.0, xx1 = 0.0;
+  for (int ch = lane; ch < nch; ch += 32) {
+    const uint4 raw0 = __ldg(r0 + ch), raw1 = __ldg(r1 + ch);
+    const __half2* h0 = reinterpret_cast<const __half2*>(&raw0);
+    const __half2* h1 = reinterpret_cast<const __half2*>(&raw1);
+    const float4 qa = *reinterpret_cast<const float4*>(q + (size_t)ch * 8);
+    const float4 qb = *reinterpret_cast<const float4*>(q + (size_t)ch * 8 + 4);
+    const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 a = __half22float2(h0[e]), b = __half22float2(h1[e]);
+      const double a0 = (double)a.x, a1 = (double)a.y, b0 = (double)b.x, b1 = (double)b.y;
+      dot0 = __fma_rn(a0, (double)qv[2 * e], dot0);
+      dot0 = __fma_rn(a1, (double)qv[2 * e + 1], dot0);
+      xx0 = __fma_rn(a0, a0, xx0);
+      xx0 = __fma_rn(a1, a1, xx0);
+      dot1 = __fma_rn(b0, (double)qv[2 * e], dot1);
+      dot1 = __fma_rn(b1, (double)qv[2 * e + 1], dot1);
+      xx1 = __fma_rn(b0, b0, xx1);
+      xx1 = __fma_rn(b1, b1, xx1);
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    dot0 += __shfl_xor_sync(0xffffffffu, dot0, o);
+    xx0 += __shfl_xor_sync(0xffffffffu, xx0, o);
+    dot1 += __shfl_xor_sync(0xffffffffu, dot1, o);
+    xx1 += __shfl_xor_sync(0xffffffffu, xx1, o);
+  }
+  const double den0 = qn * sqrt(xx0), den1 = qn * sqrt(xx1);
+  *out0 = den0 > 0.0 ? dot0 / den0 : 0.0;
+  *out1 = den1 > 0.0 ? dot1 / den1 : 0.0;
+}
+
 // Exact fp64 re-score of the window members sel[0..nsel) (composite keys) against the STORED fp16 rows and the fp32
 // query, final order (score desc, row asc), emit k results.  Whole-CTA cooperative; ek/ei are P-entry shared-memory
-// arrays (P = power of two >= nsel), qq_s a shared double.
+// arrays (P = power of two >= nsel), qq_s a shared double, q_s a shared-memory staging area for the query (d_pad floats;
+// the L2 round trip of the query per re-scored row was a third of the stage's latency).
 __device__ __forceinline__ void rescore_and_emit(const unsigned long long* sel, int nsel, int P, unsigned long long* ek,
-                                                 uint32_t* ei, double* qq_s_ptr, const RescoreArgs p) {
+                                                 uint32_t* ei, double* qq_s_ptr, float* q_s, const RescoreArgs p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
-  const double qn = query_norm_cta(p.q, p.d_pad, qq_s_ptr);
-  for (int c = warp; c < P; c += nw) {
-    const unsigned long long key = c < nsel ? sel[c] : 0ull;
-    unsigned long long okey = 0ull;
-    uint32_t idx = 0xffffffffu;
-    if (key != 0ull) {
-      idx = key32_idx(key);
-      okey = f64_orderable(exact_cosine_warp(p.rows, idx, p.q, p.d_pad, p.ch, qn, lane));
-      if (okey == 0ull) okey = 1ull;  // keep 0 reserved for "empty"
+  for (int i = tid; i < p.d_pad; i += nt) q_s[i] = p.q[i];
+  __syncthreads();
+  const double qn = query_norm_cta(q_s, p.d_pad, qq_s_ptr);
+  for (int c = warp; c < P; c += 2 * nw) {
+    const int c1 = c + nw;
+    const unsigned long long key0 = c < nsel ? sel[c] : 0ull;
+    const unsigned long long key1 = (c1 < P && c1 < nsel) ? sel[c1] : 0ull;
+    unsigned long long o0 = 0ull, o1 = 0ull;
+    uint32_t i0 = 0xffffffffu, i1 = 0xffffffffu;
+    if (key0 != 0ull && key1 != 0ull) {
+      i0 = key32_idx(key0);
+      i1 = key32_idx(key1);
+      double s0, s1;
+      exact_cosine_warp2(p.rows, i0, i1, q_s, p.d_pad, p.ch, qn, lane, &s0, &s1);
+      o0 = f64_orderable(s0);
+      o1 = f64_orderable(s1);
+    } else if (key0 != 0ull) {
+      i0 = key32_idx(key0);
+      o0 = f64_orderable(exact_cosine_warp(p.rows, i0, q_s, p.d_pad, p.ch, qn, lane));
+    } else if (key1 != 0ull) {
+      i1 = key32_idx(key1);
+      o1 = f64_orderable(exact_cosine_warp(p.rows, i1, q_s, p.d_pad, p.ch, qn, lane));
     }
+    if (key0 != 0ull && o0 == 0ull) o0 = 1ull;  // keep 0 reserved for "empty"
+    if (key1 != 0ull && o1 == 0ull) o1 = 1ull;
     if (lane == 0) {
-      ek[c] = okey;
-      ei[c] = idx;
+      ek[c] = o0;
+      ei[c] = i0;
+      if (c1 < P) {
+        ek[c1] = o1;
+        ei[c1] = i1;
+      }
     }
   }
   __syncthreads();

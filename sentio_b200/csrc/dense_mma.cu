@@ -648,7 +648,8 @@ __global__ void __launch_bounds__(kSelectThreads, 2) dense_select_kernel(const S
   ra.out_ids = p.out_ids + (size_t)qi * p.k;
   ra.out_scores = p.out_scores + (size_t)qi * p.k;
   ra.out_count = p.out_counts + qi;
-  rescore_and_emit(top, ntop, P, ek, ei, &qq_s, ra);
+  // the staged survivors are dead (the window lives in `top`): their shared memory becomes the query staging area
+  rescore_and_emit(top, ntop, P, ek, ei, &qq_s, reinterpret_cast<float*>(keys), ra);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -99,6 +99,7 @@ class B200VectorStore:
         if isinstance(query_vector, tuple):  # ("name", vector) form of the named-vector API
             query_vector = query_vector[1]
         q = np.asarray(query_vector, dtype=np.float32).reshape(1, -1)
+        limit = max(1, min(int(limit), max(len(col.ids), 1)))   # Qdrant never returns more points than the collection holds
         ids, scores, counts = col.engine.dense_topk(q, int(limit))
         out = []
         for j in range(int(counts[0])):
