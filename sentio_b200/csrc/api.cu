@@ -73,6 +73,8 @@ void sb_destroy(sb_ctx* ctx) {
   if (b.post_ratio) cudaFree(b.post_ratio);
   if (b.dnorm) cudaFree(b.dnorm);
   if (b.idf) cudaFree(b.idf);
+  if (b.dense_of_term) cudaFree(b.dense_of_term);
+  if (b.dense_ratio) cudaFree(b.dense_ratio);
   if (ctx->ce) ce_model_free(ctx->ce);
   if (ctx->enc) ce_model_free(ctx->enc);
   if (ctx->ce_tokens) ce_tokens_free(ctx->ce_tokens);

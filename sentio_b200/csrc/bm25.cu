@@ -15,7 +15,10 @@
 // memory (bm25_range_kernel below), nothing of size N is ever written or re-read in HBM / L2.
 #include <algorithm>
 #include <type_traits>
+#include <stdlib.h>
 #include <string.h>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 
@@ -43,6 +46,17 @@ __global__ void bm25_ratio_kernel(const int32_t* __restrict__ post_doc, const ui
   ratio[i] = __ddiv_rn(num, den);
 }
 
+// Dense rows of the head terms: one CTA per (slot, chunk of the term's posting list) scatters ratio[p] to row[doc[p]].
+__global__ void bm25_dense_fill_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ post_doc,
+                                       const double* __restrict__ ratio, const int32_t* __restrict__ slot_term,
+                                       int64_t n_docs, double* __restrict__ dense) {
+  const int slot = blockIdx.y;
+  const int64_t lo = indptr[slot_term[slot]], hi = indptr[slot_term[slot] + 1];
+  double* row = dense + (size_t)slot * n_docs;
+  for (int64_t p = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < hi; p += (int64_t)gridDim.x * blockDim.x)
+    row[post_doc[p]] = ratio[p];
+}
+
 // ------------------------------------------------------------------------------------------------ range scoring
 // One CTA scores ONE query over a run of consecutive doc ranges of kRange docs.  The fp64 accumulators live in shared
 // memory (64 KB per CTA), so the only memory traffic of scoring is the postings themselves (4 B doc + 8 B ratio each, most
@@ -58,6 +72,14 @@ __global__ void bm25_ratio_kernel(const int32_t* __restrict__ post_doc, const ui
 //  * inside a sub-range the terms are applied strictly in QUERY ORDER by the same warp (a doc occurs at most once per
 //    posting list), so the per-doc addition order equals NumPy's `score += ...` loop order without any atomics
 //    => bit-identical fp64 (every operation is an explicit __dmul_rn / __dadd_rn);
+//  * HEAD TERMS (df >= n_docs / 4; a handful of stop-word-like terms carry ~90 % of all postings of a Zipf corpus) are
+//    not walked through their posting lists at all: the index keeps a dense fp64 row ratio[doc] (0.0 = no posting) for each
+//    of them and the warp adds idf * row[doc] to all 512 docs of the sub-range -- 16 independent, perfectly coalesced loads,
+//    no cursor, no compare, no vote (8 instead of ~37 instructions per 32 postings).  Adding idf * 0.0 = +-0.0 to a doc
+//    without a posting leaves its accumulator bit-for-bit unchanged, exactly like rank_bm25's dense `score +=` does;
+//  * the posting-list walk addresses its shared-memory accumulators through 32-bit shared-space addresses and is
+//    branch-free (a posting beyond the sub-range adds 0.0 to a per-warp dummy slot): the first version of this kernel spent
+//    150 instructions per 128 postings on generic-address arithmetic and divergence bookkeeping (profiles/r02_run4_bm25*);
 //  * a finished sub-range is consumed by its warp according to MODE:
 //      kModeSample : (S ranges spread over the corpus, one per CTA) ceil(k/S)-th best positive score of the range, min
 //                    over the S ranges -> thr[q], a lower bound of the global k-th best score
@@ -80,6 +102,8 @@ struct RangeParams {
   const int32_t* post_doc;
   const double* ratio;
   const double* idf;
+  const int32_t* dense_of_term;  // [V] slot of the term's dense ratio row, -1 = posting list only
+  const double* dense_ratio;     // [n_dense][n_docs]
   int64_t n_terms;
   int64_t n_docs;
   double delta;          // BM25Plus
@@ -120,14 +144,24 @@ __device__ __forceinline__ int64_t warp_lower_bound(const int32_t* __restrict__ 
 __device__ unsigned long long block_kth_largest(const unsigned long long* keys, int n, int K, int* hist, int* scal,
                                                 int passes);
 
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
 template <int MODE, bool PLUS>
-__global__ void __launch_bounds__(kRsThreads, 3) bm25_range_kernel(const RangeParams p) {
+__global__ void __launch_bounds__(kRsThreads, 2) bm25_range_kernel(const RangeParams p) {
   extern __shared__ __align__(16) uint8_t rsm[];
   double* acc = reinterpret_cast<double*>(rsm);                               // [kRange]: warp w owns [w*kSub, (w+1)*kSub)
-  int64_t* s_lo = reinterpret_cast<int64_t*>(acc + kRange);                   // [max_len] first posting of the term's list
+  double* s_dummy = acc + kRange;                                             // [kRsWarps] sink of out-of-range postings
+  int64_t* s_lo = reinterpret_cast<int64_t*>(s_dummy + kRsWarps);             // [max_len] first posting of the term's list
   double* s_idf = reinterpret_cast<double*>(s_lo + p.max_len);                // [max_len] 0.0 = term contributes nothing
   int32_t* s_n = reinterpret_cast<int32_t*>(s_idf + p.max_len);               // [max_len] postings in the list (df < 2^31)
-  int32_t* s_wid = s_n + p.max_len;                                           // [max_len] chunks in flight for this term
+  int32_t* s_wid = s_n + p.max_len;                                           // [max_len] chunks in flight; -1 - slot = dense row
   int32_t* s_cur = s_wid + p.max_len;                                         // [kRsWarps][max_len] cursor, relative to s_lo
   uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_cur + (size_t)kRsWarps * p.max_len);  // [kRange / 32] PLUS: doc had a posting
   __shared__ int hist[256];
@@ -147,22 +181,28 @@ __global__ void __launch_bounds__(kRsThreads, 3) bm25_range_kernel(const RangePa
     const int t = p.q_terms[q0 + j];
     double w = 0.0;
     int64_t lo = 0, hi = 0;
+    int wid = 1;
     if (t >= 0 && t < p.n_terms) {
       w = p.idf[t];
       if (w != 0.0) {
         lo = p.indptr[t];
         hi = p.indptr[t + 1];
+        const int slot = p.dense_of_term ? p.dense_of_term[t] : -1;
+        // expected postings of the term inside one sub-range -> chunks kept in flight (rare terms must not over-read)
+        const int64_t per_sub = ((hi - lo) * kSub) / max(p.n_docs, (int64_t)1);
+        wid = slot >= 0 ? -1 - slot : (per_sub < 48 ? 1 : kRsPost);
       }
     }
     s_lo[j] = lo;
     s_n[j] = (int32_t)(hi - lo);
     s_idf[j] = w;
-    // expected postings of the term inside one sub-range -> chunks kept in flight (rare terms must not over-read)
-    const int64_t per_sub = ((hi - lo) * kSub) / max(p.n_docs, (int64_t)1);
-    s_wid[j] = per_sub < 48 ? 1 : kRsPost;
+    s_wid[j] = wid;
   }
   double* a = acc + warp * kSub;
+  const uint32_t a_s = smem_u32(a);                      // shared-space address of this warp's accumulators
+  const uint32_t dummy_s = smem_u32(s_dummy + warp);
   for (int i = lane; i < kSub; i += 32) a[i] = 0.0;
+  if (lane == 0) s_dummy[warp] = 0.0;
   uint32_t* bits = s_bits + warp * (kSub / 32);
   if (PLUS && lane < kSub / 32) bits[lane] = 0u;
   __syncthreads();
@@ -173,7 +213,7 @@ __global__ void __launch_bounds__(kRsThreads, 3) bm25_range_kernel(const RangePa
   int32_t* my_cur = s_cur + (size_t)warp * p.max_len;
   for (int j = 0; j < len; ++j) {
     int64_t pos = 0;
-    if (s_idf[j] != 0.0 && strip0 > 0 && strip0 < p.n_docs)
+    if (s_idf[j] != 0.0 && s_wid[j] > 0 && strip0 > 0 && strip0 < p.n_docs)
       pos = warp_lower_bound(p.post_doc + s_lo[j], 0, s_n[j], (int32_t)strip0, lane);
     if (lane == 0) my_cur[j] = (int32_t)pos;
   }
@@ -188,12 +228,29 @@ __global__ void __launch_bounds__(kRsThreads, 3) bm25_range_kernel(const RangePa
     for (int j = 0; j < len; ++j) {
       const double w = s_idf[j];
       if (w == 0.0) continue;  // warp-uniform
+      const int wid = s_wid[j];
+      if (wid < 0) {
+        // ---- head term: dense ratio row, every doc of the sub-range (0.0 where the doc has no posting)
+        const double* __restrict__ dr = p.dense_ratio + (size_t)(-1 - wid) * p.n_docs + s0;
+        double r[kSub / 32];
+#pragma unroll
+        for (int c = 0; c < kSub / 32; ++c) r[c] = (c * 32 + lane) < nd ? __ldg(dr + c * 32 + lane) : 0.0;
+#pragma unroll
+        for (int c = 0; c < kSub / 32; ++c) {
+          const uint32_t ad = a_s + (uint32_t)(c * 32 + lane) * 8u;
+          const double add = PLUS ? __dmul_rn(w, __dadd_rn(p.delta, r[c])) : __dmul_rn(w, r[c]);
+          if ((c * 32 + lane) < nd) sts_f64(ad, __dadd_rn(lds_f64(ad), add));
+        }
+        __syncwarp();
+        continue;
+      }
       const int32_t n = s_n[j];
       const int32_t* __restrict__ pd = p.post_doc + s_lo[j];
       const double* __restrict__ pr = p.ratio + s_lo[j];
       int32_t cur = my_cur[j];
       // chunk loop, specialised on the number of 32-posting chunks in flight (warp-uniform).  The postings of the list are
       // sorted by doc, so the ones inside [s0, s1) are a prefix of what is fetched: their count advances the cursor.
+      // Branch-free body: a posting beyond the sub-range adds 0.0 to the warp's dummy slot.
       auto walk = [&](auto width) {
         constexpr int W = decltype(width)::value;
         for (;;) {
@@ -202,26 +259,19 @@ __global__ void __launch_bounds__(kRsThreads, 3) bm25_range_kernel(const RangePa
 #pragma unroll
           for (int u = 0; u < W; ++u) {
             const int32_t i = cur + u * 32 + lane;
-            doc[u] = 0x7fffffff;
-            rat[u] = 0.0;
-            if (i < n) {
-              doc[u] = __ldg(pd + i);
-              rat[u] = __ldg(pr + i);
-            }
+            const bool ok = i < n;
+            doc[u] = ok ? __ldg(pd + (ok ? i : 0)) : 0x7fffffff;
+            rat[u] = ok ? __ldg(pr + (ok ? i : 0)) : 0.0;
           }
           int inside = 0;
 #pragma unroll
           for (int u = 0; u < W; ++u) {
             const bool in = doc[u] < s1;
-            if (in) {
-              const int x = doc[u] - s0;
-              if (PLUS) {
-                a[x] = __dadd_rn(a[x], __dmul_rn(w, __dadd_rn(p.delta, rat[u])));
-                atomicOr(&bits[x >> 5], 1u << (x & 31));
-              } else {
-                a[x] = __dadd_rn(a[x], __dmul_rn(w, rat[u]));
-              }
-            }
+            const uint32_t ad = in ? a_s + (uint32_t)(doc[u] - s0) * 8u : dummy_s;
+            const double rt = in ? rat[u] : 0.0;
+            const double add = PLUS ? __dmul_rn(w, __dadd_rn(p.delta, rt)) : __dmul_rn(w, rt);
+            sts_f64(ad, __dadd_rn(lds_f64(ad), in ? add : 0.0));
+            if (PLUS && in) atomicOr(&bits[(doc[u] - s0) >> 5], 1u << ((doc[u] - s0) & 31));
             inside += __popc(__ballot_sync(0xffffffffu, in));
           }
           cur += inside;
@@ -229,7 +279,7 @@ __global__ void __launch_bounds__(kRsThreads, 3) bm25_range_kernel(const RangePa
         }
       };
       if (cur < n) {   // warp-uniform: the list still has postings at or beyond this sub-range
-        if (s_wid[j] == 1)
+        if (wid == 1)
           walk(std::integral_constant<int, 1>());
         else
           walk(std::integral_constant<int, kRsPost>());
@@ -488,7 +538,7 @@ int pow2_at_least(int v) {
 }
 
 size_t range_smem_bytes(int max_len) {
-  return (size_t)kRange * 8 + (size_t)std::max(max_len, 1) * (8 + 8 + 4 + 4 + 4 * kRsWarps) + (kRange / 32) * 4 + 16;
+  return (size_t)kRange * 8 + kRsWarps * 8 + (size_t)std::max(max_len, 1) * (8 + 8 + 4 + 4 + 4 * kRsWarps) + (kRange / 32) * 4 + 16;
 }
 
 template <int MODE, bool PLUS>
@@ -520,6 +570,8 @@ RangeParams range_params(sb_ctx* ctx, const int32_t* q_terms_dev, const int32_t*
   rp.post_doc = ix.post_doc;
   rp.ratio = ix.post_ratio;
   rp.idf = ix.idf;
+  rp.dense_of_term = ix.n_dense > 0 ? ix.dense_of_term : nullptr;
+  rp.dense_ratio = ix.dense_ratio;
   rp.n_terms = ix.n_terms;
   rp.n_docs = ix.n_docs;
   rp.delta = ix.delta;
@@ -528,7 +580,7 @@ RangeParams range_params(sb_ctx* ctx, const int32_t* q_terms_dev, const int32_t*
 
 // consecutive ranges per CTA: long runs amortise the per-term posting-list search, short runs fill the machine
 int ranges_per_cta(sb_ctx* ctx, int nq, int64_t n_ranges) {
-  const int64_t resident = (int64_t)ctx->num_sms * 3;  // 3 CTAs of bm25_range_kernel per SM
+  const int64_t resident = (int64_t)ctx->num_sms * 2;  // 2 CTAs of bm25_range_kernel per SM (64 registers per thread)
   int64_t r = ((int64_t)nq * n_ranges) / (resident * 2);   // about two waves of CTAs: long strips, balanced tail
   if (r < 1) r = 1;
   if (r > 32) r = 32;
@@ -604,6 +656,8 @@ static void bm25_index_free(Bm25Index& ix) {
   if (ix.post_ratio) cudaFree(ix.post_ratio);
   if (ix.dnorm) cudaFree(ix.dnorm);
   if (ix.idf) cudaFree(ix.idf);
+  if (ix.dense_of_term) cudaFree(ix.dense_of_term);
+  if (ix.dense_ratio) cudaFree(ix.dense_ratio);
   ix = Bm25Index();
 }
 
@@ -629,6 +683,42 @@ static int bm25_install_build(Bm25Index& nx, const uint16_t* tf_dev, const int32
     SB_CUDA(cudaGetLastError());
   }
   SB_CUDA(cudaStreamSynchronize(st));
+  // dense ratio rows of the head terms (df >= n_docs / 4): at most 64 rows and 2 GB; env SB_BM25_DENSE=0 disables them
+  const char* dz = getenv("SB_BM25_DENSE");
+  if (nx.n_terms > 0 && nx.n_docs >= 4096 && !(dz && atoi(dz) == 0)) {
+    std::vector<int64_t> indptr_h((size_t)nx.n_terms + 1);
+    SB_CUDA(cudaMemcpy(indptr_h.data(), nx.indptr, indptr_h.size() * 8, cudaMemcpyDeviceToHost));
+    std::vector<std::pair<int64_t, int32_t>> heavy;   // (df, term)
+    for (int64_t t = 0; t < nx.n_terms; ++t) {
+      const int64_t df = indptr_h[(size_t)t + 1] - indptr_h[(size_t)t];
+      if (df * 4 >= nx.n_docs) heavy.push_back({df, (int32_t)t});
+    }
+    std::sort(heavy.begin(), heavy.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+    const size_t row_bytes = (size_t)nx.n_docs * 8;
+    const size_t max_rows = std::min<size_t>(64, (size_t)(2048ull << 20) / row_bytes);
+    if (heavy.size() > max_rows) heavy.resize(max_rows);
+    if (!heavy.empty()) {
+      std::vector<int32_t> of_term((size_t)nx.n_terms, -1), slot_term(heavy.size());
+      for (size_t sidx = 0; sidx < heavy.size(); ++sidx) {
+        of_term[(size_t)heavy[sidx].second] = (int32_t)sidx;
+        slot_term[sidx] = heavy[sidx].second;
+      }
+      int32_t* slot_term_dev = nullptr;
+      SB_CUDA(cudaMalloc(&nx.dense_of_term, of_term.size() * 4));
+      SB_CUDA(cudaMalloc(&nx.dense_ratio, heavy.size() * row_bytes));
+      SB_CUDA(cudaMalloc(&slot_term_dev, slot_term.size() * 4));
+      SB_CUDA(cudaMemcpyAsync(nx.dense_of_term, of_term.data(), of_term.size() * 4, cudaMemcpyHostToDevice, st));
+      SB_CUDA(cudaMemcpyAsync(slot_term_dev, slot_term.data(), slot_term.size() * 4, cudaMemcpyHostToDevice, st));
+      SB_CUDA(cudaMemsetAsync(nx.dense_ratio, 0, heavy.size() * row_bytes, st));
+      bm25_dense_fill_kernel<<<dim3(256, (unsigned)heavy.size()), 256, 0, st>>>(nx.indptr, nx.post_doc, nx.post_ratio,
+                                                                                slot_term_dev, nx.n_docs, nx.dense_ratio);
+      cudaError_t fe = cudaGetLastError();
+      cudaStreamSynchronize(st);
+      cudaFree(slot_term_dev);
+      SB_CUDA(fe);
+      nx.n_dense = (int32_t)heavy.size();
+    }
+  }
   return SB_OK;
 }
 

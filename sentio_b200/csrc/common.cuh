@@ -108,6 +108,11 @@ struct Bm25Index {
   double* post_ratio = nullptr; // [nnz] query-independent tf*(k1+1)/(tf+dnorm[doc]) (fp64, exact op order)
   double* dnorm = nullptr;     // [n_docs]  k1*(1-b+b*dl/avgdl), same op order as rank_bm25
   double* idf = nullptr;       // [V]
+  // head terms (df >= n_docs / 4) additionally keep a DENSE ratio row: dense_ratio[slot][doc] (0.0 where the doc has no
+  // posting); dense_of_term[t] = slot or -1.  The scoring kernel streams these rows with fully predictable addresses
+  int32_t n_dense = 0;
+  int32_t* dense_of_term = nullptr;  // [V]
+  double* dense_ratio = nullptr;     // [n_dense][n_docs]
 };
 
 struct CeModel;      // cross_encoder.cu

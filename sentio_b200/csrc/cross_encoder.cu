@@ -187,58 +187,74 @@ __global__ void ce_embed_ln_kernel(const int32_t* __restrict__ ids, const int32_
 __device__ __forceinline__ float ln_load(const float* p) { return *p; }
 __device__ __forceinline__ float ln_load(const __half* p) { return __half2float(*p); }
 
-// One warp per row: LayerNorm of the pre-LN sum (fp32, or fp16 on the fp16 residual stream) -> fp16 GEMM copy
-// (+ the fp32 residual when x32 != NULL).  Lane l owns the PER = H / 32 CONTIGUOUS columns [l * PER, (l + 1) * PER): the
-// fp16 row is read / written as 8-byte words (a lane-strided 2-byte layout cost 56 us per launch instead of 20).
+// LayerNorm of the pre-LN sum (fp32, or fp16 on the fp16 residual stream) -> fp16 GEMM copy (+ the fp32 residual when
+// x32 != NULL).  A warp normalises kLnRows CONSECUTIVE rows: all of their loads are issued before the first reduction, so
+// four rows' worth of memory latency overlap (one row per warp was latency bound: 48 us for 142 k rows, 3.4 TB/s).  Lane l
+// owns the PER = H / 32 contiguous columns [l * PER, (l + 1) * PER) of each row (8-byte / 16-byte accesses).
+constexpr int kLnRows = 4;
 template <int H, typename TIn>
 __global__ void ce_ln_kernel(const TIn* __restrict__ pre, int M_host, const int32_t* __restrict__ m_dev,
                              const float* __restrict__ g, const float* __restrict__ b, float eps,
                              float* __restrict__ x32, __half* __restrict__ x16) {
   constexpr int PER = H / 32;
   static_assert(PER % 4 == 0, "hidden size must be a multiple of 128");
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (row >= (m_dev ? __ldg(m_dev) : M_host)) return;
-  const size_t base = (size_t)row * H + (size_t)lane * PER;
-  float v[PER];
-  float sum = 0.f;
+  const int row0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kLnRows, lane = threadIdx.x & 31;
+  const int M = m_dev ? __ldg(m_dev) : M_host;
+  if (row0 >= M) return;
+  float v[kLnRows][PER];
 #pragma unroll
-  for (int i = 0; i < PER; i += 4) {
-    if constexpr (sizeof(TIn) == 2) {
-      const uint2 raw = *reinterpret_cast<const uint2*>(pre + base + i);
-      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-      const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-      v[i] = a.x; v[i + 1] = a.y; v[i + 2] = c.x; v[i + 3] = c.y;
-    } else {
-      const float4 raw = *reinterpret_cast<const float4*>(pre + base + i);
-      v[i] = raw.x; v[i + 1] = raw.y; v[i + 2] = raw.z; v[i + 3] = raw.w;
+  for (int r = 0; r < kLnRows; ++r) {
+    const size_t base = (size_t)min(row0 + r, M - 1) * H + (size_t)lane * PER;   // rows beyond M: re-read the last one
+#pragma unroll
+    for (int i = 0; i < PER; i += 4) {
+      if constexpr (sizeof(TIn) == 2) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(pre + base + i);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+        v[r][i] = a.x; v[r][i + 1] = a.y; v[r][i + 2] = c.x; v[r][i + 3] = c.y;
+      } else {
+        const float4 raw = *reinterpret_cast<const float4*>(pre + base + i);
+        v[r][i] = raw.x; v[r][i + 1] = raw.y; v[r][i + 2] = raw.z; v[r][i + 3] = raw.w;
+      }
     }
-    sum += (v[i] + v[i + 1]) + (v[i + 2] + v[i + 3]);
   }
-  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / H;
-  float var = 0.f;
+  float mean[kLnRows], rstd[kLnRows];
 #pragma unroll
-  for (int i = 0; i < PER; ++i) {
-    const float d = v[i] - mean;
-    var += d * d;
+  for (int r = 0; r < kLnRows; ++r) {
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; i += 4) sum += (v[r][i] + v[r][i + 1]) + (v[r][i + 2] + v[r][i + 3]);
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    mean[r] = sum / H;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const float d = v[r][i] - mean[r];
+      var += d * d;
+    }
+    for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    rstd[r] = rsqrtf(var / H + eps);
   }
-  for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
-  const float rstd = rsqrtf(var / H + eps);
 #pragma unroll
   for (int i = 0; i < PER; i += 4) {
     const int c = lane * PER + i;
     const float4 gg = *reinterpret_cast<const float4*>(g + c), bb = *reinterpret_cast<const float4*>(b + c);
-    float4 y;
-    y.x = (v[i] - mean) * rstd * gg.x + bb.x;
-    y.y = (v[i + 1] - mean) * rstd * gg.y + bb.y;
-    y.z = (v[i + 2] - mean) * rstd * gg.z + bb.z;
-    y.w = (v[i + 3] - mean) * rstd * gg.w + bb.w;
-    if (x32) *reinterpret_cast<float4*>(x32 + base + i) = y;
-    const __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
-    uint2 pk;
-    pk.x = *reinterpret_cast<const uint32_t*>(&h0);
-    pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-    *reinterpret_cast<uint2*>(x16 + base + i) = pk;
+#pragma unroll
+    for (int r = 0; r < kLnRows; ++r) {
+      if (row0 + r >= M) break;
+      const size_t base = (size_t)(row0 + r) * H + (size_t)c;
+      float4 y;
+      y.x = (v[r][i] - mean[r]) * rstd[r] * gg.x + bb.x;
+      y.y = (v[r][i + 1] - mean[r]) * rstd[r] * gg.y + bb.y;
+      y.z = (v[r][i + 2] - mean[r]) * rstd[r] * gg.z + bb.z;
+      y.w = (v[r][i + 3] - mean[r]) * rstd[r] * gg.w + bb.w;
+      if (x32) *reinterpret_cast<float4*>(x32 + base) = y;
+      const __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(x16 + base) = pk;
+    }
   }
 }
 
@@ -693,8 +709,9 @@ int ce_forward(sb_ctx* ctx, CeModel* m, const int32_t* ids, const int32_t* tts, 
   const sb_ce_config& c = m->cfg;
   const int M = P * S, I = c.intermediate, heads = c.heads;
   const int Mp = (M + 127) / 128 * 128;
-  const int rows_per_block = 8;
-  const unsigned ln_blocks = (unsigned)((M + rows_per_block - 1) / rows_per_block);
+  const int rows_per_block = 8;                                      // warps per block of the LayerNorm kernels
+  const unsigned ln_blocks = (unsigned)((M + rows_per_block - 1) / rows_per_block);             // embed LN: one row per warp
+  const unsigned ln4_blocks = (unsigned)((M + rows_per_block * kLnRows - 1) / (rows_per_block * kLnRows));
   ProfScope ps(ctx, SB_PROF_CE, st, 3 + (int)m->layers.size() * 7);
   int32_t* cu = m->cu;
   const int32_t* m_dev = cu + P;  // packed row count of this pass (device side only)
@@ -708,7 +725,7 @@ int ce_forward(sb_ctx* ctx, CeModel* m, const int32_t* ids, const int32_t* tts, 
   SB_CUDA(cudaGetLastError());
   int rc;
   const int Pp = (P + 127) / 128 * 128;
-  const unsigned cls_ln_blocks = (unsigned)((P + rows_per_block - 1) / rows_per_block);
+  const unsigned cls_ln_blocks = (unsigned)((P + rows_per_block * kLnRows - 1) / (rows_per_block * kLnRows));
   for (size_t li = 0; li < m->layers.size(); ++li) {
     CeLayer& L = m->layers[li];
     if ((rc = ce_gemm_launch(CE_EPI_BIAS_F16, m->m_x16, L.m_wqkv, Mp, 3 * H, H, L.bqkv, nullptr, m->qkv16, nullptr, st,
@@ -763,7 +780,7 @@ int ce_forward(sb_ctx* ctx, CeModel* m, const int32_t* ids, const int32_t* tts, 
       if ((rc = ce_gemm_launch(CE_EPI_BIAS_RES16_F16, m->m_ctx16, L.m_wo, Mp, H, H, L.bo,
                                reinterpret_cast<const float*>(m->x16), m->pre16, nullptr, st, m_dev)))
         return rc;
-      ce_ln_kernel<H, __half><<<ln_blocks, rows_per_block * 32, 0, st>>>(m->pre16, M, m_dev, L.ln1_g, L.ln1_b, c.ln_eps,
+      ce_ln_kernel<H, __half><<<ln4_blocks, rows_per_block * 32, 0, st>>>(m->pre16, M, m_dev, L.ln1_g, L.ln1_b, c.ln_eps,
                                                                          nullptr, m->x16);
       SB_CUDA(cudaGetLastError());
       if ((rc = ce_gemm_launch(CE_EPI_BIAS_GELU_F16, m->m_x16, L.m_w1, Mp, I, H, L.b1, nullptr, m->ffn16, nullptr, st,
@@ -772,7 +789,7 @@ int ce_forward(sb_ctx* ctx, CeModel* m, const int32_t* ids, const int32_t* tts, 
       if ((rc = ce_gemm_launch(CE_EPI_BIAS_RES16_F16, m->m_ffn16, L.m_w2, Mp, H, I, L.b2,
                                reinterpret_cast<const float*>(m->x16), m->pre16, nullptr, st, m_dev)))
         return rc;
-      ce_ln_kernel<H, __half><<<ln_blocks, rows_per_block * 32, 0, st>>>(m->pre16, M, m_dev, L.ln2_g, L.ln2_b, c.ln_eps,
+      ce_ln_kernel<H, __half><<<ln4_blocks, rows_per_block * 32, 0, st>>>(m->pre16, M, m_dev, L.ln2_g, L.ln2_b, c.ln_eps,
                                                                          nullptr, m->x16);
       SB_CUDA(cudaGetLastError());
       continue;
@@ -780,7 +797,7 @@ int ce_forward(sb_ctx* ctx, CeModel* m, const int32_t* ids, const int32_t* tts, 
     if ((rc = ce_gemm_launch(CE_EPI_BIAS_RES_F32, m->m_ctx16, L.m_wo, Mp, H, H, L.bo, m->x32, nullptr, m->pre32, st,
                              m_dev)))
       return rc;
-    ce_ln_kernel<H, float><<<ln_blocks, rows_per_block * 32, 0, st>>>(m->pre32, M, m_dev, L.ln1_g, L.ln1_b, c.ln_eps,
+    ce_ln_kernel<H, float><<<ln4_blocks, rows_per_block * 32, 0, st>>>(m->pre32, M, m_dev, L.ln1_g, L.ln1_b, c.ln_eps,
                                                                       m->x32, m->x16);
     SB_CUDA(cudaGetLastError());
     if ((rc = ce_gemm_launch(CE_EPI_BIAS_GELU_F16, m->m_x16, L.m_w1, Mp, I, H, L.b1, nullptr, m->ffn16, nullptr, st,
@@ -789,7 +806,7 @@ int ce_forward(sb_ctx* ctx, CeModel* m, const int32_t* ids, const int32_t* tts, 
     if ((rc = ce_gemm_launch(CE_EPI_BIAS_RES_F32, m->m_ffn16, L.m_w2, Mp, H, I, L.b2, m->x32, nullptr, m->pre32, st,
                              m_dev)))
       return rc;
-    ce_ln_kernel<H, float><<<ln_blocks, rows_per_block * 32, 0, st>>>(m->pre32, M, m_dev, L.ln2_g, L.ln2_b, c.ln_eps,
+    ce_ln_kernel<H, float><<<ln4_blocks, rows_per_block * 32, 0, st>>>(m->pre32, M, m_dev, L.ln2_g, L.ln2_b, c.ln_eps,
                                                                       m->x32, m->x16);
     SB_CUDA(cudaGetLastError());
   }
@@ -891,7 +908,8 @@ int sb_ce_gemm_test(sb_ctx* ctx, const float* a, const float* w, const float* bi
                     int32_t N, int32_t K, int32_t epi, float* out) {
   SB_REQUIRE(ctx && a && w && bias && out, SB_ERR_ARG, "sb_ce_gemm_test: NULL argument");
   SB_REQUIRE(M > 0 && N > 0 && K > 0 && N % 128 == 0 && K % 64 == 0, SB_ERR_ARG, "sb_ce_gemm_test: bad shape");
-  SB_REQUIRE(epi != CE_EPI_BIAS_RES_F32 || residual, SB_ERR_ARG, "sb_ce_gemm_test: residual required");
+  SB_REQUIRE((epi != CE_EPI_BIAS_RES_F32 && epi != CE_EPI_BIAS_RES16_F16) || residual, SB_ERR_ARG,
+             "sb_ce_gemm_test: residual required");
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
   cudaStream_t st = ctx->stream;
@@ -921,7 +939,14 @@ int sb_ce_gemm_test(sb_ctx* ctx, const float* a, const float* w, const float* bi
   CUtensorMap ma, mw;
   if ((rc = ce_make_tensor_map(&ma, a16, Mp, K))) return rc;
   if ((rc = ce_make_tensor_map(&mw, w16, N, K))) return rc;
-  if ((rc = ce_gemm_launch(epi, ma, mw, Mp, N, K, b32, r32, o16, o32, st))) return rc;
+  const float* res_arg = r32;
+  if (epi == CE_EPI_BIAS_RES16_F16) {   // the fp16 residual stream: the residual operand is fp16 (rounded here)
+    __half* r16 = nullptr;
+    if ((rc = dev_alloc(pool, (void**)&r16, (size_t)Mp * N * 2))) return rc;
+    f32_to_f16_kernel<<<(unsigned)(((size_t)Mp * N + 255) / 256), 256, 0, st>>>(r32, r16, (int64_t)Mp * N);
+    res_arg = reinterpret_cast<const float*>(r16);
+  }
+  if ((rc = ce_gemm_launch(epi, ma, mw, Mp, N, K, b32, res_arg, o16, o32, st))) return rc;
   const float* result = o32;
   if (epi != CE_EPI_BIAS_RES_F32) {
     f16_to_f32_kernel<<<(unsigned)(((size_t)Mp * N + 255) / 256), 256, 0, st>>>(o16, o32b, (int64_t)Mp * N);

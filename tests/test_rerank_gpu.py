@@ -21,19 +21,26 @@ _erf = np.vectorize(math.erf)
                                        (512, 384, 1536, 2), (77, 128, 128, 2),
                                        # >= 4 row tiles and K <= 384 -> weight-stationary persistent kernel
                                        (2048, 384, 384, 2), (5000, 1536, 384, 1), (700, 128, 64, 0), (25600, 1152, 384, 0),
-                                       (513, 256, 192, 2)])
+                                       (513, 256, 192, 2),
+                                       # M >= 2048, N >= 512, K <= 384, fp16 epilogues -> the transposed CTA-pair kernel
+                                       # (cta_group::2): odd feature tiles (640 = 2.5 x 256), ragged token tiles, K = 192
+                                       (2304, 640, 192, 0), (4100, 512, 384, 1), (9000, 1152, 384, 0), (2048, 1536, 128, 1),
+                                       # epi 3: the fp16 residual stream (residual operand and output in fp16)
+                                       (96, 384, 384, 3), (700, 384, 1536, 3), (3000, 384, 384, 3), (2600, 384, 1536, 3)])
 def test_tcgen05_gemm_matches_numpy(engine, M, N, K, epi):
     rng = np.random.default_rng(M + N + K + epi)
     a = rng.standard_normal((M, K)).astype(np.float32)
     w = (rng.standard_normal((N, K)) * 0.05).astype(np.float32)
     bias = rng.standard_normal(N).astype(np.float32) * 0.1
-    res = rng.standard_normal((M, N)).astype(np.float32) if epi == 2 else None
+    res = rng.standard_normal((M, N)).astype(np.float32) if epi in (2, 3) else None
     got = engine.ce_gemm_test(a, w, bias, epi, res)
     a16 = a.astype(np.float16).astype(np.float64)
     w16 = w.astype(np.float16).astype(np.float64)
     want = a16 @ w16.T + bias
     if epi == 1:
         want = 0.5 * want * (1.0 + _erf(want / math.sqrt(2.0)))
+    if epi == 3:
+        want = want + res.astype(np.float16).astype(np.float64)
     if epi == 2:
         want = want + res
         assert np.allclose(got, want, rtol=1e-4, atol=1e-4)
