@@ -184,7 +184,8 @@ class Workload:
     def text(self):
         if self._text is None:
             t0 = time.time()
-            self._text = self.synth.text_corpus_tokens(self.n_docs)
+            self._text = (self.synth.text_corpus_tokens_range(0, self.n_docs) if self.n_docs > 2_000_000 else
+                          self.synth.text_corpus_tokens(self.n_docs))   # > 2 M docs: the chunk-seeded corpus of the shards
             self.gen_s += time.time() - t0
         return self._text
 

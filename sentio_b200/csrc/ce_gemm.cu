@@ -583,234 +583,6 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   }
 }
 
-// ------------------------------------------------------------------------------------------------ swapped pair GEMM
-// K <= 384 GEMMs with many output features (QKV: N = 1152, FFN-up: N = 1536) are bound by what an SM can INGEST, not by
-// the tensor pipe: with a 128 x 128 tile and the weight tile resident, every tile streams 96 KB of activations for
-// 12.6 MFLOP = 131 flop/B, against a ridge of ~195 flop/B (8192 flop/clk vs ~42 B/clk of L2 -> SM bandwidth per SM); the
-// activation matrix is re-read once per 128-feature tile (9x for QKV, 12x for FFN-up; profiles/r02_run3_launches_rerank).
-// This kernel computes the TRANSPOSED product on a CTA pair,
-//     D^T[features, tokens] = W[features, K] * X[tokens, K]^T        (tcgen05.mma.cta_group::2, M = 256, N = 256)
-// so that the STREAMED operand is the one the hardware splits across the pair: each CTA keeps 128 weight rows resident
-// (A operand, 96 KB at K = 384), loads only HALF of every 256-token tile (B operand, 128 rows x 64 columns = 16 KB per
-// stage) and still multiplies its 128 features with all 256 tokens -- 25 MFLOP per 96 KB = 262 flop/B, tensor bound.
-// The accumulator D^T[128 features, 256 tokens] lives in tensor memory (2 x 256 columns, double buffered); an epilogue
-// thread owns one FEATURE (bias is a per-thread constant, no shuffles) and walks the token columns: for a fixed token the
-// 32 lanes of a warp write 32 consecutive features = one 64-byte segment, so no shared-memory staging is needed.
-constexpr int kPairEpiWarps = 16;
-constexpr int kPairThreads = 64 + 32 * kPairEpiWarps;
-constexpr int kPairTokens = 256;          // tokens per tile (UMMA N)
-constexpr int kPairStages = 6;            // 16 KB stages of the token ring
-
-__device__ __forceinline__ uint32_t pair_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t pair_mapa(uint32_t smem_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void pair_cluster_sync() {
-  __syncwarp();
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(bar_cluster)
-      : "memory");
-}
-__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-      "h"((uint16_t)3)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
-  // default semantics (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id): the tcgen05 fences order the
-  // tensor-memory reads; a cluster-scope release would add a full memory barrier per tile (8.5 % of the stall samples)
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
-}
-
-template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
-ce_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, int M_cap, int N,
-                    int K, const float* __restrict__ bias, __half* __restrict__ out16, const int* __restrict__ m_dev) {
-  const int M = m_dev ? min(M_cap, __ldg(m_dev)) : M_cap;
-  extern __shared__ uint8_t psm_raw[];
-  const uint32_t raw = smem_u32(psm_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  uint8_t* sm = psm_raw + (base - raw);
-  const int num_k = K / BK;
-  const uint32_t w_bytes = (uint32_t)num_k * kTileBBytes;            // this CTA's 128 weight rows, all of K
-  const uint32_t x0 = base + w_bytes;                                  // token ring: kPairStages x 16 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + w_bytes + kPairStages * kTileABytes);
-  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kPairStages), bar_w = smem_u32(bars + 2 * kPairStages);
-  const uint32_t bar_acc_full = smem_u32(bars + 2 * kPairStages + 1), bar_acc_empty = smem_u32(bars + 2 * kPairStages + 3);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPairStages + 5);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = pair_ctarank();
-  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int f_tiles = (N + 255) / 256;                                  // 256-feature tiles (the last one may be half empty)
-  const int t_tiles = (M + kPairTokens - 1) / kPairTokens;
-  const int f_tile = pair % f_tiles;                                    // this pair's features for its whole lifetime
-  const int peer = pair / f_tiles;
-  const int peers = (npairs - f_tile + f_tiles - 1) / f_tiles;          // pairs that own this feature tile
-  const int my_tiles = peer < t_tiles ? (t_tiles - 1 - peer) / peers + 1 : 0;
-  const int f0 = f_tile * 256 + (int)rank * 128;                        // first feature of this CTA
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kPairStages; ++s) {
-      mbar_init(bar_full + 8 * s, 1);     // leader: its own expect_tx arrival + the bytes of both CTAs
-      mbar_init(bar_empty + 8 * s, 1);    // one multicast commit per use
-    }
-    mbar_init(bar_w, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_acc_full + 8 * s, 1);
-      mbar_init(bar_acc_empty + 8 * s, 2 * kPairEpiWarps);   // leader: the epilogue warps of both CTAs
-    }
-    mbar_fence_init();
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  pair_cluster_sync();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ---------------------------------------------------------------- TMA producer (both CTAs)
-    if (lane == 0) {
-      if (rank == 0) mbar_expect_tx(bar_w, 2u * w_bytes);
-      const uint32_t lead_w = pair_mapa(bar_w, 0);
-      for (int kb = 0; kb < num_k; ++kb)   // rows beyond N (second half of an odd last feature tile) are zero filled
-        tma_load_2d_pair(base + (uint32_t)kb * kTileBBytes, &map_w, kb * BK, f0, lead_w);
-      int it = 0;
-      for (int t = 0; t < my_tiles; ++t) {
-        const int t0 = (peer + t * peers) * kPairTokens + (int)rank * 128;    // this CTA's half of the token tile
-        for (int kb = 0; kb < num_k; ++kb, ++it) {
-          const int s = it % kPairStages;
-          const uint32_t use = (uint32_t)(it / kPairStages);
-          if (it >= kPairStages) mbar_wait(bar_empty + 8 * s, (use & 1u) ^ 1u);
-          if (rank == 0) mbar_expect_tx(bar_full + 8 * s, 2u * kTileABytes);
-          tma_load_2d_pair(x0 + (uint32_t)s * kTileABytes, &map_x, kb * BK, t0, pair_mapa(bar_full + 8 * s, 0));
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 0) {
-      // kind::f16: D = f32, A = B = f16 K-major, N = 256 tokens, M = 256 features across the pair
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(kPairTokens >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-      mbar_wait(bar_w, 0);
-      int it = 0;
-      for (int t = 0; t < my_tiles; ++t) {
-        const int as = t & 1;
-        if (t >= 2) mbar_wait(bar_acc_empty + 8 * as, (((uint32_t)t >> 1) & 1u) ^ 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * kPairTokens);
-        for (int kb = 0; kb < num_k; ++kb, ++it) {
-          const int s = it % kPairStages;
-          const uint32_t use = (uint32_t)(it / kPairStages);
-          mbar_wait(bar_full + 8 * s, use & 1u);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t da = make_smem_desc(base + (uint32_t)kb * kTileBBytes);        // weights (resident)
-          const uint64_t db = make_smem_desc(x0 + (uint32_t)s * kTileABytes);           // tokens (streamed)
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_f16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-          umma_commit_pair(bar_empty + 8 * s);
-        }
-        umma_commit_pair(bar_acc_full + 8 * as);
-      }
-    }
-  } else {
-    // ---------------------------------------------------------------- epilogue: 16 warps, thread = one feature;
-    // warp e reads TMEM lane quadrant (warp & 3), token columns [64 * (e >> 2), +64)
-    const int e = warp - 2, quad = warp & 3, colgrp = e >> 2;
-    const int f = f0 + quad * 32 + lane;
-    const bool f_ok = f < N;
-    const float bias_f = f_ok ? __ldg(bias + f) : 0.f;
-    for (int t = 0; t < my_tiles; ++t) {
-      const int as = t & 1;
-      const int tok0 = (peer + t * peers) * kPairTokens + colgrp * 64;
-      mbar_wait(bar_acc_full + 8 * as, ((uint32_t)t >> 1) & 1u);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kPairTokens + colgrp * 64 + h * 32);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr)
-            : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (h == 1) {   // both halves are in registers: hand the accumulator stage back before the stores
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(pair_mapa(bar_acc_empty + 8 * as, 0));
-        }
-        const int tok = tok0 + h * 32;
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const __half2 hv = act_pack<EPI>(__uint_as_float(v[j]) + bias_f, __uint_as_float(v[j + 1]) + bias_f);
-          if (f_ok && tok + j < M) out16[(size_t)(tok + j) * N + f] = __low2half(hv);
-          if (f_ok && tok + j + 1 < M) out16[(size_t)(tok + j + 1) * N + f] = __high2half(hv);
-        }
-      }
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  pair_cluster_sync();   // no CTA leaves (or frees tensor memory) while its peer can still signal it
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
-  }
-}
-
-template <int EPI>
-int launch_pair(const CUtensorMap& map_x, const CUtensorMap& map_w, int M, int N, int K, const float* bias, __half* out16,
-                cudaStream_t st, const int* m_dev) {
-  const size_t smem = (size_t)(K / BK) * kTileBBytes + (size_t)kPairStages * kTileABytes + 1024 /*align*/ + 512 /*barriers*/;
-  static bool configured = false;
-  if (!configured) {
-    SB_CUDA(cudaFuncSetAttribute(ce_gemm_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int f_tiles = (N + 255) / 256, t_tiles = (M + kPairTokens - 1) / kPairTokens;
-  const int pairs = std::max(f_tiles, std::min(sms / 2, f_tiles * t_tiles));
-  ce_gemm_pair_kernel<EPI><<<2 * pairs, kPairThreads, smem, st>>>(map_x, map_w, M, N, K, bias, out16, m_dev);
-  SB_CUDA(cudaGetLastError());
-  return SB_OK;
-}
-
 template <int EPI, bool RESIDENT>
 int launch_ws(const CUtensorMap& map_a, const CUtensorMap& map_w, int M, int N, int K, const float* bias,
               const float* residual, __half* out16, float* out32, cudaStream_t st, const int* m_dev) {
@@ -870,12 +642,6 @@ int ce_make_tensor_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t 
 int ce_gemm_launch(int epi, const CUtensorMap& map_a, const CUtensorMap& map_w, int M, int N, int K, const float* bias,
                    const float* residual, __half* out16, float* out32, cudaStream_t st, const int* m_dev) {
   SB_REQUIRE(N % BN == 0 && K % BK == 0, SB_ERR_ARG, "ce_gemm: N=%d / K=%d must be multiples of %d / %d", N, K, BN, BK);
-  // many-feature K <= 384 GEMMs (QKV, FFN-up): the transposed CTA-pair kernel (env SB_CE_PAIR_GEMM=0 disables it)
-  static const bool pair_on = [] { const char* v = getenv("SB_CE_PAIR_GEMM"); return !(v && atoi(v) == 0); }();
-  if (pair_on && K <= 384 && N >= 512 && M >= 2048 && (epi == CE_EPI_BIAS_F16 || epi == CE_EPI_BIAS_GELU_F16)) {
-    return epi == CE_EPI_BIAS_F16 ? launch_pair<CE_EPI_BIAS_F16>(map_a, map_w, M, N, K, bias, out16, st, m_dev)
-                                  : launch_pair<CE_EPI_BIAS_GELU_F16>(map_a, map_w, M, N, K, bias, out16, st, m_dev);
-  }
   if ((M + BM - 1) / BM >= 4) {  // persistent kernels: weight-stationary when the weight tile fits, streaming otherwise
     if (K <= 384) {
       switch (epi) {

@@ -22,8 +22,6 @@ _erf = np.vectorize(math.erf)
                                        # >= 4 row tiles and K <= 384 -> weight-stationary persistent kernel
                                        (2048, 384, 384, 2), (5000, 1536, 384, 1), (700, 128, 64, 0), (25600, 1152, 384, 0),
                                        (513, 256, 192, 2),
-                                       # M >= 2048, N >= 512, K <= 384, fp16 epilogues -> the transposed CTA-pair kernel
-                                       # (cta_group::2): odd feature tiles (640 = 2.5 x 256), ragged token tiles, K = 192
                                        (2304, 640, 192, 0), (4100, 512, 384, 1), (9000, 1152, 384, 0), (2048, 1536, 128, 1),
                                        # epi 3: the fp16 residual stream (residual operand and output in fp16)
                                        (96, 384, 384, 3), (700, 384, 1536, 3), (3000, 384, 384, 3), (2600, 384, 1536, 3)])
