@@ -726,7 +726,7 @@ def main():
 
     extras = set() if (args.no_extras or kind != "dense" or args.n_docs > 2_000_000) else set(args.extras.split(","))
     workloads, lat, part = {}, None, None
-    sub_steps, sub_warm = max(3, min(args.steps, 8)), max(3, min(args.warmup, 3))
+    sub_steps, sub_warm = max(3, min(args.steps, 20)), max(3, min(args.warmup, 3))
 
     def sub_leg(k2, p, c, lo_, hi_, my_group_, idx_, rr_):
         lg = Leg(k2, p, wl, args, world, rank, local_rank, c, my_group_, lo_, hi_, idx_, rr_)
