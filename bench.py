@@ -700,7 +700,8 @@ def main():
             ln[:len(len_l)] = torch.from_numpy(len_l.astype(np.int32)).to(ln.device)
             tk_all = torch.empty((c * per, tok_l.shape[1]), dtype=torch.int16, device=tk.device)
             ln_all = torch.empty((c * per,), dtype=torch.int32, device=tk.device)
-            dist.all_gather_into_tensor(tk_all, tk, group=group_for(c))
+            # (NCCL has no 16-bit integer type: the token matrix travels as bytes)
+            dist.all_gather_into_tensor(tk_all.view(torch.uint8).view(-1), tk.view(torch.uint8).view(-1), group=group_for(c))
             dist.all_gather_into_tensor(ln_all, ln, group=group_for(c))
             bounds = [((n * r) // c, (n * (r + 1)) // c) for r in range(c)]
             doc_tok = np.concatenate([tk_all[r * per:r * per + (b_ - a_)].cpu().numpy().view(np.uint16)

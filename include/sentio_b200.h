@@ -103,8 +103,12 @@ int sb_dense_set_mode(sb_ctx* ctx, int mode);
 int64_t sb_dense_count(sb_ctx* ctx, int slot);
 int32_t sb_dense_dim(sb_ctx* ctx, int slot);
 /*
- * sb_dense_topk: B queries (row-major B x d fp32, need not be normalised), best-first top-k per query:
+ * sb_dense_topk: B queries (row-major B x d fp32, need not be normalised: any scale), best-first top-k per query, k <= 1024:
  * out_ids[B*k], out_scores[B*k] (exact fp64 cosine, ties broken by ascending id), out_counts[B] (= min(k, n)).
+ * The result is the EXACT top-k of the stored rows for every input: the scans rank by an approximate cosine with a per-query
+ * error bound eps, every row within 2 eps of the k-th best approximate score is re-scored in fp64, and a query whose window
+ * cannot be served that way is answered by a brute-force fp64 kernel (DESIGN.md K1 "Exactness").  Page-locked q / out_*
+ * buffers (sb_host_alloc) are used in place, pageable ones are staged.
  */
 int sb_dense_topk(sb_ctx* ctx, int slot, const float* q, int32_t B, int32_t k,
                   int64_t* out_ids, double* out_scores, int32_t* out_counts);

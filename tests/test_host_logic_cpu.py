@@ -221,3 +221,33 @@ def test_bm25_persistence_large_top_k_and_scroll_corpus_host_logic(tmp_path, mon
     assert client.calls == 3 and len(got) == 229
     assert got[0].id == "p0" and got[0].text == "text 0" and got[0].metadata == {"page": 0}
     assert got[7].text == "from text key" and got[8].id == "9" and got[8].text == "pc" and got[8].metadata == {}
+
+
+def test_global_bm25_stats_of_shards_equal_the_single_index(monkeypatch):
+    """index.global_bm25_stats (the host half of HybridPipeline.build_bm25_sharded): per-shard (term, df) lists of 3
+    contiguous shards -> the corpus-global idf / average idf / avgdl, bit-identical to the single-index build; and the
+    chunk-seeded text generator returns the same docs whatever range is asked for."""
+    import numpy as np
+
+    from sentio_b200 import synth
+    from sentio_b200.index import build_bm25_from_token_ids, global_bm25_stats
+
+    flat, off = synth.text_corpus_tokens(5000, vocab=800)
+    full = build_bm25_from_token_ids(flat, off)
+    bounds = [(0, 1700), (1700, 3100), (3100, 5000)]
+    parts = []
+    for a, b in bounds:
+        d = build_bm25_from_token_ids(flat[off[a]:off[b]], off[a:b + 1] - off[a])
+        term_token = np.full(d.n_terms, -1, np.int64)
+        known = np.nonzero(d.token_id_map >= 0)[0]
+        term_token[d.token_id_map[known]] = known
+        parts.append((term_token, np.diff(d.indptr), d.n_docs, int(d.doc_len.sum())))
+    idf_of, avg_idf, n_docs, avgdl = global_bm25_stats([p[0] for p in parts], [p[1] for p in parts], [p[2] for p in parts],
+                                                       [p[3] for p in parts], "okapi", 0.25)
+    assert n_docs == 5000 and avgdl == full.avgdl and avg_idf == full.average_idf
+    raw = np.nonzero(full.token_id_map >= 0)[0]
+    assert [idf_of[int(t)] for t in raw] == [float(full.idf[full.token_id_map[t]]) for t in raw]
+    a_flat, a_off = synth.text_corpus_tokens_range(0, 150_000)
+    b_flat, b_off = synth.text_corpus_tokens_range(60_000, 140_000)
+    assert np.array_equal(b_flat, a_flat[a_off[60_000]:a_off[140_000]])
+    assert np.array_equal(b_off, a_off[60_000:140_001] - a_off[60_000])
