@@ -165,6 +165,11 @@ struct MmaScanParams {
   int32_t capg;
   int32_t stages;
   int32_t prefetch;             // boxes (16 KB) prefetched into L2 beyond the shared-memory ring (0 = off)
+  // pair kernel, SAMPLING pass only: n_groups query groups of 128 operand rows handled by one launch, one after the other
+  // (group g: operand rows [128 g, 128 g + 128) of tm_q, lists at cand + g * group_cand_stride, counts + g * group_cnt_stride)
+  int32_t n_groups;
+  int64_t group_cand_stride;
+  int64_t group_cnt_stride;
 };
 
 template <int QBN>
@@ -341,12 +346,14 @@ dense_scan_mma2_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + p.stages);
   const uint32_t bar_q = smem_u32(bars + 2 * p.stages);
   const uint32_t bar_acc_full = smem_u32(bars + 2 * p.stages + 1), bar_acc_empty = smem_u32(bars + 2 * p.stages + 3);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 5);
+  const uint32_t bar_qfree = smem_u32(bars + 2 * p.stages + 5);   // every MMA of a query group has completed (both CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 6);
   volatile float* thr = reinterpret_cast<volatile float*>(tmem_slot + 2);   // [NQ]
   int* cnt = reinterpret_cast<int*>(const_cast<float*>(thr) + NQ);         // [NQ]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
+  const int n_groups = p.thr_init == nullptr ? max(p.n_groups, 1) : 1;   // several groups per launch: sampling pass only
   const int grid = gridDim.x, cta = blockIdx.x;
   const int pair = cta >> 1, npairs = grid >> 1;
   const int n_tp = (p.num_tiles + 1) >> 1;              // tile pairs of this launch
@@ -358,6 +365,7 @@ dense_scan_mma2_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid
       mbar_init(bar_empty + 8 * s, 1);   // one multicast commit per use
     }
     mbar_init(bar_q, 1);
+    mbar_init(bar_qfree, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_acc_full + 8 * s, 1);
       mbar_init(bar_acc_empty + 8 * s, 8);  // leader only: 4 epilogue warps x 2 CTAs
@@ -386,11 +394,14 @@ dense_scan_mma2_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid
     // ---------------------------------------------------------------- TMA producer (both CTAs)
     if (lane == 0) {
       const uint32_t lead_q = mapa_u32(bar_q, 0);
-      if (rank == 0) mbar_expect_tx(bar_q, 2u * q_bytes);
-      for (int kb = 0; kb < p.kb_count; ++kb)
-        tma_load_2d_pair(base + (uint32_t)kb * kQBlockBytes, &tm_q, kb * kBK, (int)rank * HQ, lead_q);
       int it = 0;
       const int total_it = my_tiles * p.kb_count;
+      for (int g = 0; g < n_groups; ++g) {
+      // the query operand of group g replaces that of group g - 1 once every MMA that read it has completed
+      if (g > 0) mbar_wait(bar_qfree, (uint32_t)(g - 1) & 1u);
+      if (rank == 0) mbar_expect_tx(bar_q, 2u * q_bytes);
+      for (int kb = 0; kb < p.kb_count; ++kb)
+        tma_load_2d_pair(base + (uint32_t)kb * kQBlockBytes, &tm_q, kb * kBK, g * NQ + (int)rank * HQ, lead_q);
       for (int t = 0; t < my_tiles; ++t) {
         const int li = 2 * (pair + t * npairs) + (int)rank;
         // the odd tile of the last pair may not exist: load tile 0 again (served by L2), the epilogue ignores it
@@ -398,7 +409,7 @@ dense_scan_mma2_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid
         for (int kb = 0; kb < p.kb_count; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t use = (uint32_t)(it / p.stages);
-          const int pf = it + p.stages + p.prefetch;   // a box the ring will only reach later: pull it into L2 now
+          const int pf = (it - g * total_it) + p.stages + p.prefetch;   // a box the ring will only reach later: L2 prefetch
           if (p.prefetch > 0 && pf < total_it) {
             const int pt = pf / p.kb_count, pkb = pf - pt * p.kb_count;
             const int pli = 2 * (pair + pt * npairs) + (int)rank;
@@ -410,17 +421,19 @@ dense_scan_mma2_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid
                            mapa_u32(bar_full + 8 * s, 0));
         }
       }
+      }
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer (leader CTA only)
     if (lane == 0 && rank == 0) {
       // kind::f16: D = f32, A = B = f16 K-major, N >> 3 at [17,23), M >> 4 at [24,29); M = 256 across the pair
       const uint32_t idesc = (1u << 4) | ((uint32_t)(NQ >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-      mbar_wait(bar_q, 0);
-      int it = 0;
-      for (int t = 0; t < my_tiles; ++t) {
-        const int as = t & 1;
-        if (t >= 2) mbar_wait(bar_acc_empty + 8 * as, (((uint32_t)t >> 1) & 1u) ^ 1u);
+      int it = 0, tt = 0;   // ring slot counter / accumulator-stage counter, both running across the query groups
+      for (int g = 0; g < n_groups; ++g) {
+      mbar_wait(bar_q, (uint32_t)g & 1u);
+      for (int t = 0; t < my_tiles; ++t, ++tt) {
+        const int as = tt & 1;
+        if (tt >= 2) mbar_wait(bar_acc_empty + 8 * as, (((uint32_t)tt >> 1) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * NQ);
         for (int kb = 0; kb < p.kb_count; ++kb, ++it) {
@@ -437,20 +450,24 @@ dense_scan_mma2_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid
         }
         umma_commit_pair(bar_acc_full + 8 * as);
       }
+      if (g + 1 < n_groups) umma_commit_pair(bar_qfree);   // arrives in both CTAs once this group's MMAs have completed
+      }
     }
   } else {
     // ---------------------------------------------------------------- epilogue warps 2..5 (both CTAs): one row per thread
     const int quad = warp & 3;
-    unsigned long long* my_cand = p.cand + (size_t)cta * p.capg;
     const size_t q_stride = (size_t)grid * p.capg;
-    for (int t = 0; t < my_tiles; ++t) {
-      const int as = t & 1;
+    int tt = 0;
+    for (int g = 0; g < n_groups; ++g) {
+    unsigned long long* my_cand = p.cand + (size_t)g * p.group_cand_stride + (size_t)cta * p.capg;
+    for (int t = 0; t < my_tiles; ++t, ++tt) {
+      const int as = tt & 1;
       const int li = 2 * (pair + t * npairs) + (int)rank;
       const int tile = p.tile_first + li * p.tile_step;
       const int64_t row = (int64_t)tile * kTileRows + quad * 32 + lane;
       const bool live = li < p.num_tiles && row < p.n;
       const float invn = live ? __ldg(p.inv_norm + row) : 0.f;
-      mbar_wait(bar_acc_full + 8 * as, ((uint32_t)t >> 1) & 1u);
+      mbar_wait(bar_acc_full + 8 * as, ((uint32_t)tt >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // 32 columns per round (two x16 loads in flight, one wait); not unrolled: 128 live accumulator registers spill
 #pragma unroll 1
@@ -480,13 +497,15 @@ dense_scan_mma2_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(bar_acc_empty + 8 * as, 0));
     }
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  for (int i = threadIdx.x; i < NQ; i += blockDim.x) {
-    const int c = p.thr_init == nullptr ? my_tiles * 4 : cnt[i];
-    p.counts[(size_t)i * grid + cta] = min(c, p.capg);
-    if (c > p.capg && p.fallback) p.fallback[i] = 1;
+  for (int i = threadIdx.x; i < NQ * n_groups; i += blockDim.x) {
+    const int g = i / NQ, qi = i - g * NQ;
+    const int c = p.thr_init == nullptr ? my_tiles * 4 : cnt[qi];
+    p.counts[(size_t)g * p.group_cnt_stride + (size_t)qi * grid + cta] = min(c, p.capg);
+    if (c > p.capg && p.fallback) p.fallback[qi] = 1;
   }
   cluster_sync_all();   // no CTA leaves (or frees tensor memory) while its peer can still signal it
   if (warp == 1) {
@@ -845,6 +864,9 @@ int dense_mma_topk_enqueue(sb_ctx* ctx, DenseIndex& ix, const float* q_pad, int 
     mp.kb_count = kb_count;
     mp.capg = capg;
     mp.prefetch = ctx->dense_prefetch;
+    mp.n_groups = 1;
+    mp.group_cand_stride = 0;
+    mp.group_cnt_stride = 0;
     SelectParams sp;
     sp.cand = cand;
     sp.counts = counts;
@@ -872,7 +894,25 @@ int dense_mma_topk_enqueue(sb_ctx* ctx, DenseIndex& ix, const float* q_pad, int 
     mp.tile_step = sample_step;
     {
       ProfScope ps(ctx, SB_PROF_DENSE_SAMPLE, st, ng + 1);   // the sampling passes + their threshold select, as one span
-      for (int g = 0; g < ng; ++g) {
+      // the leading pair groups of the chunk share ONE sampling launch (a sampling launch is ~27 us of fixed cost: launch,
+      // TMEM allocation, cluster syncs, the first operand load -- paid once instead of once per 128 queries)
+      int g_first = 0;
+      int n_pair = 0;
+      while (n_pair < ng && gs[(size_t)n_pair].pair) ++n_pair;
+      if (ctx->dense_multisample != 0 && n_pair >= 2) {
+        CUtensorMap tm_q_all;
+        if ((rc = encode_map(&tm_q_all, q16 + (size_t)c0 * ix.d_pad, (int64_t)n_pair * 128, ix.d_pad, 64))) return rc;
+        mp.cand = cand;
+        mp.counts = counts;
+        mp.stages = stages2;
+        mp.n_groups = n_pair;
+        mp.group_cand_stride = (int64_t)gsz * sgrid * capg;
+        mp.group_cnt_stride = (int64_t)gsz * sgrid;
+        if ((rc = launch_mma_pair(tm_rows, tm_q_all, mp, sgrid, smem2, st))) return rc;
+        mp.n_groups = 1;
+        g_first = n_pair;
+      }
+      for (int g = g_first; g < ng; ++g) {
         const Group& G = gs[(size_t)g];
         mp.cand = cand + (size_t)g * gsz * sgrid * capg;
         mp.counts = counts + (size_t)g * gsz * sgrid;

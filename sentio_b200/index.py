@@ -10,6 +10,7 @@
 from __future__ import annotations
 
 import math
+import os
 import pickle
 import zlib
 from dataclasses import dataclass, field
@@ -257,15 +258,25 @@ def hash_vocab_ids(n_vocab: int, prefix: str = "w") -> np.ndarray:
 
 def doc_token_matrix(flat_tokens: np.ndarray, doc_offsets: np.ndarray, vocab_ids: np.ndarray, ld: int = 120):
     """Pre-tokenised documents for the batched rerank path: (tok uint16 [N, ld], len int32 [N]) from an integer token
-    stream (doc i = flat_tokens[off[i]:off[i+1]], truncated to ld)."""
+    stream (doc i = flat_tokens[off[i]:off[i+1]], truncated to ld).  Blocks of 256 k docs are filled by a small thread
+    pool (NumPy's gather / scatter release the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+
     off = np.asarray(doc_offsets, dtype=np.int64)
+    flat = np.asarray(flat_tokens)
     n = len(off) - 1
     lens = np.minimum(np.diff(off), ld).astype(np.int32)
     tok = np.zeros((n, ld), dtype=np.uint16)
     col = np.arange(ld)[None, :]
-    mask = col < lens[:, None]
-    src = (off[:-1, None] + col)[mask]
-    tok[mask] = vocab_ids[np.asarray(flat_tokens)[src]]
+
+    def block(lo):
+        hi = min(n, lo + 262144)
+        mask = col < lens[lo:hi, None]
+        src = (off[lo:hi, None] + col)[mask]
+        tok[lo:hi][mask] = vocab_ids[flat[src]]
+
+    with ThreadPoolExecutor(max_workers=min(16, max(1, (os.cpu_count() or 1) // 2))) as ex:
+        list(ex.map(block, range(0, n, 262144)))
     return tok, lens
 
 
