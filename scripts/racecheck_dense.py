@@ -21,7 +21,7 @@ def main():
     x16 = x.astype(np.float16)
     x16[3000:5600] = x16[11]                     # 2600 exact duplicates: window > winner buffer -> brute-force fallback
     eng.load_dense(x16)
-    for B in (3, 40, 130):                       # CUDA-core scan / single-CTA tcgen05 scan / pair scan + a small group
+    for B in (3, 40, 130, 300):                       # CUDA-core scan / single-CTA tcgen05 scan / pair scan + a small group
         q = rng.standard_normal((B, d)).astype(np.float32)
         q[1] = x16[11].astype(np.float32)
         q[2] = 0.0
