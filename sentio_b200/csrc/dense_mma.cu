@@ -187,7 +187,7 @@ dense_scan_mma_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + p.stages);
   const uint32_t bar_q = smem_u32(bars + 2 * p.stages);
   const uint32_t bar_acc_full = smem_u32(bars + 2 * p.stages + 1), bar_acc_empty = smem_u32(bars + 2 * p.stages + 3);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 5);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 6);   // its own 16-byte slot (tcgen05.alloc writes it)
   volatile float* thr = reinterpret_cast<volatile float*>(tmem_slot + 2);   // [QBN]
   int* cnt = reinterpret_cast<int*>(const_cast<float*>(thr) + QBN);        // [QBN]
 
@@ -347,7 +347,7 @@ dense_scan_mma2_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid
   const uint32_t bar_q = smem_u32(bars + 2 * p.stages);
   const uint32_t bar_acc_full = smem_u32(bars + 2 * p.stages + 1), bar_acc_empty = smem_u32(bars + 2 * p.stages + 3);
   const uint32_t bar_qfree = smem_u32(bars + 2 * p.stages + 5);   // every MMA of a query group has completed (both CTAs)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 6);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 8);   // its own 16-byte slot (tcgen05.alloc writes it)
   volatile float* thr = reinterpret_cast<volatile float*>(tmem_slot + 2);   // [NQ]
   int* cnt = reinterpret_cast<int*>(const_cast<float*>(thr) + NQ);         // [NQ]
 
