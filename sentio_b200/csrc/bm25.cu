@@ -78,7 +78,7 @@ __global__ void bm25_dense_fill_kernel(const int64_t* __restrict__ indptr, const
 //    no cursor, no compare, no vote (8 instead of ~37 instructions per 32 postings).  Adding idf * 0.0 = +-0.0 to a doc
 //    without a posting leaves its accumulator bit-for-bit unchanged, exactly like rank_bm25's dense `score +=` does;
 //  * the posting-list walk addresses its shared-memory accumulators through 32-bit shared-space addresses and is
-//    branch-free (the accumulator update is one predicated ld / add / st block): the first version of this kernel spent
+//    branch-free (a posting beyond the sub-range reads a never-written per-warp dummy slot): the first version spent
 //    150 instructions per 128 postings on generic-address arithmetic and divergence bookkeeping (profiles/r02_run4_bm25*);
 //  * a finished sub-range is consumed by its warp according to MODE:
 //      kModeSample : (S ranges spread over the corpus, one per CTA) ceil(k/S)-th best positive score of the range, min
@@ -144,26 +144,21 @@ __device__ __forceinline__ int64_t warp_lower_bound(const int32_t* __restrict__ 
 __device__ unsigned long long block_kth_largest(const unsigned long long* keys, int n, int K, int* hist, int* scal,
                                                 int passes);
 
-// acc[addr] = acc[addr] + add (round to nearest), predicated on `on`: one branch-free block, nothing is touched when off
-__device__ __forceinline__ void acc_add_if(uint32_t addr, double add, bool on) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      ".reg .f64 t;\n"
-      "setp.ne.b32 p, %2, 0;\n"
-      "@p ld.shared.f64 t, [%0];\n"
-      "@p add.rn.f64 t, t, %1;\n"
-      "@p st.shared.f64 [%0], t;\n"
-      "}\n" ::"r"(addr),
-      "d"(add), "r"((int)on)
-      : "memory");
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
 
 template <int MODE, bool PLUS>
 __global__ void __launch_bounds__(kRsThreads, 2) bm25_range_kernel(const RangeParams p) {
   extern __shared__ __align__(16) uint8_t rsm[];
   double* acc = reinterpret_cast<double*>(rsm);                               // [kRange]: warp w owns [w*kSub, (w+1)*kSub)
-  int64_t* s_lo = reinterpret_cast<int64_t*>(acc + kRange);                   // [max_len] first posting of the term's list
+  double* s_dummy = acc + kRange;                                             // [kRsWarps] 0.0, read by out-of-range postings
+  int64_t* s_lo = reinterpret_cast<int64_t*>(s_dummy + kRsWarps);             // [max_len] first posting of the term's list
   double* s_idf = reinterpret_cast<double*>(s_lo + p.max_len);                // [max_len] 0.0 = term contributes nothing
   int32_t* s_n = reinterpret_cast<int32_t*>(s_idf + p.max_len);               // [max_len] postings in the list (df < 2^31)
   int32_t* s_wid = s_n + p.max_len;                                           // [max_len] chunks in flight; -1 - slot = dense row
@@ -205,7 +200,9 @@ __global__ void __launch_bounds__(kRsThreads, 2) bm25_range_kernel(const RangePa
   }
   double* a = acc + warp * kSub;
   const uint32_t a_s = smem_u32(a);                      // shared-space address of this warp's accumulators
+  const uint32_t dummy_s = smem_u32(s_dummy + warp);
   for (int i = lane; i < kSub; i += 32) a[i] = 0.0;
+  if (lane == 0) s_dummy[warp] = 0.0;
   uint32_t* bits = s_bits + warp * (kSub / 32);
   if (PLUS && lane < kSub / 32) bits[lane] = 0u;
   __syncthreads();
@@ -242,7 +239,7 @@ __global__ void __launch_bounds__(kRsThreads, 2) bm25_range_kernel(const RangePa
         for (int c = 0; c < kSub / 32; ++c) {
           const uint32_t ad = a_s + (uint32_t)(c * 32 + lane) * 8u;
           const double add = PLUS ? __dmul_rn(w, __dadd_rn(p.delta, r[c])) : __dmul_rn(w, r[c]);
-          acc_add_if(ad, add, (c * 32 + lane) < nd);
+          if ((c * 32 + lane) < nd) sts_f64(ad, __dadd_rn(lds_f64(ad), add));
         }
         __syncwarp();
         continue;
@@ -253,7 +250,7 @@ __global__ void __launch_bounds__(kRsThreads, 2) bm25_range_kernel(const RangePa
       int32_t cur = my_cur[j];
       // chunk loop, specialised on the number of 32-posting chunks in flight (warp-uniform).  The postings of the list are
       // sorted by doc, so the ones inside [s0, s1) are a prefix of what is fetched: their count advances the cursor.
-      // Branch-free body: the read-modify-write of a posting is one predicated block (nothing happens beyond the sub-range).
+      // Branch-free body: a posting beyond the sub-range reads the warp's (never written) dummy slot and stores nothing.
       auto walk = [&](auto width) {
         constexpr int W = decltype(width)::value;
         for (;;) {
@@ -270,9 +267,10 @@ __global__ void __launch_bounds__(kRsThreads, 2) bm25_range_kernel(const RangePa
 #pragma unroll
           for (int u = 0; u < W; ++u) {
             const bool in = doc[u] < s1;
-            const uint32_t ad = a_s + (uint32_t)(doc[u] - s0) * 8u;   // only dereferenced when `in`
+            const uint32_t ad = in ? a_s + (uint32_t)(doc[u] - s0) * 8u : dummy_s;   // dummy: read-only, holds 0.0
             const double add = PLUS ? __dmul_rn(w, __dadd_rn(p.delta, rat[u])) : __dmul_rn(w, rat[u]);
-            acc_add_if(ad, add, in);
+            const double sum = __dadd_rn(lds_f64(ad), add);
+            if (in) sts_f64(ad, sum);
             if (PLUS && in) atomicOr(&bits[(doc[u] - s0) >> 5], 1u << ((doc[u] - s0) & 31));
             inside += __popc(__ballot_sync(0xffffffffu, in));
           }
@@ -540,7 +538,7 @@ int pow2_at_least(int v) {
 }
 
 size_t range_smem_bytes(int max_len) {
-  return (size_t)kRange * 8 + (size_t)std::max(max_len, 1) * (8 + 8 + 4 + 4 + 4 * kRsWarps) + (kRange / 32) * 4 + 16;
+  return (size_t)kRange * 8 + kRsWarps * 8 + (size_t)std::max(max_len, 1) * (8 + 8 + 4 + 4 + 4 * kRsWarps) + (kRange / 32) * 4 + 16;
 }
 
 template <int MODE, bool PLUS>

@@ -267,8 +267,6 @@ ce_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // traffic per output tile (the 128 x 128 x 384 tiles of the plain kernel are L2-bandwidth bound at ~64 flop/B); the
 // accumulator is double buffered in tensor memory so the epilogue of tile i overlaps the MMAs of tile i + 1.
 constexpr int kWsStages = 5;
-constexpr int kWsAcc = 4;                           // accumulator stages in tensor memory (4 x 128 = all 512 columns): the MMA
-                                                    // issuer runs up to three tiles ahead of the epilogue
 constexpr int kWsEpiWarps = 16;                     // 4 per TMEM lane quadrant, 32 accumulator columns each
 constexpr int kWsThreads = 64 + 32 * kWsEpiWarps;   // TMA warp + MMA warp + epilogue warps
 constexpr uint32_t kStageRow = 80;                  // bytes per staged row (64 B of payload + 16 B pad: conflict-free 128-bit stores)
@@ -348,10 +346,8 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const uint32_t a0 = base + w_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + w_bytes + kWsStages * kRingStage);
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kWsStages), bar_w = smem_u32(bars + 2 * kWsStages);
-  const uint32_t bar_acc_full = smem_u32(bars + 2 * kWsStages + 1), bar_acc_empty = smem_u32(bars + 2 * kWsStages + 1 + kWsAcc);
-  // (slot index chosen so that the epilogue staging area behind it, tmem_slot + 2 words, is 16-byte aligned)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWsStages + 3 + 2 * kWsAcc);
-  static_assert(((2 * kWsStages + 3 + 2 * kWsAcc) * 8 + 8) % 16 == 0 && (2 * kWsStages + 3 + 2 * kWsAcc) * 8 + 8 <= 256, "barrier block layout");
+  const uint32_t bar_acc_full = smem_u32(bars + 2 * kWsStages + 1), bar_acc_empty = smem_u32(bars + 2 * kWsStages + 3);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWsStages + 5);
   uint8_t* stage_s = reinterpret_cast<uint8_t*>(tmem_slot + 2);                   // [kWsEpiWarps][32 rows][80 B]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -377,7 +373,7 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_w, 1);
-    for (int s = 0; s < kWsAcc; ++s) {
+    for (int s = 0; s < 2; ++s) {
       mbar_init(bar_acc_full + 8 * s, 1);
       mbar_init(bar_acc_empty + 8 * s, kWsEpiWarps);
     }
@@ -387,7 +383,7 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(kWsAcc * BN)
+                 "n"(2 * BN)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -422,8 +418,8 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       if (RESIDENT) mbar_wait(bar_w, 0);
       int it = 0;
       for (int t = 0; t < my_tiles; ++t) {
-        const int as = t % kWsAcc;
-        if (t >= kWsAcc) mbar_wait(bar_acc_empty + 8 * as, (((uint32_t)(t / kWsAcc)) & 1u) ^ 1u);
+        const int as = t & 1;
+        if (t >= 2) mbar_wait(bar_acc_empty + 8 * as, (((uint32_t)t >> 1) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
         for (int kb = 0; kb < num_k; ++kb, ++it) {
@@ -451,25 +447,17 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int e = warp - 2, quad = warp & 3, colgrp = e >> 2;
     uint8_t* st = stage_s + (size_t)e * kStageWarpBytes;
     const int sub = lane >> 4, c16 = lane & 15;
-    float bias_lane = 0.f;  // bias of column (col0 + lane); broadcast with shuffles in phase 1 (streaming kernels)
+    float bias_lane = 0.f;  // bias of column (col0 + lane); broadcast with shuffles in phase 1
     int bias_col0 = -1;
-    float bias_r[32];       // weight-stationary kernels: the warp's column group is fixed for the whole kernel
-    if (RESIDENT) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n_tile_fixed * BN + colgrp * 32 + j));
-        bias_r[j] = b4.x; bias_r[j + 1] = b4.y; bias_r[j + 2] = b4.z; bias_r[j + 3] = b4.w;
-      }
-    }
     for (int t = 0; t < my_tiles; ++t) {
-      const int as = t % kWsAcc;
+      const int as = t & 1;
       const int row0 = tile_m0(t) + quad * 32;
       const int col0 = tile_n0(t) + colgrp * 32;
       if (col0 != bias_col0) {
         bias_lane = __ldg(bias + col0 + lane);
         bias_col0 = col0;
       }
-      mbar_wait(bar_acc_full + 8 * as, ((uint32_t)(t / kWsAcc)) & 1u);
+      mbar_wait(bar_acc_full + 8 * as, ((uint32_t)t >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t v[32];
       {
@@ -491,12 +479,9 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
       float f[32];
-      if (RESIDENT) {   // this warp's 32 bias values never change: registers, no shuffles
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bias_r[j];
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bias_lane, j);
+      for (int j = 0; j < 32; ++j) {
+        f[j] = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bias_lane, j);
       }
       if (EPI == CE_EPI_BIAS_RES16_F16) {
         const __half* res16 = reinterpret_cast<const __half*>(residual);
@@ -594,7 +579,7 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kWsAcc * BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
   }
 }
 
