@@ -48,7 +48,6 @@ int sb_create(int device, sb_ctx** out) {
   if (const char* v = getenv("SB_DENSE_PAIR")) ctx->dense_pair = atoi(v) != 0;
   if (const char* v = getenv("SB_DENSE_SAMPLE")) ctx->dense_sample_per_cta = atoi(v) > 0 ? atoi(v) : 2;
   if (const char* v = getenv("SB_DENSE_MULTISAMPLE")) ctx->dense_multisample = atoi(v) != 0;
-  if (const char* v = getenv("SB_DENSE_SWFWD")) ctx->dense_sw_forward = atoi(v) != 0;
   if (const char* v = getenv("SB_DENSE_PREFETCH")) ctx->dense_prefetch = atoi(v) > 0 ? atoi(v) : 0;
   if (const char* v = getenv("SB_DENSE_STAGES")) ctx->dense_max_stages = atoi(v) >= 3 ? atoi(v) : 8;
   cudaError_t se = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);

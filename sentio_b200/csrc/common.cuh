@@ -136,7 +136,6 @@ struct sb_ctx {
   int dense_sample_per_cta = 2;  // tiles per CTA of the sampling pass (env SB_DENSE_SAMPLE)
   int max_clusters2 = 0;  // co-resident 2-CTA clusters of the pair kernel (0 = not queried yet)
   int dense_multisample = 1;   // the pair groups of a batch share one sampling launch (env SB_DENSE_MULTISAMPLE=0: one per group)
-  int dense_sw_forward = 0;    // pair kernel: software completion forwarding instead of cta_group::2 TMA (env SB_DENSE_SWFWD)
   int dense_prefetch = 0;      // boxes prefetched into L2 beyond the ring (env SB_DENSE_PREFETCH; 0 = off)
   int dense_max_stages = 8;    // cap on the TMA ring depth (env SB_DENSE_STAGES)
   // bookkeeping: kernels launched by this library, optional per-kernel CUDA-event timing (bench.py roofline leg)

@@ -124,11 +124,6 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
 
-// cluster-scope release: used by the software completion forwarder, whose arrival publishes operand bytes to the leader
-__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t bar_cluster) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
-}
-
 template <int N>
 struct TmemLd;
 template <>
@@ -173,8 +168,6 @@ struct MmaScanParams {
   // pair kernel, SAMPLING pass only: n_groups query groups of 128 operand rows handled by one launch, one after the other
   // (group g: operand rows [128 g, 128 g + 128) of tm_q, lists at cand + g * group_cand_stride, counts + g * group_cnt_stride)
   int32_t n_groups;
-  int32_t sw_forward;           // pair kernel: 1 = the non-leader CTA loads with plain (cta_group::1) TMA on its OWN barriers
-                                // and a forwarder thread relays each completion to the leader (experiment)
   int64_t group_cand_stride;
   int64_t group_cnt_stride;
 };
@@ -368,11 +361,10 @@ dense_scan_mma2_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      // leader: its own expect_tx arrival + the bytes of both CTAs (hardware forwarding) or + the forwarder's arrival
-      mbar_init(bar_full + 8 * s, (p.sw_forward && rank == 0) ? 2 : 1);
+      mbar_init(bar_full + 8 * s, 1);    // used in the leader only: its own expect_tx arrival + the bytes of both CTAs
       mbar_init(bar_empty + 8 * s, 1);   // one multicast commit per use
     }
-    mbar_init(bar_q, (p.sw_forward && rank == 0) ? 2 : 1);
+    mbar_init(bar_q, 1);
     mbar_init(bar_qfree, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_acc_full + 8 * s, 1);
@@ -407,15 +399,9 @@ dense_scan_mma2_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid
       for (int g = 0; g < n_groups; ++g) {
       // the query operand of group g replaces that of group g - 1 once every MMA that read it has completed
       if (g > 0) mbar_wait(bar_qfree, (uint32_t)(g - 1) & 1u);
-      if (p.sw_forward) {
-        mbar_expect_tx(bar_q, q_bytes);
-        for (int kb = 0; kb < p.kb_count; ++kb)
-          tma_load_2d(base + (uint32_t)kb * kQBlockBytes, &tm_q, kb * kBK, g * NQ + (int)rank * HQ, bar_q);
-      } else {
-        if (rank == 0) mbar_expect_tx(bar_q, 2u * q_bytes);
-        for (int kb = 0; kb < p.kb_count; ++kb)
-          tma_load_2d_pair(base + (uint32_t)kb * kQBlockBytes, &tm_q, kb * kBK, g * NQ + (int)rank * HQ, lead_q);
-      }
+      if (rank == 0) mbar_expect_tx(bar_q, 2u * q_bytes);
+      for (int kb = 0; kb < p.kb_count; ++kb)
+        tma_load_2d_pair(base + (uint32_t)kb * kQBlockBytes, &tm_q, kb * kBK, g * NQ + (int)rank * HQ, lead_q);
       for (int t = 0; t < my_tiles; ++t) {
         const int li = 2 * (pair + t * npairs) + (int)rank;
         // the odd tile of the last pair may not exist: load tile 0 again (served by L2), the epilogue ignores it
@@ -430,34 +416,15 @@ dense_scan_mma2_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid
             if (pli < p.num_tiles) tma_prefetch_l2_2d(&tm_rows, pkb * kBK, (p.tile_first + pli * p.tile_step) * kTileRows);
           }
           if (it >= p.stages) mbar_wait(bar_empty + 8 * s, (use & 1u) ^ 1u);
-          if (p.sw_forward) {
-            mbar_expect_tx(bar_full + 8 * s, kATileBytes);
-            tma_load_2d(a0 + (uint32_t)s * kATileBytes, &tm_rows, kb * kBK, tile * kTileRows, bar_full + 8 * s);
-          } else {
-            if (rank == 0) mbar_expect_tx(bar_full + 8 * s, 2u * kATileBytes);
-            tma_load_2d_pair(a0 + (uint32_t)s * kATileBytes, &tm_rows, kb * kBK, tile * kTileRows,
-                             mapa_u32(bar_full + 8 * s, 0));
-          }
+          if (rank == 0) mbar_expect_tx(bar_full + 8 * s, 2u * kATileBytes);
+          tma_load_2d_pair(a0 + (uint32_t)s * kATileBytes, &tm_rows, kb * kBK, tile * kTileRows,
+                           mapa_u32(bar_full + 8 * s, 0));
         }
       }
       }
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 1 && p.sw_forward) {
-      // forwarder (non-leader CTA): relays every local "operand landed" completion to the leader's barrier
-      int it = 0;
-      for (int g = 0; g < n_groups; ++g) {
-        mbar_wait(bar_q, (uint32_t)g & 1u);
-        mbar_arrive_cluster_release(mapa_u32(bar_q, 0));
-        for (int t = 0; t < my_tiles; ++t)
-          for (int kb = 0; kb < p.kb_count; ++kb, ++it) {
-            const int s = it % p.stages;
-            mbar_wait(bar_full + 8 * s, (uint32_t)(it / p.stages) & 1u);
-            mbar_arrive_cluster_release(mapa_u32(bar_full + 8 * s, 0));
-          }
-      }
-    }
     if (lane == 0 && rank == 0) {
       // kind::f16: D = f32, A = B = f16 K-major, N >> 3 at [17,23), M >> 4 at [24,29); M = 256 across the pair
       const uint32_t idesc = (1u << 4) | ((uint32_t)(NQ >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -898,7 +865,6 @@ int dense_mma_topk_enqueue(sb_ctx* ctx, DenseIndex& ix, const float* q_pad, int 
     mp.capg = capg;
     mp.prefetch = ctx->dense_prefetch;
     mp.n_groups = 1;
-    mp.sw_forward = ctx->dense_sw_forward;
     mp.group_cand_stride = 0;
     mp.group_cnt_stride = 0;
     SelectParams sp;
