@@ -597,8 +597,23 @@ def latency_b1(pipe, wl: Workload, idx, n_queries=200, top_k=100):
 
 
 # --------------------------------------------------------------------------------------------- main
+_RESULT_OUT = sys.stdout
+
+
+def _emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
+
 def main():
     args = parse_args()
+    # Libraries print to stdout behind our back (NCCL's "NCCL version ..." banner at communicator creation): keep a private
+    # handle on the real stdout for the result line and point fd 1 at stderr for everything else.
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -641,7 +656,7 @@ def main():
                 "cpu_baseline": {**base, "sample": f"{per_step} queries per step; " + base["sample"]},
                 "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        _emit(line)
         return 0
 
     import torch
@@ -807,7 +822,7 @@ def main():
         line["latency_b1"] = lat
     if part:
         line["partitioned"] = part
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
