@@ -10,7 +10,8 @@ import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libsentio_b200.so"
+# SENTIO_B200_LIB: load another build of the same sources (A/B measurements of kernel variants: scripts/r02_gpu11.sh)
+LIB_PATH = Path(os.environ.get("SENTIO_B200_LIB") or _PKG / "libsentio_b200.so")
 
 c_i64p = C.POINTER(C.c_int64)
 c_i32p = C.POINTER(C.c_int32)

@@ -45,6 +45,33 @@ def _digest(paths) -> str:
     return h.hexdigest()
 
 
+def build_variant(name: str, defines, verbose: bool = False) -> Path:
+    """A second library `libsentio_b200_<name>.so` from the same sources with extra -D flags (kernel A/B measurements;
+    loaded with SENTIO_B200_LIB=<path>)."""
+    nvcc = _nvcc()
+    out = PKG / f"libsentio_b200_{name}.so"
+    obj_dir = PKG / f"build_{name}"
+    obj_dir.mkdir(exist_ok=True)
+    srcs = [CSRC / s for s in SOURCES if (CSRC / s).exists()]
+    flags = [*NVCC_FLAGS, *[f"-D{d}" for d in defines]]
+
+    def compile_one(src: Path) -> Path:
+        obj = obj_dir / (src.stem + ".o")
+        r = subprocess.run([nvcc, *flags, "-c", str(src), "-o", str(obj)], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        objs = list(ex.map(compile_one, srcs))
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(out), *map(str, objs),
+            "-Xlinker", "--exclude-libs=ALL", "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+    r = subprocess.run(link, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     srcs = [CSRC / s for s in SOURCES if (CSRC / s).exists()]
     deps = srcs + sorted(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "sentio_b200.h"]
@@ -80,5 +107,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 
 if __name__ == "__main__":
+    if "--variant" in sys.argv:   # python -m sentio_b200.build --variant NAME -DFOO -DBAR
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a[2:] for a in sys.argv if a.startswith("-D")]))
+        sys.exit(0)
     path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(path)

@@ -75,29 +75,28 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// erf-GELU (the HuggingFace "gelu"): erf through Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 in exact arithmetic):
-//   z = |x| / sqrt(2);  t = 1 / (1 + 0.3275911 z);  erf(z) = 1 - (((((1.061405429 t - 1.453152027) t) + 1.421413741) t
-//   - 0.284496736) t + 0.254829592) t exp(-z^2);  gelu(x) = 0.5 x (1 + copysign(erf(z), x))
-// one reciprocal, one exponential and a 5-term Horner chain instead of the branchy libdevice erff.
-// Evaluated on a PAIR of outputs in packed half precision (HFMA2 / MUFU.*.F16x2): the FFN-up epilogue evaluates
-// 128 x 128 of these per tile and is issue-slot bound in fp32 (run 21: 78 % issue utilisation, tensor pipe 28 % busy);
-// the result is stored as fp16 anyway.  Error study (oracle forward with this GELU emulated in float16, everything else
-// fp64): sigmoid scores move by 5.7e-5 relative, the per-activation rms error after the fp16 store is 6.3e-4 vs 5.2e-4 for
-// the fp32 formula -- i.e. the storage rounding dominates either way (tolerance of the path: 1e-3).
+// erf-GELU (the HuggingFace "gelu") = 0.5 x (1 + erf(x / sqrt 2)), evaluated on a PAIR of outputs in packed half precision
+// with ONE transcendental:  erf(x / sqrt 2) ~ tanh(x (c0 + c1 x^2 + c2 x^4)),  c fitted by least squares on the GELU itself
+// over |x| <= 5.5 (scripts/fit_gelu.py): max |error| 3.0e-5 in exact arithmetic -- 16 x below the stock "tanh GELU"
+// (4.7e-4) and below half an fp16 ulp of the result wherever |gelu| > 0.06.  8 packed instructions per pair
+// (HMUL2 HMNMX2 2 x HFMA2 HMUL2 MUFU.TANH HMUL2 HFMA2); x^2 is clamped at 36 where tanh has saturated in fp16.
+// History: fp32 libdevice erff made the FFN-up epilogue issue bound (r01 run 21: 78 % issue utilisation, tensor pipe
+// 28 %); the Abramowitz-Stegun 7.1.26 form in half2 (reciprocal + exponential + 5-term Horner, 17 instructions per pair)
+// was the round-1 fix; this form cut FFN-up from 340 to 269 us (ncu launch lists of r02 run 12, same box) and the rerank
+// workload from 2741 to 2865 queries/s.  Error study (scripts/fit_gelu.py, every operation rounded to fp16, tanh with the
+// 2^-11 relative error of tanh.approx): rms |error| 2.0e-4 on N(0,1) inputs vs 2.6e-4 for the A-S form and 1.3e-4 for the
+// exact function rounded to fp16 -- the storage rounding dominates either way (tolerance of the path: 1e-3 on the score).
 __device__ __forceinline__ __half2 gelu_erf_h2(__half2 x) {
-  const __half2 one = __float2half2_rn(1.0f);
-  const __half2 z = __hmul2(__habs2(x), __float2half2_rn(0.70710678118654752440f));
-  const __half2 t = h2rcp(__hfma2(__float2half2_rn(0.3275911f), z, one));
-  __half2 p = __hfma2(__float2half2_rn(1.061405429f), t, __float2half2_rn(-1.453152027f));
-  p = __hfma2(p, t, __float2half2_rn(1.421413741f));
-  p = __hfma2(p, t, __float2half2_rn(-0.284496736f));
-  p = __hfma2(p, t, __float2half2_rn(0.254829592f));
-  const __half2 ex = h2exp2(__hmul2(__hmul2(z, z), __float2half2_rn(-1.4426950408889634f)));  // exp(-z^2)
-  const __half2 e = __hfma2(__hneg2(__hmul2(p, t)), ex, one);                                  // erf(|x| / sqrt(2)) >= 0
-  const uint32_t eb = *reinterpret_cast<const uint32_t*>(&e), xb = *reinterpret_cast<const uint32_t*>(&x);
-  const uint32_t sb = (eb & 0x7fff7fffu) | (xb & 0x80008000u);                                 // copysign(e, x)
-  const __half2 s = *reinterpret_cast<const __half2*>(&sb);
-  return __hmul2(__hmul2(__float2half2_rn(0.5f), x), __hadd2(one, s));
+  const __half2 x2 = __hmin2(__hmul2(x, x), __float2half2_rn(36.0f));
+  __half2 q = __hfma2(__float2half2_rn(-0.00035873236644f), x2, __float2half2_rn(0.0370503451315f));
+  q = __hfma2(q, x2, __float2half2_rn(0.79745847075f));
+  const __half2 u = __hmul2(x, q);
+  uint32_t tb;
+  const uint32_t ub = *reinterpret_cast<const uint32_t*>(&u);
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(tb) : "r"(ub));
+  const __half2 th = *reinterpret_cast<const __half2*>(&tb);
+  const __half2 hx = __hmul2(__float2half2_rn(0.5f), x);
+  return __hfma2(hx, th, hx);
 }
 // bias-added fp32 pair -> fp16 pair, through the activation of the epilogue
 template <int EPI>

@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(128) ce_attention_kernel(const __half* __restr
   }
 }
 
-// Masked softmax attention on the tensor cores.  One CTA per (pair, head), 4 warps x 32 query rows; the head's K and V
+// Masked softmax attention on the tensor cores.  One CTA per (pair, head), 4 warps x S_MAX / 64 query tiles of 16 rows; the head's K and V
 // (S x 32 fp16) are staged in shared memory (rows padded to 80 B: conflict-free fragment loads / ldmatrix), scores
 // S = Q K^T and O = P V are mma.sync.m16n8k16 (fp16 in, fp32 accumulate), the softmax runs on the accumulator fragments
 // in registers and the probabilities are re-used directly as the A operand of the second product (no smem round trip).
@@ -344,12 +344,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // h + 1 stream into the second shared-memory buffer with cp.async, so only the first head of a CTA waits for its operands
 // (run 16's profile: a third of all stall samples sat on the K/V staging of one-head CTAs).
 template <int S_MAX, int HPC>
-__global__ void __launch_bounds__(128, 4) ce_attention_mma_kernel(const __half* __restrict__ qkv,
+__global__ void __launch_bounds__(128, S_MAX > 128 ? 2 : 4) ce_attention_mma_kernel(const __half* __restrict__ qkv,
                                                                 const int32_t* __restrict__ lengths,
                                                                 const int32_t* __restrict__ cu, int S, int H,
                                                                 int heads, __half* __restrict__ ctx) {
   constexpr int DH = 32, LDS_ROW = 40;  // halves per padded smem row (80 B)
   constexpr int NT = S_MAX / 8;         // key tiles of 8
+  constexpr int MT = S_MAX / 64;        // 16-row query tiles per warp (4 warps cover S_MAX rows)
   constexpr int NBUF = HPC > 1 ? 2 : 1;
   __shared__ __align__(16) __half Ks_all[NBUF][S_MAX * LDS_ROW];
   __shared__ __align__(16) __half Vs_all[NBUF][S_MAX * LDS_ROW];
@@ -359,6 +360,11 @@ __global__ void __launch_bounds__(128, 4) ce_attention_mma_kernel(const __half* 
   const size_t row0 = (size_t)cu[pair];
   const int ld = 3 * H;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  // 16-row query tiles are dealt round-robin (tile j -> warp j & 3): a pair of ~90 tokens has 6 tiles, so every warp
+  // has work (the contiguous 32-rows-per-warp split left warp 3 idle for every pair shorter than 97 tokens).  Rotating
+  // the assignment per CTA to spread the two-tile warps over the SM's four schedulers was measured and changes nothing
+  // (2741 vs 2749 queries/s, profiles/r02_run12_ab_ce_{base,norot}.json).
+  const int vwarp = warp;
   const int stage_rows = min(S_MAX, (len + 31) & ~31);  // 32-key groups beyond len are never touched
   // rows [len, stage_rows) are masked keys: zeros (finite products), written once -- len belongs to the pair, not the head
   const int zero_slots = (stage_rows - len) * 4;
@@ -384,22 +390,23 @@ __global__ void __launch_bounds__(128, 4) ce_attention_mma_kernel(const __half* 
   const int head = head0 + hh;
   const __half* Ks = Ks_all[hh % NBUF];
   const __half* Vs = Vs_all[hh % NBUF];
-  // Q fragments (A operand) of both 16-row tiles of this warp, issued before waiting for K/V so the global round trips
-  // overlap: rows g / g+8, two k-steps of 16 columns (2t.. and 2t+8..)
-  uint32_t qa_all[2][2][4];
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
-    const int r0 = warp * 32 + mt * 16;
+  // Q fragments (A operand): rows g / g+8 of a 16-row tile, two k-steps of 16 columns (2t.. and 2t+8..)
+  auto load_q = [&](uint32_t (&qa)[2][4], int r0) {
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
       const __half* qlo = qkv + (row0 + min(r0 + g, len - 1)) * ld + head * DH + ks * 16 + 2 * t;
       const __half* qhi = qkv + (row0 + min(r0 + g + 8, len - 1)) * ld + head * DH + ks * 16 + 2 * t;
-      qa_all[mt][ks][0] = *reinterpret_cast<const uint32_t*>(qlo);
-      qa_all[mt][ks][1] = *reinterpret_cast<const uint32_t*>(qhi);
-      qa_all[mt][ks][2] = *reinterpret_cast<const uint32_t*>(qlo + 8);
-      qa_all[mt][ks][3] = *reinterpret_cast<const uint32_t*>(qhi + 8);
+      qa[ks][0] = *reinterpret_cast<const uint32_t*>(qlo);
+      qa[ks][1] = *reinterpret_cast<const uint32_t*>(qhi);
+      qa[ks][2] = *reinterpret_cast<const uint32_t*>(qlo + 8);
+      qa[ks][3] = *reinterpret_cast<const uint32_t*>(qhi + 8);
     }
-  }
+  };
+  // the first two tiles of this warp are fetched before waiting for K/V so the global round trips overlap (all the tiles
+  // there are when S_MAX = 128; the S_MAX = 256 variant fetches tiles 2, 3 inside the loop)
+  uint32_t qa_all[2][2][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) load_q(qa_all[mt], (mt * 4 + vwarp) * 16);
   if (hh + 1 < HPC) {  // next head's K/V into the other buffer (its last readers passed the barrier that ended hh - 1)
     stage((hh + 1) % NBUF, head + 1);
     asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -408,16 +415,20 @@ __global__ void __launch_bounds__(128, 4) ce_attention_mma_kernel(const __half* 
   }
   __syncthreads();
 #pragma unroll 1
-  for (int mt = 0; mt < 2; ++mt) {
-    const int r0 = warp * 32 + mt * 16;  // first query row of this 16-row tile
-    if (r0 >= len) break;                // no such rows in the packed layout
+  for (int mt = 0; mt < MT; ++mt) {
+    const int r0 = (mt * 4 + vwarp) * 16;  // first query row of this 16-row tile
+    if (r0 >= len) break;                  // no such rows in the packed layout
     __half* out_lo = ctx + (row0 + r0 + g) * H + head * DH;
     __half* out_hi = ctx + (row0 + r0 + g + 8) * H + head * DH;
     uint32_t qa[2][4];
+    if (mt < 2) {
 #pragma unroll
-    for (int ks = 0; ks < 2; ++ks)
+      for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) qa[ks][e] = mt ? qa_all[1][ks][e] : qa_all[0][ks][e];
+        for (int e = 0; e < 4; ++e) qa[ks][e] = mt ? qa_all[1][ks][e] : qa_all[0][ks][e];
+    } else {
+      load_q(qa, r0);
+    }
     float sc[NT][4];
 #pragma unroll
     for (int nc = 0; nc < NT / 4; ++nc) {  // groups of 32 keys: 8 independent MMAs per branch keep the tensor pipe fed
@@ -435,33 +446,52 @@ __global__ void __launch_bounds__(128, 4) ce_attention_mma_kernel(const __half* 
         }
       }
     }
-    // masked softmax over the keys; a row's values live in the 4 lanes sharing g
+    // masked softmax over the keys; a row's values live in the 4 lanes sharing g.  Work is skipped per 32-key group
+    // (CTA-uniform): groups at or beyond len hold no keys (their probabilities are never read by the P V loop below) and
+    // only the group that straddles len needs the per-key mask.  The maximum is taken on the raw scores (scale > 0) and
+    // the scale folded into the exponent: p = ex2(s * scale - m * scale), one FFMA per score.
     float mlo = -INFINITY, mhi = -INFINITY;
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      const int key = nt * 8 + 2 * t;
+    for (int nc = 0; nc < NT / 4; ++nc) {
+      if (nc * 32 < len) {
+        if (nc * 32 + 32 > len) {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const bool ok = key + e < len;
-        sc[nt][e] = ok ? sc[nt][e] * scale : -INFINITY;
-        sc[nt][2 + e] = ok ? sc[nt][2 + e] * scale : -INFINITY;
-        mlo = fmaxf(mlo, sc[nt][e]);
-        mhi = fmaxf(mhi, sc[nt][2 + e]);
+          for (int i = 0; i < 4; ++i) {
+            const int nt = nc * 4 + i, key = nt * 8 + 2 * t;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              if (key + e >= len) sc[nt][e] = sc[nt][2 + e] = -INFINITY;
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int nt = nc * 4 + i;
+          mlo = fmaxf(mlo, fmaxf(sc[nt][0], sc[nt][1]));
+          mhi = fmaxf(mhi, fmaxf(sc[nt][2], sc[nt][3]));
+        }
       }
     }
     mlo = fmaxf(mlo, __shfl_xor_sync(0xffffffffu, mlo, 1));
     mlo = fmaxf(mlo, __shfl_xor_sync(0xffffffffu, mlo, 2));
     mhi = fmaxf(mhi, __shfl_xor_sync(0xffffffffu, mhi, 1));
     mhi = fmaxf(mhi, __shfl_xor_sync(0xffffffffu, mhi, 2));
+    const float nlo = -mlo * scale, nhi = -mhi * scale;
     float llo = 0.f, lhi = 0.f;
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
+    for (int nc = 0; nc < NT / 4; ++nc) {
+      if (nc * 32 < len) {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        sc[nt][e] = ex2_approx(sc[nt][e] - mlo);
-        sc[nt][2 + e] = ex2_approx(sc[nt][2 + e] - mhi);
-        llo += sc[nt][e];
-        lhi += sc[nt][2 + e];
+        for (int i = 0; i < 4; ++i) {
+          const int nt = nc * 4 + i;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            sc[nt][e] = ex2_approx(fmaf(sc[nt][e], scale, nlo));
+            sc[nt][2 + e] = ex2_approx(fmaf(sc[nt][2 + e], scale, nhi));
+            llo += sc[nt][e];
+            lhi += sc[nt][2 + e];
+          }
+        }
       }
     }
     llo += __shfl_xor_sync(0xffffffffu, llo, 1);

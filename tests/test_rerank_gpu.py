@@ -65,6 +65,24 @@ def test_small_model_vs_numpy_oracle(engine):
     assert np.allclose(logits, want_l, rtol=1e-2, atol=2e-3)
 
 
+@pytest.mark.parametrize("seq_len", [200, 256, 320])
+def test_windows_longer_than_128_tokens(engine, seq_len):
+    """128 < S <= 256 runs the 256-key tensor-core attention (8 query tiles per warp pair), S > 256 the generic kernel;
+    every query row of a long pair must be attended (round 1 only covered the first 128 rows of the 256-key variant)."""
+    cfg = dict(vocab_size=30522, hidden=128, layers=2, heads=4, intermediate=256, max_pos=512, type_vocab=2, ln_eps=1e-12)
+    w = CrossEncoderWeights.random(cfg, seed=5, std=0.1)   # scores spread over 0.45 .. 0.73 (std 0.05: all ~0.547)
+    engine.ce_load(w.blob(), cfg)
+    flat, off = synth.text_corpus_tokens(40, vocab=4000)
+    docs = synth.texts_from_tokens(flat, off)
+    long_docs = [" ".join(docs[i:i + 1 + i % 5]) for i in range(0, 30, 2)] + ["", "w1 " * 600]
+    ids, tt, lens = hash_tokenize_pairs("w1 w5 w9 w100 w3 w7", long_docs, seq_len)
+    assert int(lens.max()) == seq_len and int((lens > 128).sum()) >= 4 and int((lens < 128).sum()) >= 2
+    logits, sig = engine.ce_score(ids, tt, lens)
+    want_l, want_s = ce_oracle.numpy_forward(w, ids, tt, lens)
+    assert want_s.max() - want_s.min() > 0.2
+    assert np.allclose(sig, want_s, rtol=2e-3, atol=2e-4), np.abs(sig - want_s).max()   # 5 x the init scale of the path's test
+
+
 def test_minilm_l6_vs_huggingface_oracle(engine):
     model = ce_oracle.hf_model(MINILM_L6, seed=0)
     w = CrossEncoderWeights.from_hf_state_dict(model.state_dict(), MINILM_L6)
