@@ -14,6 +14,16 @@ for v in old new old2 new2; do
 done
 timeout 600 python bench.py --workload rerank --cpu-sample 0 --no-extras > gpurun_out/bench_rerank.json 2> gpurun_out/bench_rerank.err
 echo "bench rerank rc=$?" >> gpurun_out/status.txt
+for v in acc4 acc4b; do
+  SENTIO_B200_LIB=$PWD/sentio_b200/libsentio_b200_$v.so timeout 600 python bench.py --workload rerank --cpu-sample 0 --no-extras > gpurun_out/ab_ce_$v.json 2> gpurun_out/ab_ce_$v.err
+  echo "bench $v rc=$?" >> gpurun_out/status.txt
+  tail -1 gpurun_out/ab_ce_$v.json | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('$v rerank', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), d['roofline']['cross_encoder']['frac'])" >> gpurun_out/status.txt
+done
+SENTIO_B200_LIB=$PWD/sentio_b200/libsentio_b200_acc4b.so timeout 600 python -m pytest tests/test_rerank_gpu.py -m gpu -x -q --timeout=600 > gpurun_out/pytest_ce_acc4b.log 2>&1
+echo "pytest_ce_acc4b rc=$?" >> gpurun_out/status.txt
+SENTIO_B200_LIB=$PWD/sentio_b200/libsentio_b200_acc4b.so timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 260 --csv --log-file gpurun_out/launches_rerank_acc4b.csv python bench.py --workload rerank --steps 1 --warmup 1 --inner 1 --cpu-sample 0 --no-extras > gpurun_out/ncu_launch_rerank_acc4b.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches_hybrid.csv python bench.py --workload hybrid --steps 1 --warmup 1 --inner 1 --cpu-sample 0 --no-extras > gpurun_out/ncu_launch_hybrid.log 2>&1
 cat gpurun_out/status.txt; tail -3 gpurun_out/pytest_part.log | cut -c1-300
 for v in old new old2 new2; do tail -1 gpurun_out/ab_bm25_$v.json | python -c "

@@ -115,26 +115,6 @@ struct RangeParams {
   double* dump;              // [nq][n_docs]   kModeDump
 };
 
-// per-term state of a query, 32 bytes so that a warp reads it with two 128-bit shared loads (the first version kept four
-// arrays and paid one dependent shared-memory round trip per field and branch: ~6 % of the collect pass's stall samples)
-struct __align__(16) TermState {
-  double idf;      // 0.0 = the term contributes nothing
-  int64_t lo;      // first posting of the term's list
-  int32_t n;       // postings in the list (df < 2^31)
-  int32_t wid;     // chunks in flight; -1 - slot = dense row
-  int32_t pad[2];
-};
-__device__ __forceinline__ TermState load_term(const TermState* t) {
-  const int4 a = reinterpret_cast<const int4*>(t)[0], b = reinterpret_cast<const int4*>(t)[1];
-  TermState r;
-  r.idf = __hiloint2double(a.y, a.x);
-  r.lo = (int64_t)(((unsigned long long)(unsigned)a.w << 32) | (unsigned)a.z);
-  r.n = b.x;
-  r.wid = b.y;
-  r.pad[0] = r.pad[1] = 0;
-  return r;
-}
-
 // first p in [lo, hi) with a[p] >= target (hi if none); all 32 lanes of the warp participate and return the same value
 __device__ __forceinline__ int64_t warp_lower_bound(const int32_t* __restrict__ a, int64_t lo, int64_t hi, int32_t target,
                                                     int lane) {
@@ -164,16 +144,6 @@ __device__ __forceinline__ int64_t warp_lower_bound(const int32_t* __restrict__ 
 __device__ unsigned long long block_kth_largest(const unsigned long long* keys, int n, int K, int* hist, int* scal,
                                                 int passes);
 
-// dense head-term rows are streamed once per (query, sub-range): keep them out of L1 so that the posting-list lines the
-// tail terms re-read from one sub-range to the next (and the prefetched ones) survive there
-__device__ __forceinline__ double ldg_stream_f64(const double* ptr) {
-  double v;
-  asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(ptr));
-  return v;
-}
-__device__ __forceinline__ void prefetch_l1(const void* ptr) {
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
-}
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
@@ -188,8 +158,11 @@ __global__ void __launch_bounds__(kRsThreads, 2) bm25_range_kernel(const RangePa
   extern __shared__ __align__(16) uint8_t rsm[];
   double* acc = reinterpret_cast<double*>(rsm);                               // [kRange]: warp w owns [w*kSub, (w+1)*kSub)
   double* s_dummy = acc + kRange;                                             // [kRsWarps] 0.0, read by out-of-range postings
-  TermState* s_ts = reinterpret_cast<TermState*>(s_dummy + kRsWarps);         // [max_len] per-term state, one 32-byte record
-  int32_t* s_cur = reinterpret_cast<int32_t*>(s_ts + p.max_len);              // [kRsWarps][max_len] cursor, relative to lo
+  int64_t* s_lo = reinterpret_cast<int64_t*>(s_dummy + kRsWarps);             // [max_len] first posting of the term's list
+  double* s_idf = reinterpret_cast<double*>(s_lo + p.max_len);                // [max_len] 0.0 = term contributes nothing
+  int32_t* s_n = reinterpret_cast<int32_t*>(s_idf + p.max_len);               // [max_len] postings in the list (df < 2^31)
+  int32_t* s_wid = s_n + p.max_len;                                           // [max_len] chunks in flight; -1 - slot = dense row
+  int32_t* s_cur = s_wid + p.max_len;                                         // [kRsWarps][max_len] cursor, relative to s_lo
   uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_cur + (size_t)kRsWarps * p.max_len);  // [kRange / 32] PLUS: doc had a posting
   __shared__ int hist[256];
   __shared__ int scal[4];
@@ -220,13 +193,10 @@ __global__ void __launch_bounds__(kRsThreads, 2) bm25_range_kernel(const RangePa
         wid = slot >= 0 ? -1 - slot : (per_sub < 48 ? 1 : kRsPost);
       }
     }
-    TermState ts;
-    ts.idf = w;
-    ts.lo = lo;
-    ts.n = (int32_t)(hi - lo);
-    ts.wid = wid;
-    ts.pad[0] = ts.pad[1] = 0;
-    s_ts[j] = ts;
+    s_lo[j] = lo;
+    s_n[j] = (int32_t)(hi - lo);
+    s_idf[j] = w;
+    s_wid[j] = wid;
   }
   double* a = acc + warp * kSub;
   const uint32_t a_s = smem_u32(a);                      // shared-space address of this warp's accumulators
@@ -243,9 +213,8 @@ __global__ void __launch_bounds__(kRsThreads, 2) bm25_range_kernel(const RangePa
   int32_t* my_cur = s_cur + (size_t)warp * p.max_len;
   for (int j = 0; j < len; ++j) {
     int64_t pos = 0;
-    const TermState ts = load_term(s_ts + j);
-    if (ts.idf != 0.0 && ts.wid > 0 && strip0 > 0 && strip0 < p.n_docs)
-      pos = warp_lower_bound(p.post_doc + ts.lo, 0, ts.n, (int32_t)strip0, lane);
+    if (s_idf[j] != 0.0 && s_wid[j] > 0 && strip0 > 0 && strip0 < p.n_docs)
+      pos = warp_lower_bound(p.post_doc + s_lo[j], 0, s_n[j], (int32_t)strip0, lane);
     if (lane == 0) my_cur[j] = (int32_t)pos;
   }
   __syncwarp();
@@ -256,35 +225,16 @@ __global__ void __launch_bounds__(kRsThreads, 2) bm25_range_kernel(const RangePa
     const int32_t s0 = (int32_t)s0l;
     const int32_t s1 = (int32_t)min(s0l + kSub, p.n_docs);
     const int nd = s1 - s0;
-    // every posting-list term of the query fetches its next chunk of 32 postings at a cursor that is already known:
-    // lane j asks for term j's lines now (doc ids: <= 2 lines, ratios: <= 3), so that the walk below finds them in L1
-    // instead of paying one L2 round trip per term, one after the other (ncu, run 13: 35 % of the stall samples of the
-    // collect pass were long-scoreboard waits, a third of them on the first use of a posting's doc id)
-    for (int j = lane; j < len; j += 32) {
-      const TermState ts = load_term(s_ts + j);
-      const int32_t cur = my_cur[j], n = ts.n;
-      if (ts.idf != 0.0 && ts.wid > 0 && cur < n) {
-        const int32_t endp = min(cur + 31, n - 1);
-        const int32_t* pd = p.post_doc + ts.lo;
-        const double* pr = p.ratio + ts.lo;
-        prefetch_l1(pd + cur);
-        prefetch_l1(pd + endp);
-        prefetch_l1(pr + cur);
-        prefetch_l1(pr + min(cur + 16, n - 1));
-        prefetch_l1(pr + endp);
-      }
-    }
     for (int j = 0; j < len; ++j) {
-      const TermState ts = load_term(s_ts + j);   // two 128-bit shared loads: all fields arrive together
-      const double w = ts.idf;
+      const double w = s_idf[j];
       if (w == 0.0) continue;  // warp-uniform
-      const int wid = ts.wid;
+      const int wid = s_wid[j];
       if (wid < 0) {
         // ---- head term: dense ratio row, every doc of the sub-range (0.0 where the doc has no posting)
         const double* __restrict__ dr = p.dense_ratio + (size_t)(-1 - wid) * p.n_docs + s0;
         double r[kSub / 32];
 #pragma unroll
-        for (int c = 0; c < kSub / 32; ++c) r[c] = (c * 32 + lane) < nd ? ldg_stream_f64(dr + c * 32 + lane) : 0.0;
+        for (int c = 0; c < kSub / 32; ++c) r[c] = (c * 32 + lane) < nd ? __ldg(dr + c * 32 + lane) : 0.0;
 #pragma unroll
         for (int c = 0; c < kSub / 32; ++c) {
           const uint32_t ad = a_s + (uint32_t)(c * 32 + lane) * 8u;
@@ -294,9 +244,9 @@ __global__ void __launch_bounds__(kRsThreads, 2) bm25_range_kernel(const RangePa
         __syncwarp();
         continue;
       }
-      const int32_t n = ts.n;
-      const int32_t* __restrict__ pd = p.post_doc + ts.lo;
-      const double* __restrict__ pr = p.ratio + ts.lo;
+      const int32_t n = s_n[j];
+      const int32_t* __restrict__ pd = p.post_doc + s_lo[j];
+      const double* __restrict__ pr = p.ratio + s_lo[j];
       int32_t cur = my_cur[j];
       // chunk loop, specialised on the number of 32-posting chunks in flight (warp-uniform).  The postings of the list are
       // sorted by doc, so the ones inside [s0, s1) are a prefix of what is fetched: their count advances the cursor.
@@ -588,7 +538,7 @@ int pow2_at_least(int v) {
 }
 
 size_t range_smem_bytes(int max_len) {
-  return (size_t)kRange * 8 + kRsWarps * 8 + (size_t)std::max(max_len, 1) * (sizeof(TermState) + 4 * kRsWarps) + (kRange / 32) * 4 + 16;
+  return (size_t)kRange * 8 + kRsWarps * 8 + (size_t)std::max(max_len, 1) * (8 + 8 + 4 + 4 + 4 * kRsWarps) + (kRange / 32) * 4 + 16;
 }
 
 template <int MODE, bool PLUS>

@@ -266,6 +266,10 @@ ce_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // traffic per output tile (the 128 x 128 x 384 tiles of the plain kernel are L2-bandwidth bound at ~64 flop/B); the
 // accumulator is double buffered in tensor memory so the epilogue of tile i overlaps the MMAs of tile i + 1.
 constexpr int kWsStages = 5;
+constexpr int kWsAcc = 2;   // accumulator stages in tensor memory.  4 (all 512 columns, the MMA issuer up to three tiles ahead
+                            // of the epilogue) was measured twice and changes nothing: QKV 196.6 -> 195.1 us, FFN-up 269.3 ->
+                            // 268.0 (profiles/r02_run15_launches_rerank_{base,acc4}.csv) -- the K = 384 GEMMs wait for the
+                            // epilogue of the CURRENT tile, not for accumulator space
 constexpr int kWsEpiWarps = 16;                     // 4 per TMEM lane quadrant, 32 accumulator columns each
 constexpr int kWsThreads = 64 + 32 * kWsEpiWarps;   // TMA warp + MMA warp + epilogue warps
 constexpr uint32_t kStageRow = 80;                  // bytes per staged row (64 B of payload + 16 B pad: conflict-free 128-bit stores)
@@ -345,8 +349,11 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const uint32_t a0 = base + w_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + w_bytes + kWsStages * kRingStage);
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kWsStages), bar_w = smem_u32(bars + 2 * kWsStages);
-  const uint32_t bar_acc_full = smem_u32(bars + 2 * kWsStages + 1), bar_acc_empty = smem_u32(bars + 2 * kWsStages + 3);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWsStages + 5);
+  const uint32_t bar_acc_full = smem_u32(bars + 2 * kWsStages + 1), bar_acc_empty = smem_u32(bars + 2 * kWsStages + 1 + kWsAcc);
+  // (slot index chosen so that the epilogue staging area behind it, tmem_slot + 2 words, is 16-byte aligned)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWsStages + 3 + 2 * kWsAcc);
+  static_assert(((2 * kWsStages + 3 + 2 * kWsAcc) * 8 + 8) % 16 == 0 && (2 * kWsStages + 3 + 2 * kWsAcc) * 8 + 8 <= 256,
+                "barrier block layout");
   uint8_t* stage_s = reinterpret_cast<uint8_t*>(tmem_slot + 2);                   // [kWsEpiWarps][32 rows][80 B]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -372,7 +379,7 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_w, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kWsAcc; ++s) {
       mbar_init(bar_acc_full + 8 * s, 1);
       mbar_init(bar_acc_empty + 8 * s, kWsEpiWarps);
     }
@@ -382,7 +389,7 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(2 * BN)
+                 "n"(kWsAcc * BN)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -417,8 +424,8 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       if (RESIDENT) mbar_wait(bar_w, 0);
       int it = 0;
       for (int t = 0; t < my_tiles; ++t) {
-        const int as = t & 1;
-        if (t >= 2) mbar_wait(bar_acc_empty + 8 * as, (((uint32_t)t >> 1) & 1u) ^ 1u);
+        const int as = t % kWsAcc;
+        if (t >= kWsAcc) mbar_wait(bar_acc_empty + 8 * as, (((uint32_t)(t / kWsAcc)) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
         for (int kb = 0; kb < num_k; ++kb, ++it) {
@@ -448,15 +455,38 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int sub = lane >> 4, c16 = lane & 15;
     float bias_lane = 0.f;  // bias of column (col0 + lane); broadcast with shuffles in phase 1
     int bias_col0 = -1;
+    // weight-stationary bias / GELU kernels: the warp's column group is fixed for the whole kernel -> its 32 bias values
+    // live in registers instead of being broadcast with 32 shuffles per tile (QKV 196.6 -> 185.6 us, FFN-up 269.3 -> 257.9,
+    // profiles/r02_run15_launches_rerank_{base,acc4b}.csv).  The residual epilogues keep the shuffles (an earlier attempt
+    // with registers there doubled the out-projection's time, profiles/r02_run9_launches_rerank_4acc_biasregs.csv).
+    constexpr bool kBiasRegs = RESIDENT && (EPI == CE_EPI_BIAS_F16 || EPI == CE_EPI_BIAS_GELU_F16);
+    float bias_r[kBiasRegs ? 32 : 1];
+    if (kBiasRegs) {
+#pragma unroll
+      for (int j = 0; j < (kBiasRegs ? 32 : 0); j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n_tile_fixed * BN + colgrp * 32 + j));
+        bias_r[j] = b4.x; bias_r[j + 1] = b4.y; bias_r[j + 2] = b4.z; bias_r[j + 3] = b4.w;
+      }
+    }
     for (int t = 0; t < my_tiles; ++t) {
-      const int as = t & 1;
+      const int as = t % kWsAcc;
       const int row0 = tile_m0(t) + quad * 32;
       const int col0 = tile_n0(t) + colgrp * 32;
       if (col0 != bias_col0) {
         bias_lane = __ldg(bias + col0 + lane);
         bias_col0 = col0;
       }
-      mbar_wait(bar_acc_full + 8 * as, ((uint32_t)t >> 1) & 1u);
+      // BIAS_RES16: this thread's residual row segment (32 fp16 = 64 bytes of row row0 + lane) is requested before the
+      // accumulator wait, so its latency hides behind the MMAs of the tile
+      uint4 rres[EPI == CE_EPI_BIAS_RES16_F16 ? 4 : 1];
+      if (EPI == CE_EPI_BIAS_RES16_F16) {
+        const int row = row0 + lane;
+        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(residual) + (size_t)row * N + col0);
+#pragma unroll
+        for (int i = 0; i < (EPI == CE_EPI_BIAS_RES16_F16 ? 4 : 0); ++i)
+          rres[i] = row < M ? __ldg(rp + i) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      mbar_wait(bar_acc_full + 8 * as, ((uint32_t)(t / kWsAcc)) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t v[32];
       {
@@ -478,48 +508,27 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
       float f[32];
+      if (kBiasRegs) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        f[j] = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bias_lane, j);
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bias_r[kBiasRegs ? j : 0];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bias_lane, j);
       }
       if (EPI == CE_EPI_BIAS_RES16_F16) {
-        const __half* res16 = reinterpret_cast<const __half*>(residual);
-#pragma unroll 1
-        for (int p2 = 0; p2 < 2; ++p2) {  // the fp32 sums are staged (no double rounding), the residual joins on the way out
+        // the fp32 sums acc + bias + residual are rounded ONCE, to the fp16 row that is staged and drained below
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 w;
-            w.x = p2 ? f[16 + j + 0] : f[j + 0];
-            w.y = p2 ? f[16 + j + 1] : f[j + 1];
-            w.z = p2 ? f[16 + j + 2] : f[j + 2];
-            w.w = p2 ? f[16 + j + 3] : f[j + 3];
-            *reinterpret_cast<float4*>(st + (size_t)lane * kStageRow + (size_t)j * 4) = w;
+        for (int i = 0; i < (EPI == CE_EPI_BIAS_RES16_F16 ? 4 : 0); ++i) {
+          const __half2* h = reinterpret_cast<const __half2*>(&rres[i]);
+#pragma unroll
+          for (int e2 = 0; e2 < 4; ++e2) {
+            const float2 rf = __half22float2(h[e2]);
+            f[8 * i + 2 * e2] += rf.x;
+            f[8 * i + 2 * e2 + 1] += rf.y;
           }
-          __syncwarp();
-          // drain: lane = (row parity `sub`, column pair c8 of 8) x 2 row groups -> 4 rows per instruction, every global
-          // access a full 32-byte sector (16 fp16 columns of one row)
-          const int c8 = lane & 7, rsel = lane >> 3;            // rsel in [0, 4)
-          const int col = col0 + 16 * p2 + 2 * c8;
-#pragma unroll 1
-          for (int r0 = 0; r0 < 32; r0 += 16) {
-            uint32_t res[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int row = row0 + r0 + 4 * u + rsel;
-              res[u] = row < M ? __ldg(reinterpret_cast<const uint32_t*>(res16 + (size_t)row * N + col)) : 0u;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int rr = r0 + 4 * u + rsel, row = row0 + rr;
-              const float2 x = *reinterpret_cast<const float2*>(st + (size_t)rr * kStageRow + (size_t)c8 * 8);
-              const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(&res[u]));
-              const __half2 h = __floats2half2_rn(x.x + rf.x, x.y + rf.y);
-              if (row < M) *reinterpret_cast<uint32_t*>(out16 + (size_t)row * N + col) = *reinterpret_cast<const uint32_t*>(&h);
-            }
-          }
-          __syncwarp();
         }
-      } else if (EPI == CE_EPI_BIAS_RES_F32) {
+      }
+      if (EPI == CE_EPI_BIAS_RES_F32) {
 #pragma unroll 1
         for (int p2 = 0; p2 < 2; ++p2) {  // two passes of 16 fp32 columns (64 bytes per staged row)
 #pragma unroll
@@ -563,14 +572,29 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           *reinterpret_cast<uint4*>(st + (size_t)lane * kStageRow + (size_t)j * 2) = pk;
         }
         __syncwarp();
+        // drain: four 64-byte row segments (32 fp16 columns each) per instruction, 8 bytes per lane.  A half-warp reads
+        // rows (r, r + 4): 4 x 80 B = 80 words = 16 mod 32, so its two 64-byte segments fall on disjoint banks.
+#ifdef SB_CE_DRAIN32   // the previous drain (two rows per instruction, 4 bytes per lane), kept for A/B builds
 #pragma unroll 4
-        for (int r = 0; r < 32; r += 2) {  // two 64-byte row segments (32 fp16 columns each) per instruction
+        for (int r = 0; r < 32; r += 2) {
           const int rr = r + sub, row = row0 + rr;
           if (row < M) {
             const uint32_t x = *reinterpret_cast<const uint32_t*>(st + (size_t)rr * kStageRow + (size_t)c16 * 4);
             *reinterpret_cast<uint32_t*>(out16 + (size_t)row * N + col0 + 2 * c16) = x;
           }
         }
+#else
+        const int c8 = lane & 7, rsel = lane >> 3;
+        const int rmap = (rsel & 1) * 4 + (rsel >> 1);   // {0, 4, 1, 5}
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = (it >> 1) * 8 + (it & 1) * 2 + rmap, row = row0 + rr;
+          if (row < M) {
+            const uint2 x = *reinterpret_cast<const uint2*>(st + (size_t)rr * kStageRow + (size_t)c8 * 8);
+            *reinterpret_cast<uint2*>(out16 + (size_t)row * N + col0 + 4 * c8) = x;
+          }
+        }
+#endif
         __syncwarp();
       }
     }
@@ -578,7 +602,7 @@ ce_gemm_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kWsAcc * BN) : "memory");
   }
 }
 
