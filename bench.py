@@ -505,13 +505,14 @@ class Leg:
                 t = self.term_lists[i]
                 postings += int(df[t[t >= 0]].sum())
         postings = postings * res["n_batches"] / self.ring
-        return {"bound": "issue", "kernel": "bm25_range_kernel (sample + collect)",
+        return {"bound": "latency + l1tex", "kernel": "bm25_range_kernel (sample + collect)",
                 "postings_per_s": postings / (bm_ms * 1e-3), "postings_per_query": postings / (self.B * res["n_batches"]),
                 "algorithmic_bytes": postings * 12, "posting_GBps": postings * 12 / (bm_ms * 1e-3) / 1e9,
                 "frac_of_hbm_peak_if_every_posting_came_from_dram": postings * 12 / (bm_ms * 1e-3) / 1e9 / hbm,
                 "ms_total": bm_ms, "share_of_step": bm_ms / res["ms_total"],
-                "note": "the posting lists shared by a batch are served by L2 (ncu: DRAM traffic << posting bytes); the "
-                        "kernel is instruction-issue bound, so postings/s is the figure of merit, not GB/s"}
+                "note": "the posting lists shared by a batch are served by L2 (ncu: DRAM traffic << posting bytes); ncu of the "
+                        "collect pass (profiles/r02_run13_bm25_range_ncu.md): issue slots 55 % busy, L1TEX 69 %, a third of "
+                        "the stalls on load latency -- no single limiter, so postings/s is the figure of merit, not GB/s"}
 
     def roofline_ce(self, res):
         _, tpeak, _ = peaks()

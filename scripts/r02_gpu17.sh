@@ -13,6 +13,8 @@ echo "bench reference rc=$?" >> gpurun_out/status.txt
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_dense.csv python bench.py --steps 1 --warmup 1 --inner 2 --cpu-sample 0 --no-extras > gpurun_out/ncu_launch_dense.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches_hybrid.csv python bench.py --workload hybrid --steps 1 --warmup 1 --inner 1 --cpu-sample 0 --no-extras > gpurun_out/ncu_launch_hybrid.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 260 --csv --log-file gpurun_out/launches_rerank.csv python bench.py --workload rerank --steps 1 --warmup 1 --inner 1 --cpu-sample 0 --no-extras > gpurun_out/ncu_launch_rerank.log 2>&1
+timeout 500 ncu --set full --clock-control none --import-source on -k "regex:ce_gemm_ws_kernel|ce_attention_mma|ce_ln_kernel" -s 12 -c 7 -o gpurun_out/prof_ce_final python bench.py --workload rerank --steps 1 --warmup 1 --inner 1 --batch 16 --cpu-sample 0 --no-extras > gpurun_out/ncu_full_ce.log 2>&1
+echo "ncu full ce rc=$?" >> gpurun_out/status.txt
 tail -2 gpurun_out/smoke.log | cut -c1-200; tail -4 gpurun_out/pytest_gpu.log | cut -c1-300; cat gpurun_out/status.txt
 for f in full reference; do tail -1 gpurun_out/bench_$f.json | python -c "
 import json,sys
