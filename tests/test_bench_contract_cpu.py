@@ -13,8 +13,9 @@ def _run(*extra):
            "--steps", "2", "--warmup", "1", *extra]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
-    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
-    assert len(lines) == 1, out.stdout
+    # stdout carries the result line and NOTHING else (library banners such as NCCL's are routed to stderr)
+    lines = out.stdout.splitlines()
+    assert len(lines) == 1 and lines[0].startswith("{"), out.stdout
     return json.loads(lines[0])
 
 
