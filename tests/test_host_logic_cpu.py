@@ -251,3 +251,19 @@ def test_global_bm25_stats_of_shards_equal_the_single_index(monkeypatch):
     b_flat, b_off = synth.text_corpus_tokens_range(60_000, 140_000)
     assert np.array_equal(b_flat, a_flat[a_off[60_000]:a_off[140_000]])
     assert np.array_equal(b_off, a_off[60_000:140_001] - a_off[60_000])
+
+
+def test_library_path_override(monkeypatch, tmp_path):
+    """SENTIO_B200_LIB selects another build of the same sources (kernel A/B measurements); unset = the in-tree library."""
+    import importlib
+
+    import sentio_b200._lib as lib
+
+    default = lib.LIB_PATH
+    assert default.name == "libsentio_b200.so" and default.parent.name == "sentio_b200"
+    monkeypatch.setenv("SENTIO_B200_LIB", str(tmp_path / "libsentio_b200_x.so"))
+    try:
+        assert importlib.reload(lib).LIB_PATH == tmp_path / "libsentio_b200_x.so"
+    finally:
+        monkeypatch.delenv("SENTIO_B200_LIB")
+        assert importlib.reload(lib).LIB_PATH == default
